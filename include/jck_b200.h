@@ -1,0 +1,177 @@
+/*
+ * jck_b200.h -- C ABI of libjck_b200.so: the sm_100a kernels under the DCGAN / CGAN train step.
+ *
+ * The reference (hy-vision-learning/jck-generation) has no native code and no FFI: its hot path is
+ * Python calling torch operators.  Each entry point below therefore names the reference call site
+ * (file:line, relative to the reference root) whose torch operator it replaces.  The boundary is
+ * plain C: raw device pointers, int / float scalars, a cudaStream_t passed as void*.  No torch
+ * types.  The Python host (jck_generation_b200/_lib.py) binds it with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative JCK_E_* code; the message is available from
+ *     jck_last_error_string() (thread-local).  Nothing throws, exits, or falls back to a CPU path.
+ *   - all work is asynchronous on `stream`; no entry point synchronises, allocates device memory,
+ *     or reads device data on the host, so a whole train step is CUDA-graph capturable.
+ *   - caller owns every buffer, workspaces included (sizes from the *_workspace_bytes queries).
+ *   - activations are NHWC ("pixels x channels"), dtype JCK_F32 or JCK_BF16; images at the API edge
+ *     are NCHW fp32 as in the reference; parameters / gradients / optimizer state are fp32 in the
+ *     reference's own layouts ([Cout,Cin,4,4] for Conv2d, [Cin,Cout,4,4] for ConvTranspose2d).
+ *   - every 4x4 stride-2 pad-1 layer is described by (Ca, Cb, Hs, Ws): Ca = channels of its
+ *     low-resolution side ("small", Hs x Ws), Cb = channels of its high-resolution side ("large",
+ *     2Hs x 2Ws).  Conv2d: Ca = Cout, Cb = Cin.  ConvTranspose2d: Ca = Cin, Cb = Cout.  Both store
+ *     their weight as w4[Ca][Cb][4][4], so one packing serves both.
+ *         down : large -> small   Conv2d forward            / ConvTranspose2d input-gradient
+ *         up   : small -> large   ConvTranspose2d forward   / Conv2d input-gradient
+ *         wgrad: (small, large) -> dw4                        weight gradient of either
+ */
+#ifndef JCK_B200_H_
+#define JCK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JCK_OK 0
+#define JCK_E_BADARG (-1)
+#define JCK_E_UNSUPPORTED_SHAPE (-2)
+#define JCK_E_CUDA (-3)
+#define JCK_E_DRIVER (-4)
+
+/* activation dtypes */
+#define JCK_F32 0
+#define JCK_BF16 1
+
+/* conv algorithm selector */
+#define JCK_ALGO_AUTO 0  /* tcgen05 where dtype/shape allow, else SIMT */
+#define JCK_ALGO_SIMT 1  /* CUDA-core fp32-FMA implicit GEMM (exact-fp32 parity mode; edge layers) */
+#define JCK_ALGO_TC 2    /* tcgen05 / TMEM / TMA implicit GEMM; error if unsupported */
+
+int jck_version(void);
+const char* jck_last_error_string(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+unsigned long long jck_launch_count(void);
+
+/* ---- image edge ------------------------------------------------------------------------------
+ * out_nhwc[n,h,w,c] = v,  v = a1*x1 + b1*m1            (m1 may be NULL)
+ *                       v = alpha[n]*v + (1-alpha[n])*x2 (when alpha != NULL)
+ * x1, m1, x2: NCHW fp32.  Optional out_nchw_f32 receives v as NCHW fp32.
+ * Replaces: instance noise `0.9*real + 0.1*randn` train/dcgan_trainer.py:160,171 and the
+ * interpolation `alpha*real + (1-alpha)*fake` train/dcgan_trainer.py:112. */
+int jck_prep_image(const float* x1, const float* m1, float a1, float b1, const float* x2,
+                   const float* alpha, void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W,
+                   int dtype, void* stream);
+
+/* NHWC activation-dtype tensor -> NCHW fp32 (e.g. the GP input-gradient handed back to the caller). */
+int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int dtype,
+                         void* stream);
+
+/* ---- weights ---------------------------------------------------------------------------------
+ * w4[Ca][Cb][4][4] fp32 -> w_down[Ca][16][Cb] and w_up[4 phases][Cb][4 taps][Ca] (dtype).
+ * Either output may be NULL. */
+int jck_pack_weights(const float* w4, void* w_down, void* w_up, int Ca, int Cb, int dtype, void* stream);
+
+/* ---- 4x4 stride-2 convolutions ---------------------------------------------------------------
+ * stats (nullable): fp32 [groups][2*Cout] receiving per-channel sum and sum of squares of the
+ * fp32 accumulators, ADDED atomically (caller zeroes); image n belongs to group n / imgs_per_group.
+ * Replaces: nn.Conv2d forward model/DCGAN.py:30-33, nn.ConvTranspose2d forward model/DCGAN.py:63-66,
+ * and aten::convolution_backward (autograd of the above; train/dcgan_trainer.py:164,175,187,116). */
+int jck_conv_down(const void* in_large, const void* w_down, void* out_small, float* stats, int B, int Hs,
+                  int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
+int jck_conv_up(const void* in_small, const void* w_up, void* out_large, float* stats, int B, int Hs,
+                int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
+/* dw4[Ca][Cb][4][4] (+)= sum over pixels small (x) large.  workspace: jck_conv_wgrad_workspace_bytes. */
+size_t jck_conv_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo);
+int jck_conv_wgrad(const void* small, const void* large, float* dw4, void* workspace, size_t workspace_bytes,
+                   int B, int Hs, int Ws, int Ca, int Cb, int accumulate, int dtype, int algo, void* stream);
+
+/* ---- dense layers (G.conv1: a 1x1 -> 4x4 transposed conv is a matrix product) -----------------
+ * out[m][n] = sum_k x[m][k] * w[n][k];  x fp32 [M][K]; w, out activation dtype; stats per channel
+ * (n % C).  Replaces nn.ConvTranspose2d(100,512,4,1,0) model/DCGAN.py:42,62. */
+int jck_fc_fwd(const float* x, const void* w, void* out, float* stats, int M, int N, int K, int C,
+               int dtype, void* stream);
+/* dw[n][k] (+)= sum_m dy[m][n] * x[m][k]  (fp32 out) */
+int jck_fc_wgrad(const void* dy, const float* x, float* dw, int M, int N, int K, int accumulate, int dtype,
+                 void* stream);
+/* G.conv1 weight w4[K][C][16] fp32 <-> fc layout w[n = tap*C + c][k] */
+int jck_pack_fc(const float* w4, void* w_fc, int K, int C, int dtype, void* stream);
+int jck_unpack_fc_grad(const float* dw_fc, float* dw4, int K, int C, int accumulate, void* stream);
+
+/* ---- BatchNorm2d (train mode) + activation ---------------------------------------------------
+ * Replaces nn.BatchNorm2d + nn.LeakyReLU(0.2)/nn.ReLU model/DCGAN.py:11-12,43-44 (forward) and
+ * aten::native_batch_norm_backward / leaky_relu_backward / threshold_backward (autograd).
+ * finalize: for each group g in order: mean, biased var from stats[g] over `count` samples;
+ *   running_mean/var momentum update with UNBIASED var; num_batches_tracked += 1;
+ *   scale_shift[g] = {gamma*rstd, beta - mean*gamma*rstd};  mean_rstd[g] = {mean, rstd}. */
+int jck_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float* scale_shift,
+                    float* mean_rstd, int C, int groups, float count, float eps, float momentum,
+                    void* stream);
+/* a = act(scale*y + shift); slope 0 -> ReLU, 0.2 -> LeakyReLU.  pix_per_group pixels per group. */
+int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, long long npix, int C,
+                   long long pix_per_group, float slope, int dtype, void* stream);
+/* g = da * act'(scale*y+shift); sums[g] += {sum g, sum g*xhat} (caller zeroes sums [groups][2C]) */
+int jck_bn_act_bwd_reduce(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
+                          float* sums, long long npix, int C, long long pix_per_group, float slope,
+                          int dtype, void* stream);
+/* dy = gamma*rstd*(g - sum_g/count - xhat*sum_gx/count) */
+int jck_bn_act_bwd_apply(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
+                         const float* gamma, const float* sums, void* dy, long long npix, int C,
+                         long long pix_per_group, float count, float slope, int dtype, void* stream);
+/* dgamma (+)= sum over groups of sum_gx ; dbeta (+)= sum over groups of sum_g */
+int jck_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int groups, int accumulate,
+                      void* stream);
+
+/* ---- DCGAN discriminator head: conv5 (K = 16*C4 dot product) + sigmoid + BCE ------------------
+ * Replaces nn.Conv2d(512,1,4,1,0)+nn.Sigmoid model/DCGAN.py:26-27,34 and nn.BCELoss
+ * train/dcgan_trainer.py:64,163,174,186 (log clamped at -100 as torch does).
+ * scalars (fp32, ADDED): scalars[0] += BCE mean, scalars[1] += mean(prob). w5 is NHWC-ordered. */
+int jck_head_fwd(const void* a4, const void* w5, float* prob, float target, float* scalars, int B, int K,
+                 int dtype, void* stream);
+/* mode 0: dlogit = (p-target)/max(p(1-p),1e-12) * p(1-p) / B   (BCE mean backward through sigmoid)
+ * mode 1: dlogit = p(1-p)                                   (grad_outputs = ones, the GP sweep)
+ * da4[b][k] = dlogit[b]*w5[k];  dw5[k] (+)= sum_b dlogit[b]*a4[b][k] when dw5 != NULL (fp32, NHWC order) */
+int jck_head_bwd(const float* prob, float target, const void* w5, const void* a4, void* da4, float* dw5,
+                 int B, int K, int mode, int accumulate, int dtype, void* stream);
+/* conv5 weight [1][C4][4][4] fp32 <-> NHWC-ordered [16*C4] */
+int jck_pack_head(const float* w4, void* w5, int C4, int dtype, void* stream);
+int jck_unpack_head_grad(const float* dw5, float* dw4, int C4, int accumulate, void* stream);
+
+/* ---- generator output edge ---------------------------------------------------------------------
+ * fake_raw = tanh(y5) (NCHW fp32); fake_mix = a*fake_raw + b*noise (NCHW fp32 and NHWC dtype).
+ * Replaces nn.Tanh model/DCGAN.py:59,66 + train/dcgan_trainer.py:171.  Outputs nullable. */
+int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, float* fake_raw_nchw,
+                  float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int dtype,
+                  void* stream);
+/* dy5 = a * dmix * (1 - fake_raw^2)  (dmix NHWC dtype, fake_raw NCHW fp32, dy5 NHWC dtype) */
+int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, float a, void* dy5_nhwc, int B, int C,
+                  int H, int W, int dtype, void* stream);
+
+/* ---- gradient penalty --------------------------------------------------------------------------
+ * scalars[0] += mean_n (||dx[n,:]||_2 - 1)^2.  Replaces train/dcgan_trainer.py:125-126. */
+int jck_gp_penalty(const void* dx, float* scalars, int B, long long per_sample, int dtype, void* stream);
+
+/* ---- Adam (lr, betas, eps as torch.optim.Adam; no weight decay, no amsgrad) --------------------
+ * One launch over a flat fp32 buffer.  step_count: device int32, the step number BEFORE this update
+ * (kernel uses step_count+1; jck_adam_advance increments it) so a captured graph replays correctly.
+ * Replaces optim.Adam.step train/dcgan_trainer.py:61-62,180,189. */
+int jck_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+             float beta1, float beta2, float eps, const int* step_count, void* stream);
+int jck_adam_advance(int* step_count, void* stream);
+
+/* ---- random numbers (Philox4x32-10; performance mode only -- parity tests inject host tensors) --
+ * counter_base: device uint64 advanced by jck_rng_advance.  Replaces torch.randn / torch.rand
+ * train/dcgan_trainer.py:111,160,168,171. */
+int jck_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
+              const unsigned long long* counter_base, void* stream);
+int jck_rand(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
+             const unsigned long long* counter_base, void* stream);
+int jck_rng_advance(unsigned long long* counter_base, unsigned long long by, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JCK_B200_H_ */
