@@ -1,0 +1,589 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for the 4x4 stride-2 layers (bf16 in, fp32 accumulate).
+//
+// All three GEMM-shaped operations of a layer (Ca = low-res channels, Cb = high-res channels):
+//   down  : out_small[pix][a]   = sum_{tap,b} in_large[shift_tap(pix)][b] * Wdown[a][tap][b]
+//   up    : out_large[2pix+ph][b] = sum_{t,a} in_small[shift_t(pix)][a]   * Wup[ph][b][t][a]
+//   wgrad : dW[a][tap][b]       = sum_pix   small[pix][a] * large[shift_tap(pix)][b]
+// The im2col never exists: because activations are NHWC, one filter tap of a 128-pixel output patch is
+// a dense [128 pixels][64 channels] box of the input tensor at a shifted coordinate, which TMA tiled
+// mode fetches in one instruction and zero-fills outside the image (= the conv padding).  The stride-2
+// side is addressed through a 5-D "parity" view  (2C | W/2 | 2 | H/2 | B)  so that a tap is again a
+// dense box.  Tiles land 128B-swizzled in shared memory exactly as UMMA wants them (K-major for
+// down/up, MN-major for wgrad where the contraction runs over pixels).
+//
+// Kernel anatomy (one output tile per CTA): warp 0 = TMA producer, warp 1 = TMEM allocator + single
+// thread MMA issuer, warps 2..5 = epilogue (tcgen05.ld -> BatchNorm partial sums by warp shuffles ->
+// bf16 -> global).  smem ring: full/empty mbarriers; accumulator handed over by tcgen05.commit.
+#include "tc_common.cuh"
+
+namespace jck {
+
+// SIMT fallbacks / helpers from conv_simt.cu
+template <typename T> int simt_down(const void*, const void*, void*, float*, int, int, int, int, int, int, cudaStream_t);
+template <typename T> int simt_up(const void*, const void*, void*, float*, int, int, int, int, int, int, cudaStream_t);
+template <typename T> int simt_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
+int simt_wgrad_splits(int B, int Hs, int Ws, int Ca, int Cb);
+int launch_wgrad_unpack(const float* part, float* dw4, int Ca, int Cb, int splits, int accumulate, cudaStream_t st);
+
+namespace {
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------
+// Tensor maps (driver entry point resolved through the runtime: the library never links libcuda,
+// so it still loads on a machine without a driver).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return set_error(JCK_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(JCK_E_DRIVER, "cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
+    return JCK_OK;
+}
+
+// plain NHWC view (C | W | H | B), box (64 | bw | bh | nb)
+int map_small(CUtensorMap* m, const void* p, int C, int W, int H, int B, int bw, int bh, int nb) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)nb};
+    return encode(m, p, 4, dims, str, box);
+}
+// parity view of an NHWC tensor with H2 x W2 pixels: (2C | W2/2 | 2 | H2/2 | B), box (64 | bw | 1 | bh | nb).
+// element (px*C + c, xh, py, yh, n)  ==  pixel (n, 2*yh + py, 2*xh + px), channel c.
+int map_large(CUtensorMap* m, const void* p, int C, int W2, int H2, int B, int bw, int bh, int nb) {
+    cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W2 / 2, 2, (cuuint64_t)H2 / 2, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)2 * C * 2, (cuuint64_t)W2 * C * 2, (cuuint64_t)2 * W2 * C * 2,
+                         (cuuint64_t)H2 * W2 * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)nb};
+    return encode(m, p, 5, dims, str, box);
+}
+// row-major matrix [rows][cols] bf16, box (64 | box_rows)
+int map_matrix(CUtensorMap* m, const void* p, int rows, int cols, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    return encode(m, p, 2, dims, str, box);
+}
+
+struct PatchGeom { int bw, bh, nb; };
+// rows of a tile = bw x bh x nb output pixels (x fastest), bw*bh*nb == npix
+bool patch_geom(int Hs, int Ws, int npix, PatchGeom* g) {
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    if (!pow2(Hs) || !pow2(Ws) || Ws > npix) return false;
+    g->bw = Ws;
+    g->bh = Hs < npix / g->bw ? Hs : npix / g->bw;
+    g->nb = npix / (g->bw * g->bh);
+    return g->bw <= 256 && g->bh <= 256 && g->nb <= 256 && g->bw * g->bh * g->nb == npix;
+}
+
+// ------------------------------------------------------------------------------------------------
+// down / up
+// ------------------------------------------------------------------------------------------------
+struct ConvTcParams {
+    int B, Hs, Ws, Ca, Cb;     // layer geometry
+    int bw, bh, nb;            // tile patch
+    int tiles_x, tiles_y;      // patches per image row / column
+    int ipg;                   // images per BatchNorm group
+};
+
+constexpr int kConvThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kBK = 64;  // bf16 elements per K step = one 128-byte swizzle row
+
+template <int BN_, int STAGES>
+struct ConvSmem {
+    static constexpr int kABytes = kTileM * kBK * 2;
+    static constexpr int kBBytes = BN_ * kBK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kBarOff = STAGES * kStage;
+    static constexpr int kRedOff = kBarOff + 256;
+    static constexpr int kTotal = kRedOff + 4 * 2 * BN_ * 4 + 1024;  // + alignment slack
+};
+
+template <int BN_, int STAGES, bool kUp>
+__global__ void __launch_bounds__(kConvThreads)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p) {
+    using L = ConvSmem<BN_, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* red = reinterpret_cast<float*>(smem + L::kRedOff);  // [4 warps][2][BN_]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    const int mt = blockIdx.x;
+    const int x0 = (mt % p.tiles_x) * p.bw;
+    const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+    const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.nb;
+    const int nt = blockIdx.y;
+    const int phase = kUp ? blockIdx.z : 0;
+    const int py = phase >> 1, px = phase & 1;
+    const int Cin = kUp ? p.Ca : p.Cb;    // contraction channels
+    const int Cout = kUp ? p.Cb : p.Ca;
+    const int cchunks = Cin / kBK;
+    const int ksteps = (kUp ? 4 : 16) * cchunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN_ < 32 ? 32 : BN_);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int s = ks % STAGES;
+                const uint32_t ph = (ks / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* sa = smem + s * L::kStage;
+                uint8_t* sb = sa + L::kABytes;
+                mbar_arrive_expect_tx(&full[s], L::kStage);
+                const int tap = ks / cchunks, cc = ks - tap * cchunks;
+                if (!kUp) {
+                    const int ky = tap >> 2, kx = tap & 3;
+                    const int dy = (ky - 1) >> 1, qy = (ky - 1) & 1;   // input row 2*oy + ky - 1 = 2*(oy+dy) + qy
+                    const int dx = (kx - 1) >> 1, qx = (kx - 1) & 1;
+                    tma_load_5d(sa, &mapA, &full[s], qx * p.Cb + cc * kBK, x0 + dx, qy, y0 + dy, n0);
+                    tma_load_2d(sb, &mapB, &full[s], tap * p.Cb + cc * kBK, nt * BN_);
+                } else {
+                    const int dy = up_d(py, tap >> 1), dx = up_d(px, tap & 1);
+                    tma_load_4d(sa, &mapA, &full[s], cc * kBK, x0 + dx, y0 + dy, n0);
+                    tma_load_2d(sb, &mapB, &full[s], tap * p.Ca + cc * kBK, phase * p.Cb + nt * BN_);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc = make_idesc(BN_, 0, 0);
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int s = ks % STAGES;
+            const uint32_t ph = (ks / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + s * L::kStage);
+                const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t da = make_sdesc(a_addr + k * 32, 0, 1024);
+                    const uint64_t db = make_sdesc(b_addr + k * 32, 0, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
+                if (ks == ksteps - 1) umma_commit(tmem_full); // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- epilogue (warps 2..5) ----------------
+        const int wq = warp & 3;                 // TMEM lane quarter this warp may read
+        const int r = wq * 32 + lane;            // tile row = output pixel
+        const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+        const int n = n0 + nl;
+        const bool valid = n < p.B;
+        size_t pix;
+        if (!kUp) pix = ((size_t)n * p.Hs + (y0 + yl)) * p.Ws + (x0 + xl);
+        else pix = ((size_t)n * 2 * p.Hs + 2 * (y0 + yl) + py) * (2 * p.Ws) + 2 * (x0 + xl) + px;
+        __nv_bfloat16* orow = out + pix * Cout + nt * BN_;
+
+        mbar_wait(tmem_full, 0);
+        fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < BN_ / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
+            tmem_ld_wait();
+            if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                    dst[q] = u;
+                }
+            }
+            if (stats != nullptr) {
+                // rows past the batch hold exact zeros (TMA zero fill), so no masking is needed
+                float sq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+                const float s1 = warp_transpose_sum(v, lane);
+                const float s2 = warp_transpose_sum(sq, lane);
+                red[(wq * 2 + 0) * BN_ + c * 32 + lane] = s1;
+                red[(wq * 2 + 1) * BN_ + c * 32 + lane] = s2;
+            }
+        }
+        if (stats != nullptr) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+            const int e = threadIdx.x - 64;                  // 0..127
+            float* sp = stats + (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
+            for (int col = e; col < 2 * BN_; col += 128) {
+                const int which = col / BN_, cc = col % BN_;
+                const float s = red[(0 * 2 + which) * BN_ + cc] + red[(1 * 2 + which) * BN_ + cc] +
+                                red[(2 * 2 + which) * BN_ + cc] + red[(3 * 2 + which) * BN_ + cc];
+                atomicAdd(sp + which * Cout + cc, s);
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, BN_ < 32 ? 32 : BN_);
+    }
+}
+
+template <int BN_, int STAGES, bool kUp>
+int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
+                   int m_tiles, int n_tiles, cudaStream_t st) {
+    using L = ConvSmem<BN_, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, STAGES, kUp>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc smem attr: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid(m_tiles, n_tiles, kUp ? 4 : 1);
+    conv_tc_kernel<BN_, STAGES, kUp><<<grid, kConvThreads, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats, p);
+    JCK_LAUNCH_CHECK(kUp ? "conv_up_tc" : "conv_down_tc");
+    return JCK_OK;
+}
+
+bool tc_conv_supported(int B, int Hs, int Ws, int Ca, int Cb, int ipg, bool up, PatchGeom* g) {
+    const int Cin = up ? Ca : Cb, Cout = up ? Cb : Ca;
+    if (Cin % 64 != 0 || Cout % 64 != 0) return false;
+    if (!patch_geom(Hs, Ws, kTileM, g)) return false;
+    if (ipg < B && (ipg % g->nb) != 0) return false;   // a tile must not straddle BatchNorm groups
+    return B > 0;
+}
+
+template <bool kUp>
+int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int Hs, int Ws, int Ca, int Cb, int ipg,
+            cudaStream_t st) {
+    PatchGeom g;
+    if (!tc_conv_supported(B, Hs, Ws, Ca, Cb, ipg, kUp, &g))
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv tc: unsupported shape B=%d Hs=%d Ws=%d Ca=%d Cb=%d", B, Hs, Ws, Ca, Cb);
+    const int Cout = kUp ? Cb : Ca;
+    const int bn = (Cout % 128 == 0) ? 128 : 64;
+    ConvTcParams p{B, Hs, Ws, Ca, Cb, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, ipg};
+    const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
+    CUtensorMap mA, mB;
+    int rc;
+    if (!kUp) {
+        if ((rc = map_large(&mA, in, Cb, 2 * Ws, 2 * Hs, B, g.bw, g.bh, g.nb))) return rc;
+        if ((rc = map_matrix(&mB, w, Ca, 16 * Cb, bn))) return rc;
+    } else {
+        if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
+        if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn))) return rc;
+    }
+    if (bn == 128) return launch_conv_tc<128, 3, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 128, st);
+    return launch_conv_tc<64, 4, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 64, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[a][tap, b] = sum over pixels small[pix][a] * large[shift_tap(pix)][b]   (split over pixels)
+// Both operands are MN-major (channels contiguous, contraction over rows).  One CTA owns 128 `a`
+// channels x (G taps x BNW `b` channels) = 512 TMEM columns and a contiguous range of 64-pixel K steps;
+// partial tiles go to a workspace that wgrad_unpack reduces into the reference's [Ca][Cb][4][4] layout.
+// ------------------------------------------------------------------------------------------------
+struct WgradTcParams {
+    int B, Hs, Ws, Ca, Cb;
+    int kbw, kbh, knb;         // 64-pixel K patch
+    int kx_tiles, ky_tiles;    // patches per image
+    int total_steps, steps_per_split;
+    int b_tiles;               // Cb / BNW
+};
+
+constexpr int kWgradStages = 2;
+constexpr int kWgradKPix = 64;
+constexpr int kWgradABytes = 2 * kWgradKPix * 128;       // two 64-channel atoms of `a`
+constexpr int kWgradBBytes = 8 * kWgradKPix * 128;       // G * BNW / 64 = 8 atoms
+constexpr int kWgradStage = kWgradABytes + kWgradBBytes; // 80 KB
+constexpr int kWgradSmem = kWgradStages * kWgradStage + 256 + 1024;
+
+template <int BNW>  // 64 (G = 8 taps) or 128 (G = 4 taps)
+__global__ void __launch_bounds__(kConvThreads)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapL,
+                float* __restrict__ part, const WgradTcParams p) {
+    constexpr int G = 512 / BNW;
+    constexpr int ATOMS_B = BNW / 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgradStages * kWgradStage);
+    uint64_t* empty = full + kWgradStages;
+    uint64_t* tmem_full = empty + kWgradStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int a_tile = blockIdx.y / p.b_tiles, b_tile = blockIdx.y % p.b_tiles;
+    const int tap0 = blockIdx.z * G;
+    const int step_beg = split * p.steps_per_split;
+    const int step_end = min(p.total_steps, step_beg + p.steps_per_split);
+    const int nsteps = max(0, step_end - step_beg);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapS);
+        prefetch_tmap(&mapL);
+        for (int s = 0; s < kWgradStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % kWgradStages;
+                const uint32_t ph = (it / kWgradStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* sa = smem + s * kWgradStage;
+                uint8_t* sb = sa + kWgradABytes;
+                mbar_arrive_expect_tx(&full[s], kWgradStage);
+                const int st = step_beg + it;
+                const int xs = (st % p.kx_tiles) * p.kbw;
+                const int ys = ((st / p.kx_tiles) % p.ky_tiles) * p.kbh;
+                const int ns = (st / (p.kx_tiles * p.ky_tiles)) * p.knb;
+                tma_load_4d(sa, &mapS, &full[s], a_tile * 128, xs, ys, ns);
+                tma_load_4d(sa + kWgradKPix * 128, &mapS, &full[s], a_tile * 128 + 64, xs, ys, ns);
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    const int tap = tap0 + g;
+                    const int ky = tap >> 2, kx = tap & 3;
+                    const int dy = (ky - 1) >> 1, qy = (ky - 1) & 1;
+                    const int dx = (kx - 1) >> 1, qx = (kx - 1) & 1;
+                    for (int at = 0; at < ATOMS_B; ++at)
+                        tma_load_5d(sb + (g * ATOMS_B + at) * (kWgradKPix * 128), &mapL, &full[s],
+                                    qx * p.Cb + b_tile * BNW + at * 64, xs + dx, qy, ys + dy, ns);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BNW, 1, 1);
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % kWgradStages;
+            const uint32_t ph = (it / kWgradStages) & 1;
+            mbar_wait(&full[s], ph);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + s * kWgradStage);
+                const uint32_t b_addr = a_addr + kWgradABytes;
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+#pragma unroll
+                    for (int k = 0; k < kWgradKPix / 16; ++k) {
+                        const uint64_t da = make_sdesc(a_addr + k * 2048, kWgradKPix * 128, 1024);
+                        const uint64_t db = make_sdesc(b_addr + g * ATOMS_B * (kWgradKPix * 128) + k * 2048,
+                                                       kWgradKPix * 128, 1024);
+                        umma_bf16(tmem_base + g * BNW, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (it == nsteps - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int wq = warp & 3;
+        const int a = a_tile * 128 + wq * 32 + lane;
+        float* prow = part + ((size_t)split * p.Ca + a) * 16 * p.Cb;
+        if (nsteps > 0) {
+            mbar_wait(tmem_full, 0);
+            fence_after_sync();
+        }
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            float* dst = prow + (size_t)(tap0 + g) * p.Cb + b_tile * BNW;
+#pragma unroll 1
+            for (int c = 0; c < BNW / 32; ++c) {
+                float v[32];
+                if (nsteps > 0) {
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + g * BNW + c * 32, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+                float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+struct WgradPlan { bool ok; int bnw, G, splits, steps_per_split, total_steps; PatchGeom g; };
+
+WgradPlan wgrad_plan(int B, int Hs, int Ws, int Ca, int Cb) {
+    WgradPlan pl{};
+    pl.ok = false;
+    if (Ca % 128 != 0 || Cb % 64 != 0) return pl;
+    if (!patch_geom(Hs, Ws, kWgradKPix, &pl.g)) return pl;
+    pl.bnw = (Cb % 128 == 0) ? 128 : 64;
+    pl.G = 512 / pl.bnw;
+    const int tiles = (Ca / 128) * (Cb / pl.bnw) * (16 / pl.G);
+    pl.total_steps = (Ws / pl.g.bw) * (Hs / pl.g.bh) * ((B + pl.g.nb - 1) / pl.g.nb);
+    int splits = kNumSMs / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > pl.total_steps) splits = pl.total_steps;
+    pl.steps_per_split = (pl.total_steps + splits - 1) / splits;
+    pl.splits = (pl.total_steps + pl.steps_per_split - 1) / pl.steps_per_split;
+    pl.ok = true;
+    return pl;
+}
+
+int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan& pl, int B, int Hs, int Ws, int Ca,
+             int Cb, cudaStream_t st) {
+    CUtensorMap mS, mL;
+    int rc;
+    if ((rc = map_small(&mS, small, Ca, Ws, Hs, B, pl.g.bw, pl.g.bh, pl.g.nb))) return rc;
+    if ((rc = map_large(&mL, large, Cb, 2 * Ws, 2 * Hs, B, pl.g.bw, pl.g.bh, pl.g.nb))) return rc;
+    WgradTcParams p{B, Hs, Ws, Ca, Cb, pl.g.bw, pl.g.bh, pl.g.nb, Ws / pl.g.bw, Hs / pl.g.bh,
+                    pl.total_steps, pl.steps_per_split, Cb / pl.bnw};
+    dim3 grid(pl.splits, (Ca / 128) * (Cb / pl.bnw), 16 / pl.G);
+    static bool cfg64 = false, cfg128 = false;
+    if (pl.bnw == 64) {
+        if (!cfg64) {
+            cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
+            if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
+            cfg64 = true;
+        }
+        wgrad_tc_kernel<64><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, part, p);
+    } else {
+        if (!cfg128) {
+            cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
+            if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
+            cfg128 = true;
+        }
+        wgrad_tc_kernel<128><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, part, p);
+    }
+    JCK_LAUNCH_CHECK("wgrad_tc");
+    return JCK_OK;
+}
+
+bool want_tc(int dtype, int algo) { return dtype == JCK_BF16 && algo != JCK_ALGO_SIMT; }
+
+}  // namespace
+}  // namespace jck
+
+using namespace jck;
+
+extern "C" int jck_conv_down(const void* in_large, const void* w_down, void* out_small, float* stats, int B, int Hs,
+                             int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream) {
+    JCK_REQUIRE(in_large && w_down && out_small && B > 0 && Hs > 0 && Ws > 0 && Ca > 0 && Cb > 0, "conv_down: bad argument");
+    if (imgs_per_group <= 0) imgs_per_group = B;
+    cudaStream_t st = as_stream(stream);
+    if (want_tc(dtype, algo)) {
+        PatchGeom g;
+        if (tc_conv_supported(B, Hs, Ws, Ca, Cb, imgs_per_group, false, &g))
+            return conv_tc<false>(in_large, w_down, out_small, stats, B, Hs, Ws, Ca, Cb, imgs_per_group, st);
+        if (algo == JCK_ALGO_TC)
+            return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_down: no tcgen05 tile for Ca=%d Cb=%d Hs=%d Ws=%d", Ca, Cb, Hs, Ws);
+    } else if (algo == JCK_ALGO_TC) {
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_down: tcgen05 path is bf16 only");
+    }
+    if (dtype == JCK_F32) return simt_down<float>(in_large, w_down, out_small, stats, B, Hs, Ws, Ca, Cb, imgs_per_group, st);
+    if (dtype == JCK_BF16) return simt_down<__nv_bfloat16>(in_large, w_down, out_small, stats, B, Hs, Ws, Ca, Cb, imgs_per_group, st);
+    return set_error(JCK_E_BADARG, "conv_down: dtype %d", dtype);
+}
+
+extern "C" int jck_conv_up(const void* in_small, const void* w_up, void* out_large, float* stats, int B, int Hs, int Ws,
+                           int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream) {
+    JCK_REQUIRE(in_small && w_up && out_large && B > 0 && Hs > 0 && Ws > 0 && Ca > 0 && Cb > 0, "conv_up: bad argument");
+    if (imgs_per_group <= 0) imgs_per_group = B;
+    cudaStream_t st = as_stream(stream);
+    if (want_tc(dtype, algo)) {
+        PatchGeom g;
+        if (tc_conv_supported(B, Hs, Ws, Ca, Cb, imgs_per_group, true, &g))
+            return conv_tc<true>(in_small, w_up, out_large, stats, B, Hs, Ws, Ca, Cb, imgs_per_group, st);
+        if (algo == JCK_ALGO_TC)
+            return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_up: no tcgen05 tile for Ca=%d Cb=%d Hs=%d Ws=%d", Ca, Cb, Hs, Ws);
+    } else if (algo == JCK_ALGO_TC) {
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_up: tcgen05 path is bf16 only");
+    }
+    if (dtype == JCK_F32) return simt_up<float>(in_small, w_up, out_large, stats, B, Hs, Ws, Ca, Cb, imgs_per_group, st);
+    if (dtype == JCK_BF16) return simt_up<__nv_bfloat16>(in_small, w_up, out_large, stats, B, Hs, Ws, Ca, Cb, imgs_per_group, st);
+    return set_error(JCK_E_BADARG, "conv_up: dtype %d", dtype);
+}
+
+static bool wgrad_uses_tc(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo, WgradPlan* pl) {
+    if (!want_tc(dtype, algo)) return false;
+    *pl = wgrad_plan(B, Hs, Ws, Ca, Cb);
+    return pl->ok;
+}
+
+extern "C" size_t jck_conv_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo) {
+    WgradPlan pl;
+    int splits = wgrad_uses_tc(B, Hs, Ws, Ca, Cb, dtype, algo, &pl) ? pl.splits : simt_wgrad_splits(B, Hs, Ws, Ca, Cb);
+    return (size_t)splits * Ca * 16 * Cb * sizeof(float);
+}
+
+extern "C" int jck_conv_wgrad(const void* small, const void* large, float* dw4, void* workspace, size_t workspace_bytes,
+                              int B, int Hs, int Ws, int Ca, int Cb, int accumulate, int dtype, int algo, void* stream) {
+    JCK_REQUIRE(small && large && dw4 && workspace && B > 0 && Hs > 0 && Ws > 0 && Ca > 0 && Cb > 0, "conv_wgrad: bad argument");
+    cudaStream_t st = as_stream(stream);
+    const size_t need = jck_conv_wgrad_workspace_bytes(B, Hs, Ws, Ca, Cb, dtype, algo);
+    JCK_REQUIRE(workspace_bytes >= need, "conv_wgrad: workspace %zu < %zu bytes", workspace_bytes, need);
+    WgradPlan pl;
+    int rc, splits;
+    if (wgrad_uses_tc(B, Hs, Ws, Ca, Cb, dtype, algo, &pl)) {
+        splits = pl.splits;
+        rc = wgrad_tc(small, large, (float*)workspace, pl, B, Hs, Ws, Ca, Cb, st);
+    } else {
+        if (algo == JCK_ALGO_TC) return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_wgrad: no tcgen05 path for this shape/dtype");
+        splits = simt_wgrad_splits(B, Hs, Ws, Ca, Cb);
+        if (dtype == JCK_F32) rc = simt_wgrad<float>(small, large, (float*)workspace, splits, B, Hs, Ws, Ca, Cb, st);
+        else if (dtype == JCK_BF16) rc = simt_wgrad<__nv_bfloat16>(small, large, (float*)workspace, splits, B, Hs, Ws, Ca, Cb, st);
+        else return set_error(JCK_E_BADARG, "conv_wgrad: dtype %d", dtype);
+    }
+    if (rc) return rc;
+    return launch_wgrad_unpack((const float*)workspace, dw4, Ca, Cb, splits, accumulate, st);
+}

@@ -1,0 +1,704 @@
+// HBM-bound kernels of the train step: image edge conversion, weight packing, BatchNorm finalize /
+// apply / backward, the DCGAN head (conv5 dot product + sigmoid + BCE), generator output edge,
+// gradient-penalty norm, fused Adam, Philox random numbers.  All are streaming passes: 128-bit
+// accesses on the NHWC tensors, fp32 math, grid sized in multiples of the SM count.
+#include <stdarg.h>
+#include <math.h>
+#include "common.cuh"
+
+namespace jck {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+
+inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+    long long b = (work_items + threads - 1) / threads;
+    long long cap = (long long)kNumSMs * max_waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---- 8-wide channel vectors ------------------------------------------------------------------
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+
+// ---- image edge ------------------------------------------------------------------------------
+template <typename T>
+__global__ void prep_image_kernel(const float* __restrict__ x1, const float* __restrict__ m1, float a1, float b1,
+                                  const float* __restrict__ x2, const float* __restrict__ alpha,
+                                  T* __restrict__ out_nhwc, float* __restrict__ out_nchw, int B, int C, int HW) {
+    const long long total = (long long)B * HW;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        const float al = alpha ? alpha[n] : 1.f;
+        for (int c = 0; c < C; ++c) {
+            const size_t src = ((size_t)n * C + c) * HW + hw;
+            float v = a1 * x1[src];
+            if (m1) v += b1 * m1[src];
+            if (alpha) v = al * v + (1.f - al) * x2[src];
+            if (out_nhwc) st_act(out_nhwc + pix * C + c, v);
+            if (out_nchw) out_nchw[src] = v;
+        }
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int C, int HW) {
+    const long long total = (long long)B * HW;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        for (int c = 0; c < C; ++c) out[((size_t)n * C + c) * HW + hw] = ld_act(in + pix * C + c);
+    }
+}
+
+// ---- weight packing --------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ w4, T* __restrict__ w_down, T* __restrict__ w_up, int Ca,
+                                    int Cb) {
+    const long long total = (long long)Ca * Cb * 16;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % 16);
+        const long long ab = idx / 16;
+        const int b = (int)(ab % Cb), a = (int)(ab / Cb);
+        const float v = w4[idx];
+        if (w_down) st_act(w_down + ((size_t)a * 16 + tap) * Cb + b, v);
+        if (w_up) {
+            const int ky = tap >> 2, kx = tap & 3;
+            // which output parity / tap slot uses this kernel row: see up_k() in common.cuh
+            const int py = (ky == 1 || ky == 3) ? 0 : 1, ty = (ky == 1 || ky == 2) ? 0 : 1;
+            const int px = (kx == 1 || kx == 3) ? 0 : 1, tx = (kx == 1 || kx == 2) ? 0 : 1;
+            const int phase = py * 2 + px, t = ty * 2 + tx;
+            st_act(w_up + (((size_t)phase * Cb + b) * 4 + t) * Ca + a, v);
+        }
+    }
+}
+
+template <typename T>
+__global__ void pack_fc_kernel(const float* __restrict__ w4, T* __restrict__ w_fc, int K, int C) {
+    const long long total = (long long)K * C * 16;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % 16);
+        const long long kc = idx / 16;
+        const int c = (int)(kc % C), k = (int)(kc / C);
+        st_act(w_fc + ((size_t)tap * C + c) * K + k, w4[idx]);
+    }
+}
+__global__ void unpack_fc_grad_kernel(const float* __restrict__ dw_fc, float* __restrict__ dw4, int K, int C, int accumulate) {
+    const long long total = (long long)K * C * 16;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % 16);
+        const long long kc = idx / 16;
+        const int c = (int)(kc % C), k = (int)(kc / C);
+        const float v = dw_fc[((size_t)tap * C + c) * K + k];
+        dw4[idx] = accumulate ? dw4[idx] + v : v;
+    }
+}
+template <typename T>
+__global__ void pack_head_kernel(const float* __restrict__ w4, T* __restrict__ w5, int C4) {
+    const int total = C4 * 16;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int tap = idx % 16, c = idx / 16;
+        st_act(w5 + tap * C4 + c, w4[idx]);
+    }
+}
+__global__ void unpack_head_grad_kernel(const float* __restrict__ dw5, float* __restrict__ dw4, int C4, int accumulate) {
+    const int total = C4 * 16;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int tap = idx % 16, c = idx / 16;
+        const float v = dw5[tap * C4 + c];
+        dw4[idx] = accumulate ? dw4[idx] + v : v;
+    }
+}
+
+// ---- BatchNorm -------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ nbt,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_rstd, int C, int groups,
+                                   float count, float eps, float momentum) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+        for (int g = 0; g < groups; ++g) {   // in order: the reference updates running stats pass by pass
+            const double s1 = stats[(size_t)g * 2 * C + c], s2 = stats[(size_t)g * 2 * C + C + c];
+            const double mean = s1 / count;
+            double var = s2 / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+            const float sc = gamma[c] * rstd;
+            scale_shift[(size_t)g * 2 * C + c] = sc;
+            scale_shift[(size_t)g * 2 * C + C + c] = beta[c] - (float)mean * sc;
+            mean_rstd[(size_t)g * 2 * C + c] = (float)mean;
+            mean_rstd[(size_t)g * 2 * C + C + c] = rstd;
+            const float unbiased = (float)(count > 1.f ? var * (double)count / ((double)count - 1.0) : var);
+            rm = (1.f - momentum) * rm + momentum * (float)mean;
+            rv = (1.f - momentum) * rv + momentum * unbiased;
+        }
+        if (running_mean) running_mean[c] = rm;
+        if (running_var) running_var[c] = rv;
+    }
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += groups;
+}
+
+template <typename T>
+__global__ void bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift, T* __restrict__ a,
+                                  long long nvec, int C, long long vec_per_group, float slope) {
+    const int cv = C / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8;
+        const float* ss = scale_shift + (size_t)(i / vec_per_group) * 2 * C;
+        float v[8], sc[8], sh[8];
+        Vec8<T>::load(y + i * 8, v);
+        Vec8<float>::load(ss + c0, sc);
+        Vec8<float>::load(ss + C + c0, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float pre = fmaf(v[j], sc[j], sh[j]);
+            v[j] = pre > 0.f ? pre : pre * slope;
+        }
+        Vec8<T>::store(a + i * 8, v);
+    }
+}
+
+// sums[g][0:C] += sum g,  sums[g][C:2C] += sum g*xhat, g = da * act'(pre)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
+                         const float* __restrict__ mean_rstd, float* __restrict__ sums, int C, long long pix_per_group,
+                         long long slab, float slope) {
+    __shared__ float red[256][17];
+    const int cv = C / 8;              // channel vectors per pixel; 256 % cv == 0
+    const int rows = 256 / cv;
+    const int myc = threadIdx.x % cv, myr = threadIdx.x / cv;
+    const int g = blockIdx.y;
+    const long long p_beg = (long long)blockIdx.x * slab;
+    const long long p_end = min(pix_per_group, p_beg + slab);
+    const int c0 = myc * 8;
+    float sc[8], sh[8], mu[8], rs[8];
+    Vec8<float>::load(scale_shift + (size_t)g * 2 * C + c0, sc);
+    Vec8<float>::load(scale_shift + (size_t)g * 2 * C + C + c0, sh);
+    Vec8<float>::load(mean_rstd + (size_t)g * 2 * C + c0, mu);
+    Vec8<float>::load(mean_rstd + (size_t)g * 2 * C + C + c0, rs);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    for (long long pp = p_beg + myr; pp < p_end; pp += rows) {
+        const size_t off = ((size_t)(g * pix_per_group + pp)) * C + c0;
+        float d[8], v[8];
+        Vec8<T>::load(da + off, d);
+        Vec8<T>::load(y + off, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float pre = fmaf(v[j], sc[j], sh[j]);
+            const float gg = pre > 0.f ? d[j] : d[j] * slope;
+            s1[j] += gg;
+            s2[j] += gg * (v[j] - mu[j]) * rs[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
+    __syncthreads();
+    // thread t < 2*C: column (which, channel) summed over `rows` partials
+    for (int col = threadIdx.x; col < 2 * C; col += 256) {
+        const int which = col / C, ch = col % C;
+        const int vc = ch / 8, j = ch % 8;
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += red[r * cv + vc][which * 8 + j];
+        atomicAdd(sums + (size_t)g * 2 * C + which * C + ch, s);
+    }
+}
+
+template <typename T>
+__global__ void bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y,
+                                        const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
+                                        const float* __restrict__ gamma, const float* __restrict__ sums,
+                                        T* __restrict__ dy, long long nvec, int C, long long vec_per_group,
+                                        float inv_count, float slope) {
+    const int cv = C / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8;
+        const size_t gofs = (size_t)(i / vec_per_group) * 2 * C;
+        float d[8], v[8], sc[8], sh[8], mu[8], rs[8], ga[8], sg[8], sgx[8];
+        Vec8<T>::load(da + i * 8, d);
+        Vec8<T>::load(y + i * 8, v);
+        Vec8<float>::load(scale_shift + gofs + c0, sc);
+        Vec8<float>::load(scale_shift + gofs + C + c0, sh);
+        Vec8<float>::load(mean_rstd + gofs + c0, mu);
+        Vec8<float>::load(mean_rstd + gofs + C + c0, rs);
+        Vec8<float>::load(gamma + c0, ga);
+        Vec8<float>::load(sums + gofs + c0, sg);
+        Vec8<float>::load(sums + gofs + C + c0, sgx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float pre = fmaf(v[j], sc[j], sh[j]);
+            const float gg = pre > 0.f ? d[j] : d[j] * slope;
+            const float xh = (v[j] - mu[j]) * rs[j];
+            d[j] = ga[j] * rs[j] * (gg - sg[j] * inv_count - xh * sgx[j] * inv_count);
+        }
+        Vec8<T>::store(dy + i * 8, d);
+    }
+}
+
+__global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     int C, int groups, int accumulate) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        float sb = 0.f, sg = 0.f;
+        for (int g = 0; g < groups; ++g) { sb += sums[(size_t)g * 2 * C + c]; sg += sums[(size_t)g * 2 * C + C + c]; }
+        dgamma[c] = accumulate ? dgamma[c] + sg : sg;
+        dbeta[c] = accumulate ? dbeta[c] + sb : sb;
+    }
+}
+
+// ---- DCGAN head ------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const T* __restrict__ a4, const T* __restrict__ w5, float* __restrict__ prob, float target,
+                float* __restrict__ scalars, int B, int K) {
+    __shared__ float wsum[8];
+    const int b = blockIdx.x;
+    float acc = 0.f;
+    for (int k = threadIdx.x * 8; k < K; k += 256 * 8) {
+        float x[8], w[8];
+        Vec8<T>::load(a4 + (size_t)b * K + k, x);
+        Vec8<T>::load(w5 + k, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(x[j], w[j], acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float z = 0.f;
+        for (int i = 0; i < 8; ++i) z += wsum[i];
+        const float p = 1.f / (1.f + expf(-z));
+        prob[b] = p;
+        if (scalars) {
+            // torch BCELoss: -(t*max(log p,-100) + (1-t)*max(log1p(-p),-100)), mean over the batch
+            const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);
+            atomicAdd(scalars + 0, -(target * lp + (1.f - target) * lq) / (float)B);
+            atomicAdd(scalars + 1, p / (float)B);
+        }
+    }
+}
+
+__device__ __forceinline__ float head_dlogit(float p, float dp, float target, int mode, float invB) {
+    const float pq = p * (1.f - p);
+    if (mode == 1) return pq;
+    if (mode == 2) return dp * pq;
+    return (p - target) / fmaxf(pq, 1e-12f) * pq * invB;
+}
+
+// grid (K/8/256, sample chunks): da4 = dlogit (x) w5 ; dw5 += dlogit^T a4
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob, float target, const T* __restrict__ w5,
+                const T* __restrict__ a4,
+                T* __restrict__ da4, float* __restrict__ dw5, int B, int K, int mode, int chunk) {
+    const int k = (blockIdx.x * 256 + threadIdx.x) * 8;
+    if (k >= K) return;
+    float w[8], acc[8];
+    Vec8<T>::load(w5 + k, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int b_beg = blockIdx.y * chunk, b_end = min(B, b_beg + chunk);
+    const float invB = 1.f / (float)B;
+    for (int b = b_beg; b < b_end; ++b) {
+        const float dl = head_dlogit(prob[b], dprob ? dprob[b] : 0.f, target, mode, invB);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = dl * w[j];
+        Vec8<T>::store(da4 + (size_t)b * K + k, o);
+        if (dw5) {
+            float x[8];
+            Vec8<T>::load(a4 + (size_t)b * K + k, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(dl, x[j], acc[j]);
+        }
+    }
+    if (dw5) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dw5 + k + j, acc[j]);
+    }
+}
+
+// ---- generator output edge -------------------------------------------------------------------
+template <typename T>
+__global__ void g_out_fwd_kernel(const T* __restrict__ y5, const float* __restrict__ noise, float a, float b,
+                                 float* __restrict__ fake_raw, float* __restrict__ fake_mix, T* __restrict__ mix_nhwc,
+                                 int B, int C, int HW) {
+    const long long total = (long long)B * HW;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        for (int c = 0; c < C; ++c) {
+            const size_t dst = ((size_t)n * C + c) * HW + hw;
+            const float t = tanhf(ld_act(y5 + pix * C + c));
+            if (fake_raw) fake_raw[dst] = t;
+            const float m = noise ? a * t + b * noise[dst] : a * t;
+            if (fake_mix) fake_mix[dst] = m;
+            if (mix_nhwc) st_act(mix_nhwc + pix * C + c, m);
+        }
+    }
+}
+template <typename T>
+__global__ void g_out_bwd_kernel(const T* __restrict__ dmix, const float* __restrict__ fake_raw, float a,
+                                 T* __restrict__ dy5, int B, int C, int HW) {
+    const long long total = (long long)B * HW;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        for (int c = 0; c < C; ++c) {
+            const float t = fake_raw[((size_t)n * C + c) * HW + hw];
+            st_act(dy5 + pix * C + c, a * ld_act(dmix + pix * C + c) * (1.f - t * t));
+        }
+    }
+}
+
+// ---- gradient penalty ------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gp_penalty_kernel(const T* __restrict__ dx, float* __restrict__ scalars, int B, long long per_sample) {
+    __shared__ float wsum[8];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < per_sample; i += 256) {
+        const float v = ld_act(dx + (size_t)n * per_sample + i);
+        acc = fmaf(v, v, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += wsum[i];
+        const float d = sqrtf(s) - 1.f;
+        atomicAdd(scalars, d * d / (float)B);
+    }
+}
+
+// ---- Adam ------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, const int* __restrict__ step_count) {
+    const float t = (float)(*step_count + 1);
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);          // lerp, as torch's _single_tensor_adam
+        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+__global__ void adam_advance_kernel(int* step_count) { *step_count += 1; }
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.f / 16777216.f); }  // (0,1)
+
+template <bool kNormal>
+__global__ void rng_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long stream_id,
+                           const unsigned long long* __restrict__ counter_base) {
+    const unsigned long long base = counter_base ? *counter_base : 0ull;
+    const long long nquads = (n + 3) / 4;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquads; q += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = base + (unsigned long long)q;
+        const uint4 r = philox(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)),
+                               make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        float o[4];
+        if (kNormal) {
+            const float r0 = sqrtf(-2.f * logf(u01(r.x))), r1 = sqrtf(-2.f * logf(u01(r.z)));
+            float s0, c0, s1, c1;
+            sincospif(2.f * u01(r.y), &s0, &c0);
+            sincospif(2.f * u01(r.w), &s1, &c1);
+            o[0] = r0 * c0; o[1] = r0 * s0; o[2] = r1 * c1; o[3] = r1 * s1;
+        } else {
+            o[0] = (float)(r.x >> 8) * (1.f / 16777216.f); o[1] = (float)(r.y >> 8) * (1.f / 16777216.f);
+            o[2] = (float)(r.z >> 8) * (1.f / 16777216.f); o[3] = (float)(r.w >> 8) * (1.f / 16777216.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (q * 4 + j < n) out[q * 4 + j] = o[j];
+    }
+}
+__global__ void rng_advance_kernel(unsigned long long* c, unsigned long long by) { *c += by; }
+
+}  // namespace
+}  // namespace jck
+
+using namespace jck;
+
+#define DISPATCH_DTYPE(dtype, name, ...)                                        \
+    if ((dtype) == JCK_F32) { using T = float; __VA_ARGS__ }                    \
+    else if ((dtype) == JCK_BF16) { using T = __nv_bfloat16; __VA_ARGS__ }      \
+    else return set_error(JCK_E_BADARG, name ": dtype %d", (int)(dtype));
+
+extern "C" int jck_version(void) { return 100; }
+extern "C" const char* jck_last_error_string(void) { return g_err; }
+extern "C" unsigned long long jck_launch_count(void) { return g_launches.load(); }
+
+extern "C" int jck_prep_image(const float* x1, const float* m1, float a1, float b1, const float* x2, const float* alpha,
+                              void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W, int dtype, void* stream) {
+    JCK_REQUIRE(x1 && (out_nhwc || out_nchw_f32) && B > 0 && C > 0 && H > 0 && W > 0, "prep_image: bad argument");
+    JCK_REQUIRE(!alpha || x2, "prep_image: alpha needs x2");
+    const long long total = (long long)B * H * W;
+    DISPATCH_DTYPE(dtype, "prep_image",
+        prep_image_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x1, m1, a1, b1, x2, alpha, (T*)out_nhwc,
+                                                                                  out_nchw_f32, B, C, H * W);)
+    JCK_LAUNCH_CHECK("prep_image");
+    return JCK_OK;
+}
+
+extern "C" int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int dtype, void* stream) {
+    JCK_REQUIRE(in_nhwc && out_nchw && B > 0 && C > 0, "nhwc_to_nchw: bad argument");
+    const long long total = (long long)B * H * W;
+    DISPATCH_DTYPE(dtype, "nhwc_to_nchw",
+        nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)in_nhwc, out_nchw, B, C, H * W);)
+    JCK_LAUNCH_CHECK("nhwc_to_nchw");
+    return JCK_OK;
+}
+
+extern "C" int jck_pack_weights(const float* w4, void* w_down, void* w_up, int Ca, int Cb, int dtype, void* stream) {
+    JCK_REQUIRE(w4 && (w_down || w_up) && Ca > 0 && Cb > 0, "pack_weights: bad argument");
+    const long long total = (long long)Ca * Cb * 16;
+    DISPATCH_DTYPE(dtype, "pack_weights",
+        pack_weights_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w_down, (T*)w_up, Ca, Cb);)
+    JCK_LAUNCH_CHECK("pack_weights");
+    return JCK_OK;
+}
+
+extern "C" int jck_pack_fc(const float* w4, void* w_fc, int K, int C, int dtype, void* stream) {
+    JCK_REQUIRE(w4 && w_fc && K > 0 && C > 0, "pack_fc: bad argument");
+    DISPATCH_DTYPE(dtype, "pack_fc",
+        pack_fc_kernel<T><<<grid_for((long long)K * C * 16, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w_fc, K, C);)
+    JCK_LAUNCH_CHECK("pack_fc");
+    return JCK_OK;
+}
+extern "C" int jck_unpack_fc_grad(const float* dw_fc, float* dw4, int K, int C, int accumulate, void* stream) {
+    JCK_REQUIRE(dw_fc && dw4 && K > 0 && C > 0, "unpack_fc_grad: bad argument");
+    unpack_fc_grad_kernel<<<grid_for((long long)K * C * 16, 256), 256, 0, as_stream(stream)>>>(dw_fc, dw4, K, C, accumulate);
+    JCK_LAUNCH_CHECK("unpack_fc_grad");
+    return JCK_OK;
+}
+extern "C" int jck_pack_head(const float* w4, void* w5, int C4, int dtype, void* stream) {
+    JCK_REQUIRE(w4 && w5 && C4 > 0, "pack_head: bad argument");
+    DISPATCH_DTYPE(dtype, "pack_head",
+        pack_head_kernel<T><<<grid_for(C4 * 16, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w5, C4);)
+    JCK_LAUNCH_CHECK("pack_head");
+    return JCK_OK;
+}
+extern "C" int jck_unpack_head_grad(const float* dw5, float* dw4, int C4, int accumulate, void* stream) {
+    JCK_REQUIRE(dw5 && dw4 && C4 > 0, "unpack_head_grad: bad argument");
+    unpack_head_grad_kernel<<<grid_for(C4 * 16, 256), 256, 0, as_stream(stream)>>>(dw5, dw4, C4, accumulate);
+    JCK_LAUNCH_CHECK("unpack_head_grad");
+    return JCK_OK;
+}
+
+extern "C" int jck_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_rstd,
+                               int C, int groups, float count, float eps, float momentum, void* stream) {
+    JCK_REQUIRE(stats && gamma && beta && scale_shift && mean_rstd && C > 0 && groups > 0 && count > 0, "bn_finalize: bad argument");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, gamma, beta, running_mean, running_var,
+                                                                       num_batches_tracked, scale_shift, mean_rstd, C,
+                                                                       groups, count, eps, momentum);
+    JCK_LAUNCH_CHECK("bn_finalize");
+    return JCK_OK;
+}
+
+static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (256 % (C / 8)) == 0; }
+
+extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, long long npix, int C, long long pix_per_group,
+                              float slope, int dtype, void* stream) {
+    JCK_REQUIRE(y && scale_shift && a && npix > 0 && C % 8 == 0 && pix_per_group > 0, "bn_act_fwd: bad argument");
+    const long long nvec = npix * (C / 8);
+    DISPATCH_DTYPE(dtype, "bn_act_fwd",
+        bn_act_fwd_kernel<T><<<grid_for(nvec, 256), 256, 0, as_stream(stream)>>>((const T*)y, scale_shift, (T*)a, nvec, C,
+                                                                               pix_per_group * (C / 8), slope);)
+    JCK_LAUNCH_CHECK("bn_act_fwd");
+    return JCK_OK;
+}
+
+extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
+                                     float* sums, long long npix, int C, long long pix_per_group, float slope, int dtype,
+                                     void* stream) {
+    JCK_REQUIRE(da && y && scale_shift && mean_rstd && sums && npix > 0 && pix_per_group > 0 && npix % pix_per_group == 0,
+                "bn_act_bwd_reduce: bad argument");
+    if (!bn_c_ok(C)) return set_error(JCK_E_UNSUPPORTED_SHAPE, "bn_act_bwd_reduce: C=%d (need C/8 dividing 256)", C);
+    const int groups = (int)(npix / pix_per_group);
+    const int rows = 256 / (C / 8);
+    long long bpg = (2LL * kNumSMs + groups - 1) / groups;                    // blocks per group: ~2 waves total
+    const long long max_b = (pix_per_group + rows * 4 - 1) / (rows * 4);      // at least 4 pixels per thread row
+    if (bpg > max_b) bpg = max_b;
+    if (bpg < 1) bpg = 1;
+    const long long slab = (pix_per_group + bpg - 1) / bpg;
+    dim3 grid((unsigned)bpg, (unsigned)groups);
+    DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
+        bn_act_bwd_reduce_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)da, (const T*)y, scale_shift, mean_rstd,
+                                                                       sums, C, pix_per_group, slab, slope);)
+    JCK_LAUNCH_CHECK("bn_act_bwd_reduce");
+    return JCK_OK;
+}
+
+extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
+                                    const float* gamma, const float* sums, void* dy, long long npix, int C,
+                                    long long pix_per_group, float count, float slope, int dtype, void* stream) {
+    JCK_REQUIRE(da && y && scale_shift && mean_rstd && gamma && sums && dy && npix > 0 && C % 8 == 0 && count > 0,
+                "bn_act_bwd_apply: bad argument");
+    const long long nvec = npix * (C / 8);
+    DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
+        bn_act_bwd_apply_kernel<T><<<grid_for(nvec, 256), 256, 0, as_stream(stream)>>>(
+            (const T*)da, (const T*)y, scale_shift, mean_rstd, gamma, sums, (T*)dy, nvec, C, pix_per_group * (C / 8),
+            1.f / count, slope);)
+    JCK_LAUNCH_CHECK("bn_act_bwd_apply");
+    return JCK_OK;
+}
+
+extern "C" int jck_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int groups, int accumulate, void* stream) {
+    JCK_REQUIRE(sums && dgamma && dbeta && C > 0 && groups > 0, "bn_param_grad: bad argument");
+    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(sums, dgamma, dbeta, C, groups, accumulate);
+    JCK_LAUNCH_CHECK("bn_param_grad");
+    return JCK_OK;
+}
+
+extern "C" int jck_head_fwd(const void* a4, const void* w5, float* prob, float target, float* scalars, int B, int K,
+                            int dtype, void* stream) {
+    JCK_REQUIRE(a4 && w5 && prob && B > 0 && K > 0 && K % 8 == 0, "head_fwd: bad argument");
+    DISPATCH_DTYPE(dtype, "head_fwd",
+        head_fwd_kernel<T><<<B, 256, 0, as_stream(stream)>>>((const T*)a4, (const T*)w5, prob, target, scalars, B, K);)
+    JCK_LAUNCH_CHECK("head_fwd");
+    return JCK_OK;
+}
+
+extern "C" int jck_head_bwd(const float* prob, const float* dprob, float target, const void* w5, const void* a4, void* da4,
+                            float* dw5, int B, int K, int mode, int accumulate, int dtype, void* stream) {
+    JCK_REQUIRE(prob && w5 && da4 && B > 0 && K > 0 && K % 8 == 0 && (!dw5 || a4) && (mode != 2 || dprob),
+                "head_bwd: bad argument");
+    cudaStream_t st = as_stream(stream);
+    if (dw5 && !accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw5, 0, sizeof(float) * K, st);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "head_bwd memset: %s", cudaGetErrorString(e));
+    }
+    int chunks = B < 64 ? B : 64;
+    const int chunk = (B + chunks - 1) / chunks;
+    chunks = (B + chunk - 1) / chunk;
+    dim3 grid((K / 8 + 255) / 256, chunks);
+    DISPATCH_DTYPE(dtype, "head_bwd",
+        head_bwd_kernel<T><<<grid, 256, 0, st>>>(prob, dprob, target, (const T*)w5, (const T*)a4, (T*)da4, dw5, B, K, mode, chunk);)
+    JCK_LAUNCH_CHECK("head_bwd");
+    return JCK_OK;
+}
+
+extern "C" int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, float* fake_raw_nchw,
+                             float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int dtype, void* stream) {
+    JCK_REQUIRE(y5_nhwc && B > 0 && C > 0 && H > 0 && W > 0, "g_out_fwd: bad argument");
+    const long long total = (long long)B * H * W;
+    DISPATCH_DTYPE(dtype, "g_out_fwd",
+        g_out_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)y5_nhwc, noise, a, b, fake_raw_nchw,
+                                                                               fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W);)
+    JCK_LAUNCH_CHECK("g_out_fwd");
+    return JCK_OK;
+}
+extern "C" int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, float a, void* dy5_nhwc, int B, int C, int H,
+                             int W, int dtype, void* stream) {
+    JCK_REQUIRE(dmix_nhwc && fake_raw_nchw && dy5_nhwc && B > 0 && C > 0, "g_out_bwd: bad argument");
+    const long long total = (long long)B * H * W;
+    DISPATCH_DTYPE(dtype, "g_out_bwd",
+        g_out_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)dmix_nhwc, fake_raw_nchw, a,
+                                                                               (T*)dy5_nhwc, B, C, H * W);)
+    JCK_LAUNCH_CHECK("g_out_bwd");
+    return JCK_OK;
+}
+
+extern "C" int jck_gp_penalty(const void* dx, float* scalars, int B, long long per_sample, int dtype, void* stream) {
+    JCK_REQUIRE(dx && scalars && B > 0 && per_sample > 0, "gp_penalty: bad argument");
+    DISPATCH_DTYPE(dtype, "gp_penalty",
+        gp_penalty_kernel<T><<<B, 256, 0, as_stream(stream)>>>((const T*)dx, scalars, B, per_sample);)
+    JCK_LAUNCH_CHECK("gp_penalty");
+    return JCK_OK;
+}
+
+extern "C" int jck_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                        float beta1, float beta2, float eps, const int* step_count, void* stream) {
+    JCK_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step_count, "adam: bad argument");
+    adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                 step_count);
+    JCK_LAUNCH_CHECK("adam");
+    return JCK_OK;
+}
+extern "C" int jck_adam_advance(int* step_count, void* stream) {
+    JCK_REQUIRE(step_count, "adam_advance: bad argument");
+    adam_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(step_count);
+    JCK_LAUNCH_CHECK("adam_advance");
+    return JCK_OK;
+}
+
+extern "C" int jck_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
+                         const unsigned long long* counter_base, void* stream) {
+    JCK_REQUIRE(out && n > 0, "randn: bad argument");
+    rng_kernel<true><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(out, n, seed, stream_id, counter_base);
+    JCK_LAUNCH_CHECK("randn");
+    return JCK_OK;
+}
+extern "C" int jck_rand(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
+                        const unsigned long long* counter_base, void* stream) {
+    JCK_REQUIRE(out && n > 0, "rand: bad argument");
+    rng_kernel<false><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(out, n, seed, stream_id, counter_base);
+    JCK_LAUNCH_CHECK("rand");
+    return JCK_OK;
+}
+extern "C" int jck_rng_advance(unsigned long long* counter_base, unsigned long long by, void* stream) {
+    JCK_REQUIRE(counter_base, "rng_advance: bad argument");
+    rng_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(counter_base, by);
+    JCK_LAUNCH_CHECK("rng_advance");
+    return JCK_OK;
+}

@@ -1,0 +1,329 @@
+"""Explicit forward / backward of the DCGAN generator and discriminator stacks on the sm_100a kernels.
+
+This is the host side of the hot path: it sequences the C-ABI kernels (ops.py) for
+    model/DCGAN.py:29-35   Discriminator.forward   (+ its autograd backward)
+    model/DCGAN.py:61-67   Generator.forward       (+ its autograd backward)
+without torch.autograd: every gradient kernel is ours, launched explicitly, so the whole train step is
+a fixed launch sequence (CUDA-graph capturable).  The nn.Module mirrors (model/DCGAN.py) and the
+trainers (train/*.py) are thin layers over the two engines here.
+
+Data layout: activations NHWC in `dtype` (bf16 = tcgen05 path, fp32 = exact-parity CUDA-core path);
+parameters stay the reference's fp32 nn.Parameters in the reference's layouts; packed copies of the
+conv weights (GEMM operand layouts, activation dtype) are private caches refreshed after each update.
+
+BatchNorm "groups": D is run on several independent batches at once (real / fake / interpolated), each
+with its own batch statistics, exactly as the reference's separate D(...) calls -- the conv kernels
+take the whole concatenation, the statistics are kept per group.
+"""
+import torch
+
+from . import ops
+from .parallel import LocalComm
+
+LRELU = 0.2
+BN_EPS = 1e-5
+BN_MOM = 0.1
+
+
+class _Conv:
+    """One 4x4 stride-2 layer: weight w4[Ca][Cb][4][4] + packed operand caches."""
+
+    def __init__(self, weight, Hs, dtype):
+        self.weight = weight
+        self.Ca, self.Cb = int(weight.shape[0]), int(weight.shape[1])
+        self.Hs = self.Ws = Hs
+        dev = weight.device
+        self.w_down = torch.empty(self.Ca * 16 * self.Cb, dtype=dtype, device=dev)
+        self.w_up = torch.empty(16 * self.Cb * self.Ca, dtype=dtype, device=dev)
+        self._seen = None
+
+    def refresh(self, force=False):
+        key = (self.weight._version, self.weight.data_ptr())
+        if force or key != self._seen:
+            ops.pack_weights(self.weight.detach(), self.w_down, self.w_up)
+            self._seen = key
+
+
+class _Norm:
+    def __init__(self, bn):
+        self.bn = bn
+        self.C = bn.num_features
+
+    @property
+    def gamma(self):
+        return self.bn.weight.detach()
+
+    @property
+    def beta(self):
+        return self.bn.bias.detach()
+
+
+class Ctx:
+    """Saved tensors of one forward pass (raw conv outputs, activations, BN coefficients)."""
+
+    def __init__(self):
+        self.x = None          # network input (NHWC)
+        self.y = {}            # raw conv outputs per layer
+        self.a = {}            # activations per layer
+        self.ss = {}           # BN scale/shift [groups][2C]
+        self.mr = {}           # BN mean/rstd   [groups][2C]
+        self.prob = None
+        self.groups = 1
+        self.B = 0
+
+    def slice(self, g0, g1):
+        """View of groups [g0, g1) of a grouped pass."""
+        per = self.B // self.groups
+        s = Ctx()
+        s.groups, s.B = g1 - g0, per * (g1 - g0)
+        lo, hi = per * g0, per * g1
+        s.x = self.x[lo:hi]
+        s.y = {k: v[lo:hi] for k, v in self.y.items()}
+        s.a = {k: v[lo:hi] for k, v in self.a.items()}
+        s.ss = {k: v[g0:g1] for k, v in self.ss.items()}
+        s.mr = {k: v[g0:g1] for k, v in self.mr.items()}
+        s.prob = self.prob[lo:hi] if self.prob is not None else None
+        return s
+
+
+class _Workspace:
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        if self.buf is None or self.buf.numel() * 4 < nbytes:
+            self.buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        return self.buf
+
+
+class _GradTarget:
+    """Where parameter gradients are written: the parameters' own .grad buffers (trainer hot path) or,
+    when `sink` is a dict, fresh tensors collected for torch.autograd (module API)."""
+    sink = None
+
+    def _gb(self, p):
+        if self.sink is not None:
+            buf = self.sink.get(id(p))
+            if buf is None:
+                buf = self.sink[id(p)] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            return buf
+        if p.grad is None:
+            p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        return p.grad
+
+
+class DiscriminatorEngine(_GradTarget):
+    """conv1..4 (down) + BN + LeakyReLU(0.2), conv5 + sigmoid head.  model/DCGAN.py:6-35."""
+
+    def __init__(self, module, dtype=torch.bfloat16, comm=None, algo=ops.ALGO_AUTO):
+        self.m = module
+        self.dtype = dtype
+        self.algo = algo
+        self.comm = comm or LocalComm()
+        dev = module.conv1.weight.device
+        self.dev = dev
+        self.nc = module.conv1.weight.shape[1]
+        self.convs = {k: _Conv(getattr(module, f"conv{k}").weight, 64 >> k, dtype) for k in range(1, 5)}
+        self.norms = {k: _Norm(getattr(module, f"norm{k}")) for k in range(1, 5)}
+        self.has_head = hasattr(module, "conv5")
+        if self.has_head:
+            self.K5 = 16 * self.convs[4].Ca
+            self.w5 = torch.empty(self.K5, dtype=dtype, device=dev)
+            self.dw5 = torch.zeros(self.K5, dtype=torch.float32, device=dev)
+            self._w5_seen = None
+        self.ws = _Workspace(dev)
+
+    def refresh(self, force=False):
+        for c in self.convs.values():
+            c.refresh(force)
+        if self.has_head:
+            w = self.m.conv5.weight
+            key = (w._version, w.data_ptr())
+            if force or key != self._w5_seen:
+                ops.pack_head(w.detach(), self.w5)
+                self._w5_seen = key
+
+    # ---- forward -----------------------------------------------------------------------------------
+    def trunk_forward(self, x_nhwc, groups=1, update_running=True):
+        self.refresh()
+        B = x_nhwc.shape[0]
+        assert B % groups == 0
+        ctx = Ctx()
+        ctx.x, ctx.groups, ctx.B = x_nhwc, groups, B
+        cur = x_nhwc
+        world = self.comm.world_size
+        for k in range(1, 5):
+            cv, nm = self.convs[k], self.norms[k]
+            y = torch.empty(B, cv.Hs, cv.Ws, cv.Ca, dtype=self.dtype, device=self.dev)
+            stats = torch.zeros(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
+            ops.conv_down(cur, cv.w_down, y, stats, cv.Ca, cv.Cb, ipg=B // groups, algo=self.algo)
+            self.comm.allreduce_sum_(stats)                                  # SyncBN: global batch statistics
+            ss = torch.empty(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
+            mr = torch.empty(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
+            count = (B // groups) * cv.Hs * cv.Ws * world
+            bn = nm.bn
+            ops.bn_finalize(stats, nm.gamma, nm.beta,
+                            bn.running_mean if update_running else None,
+                            bn.running_var if update_running else None,
+                            bn.num_batches_tracked if update_running else None,
+                            ss, mr, cv.Ca, groups, count, BN_EPS, BN_MOM)
+            a = torch.empty_like(y)
+            ops.bn_act_fwd(y, ss, a, cv.Ca, groups, LRELU)
+            ctx.y[k], ctx.a[k], ctx.ss[k], ctx.mr[k] = y, a, ss, mr
+            cur = a
+        return ctx
+
+    def head_forward(self, ctx, targets=None, scalars=None):
+        """prob = sigmoid(conv5(a4)); with `targets` (one per group) also accumulates, per group g,
+        scalars[g][0] += BCE mean and scalars[g][1] += mean(prob)."""
+        B, per = ctx.B, ctx.B // ctx.groups
+        prob = torch.empty(B, dtype=torch.float32, device=self.dev)
+        a4 = ctx.a[4].view(B, self.K5)
+        for g in range(ctx.groups):
+            sc = scalars[g] if (scalars is not None and targets is not None and targets[g] is not None) else None
+            t = targets[g] if (targets is not None and targets[g] is not None) else 0.0
+            ops.head_fwd(a4[g * per:(g + 1) * per], self.w5, prob[g * per:(g + 1) * per], t, sc)
+        ctx.prob = prob
+        return prob
+
+    # ---- backward ----------------------------------------------------------------------------------
+    def head_backward(self, ctx, mode, targets=None, dprob=None, wgrad=True, accumulate=False):
+        """d(loss)/d(a4) (+ conv5 weight gradient).  mode 0 BCE-mean, 1 ones (GP sweep), 2 upstream dprob."""
+        B, per = ctx.B, ctx.B // ctx.groups
+        da4 = torch.empty(B, self.K5, dtype=self.dtype, device=self.dev)
+        a4 = ctx.a[4].view(B, self.K5)
+        if wgrad:
+            self.dw5.zero_()
+        for g in range(ctx.groups):
+            sl = slice(g * per, (g + 1) * per)
+            ops.head_bwd(ctx.prob[sl], targets[g] if targets is not None else 0.0, self.w5, a4[sl], da4[sl],
+                         self.dw5 if wgrad else None, mode, True,
+                         dprob=dprob[sl] if dprob is not None else None)
+        if wgrad:
+            ops.unpack_head_grad(self.dw5, self._gb(self.m.conv5.weight), accumulate)
+        return da4.view(B, 4, 4, self.convs[4].Ca)
+
+    def trunk_backward(self, ctx, da4, wgrad=True, input_grad=False, accumulate=False):
+        """Backward through conv4..conv1 given d/d(a4).  Returns d/d(input) (NHWC) when asked."""
+        B, groups = ctx.B, ctx.groups
+        world = self.comm.world_size
+        da = da4
+        for k in range(4, 0, -1):
+            cv, nm = self.convs[k], self.norms[k]
+            C = cv.Ca
+            sums = torch.zeros(groups, 2 * C, dtype=torch.float32, device=self.dev)
+            ops.bn_act_bwd_reduce(da, ctx.y[k], ctx.ss[k], ctx.mr[k], sums, C, groups, LRELU)
+            if wgrad:   # parameter gradients are this rank's contribution; ranks are averaged later
+                ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, groups, accumulate)
+            self.comm.allreduce_sum_(sums)
+            dy = torch.empty_like(ctx.y[k])
+            count = (B // groups) * cv.Hs * cv.Ws * world
+            ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count, LRELU)
+            inp = ctx.a[k - 1] if k > 1 else ctx.x
+            if wgrad:
+                nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
+                ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
+                               algo=self.algo)
+            if k > 1 or input_grad:
+                da = torch.empty_like(inp)
+                ops.conv_up(dy, cv.w_up, da, None, cv.Ca, cv.Cb, algo=self.algo)
+            else:
+                da = None
+        return da
+
+
+class GeneratorEngine(_GradTarget):
+    """conv1 (dense 1x1 -> 4x4) + 3x (BN, ReLU, up) + conv5 up + tanh.  model/DCGAN.py:38-67."""
+
+    def __init__(self, module, dtype=torch.bfloat16, comm=None, algo=ops.ALGO_AUTO):
+        self.m = module
+        self.dtype = dtype
+        self.algo = algo
+        self.comm = comm or LocalComm()
+        dev = module.conv1.weight.device
+        self.dev = dev
+        w1 = module.conv1.weight
+        self.K1, self.C1 = int(w1.shape[0]), int(w1.shape[1])
+        self.w_fc = torch.empty(16 * self.C1, self.K1, dtype=dtype, device=dev)
+        self.dw_fc = torch.empty(16 * self.C1, self.K1, dtype=torch.float32, device=dev)
+        self._w1_seen = None
+        self.convs = {k: _Conv(getattr(module, f"conv{k}").weight, 2 << (k - 1), dtype) for k in range(2, 6)}
+        self.norms = {k: _Norm(getattr(module, f"norm{k}")) for k in range(1, 5)}
+        self.nc = self.convs[5].Cb
+        self.ws = _Workspace(dev)
+
+    def refresh(self, force=False):
+        w = self.m.conv1.weight
+        key = (w._version, w.data_ptr())
+        if force or key != self._w1_seen:
+            ops.pack_fc(w.detach(), self.w_fc)
+            self._w1_seen = key
+        for c in self.convs.values():
+            c.refresh(force)
+
+    def _bn_relu(self, ctx, k, y, stats, groups, update_running):
+        nm = self.norms[k]
+        C = nm.C
+        self.comm.allreduce_sum_(stats)
+        ss = torch.empty(groups, 2 * C, dtype=torch.float32, device=self.dev)
+        mr = torch.empty(groups, 2 * C, dtype=torch.float32, device=self.dev)
+        count = (y.numel() // C // groups) * self.comm.world_size
+        bn = nm.bn
+        ops.bn_finalize(stats, nm.gamma, nm.beta,
+                        bn.running_mean if update_running else None,
+                        bn.running_var if update_running else None,
+                        bn.num_batches_tracked if update_running else None,
+                        ss, mr, C, groups, count, BN_EPS, BN_MOM)
+        a = torch.empty_like(y)
+        ops.bn_act_fwd(y, ss, a, C, groups, 0.0)
+        ctx.y[k], ctx.a[k], ctx.ss[k], ctx.mr[k] = y, a, ss, mr
+        return a
+
+    def forward(self, z2d, update_running=True):
+        """z2d: [B, K1] fp32 (z, or cat(z, one-hot) for CGAN).  Returns ctx; ctx.y[5] is the raw conv5
+        output [B,64,64,nc] (tanh is applied by ops.g_out_fwd at the image edge)."""
+        self.refresh()
+        B = z2d.shape[0]
+        ctx = Ctx()
+        ctx.x, ctx.B, ctx.groups = z2d, B, 1
+        y1 = torch.empty(B, 4, 4, self.C1, dtype=self.dtype, device=self.dev)
+        stats = torch.zeros(1, 2 * self.C1, dtype=torch.float32, device=self.dev)
+        ops.fc_fwd(z2d, self.w_fc, y1, stats, self.C1)
+        cur = self._bn_relu(ctx, 1, y1, stats, 1, update_running)
+        for k in range(2, 6):
+            cv = self.convs[k]
+            y = torch.empty(B, 2 * cv.Hs, 2 * cv.Ws, cv.Cb, dtype=self.dtype, device=self.dev)
+            if k < 5:
+                stats = torch.zeros(1, 2 * cv.Cb, dtype=torch.float32, device=self.dev)
+                ops.conv_up(cur, cv.w_up, y, stats, cv.Ca, cv.Cb, algo=self.algo)
+                cur = self._bn_relu(ctx, k, y, stats, 1, update_running)
+            else:
+                ops.conv_up(cur, cv.w_up, y, None, cv.Ca, cv.Cb, algo=self.algo)
+                ctx.y[5] = y
+        return ctx
+
+    def backward(self, ctx, dy5, accumulate=False):
+        """dy5: gradient w.r.t. the raw conv5 output (NHWC).  Fills .grad of every generator parameter."""
+        B = ctx.B
+        world = self.comm.world_size
+        d_large = dy5
+        for k in range(5, 1, -1):
+            cv = self.convs[k]
+            nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
+            ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,
+                           accumulate, algo=self.algo)
+            da = torch.empty_like(ctx.a[k - 1])
+            ops.conv_down(d_large, cv.w_down, da, None, cv.Ca, cv.Cb, algo=self.algo)
+            nm = self.norms[k - 1]
+            C = nm.C
+            sums = torch.zeros(1, 2 * C, dtype=torch.float32, device=self.dev)
+            ops.bn_act_bwd_reduce(da, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], sums, C, 1, 0.0)
+            ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, 1, accumulate)
+            self.comm.allreduce_sum_(sums)
+            dy = torch.empty_like(ctx.y[k - 1])
+            count = (ctx.y[k - 1].numel() // C) * world
+            ops.bn_act_bwd_apply(da, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], nm.gamma, sums, dy, C, 1, count, 0.0)
+            d_large = dy
+        ops.fc_wgrad(d_large.view(B, 16 * self.C1), ctx.x, self.dw_fc, accumulate=False)
+        ops.unpack_fc_grad(self.dw_fc, self._gb(self.m.conv1.weight), accumulate)

@@ -1,0 +1,183 @@
+"""Tensor-level wrappers over the C ABI (include/jck_b200.h).  PyTorch is plumbing here: it owns
+device memory and streams; every arithmetic kernel is ours.  Nothing in this module computes on
+the CPU or through torch operators."""
+import torch
+
+from . import _lib
+from ._lib import JCK_BF16, JCK_F32, ALGO_AUTO, ALGO_SIMT, ALGO_TC, check  # noqa: F401
+
+_DT = {torch.float32: JCK_F32, torch.bfloat16: JCK_BF16}
+
+
+def dt(t_or_dtype):
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    return _DT[d]
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "jck ops need contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def L():
+    return _lib.load()
+
+
+# ---- image edge ----------------------------------------------------------------------------------
+def prep_image(x1, out_nhwc=None, m1=None, a1=1.0, b1=0.0, x2=None, alpha=None, out_nchw=None):
+    B, C, H, W = x1.shape
+    d = dt(out_nhwc) if out_nhwc is not None else JCK_F32
+    check(L().jck_prep_image(_p(x1), _p(m1), a1, b1, _p(x2), _p(alpha), _p(out_nhwc), _p(out_nchw),
+                             B, C, H, W, d, _s()), "prep_image")
+
+
+def nhwc_to_nchw(x_nhwc, out_nchw):
+    B, C, H, W = out_nchw.shape
+    check(L().jck_nhwc_to_nchw_f32(_p(x_nhwc), _p(out_nchw), B, C, H, W, dt(x_nhwc), _s()), "nhwc_to_nchw")
+
+
+# ---- weights ---------------------------------------------------------------------------------------
+def pack_weights(w4, w_down, w_up):
+    Ca, Cb = w4.shape[0], w4.shape[1]
+    d = dt(w_down if w_down is not None else w_up)
+    check(L().jck_pack_weights(_p(w4), _p(w_down), _p(w_up), Ca, Cb, d, _s()), "pack_weights")
+
+
+def pack_fc(w4, w_fc):
+    K, C = w4.shape[0], w4.shape[1]
+    check(L().jck_pack_fc(_p(w4), _p(w_fc), K, C, dt(w_fc), _s()), "pack_fc")
+
+
+def unpack_fc_grad(dw_fc, dw4, accumulate):
+    K, C = dw4.shape[0], dw4.shape[1]
+    check(L().jck_unpack_fc_grad(_p(dw_fc), _p(dw4), K, C, int(accumulate), _s()), "unpack_fc_grad")
+
+
+def pack_head(w4, w5):
+    check(L().jck_pack_head(_p(w4), _p(w5), w4.shape[1], dt(w5), _s()), "pack_head")
+
+
+def unpack_head_grad(dw5, dw4, accumulate):
+    check(L().jck_unpack_head_grad(_p(dw5), _p(dw4), dw4.shape[1], int(accumulate), _s()), "unpack_head_grad")
+
+
+# ---- convolutions ------------------------------------------------------------------------------------
+def conv_down(x_large, w_down, out_small, stats, Ca, Cb, ipg=0, algo=ALGO_AUTO):
+    B, Hs, Ws = out_small.shape[0], out_small.shape[1], out_small.shape[2]
+    check(L().jck_conv_down(_p(x_large), _p(w_down), _p(out_small), _p(stats), B, Hs, Ws, Ca, Cb, ipg,
+                            dt(x_large), algo, _s()), "conv_down")
+
+
+def conv_up(x_small, w_up, out_large, stats, Ca, Cb, ipg=0, algo=ALGO_AUTO):
+    B, Hs, Ws = x_small.shape[0], x_small.shape[1], x_small.shape[2]
+    check(L().jck_conv_up(_p(x_small), _p(w_up), _p(out_large), _p(stats), B, Hs, Ws, Ca, Cb, ipg,
+                          dt(x_small), algo, _s()), "conv_up")
+
+
+def wgrad_workspace_bytes(B, Hs, Ws, Ca, Cb, dtype, algo=ALGO_AUTO):
+    return int(L().jck_conv_wgrad_workspace_bytes(B, Hs, Ws, Ca, Cb, dt(dtype), algo))
+
+
+def conv_wgrad(small, large, dw4, workspace, Ca, Cb, accumulate, algo=ALGO_AUTO):
+    B, Hs, Ws = small.shape[0], small.shape[1], small.shape[2]
+    check(L().jck_conv_wgrad(_p(small), _p(large), _p(dw4), _p(workspace), workspace.numel() * workspace.element_size(),
+                             B, Hs, Ws, Ca, Cb, int(accumulate), dt(small), algo, _s()), "conv_wgrad")
+
+
+def fc_fwd(x, w_fc, out, stats, C):
+    M, K = x.shape
+    N = w_fc.shape[0]
+    check(L().jck_fc_fwd(_p(x), _p(w_fc), _p(out), _p(stats), M, N, K, C, dt(w_fc), _s()), "fc_fwd")
+
+
+def fc_wgrad(dy, x, dw_fc, accumulate=False):
+    M, K = x.shape
+    N = dw_fc.shape[0]
+    check(L().jck_fc_wgrad(_p(dy), _p(x), _p(dw_fc), M, N, K, int(accumulate), dt(dy), _s()), "fc_wgrad")
+
+
+# ---- BatchNorm + activation ----------------------------------------------------------------------------
+def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale_shift, mean_rstd, C, groups, count,
+                eps=1e-5, momentum=0.1):
+    check(L().jck_bn_finalize(_p(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt),
+                              _p(scale_shift), _p(mean_rstd), C, groups, float(count), eps, momentum, _s()),
+          "bn_finalize")
+
+
+def bn_act_fwd(y, scale_shift, a, C, groups, slope):
+    npix = y.numel() // C
+    check(L().jck_bn_act_fwd(_p(y), _p(scale_shift), _p(a), npix, C, npix // groups, slope, dt(y), _s()), "bn_act_fwd")
+
+
+def bn_act_bwd_reduce(da, y, scale_shift, mean_rstd, sums, C, groups, slope):
+    npix = y.numel() // C
+    check(L().jck_bn_act_bwd_reduce(_p(da), _p(y), _p(scale_shift), _p(mean_rstd), _p(sums), npix, C,
+                                    npix // groups, slope, dt(y), _s()), "bn_act_bwd_reduce")
+
+
+def bn_act_bwd_apply(da, y, scale_shift, mean_rstd, gamma, sums, dy, C, groups, count, slope):
+    npix = y.numel() // C
+    check(L().jck_bn_act_bwd_apply(_p(da), _p(y), _p(scale_shift), _p(mean_rstd), _p(gamma), _p(sums), _p(dy),
+                                   npix, C, npix // groups, float(count), slope, dt(y), _s()), "bn_act_bwd_apply")
+
+
+def bn_param_grad(sums, dgamma, dbeta, C, groups, accumulate):
+    check(L().jck_bn_param_grad(_p(sums), _p(dgamma), _p(dbeta), C, groups, int(accumulate), _s()), "bn_param_grad")
+
+
+# ---- DCGAN head --------------------------------------------------------------------------------------------
+def head_fwd(a4, w5, prob, target, scalars):
+    B = prob.shape[0]
+    K = w5.numel()
+    check(L().jck_head_fwd(_p(a4), _p(w5), _p(prob), float(target), _p(scalars), B, K, dt(a4), _s()), "head_fwd")
+
+
+def head_bwd(prob, target, w5, a4, da4, dw5, mode, accumulate, dprob=None):
+    B = prob.shape[0]
+    K = w5.numel()
+    check(L().jck_head_bwd(_p(prob), _p(dprob), float(target), _p(w5), _p(a4), _p(da4), _p(dw5), B, K, mode, int(accumulate),
+                           dt(da4), _s()), "head_bwd")
+
+
+# ---- generator output, GP, Adam, RNG ---------------------------------------------------------------------------
+def g_out_fwd(y5, noise, a, b, fake_raw, fake_mix, mix_nhwc):
+    B, H, W, C = y5.shape
+    check(L().jck_g_out_fwd(_p(y5), _p(noise), a, b, _p(fake_raw), _p(fake_mix), _p(mix_nhwc), B, C, H, W, dt(y5),
+                            _s()), "g_out_fwd")
+
+
+def g_out_bwd(dmix, fake_raw, a, dy5):
+    B, H, W, C = dmix.shape
+    check(L().jck_g_out_bwd(_p(dmix), _p(fake_raw), a, _p(dy5), B, C, H, W, dt(dmix), _s()), "g_out_bwd")
+
+
+def gp_penalty(dx, scalars):
+    B = dx.shape[0]
+    check(L().jck_gp_penalty(_p(dx), _p(scalars), B, dx.numel() // B, dt(dx), _s()), "gp_penalty")
+
+
+def adam(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step_count):
+    check(L().jck_adam(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps,
+                       _p(step_count), _s()), "adam")
+
+
+def adam_advance(step_count):
+    check(L().jck_adam_advance(_p(step_count), _s()), "adam_advance")
+
+
+def randn(out, seed, stream_id, counter):
+    check(L().jck_randn(_p(out), out.numel(), seed, stream_id, _p(counter), _s()), "randn")
+
+
+def rand(out, seed, stream_id, counter):
+    check(L().jck_rand(_p(out), out.numel(), seed, stream_id, _p(counter), _s()), "rand")
+
+
+def rng_advance(counter, by):
+    check(L().jck_rng_advance(_p(counter), by, _s()), "rng_advance")

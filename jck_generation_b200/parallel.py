@@ -1,0 +1,113 @@
+"""Data parallelism over the batch: one process per GPU, torch.distributed (NCCL over NVLink) for the
+plumbing.  The reference has no distributed code at all; what has to be exchanged for
+an N-GPU run to equal the reference at the global batch size is exactly
+  * BatchNorm batch statistics, forward  [sum x, sum x^2]    2C fp32 per layer per pass   (SyncBN)
+  * BatchNorm backward reductions        [sum g, sum g*xhat] 2C fp32 per layer per pass
+  * parameter gradients (sum over the global batch)           one flat bucket per network
+  * logged scalars (means over the global batch).
+Rank r owns rows [r*B/W, (r+1)*B/W) of every per-sample tensor; parameters, Adam state and BN buffers
+are replicated and stay identical because every rank applies the same update to the same reduced
+gradient."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class LocalComm:
+    """World of one: every collective is the identity."""
+    world_size = 1
+    rank = 0
+
+    def allreduce_sum_(self, t):
+        return t
+
+    def allreduce_mean_(self, t):
+        return t
+
+    def barrier(self):
+        pass
+
+
+class TorchComm:
+    """Collectives through an initialised torch.distributed process group (nccl on GPUs, gloo in the
+    CPU tests)."""
+
+    def __init__(self, group=None):
+        assert dist.is_initialized(), "init the process group first (see init_from_env)"
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def allreduce_sum_(self, t):
+        if self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allreduce_mean_(self, t):
+        if self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world_size)
+        return t
+
+    def barrier(self):
+        if self.world_size > 1:
+            dist.barrier(group=self.group)
+
+
+def init_from_env(backend=None):
+    """Build the communicator torchrun's environment describes (RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_ADDR / MASTER_PORT); world of one when launched plainly."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return LocalComm()
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend=backend)
+    return TorchComm()
+
+
+def shard_rows(t, comm):
+    """Rows of a global per-sample tensor owned by this rank."""
+    n = t.shape[0]
+    assert n % comm.world_size == 0, "global batch must divide by the world size"
+    per = n // comm.world_size
+    return t[comm.rank * per:(comm.rank + 1) * per]
+
+
+class FlatParams:
+    """Re-home a module's parameters, gradients and Adam moments into flat fp32 buffers (views keep the
+    nn.Parameter API intact): Adam becomes one launch per network and the gradient exchange one
+    all-reduce per network."""
+
+    def __init__(self, module):
+        params = [p for p in module.parameters()]
+        self.params = params
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets = []
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            self.offsets.append((off, k))
+            off += k
+        self.numel = n
+
+    def views(self, flat):
+        return [flat[o:o + k].view(p.shape) for (o, k), p in zip(self.offsets, self.params)]
+
+    def rebind(self):
+        """Re-attach .grad views (model.zero_grad() sets them to None by default)."""
+        for (o, k), p in zip(self.offsets, self.params):
+            if p.grad is None or p.grad.data_ptr() != self.grad[o:o + k].data_ptr():
+                p.grad = self.grad[o:o + k].view(p.shape)

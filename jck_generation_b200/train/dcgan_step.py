@@ -1,0 +1,157 @@
+"""The DCGAN G+D train step as one fixed launch sequence of sm_100a kernels.
+
+Semantics: exactly the body of the reference's loop, train/dcgan_trainer.py:155-189 --
+  A  D(0.9*real + 0.1*n1) vs label .9  -> backward          (:155-165)
+  B  fake = G(z); D((0.9*fake + 0.1*n2).detach()) vs .1 -> backward, grads accumulate on A   (:168-176)
+  C  gradient penalty on x_hat = a*real_n + (1-a)*fake_n: a D forward in train mode (it moves the BN
+     running statistics) and an input-gradient sweep; the value is only logged (:178-179)
+     optimizer_d.step()                                                                      (:180)
+  D  D(fake_n) with the updated D vs label .9 -> backward into G; optimizer_g.step()       (:182-189)
+What differs is scheduling, not arithmetic: passes A, B, C read the same D weights, so they run as ONE
+3B-image forward with three BatchNorm statistic groups (running statistics updated in A, B, C order);
+the reference's wasted D weight-gradient of pass D (zeroed at :155 before any use) is not computed.
+
+Random tensors: `rng` injects host-made tensors (parity mode -- CPU mt19937 and Philox streams can
+never agree); otherwise they are drawn on the device by our Philox kernel.
+"""
+import torch
+
+from .. import ops
+
+LABEL_REAL = 0.9
+LABEL_FAKE = 0.1
+
+# rows of the per-step scalar block
+S_REAL, S_FAKE, S_GP, S_G = 0, 1, 2, 3
+
+
+class DCGANStep:
+    def __init__(self, model_g, model_d, opt_g, opt_d, flat_g, flat_d, comm, lambda_gp=10.0, seed=12345):
+        self.g, self.d = model_g, model_d
+        self.eg, self.ed = model_g.engine(), model_d.engine()
+        self.opt_g, self.opt_d = opt_g, opt_d
+        self.flat_g, self.flat_d = flat_g, flat_d
+        self.comm = comm
+        self.lambda_gp = lambda_gp
+        self.seed = seed
+        self.dev = self.ed.dev
+        self.dtype = self.ed.dtype
+        self.nc = self.ed.nc
+        self.nz = self.eg.K1
+        self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._graph = None
+        self._static = None
+
+    # ---- random tensors ----------------------------------------------------------------------------
+    def draw(self, B):
+        sid = 16 * self.comm.rank
+        dev = self.dev
+        r = {"noise_real": torch.empty(B, self.nc, 64, 64, device=dev),
+             "z": torch.empty(B, self.nz, 1, 1, device=dev),
+             "noise_fake": torch.empty(B, self.nc, 64, 64, device=dev),
+             "alpha": torch.empty(B, 1, 1, 1, device=dev)}
+        ops.randn(r["noise_real"], self.seed, sid + 1, self.rng_counter)
+        ops.randn(r["z"], self.seed, sid + 2, self.rng_counter)
+        ops.randn(r["noise_fake"], self.seed, sid + 3, self.rng_counter)
+        ops.rand(r["alpha"], self.seed, sid + 4, self.rng_counter)
+        ops.rng_advance(self.rng_counter, (B * self.nc * 64 * 64 + 3) // 4)
+        return r
+
+    # ---- the step ------------------------------------------------------------------------------------
+    def run(self, real, rng=None):
+        """real: [B,nc,64,64] fp32 on the device (this rank's rows).  Returns a [4,2] fp32 device tensor:
+        rows (real, fake, gp, g), columns (BCE mean | GP value, mean D output) -- local-batch means."""
+        ed, eg = self.ed, self.eg
+        B = real.shape[0]
+        dev, dt = self.dev, self.dtype
+        r = rng if rng is not None else self.draw(B)
+        self.flat_d.rebind()
+        self.flat_g.rebind()
+
+        X = torch.empty(3 * B, 64, 64, self.nc, dtype=dt, device=dev)         # [real_n | fake_n | x_hat]
+        real_n = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
+        ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n)       # :160
+
+        gctx = eg.forward(r["z"].reshape(B, self.nz))                                                      # :169
+        fake_raw = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
+        fake_n = torch.empty_like(fake_raw)
+        ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B])                  # :171
+        ops.prep_image(real_n, out_nhwc=X[2 * B:3 * B], a1=1.0, x2=fake_n, alpha=r["alpha"].reshape(B))    # :112
+
+        scal = torch.zeros(4, 2, dtype=torch.float32, device=dev)
+        ctx = ed.trunk_forward(X, groups=3)                                                                # :162,173,114
+        ed.head_forward(ctx, targets=[LABEL_REAL, LABEL_FAKE, None], scalars=scal)
+
+        cab = ctx.slice(0, 2)                                                                              # :164,175
+        da4 = ed.head_backward(cab, mode=0, targets=[LABEL_REAL, LABEL_FAKE], wgrad=True, accumulate=False)
+        ed.trunk_backward(cab, da4, wgrad=True, input_grad=False, accumulate=False)
+
+        cc = ctx.slice(2, 3)                                                                               # :116-126
+        da4 = ed.head_backward(cc, mode=1, wgrad=False)
+        dx = ed.trunk_backward(cc, da4, wgrad=False, input_grad=True)
+        ops.gp_penalty(dx, scal[S_GP])
+
+        self.comm.allreduce_mean_(self.flat_d.grad)
+        self.opt_d.step()                                                                                  # :180
+        ed.refresh(force=True)
+
+        ctx2 = ed.trunk_forward(X[B:2 * B], groups=1)                                                      # :185
+        ed.head_forward(ctx2, targets=[LABEL_REAL], scalars=scal[S_G:S_G + 1])
+        da4 = ed.head_backward(ctx2, mode=0, targets=[LABEL_REAL], wgrad=False)                            # :187
+        dmix = ed.trunk_backward(ctx2, da4, wgrad=False, input_grad=True)
+        dy5 = torch.empty_like(dmix)
+        ops.g_out_bwd(dmix, fake_raw, 0.9, dy5)
+        eg.backward(gctx, dy5, accumulate=False)
+        self.comm.allreduce_mean_(self.flat_g.grad)
+        self.opt_g.step()                                                                                  # :189
+        eg.refresh(force=True)
+        self.last = {"fake_raw": fake_raw, "gp_grad_nhwc": dx, "ctx": ctx, "ctx_g": gctx, "ctx_d": ctx2}
+        return scal
+
+    # ---- CUDA graph ---------------------------------------------------------------------------------
+    def capture(self, batch):
+        """Capture one step (device-drawn random tensors) into a CUDA graph; replay() then costs one
+        launch.  Single-process only: collectives stay outside graphs in this round."""
+        assert self.comm.world_size == 1, "graph capture is single-GPU in this round"
+        self._static = torch.zeros(batch, self.nc, 64, 64, dtype=torch.float32, device=self.dev)
+        # warm-up steps really train; put the training state back afterwards
+        bufs = [b for m in (self.g, self.d) for b in m.buffers()]
+        keep = [t.clone() for t in (self.flat_g.flat, self.flat_g.exp_avg, self.flat_g.exp_avg_sq,
+                                    self.flat_d.flat, self.flat_d.exp_avg, self.flat_d.exp_avg_sq,
+                                    self.opt_g.step_dev, self.opt_d.step_dev, self.rng_counter, *bufs)]
+        steps = (self.opt_g.steps_done, self.opt_d.steps_done)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):                      # warm-up: allocator pools, smem attributes, packs
+                self.run(self._static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self.run(self._static)
+        for dst, src in zip((self.flat_g.flat, self.flat_g.exp_avg, self.flat_g.exp_avg_sq,
+                             self.flat_d.flat, self.flat_d.exp_avg, self.flat_d.exp_avg_sq,
+                             self.opt_g.step_dev, self.opt_d.step_dev, self.rng_counter, *bufs), keep):
+            dst.copy_(src)
+        self.opt_g.steps_done, self.opt_d.steps_done = steps
+        self.eg.refresh(force=True)
+        self.ed.refresh(force=True)
+        torch.cuda.synchronize()
+        return self
+
+    def replay(self, real):
+        self._static.copy_(real, non_blocking=True)
+        self._graph.replay()
+        self.opt_d.steps_done += 1
+        self.opt_g.steps_done += 1
+        return self._graph_out
+
+    @staticmethod
+    def summarize(scal, lambda_gp=10.0):
+        """host view of a scalar block: the quantities the reference logs (:191-196)."""
+        s = scal.detach().float().cpu()
+        return {"loss_d": float(s[S_REAL, 0] + s[S_FAKE, 0] + lambda_gp * s[S_GP, 0]),
+                "loss_g": float(s[S_G, 0]), "x_d": float(s[S_REAL, 1]), "z1_gd": float(s[S_FAKE, 1]),
+                "z2_gd": float(s[S_G, 1]), "gp": float(s[S_GP, 0]),
+                "err_real": float(s[S_REAL, 0]), "err_fake": float(s[S_FAKE, 0])}

@@ -1,0 +1,316 @@
+"""Per-kernel parity checks through the C ABI against torch CPU operators (the arithmetic the
+reference itself runs).  Used by tests/test_gpu_kernels.py, and runnable on its own with every case
+in a fresh subprocess under a timeout so that one trapped kernel cannot take the rest down:
+
+    python -m tests.kernel_checks --isolate
+"""
+import json
+import subprocess
+import sys
+
+import torch
+import torch.nn.functional as F
+
+# (Ca, Cb, Hs): the three GEMM-shaped layer geometries + the image-edge geometry
+SHAPES = {"c2": (128, 64, 16), "c3": (256, 128, 8), "c4": (512, 256, 4), "edge": (64, 3, 32)}
+
+
+def _rel(got, want):
+    got, want = got.double().cpu(), want.double().cpu()
+    return float((got - want).norm() / max(float(want.norm()), 1e-30))
+
+
+def _mk(shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(*shape, generator=g) * scale
+    return t.to(dtype).float() if dtype == torch.bfloat16 else t
+
+
+def _packed(w4, dtype):
+    from jck_generation_b200 import ops
+    Ca, Cb = w4.shape[:2]
+    wd = torch.empty(Ca * 16 * Cb, dtype=dtype, device="cuda")
+    wu = torch.empty(Ca * 16 * Cb, dtype=dtype, device="cuda")
+    ops.pack_weights(w4.cuda().contiguous(), wd, wu)
+    return wd, wu
+
+
+def check_down(shape, dtype, algo, B=8, groups=1):
+    from jck_generation_b200 import ops
+    Ca, Cb, Hs = SHAPES[shape]
+    x = _mk((B, Cb, 2 * Hs, 2 * Hs), dtype, 1)
+    w4 = _mk((Ca, Cb, 4, 4), dtype, 2, 0.05)
+    want = F.conv2d(x, w4, stride=2, padding=1)
+    wd, _ = _packed(w4, dtype)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    out = torch.full((B, Hs, Hs, Ca), float("nan"), dtype=dtype, device="cuda")
+    stats = torch.zeros(groups, 2 * Ca, device="cuda")
+    ops.conv_down(xin, wd, out, stats, Ca, Cb, ipg=B // groups, algo=algo)
+    torch.cuda.synchronize()
+    per = B // groups
+    ws = torch.stack([torch.cat([want[g * per:(g + 1) * per].sum((0, 2, 3)),
+                                 (want[g * per:(g + 1) * per] ** 2).sum((0, 2, 3))]) for g in range(groups)])
+    return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats, ws)}
+
+
+def check_up(shape, dtype, algo, B=8, groups=1):
+    from jck_generation_b200 import ops
+    Ca, Cb, Hs = SHAPES[shape]
+    x = _mk((B, Ca, Hs, Hs), dtype, 3)
+    w4 = _mk((Ca, Cb, 4, 4), dtype, 4, 0.05)
+    want = F.conv_transpose2d(x, w4, stride=2, padding=1)
+    _, wu = _packed(w4, dtype)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    out = torch.full((B, 2 * Hs, 2 * Hs, Cb), float("nan"), dtype=dtype, device="cuda")
+    stats = torch.zeros(groups, 2 * Cb, device="cuda")
+    ops.conv_up(xin, wu, out, stats, Ca, Cb, ipg=B // groups, algo=algo)
+    torch.cuda.synchronize()
+    per = B // groups
+    ws = torch.stack([torch.cat([want[g * per:(g + 1) * per].sum((0, 2, 3)),
+                                 (want[g * per:(g + 1) * per] ** 2).sum((0, 2, 3))]) for g in range(groups)])
+    return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats, ws)}
+
+
+def check_wgrad(shape, dtype, algo, B=8):
+    from jck_generation_b200 import ops
+    Ca, Cb, Hs = SHAPES[shape]
+    small = _mk((B, Ca, Hs, Hs), dtype, 5)
+    large = _mk((B, Cb, 2 * Hs, 2 * Hs), dtype, 6)
+    want = torch.nn.grad.conv2d_weight(large, (Ca, Cb, 4, 4), small, stride=2, padding=1)
+    s = small.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    l = large.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    nbytes = ops.wgrad_workspace_bytes(B, Hs, Hs, Ca, Cb, dtype, algo)
+    ws = torch.empty(nbytes // 4, device="cuda")
+    dw = torch.full((Ca, Cb, 4, 4), float("nan"), device="cuda")
+    ops.conv_wgrad(s, l, dw, ws, Ca, Cb, accumulate=False, algo=algo)
+    ops.conv_wgrad(s, l, dw, ws, Ca, Cb, accumulate=True, algo=algo)
+    torch.cuda.synchronize()
+    return {"dw": _rel(dw, 2 * want)}
+
+
+def check_bn(dtype, C=128, B=8, H=16, groups=2):
+    """stats -> finalize -> apply -> backward against F.batch_norm + leaky_relu autograd, per group."""
+    from jck_generation_b200 import ops
+    y = _mk((B, C, H, H), dtype, 7) * 1.5 + 0.3
+    da = _mk((B, C, H, H), dtype, 8)
+    gamma = 1 + 0.1 * _mk((C,), torch.float32, 9)
+    beta = 0.1 * _mk((C,), torch.float32, 10)
+    per = B // groups
+    rm, rv = torch.zeros(C), torch.ones(C)
+    want_a, want_dy, want_dg, want_db = [], [], torch.zeros(C), torch.zeros(C)
+    for g in range(groups):
+        yy = y[g * per:(g + 1) * per].clone().requires_grad_(True)
+        gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        a = F.leaky_relu(F.batch_norm(yy, rm, rv, gm, bt, True, 0.1, 1e-5), 0.2)
+        a.backward(da[g * per:(g + 1) * per])
+        want_a.append(a.detach()); want_dy.append(yy.grad)
+        want_dg += gm.grad; want_db += bt.grad
+    want_a, want_dy = torch.cat(want_a), torch.cat(want_dy)
+
+    yn = y.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dn = da.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    yf = yn.float()
+    stats = torch.stack([torch.cat([yf[g * per:(g + 1) * per].sum((0, 1, 2)), (yf[g * per:(g + 1) * per] ** 2).sum((0, 1, 2))])
+                         for g in range(groups)]).contiguous()
+    ss = torch.empty(groups, 2 * C, device="cuda"); mr = torch.empty(groups, 2 * C, device="cuda")
+    rmd, rvd = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    gd, bd = gamma.cuda(), beta.cuda()
+    ops.bn_finalize(stats, gd, bd, rmd, rvd, nbt, ss, mr, C, groups, per * H * H)
+    a = torch.empty_like(yn)
+    ops.bn_act_fwd(yn, ss, a, C, groups, 0.2)
+    sums = torch.zeros(groups, 2 * C, device="cuda")
+    ops.bn_act_bwd_reduce(dn, yn, ss, mr, sums, C, groups, 0.2)
+    dy = torch.empty_like(yn)
+    ops.bn_act_bwd_apply(dn, yn, ss, mr, gd, sums, dy, C, groups, per * H * H, 0.2)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.bn_param_grad(sums, dg, db, C, groups, False)
+    torch.cuda.synchronize()
+    return {"a": _rel(a.float().permute(0, 3, 1, 2), want_a), "dy": _rel(dy.float().permute(0, 3, 1, 2), want_dy),
+            "dgamma": _rel(dg, want_dg), "dbeta": _rel(db, want_db), "running_mean": _rel(rmd, rm),
+            "running_var": _rel(rvd, rv), "nbt": abs(int(nbt) - groups)}
+
+
+def check_head(dtype, B=8, C4=512):
+    from jck_generation_b200 import ops
+    K = 16 * C4
+    a4 = _mk((B, C4, 4, 4), dtype, 11, 0.5)
+    w = _mk((1, C4, 4, 4), dtype, 12, 0.02)
+    a4r = a4.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+    p = torch.sigmoid(F.conv2d(a4r, wr)).view(-1)
+    loss = F.binary_cross_entropy(p, torch.full((B,), 0.9))
+    loss.backward()
+    an = a4.permute(0, 2, 3, 1).contiguous().to(dtype).cuda().view(B, K)
+    w5 = torch.empty(K, dtype=dtype, device="cuda")
+    ops.pack_head(w.cuda().contiguous(), w5)
+    prob = torch.empty(B, device="cuda"); scal = torch.zeros(2, device="cuda")
+    ops.head_fwd(an, w5, prob, 0.9, scal)
+    da4 = torch.empty(B, K, dtype=dtype, device="cuda"); dw5 = torch.zeros(K, device="cuda")
+    ops.head_bwd(prob, 0.9, w5, an, da4, dw5, 0, False)
+    dw4 = torch.zeros(1, C4, 4, 4, device="cuda")
+    ops.unpack_head_grad(dw5, dw4, False)
+    torch.cuda.synchronize()
+    return {"prob": _rel(prob, p.detach()), "loss": abs(float(scal[0]) - float(loss)) / abs(float(loss)),
+            "da4": _rel(da4.float().view(B, 4, 4, C4).permute(0, 3, 1, 2), a4r.grad), "dw5": _rel(dw4, wr.grad)}
+
+
+def check_fc(dtype, B=8, K=100, C=512):
+    from jck_generation_b200 import ops
+    z = _mk((B, K, 1, 1), torch.float32, 13)
+    w4 = _mk((K, C, 4, 4), dtype, 14, 0.05)
+    want = F.conv_transpose2d(z, w4, stride=1, padding=0)               # [B,C,4,4]
+    dy = _mk((B, C, 4, 4), dtype, 15)
+    want_dw = torch.einsum("bk,bcyx->kcyx", z.view(B, K), dy)
+    wfc = torch.empty(16 * C, K, dtype=dtype, device="cuda")
+    ops.pack_fc(w4.cuda().contiguous(), wfc)
+    out = torch.empty(B, 4, 4, C, dtype=dtype, device="cuda"); stats = torch.zeros(1, 2 * C, device="cuda")
+    ops.fc_fwd(z.view(B, K).cuda().contiguous(), wfc, out, stats, C)
+    dwfc = torch.empty(16 * C, K, device="cuda")
+    ops.fc_wgrad(dy.permute(0, 2, 3, 1).contiguous().to(dtype).cuda().view(B, 16 * C), z.view(B, K).cuda().contiguous(), dwfc)
+    dw4 = torch.zeros(K, C, 4, 4, device="cuda")
+    ops.unpack_fc_grad(dwfc, dw4, False)
+    torch.cuda.synchronize()
+    ws = torch.cat([want.sum((0, 2, 3)), (want ** 2).sum((0, 2, 3))])
+    return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats.view(-1), ws), "dw": _rel(dw4, want_dw)}
+
+
+def check_misc():
+    """image edge, generator edge, gp, adam, rng."""
+    from jck_generation_b200 import ops
+    B, C = 4, 3
+    x, m, x2 = _mk((B, C, 64, 64), torch.float32, 16), _mk((B, C, 64, 64), torch.float32, 17), _mk((B, C, 64, 64), torch.float32, 18)
+    al = torch.rand(B, generator=torch.Generator().manual_seed(19))
+    want = al.view(B, 1, 1, 1) * (0.9 * x + 0.1 * m) + (1 - al.view(B, 1, 1, 1)) * x2
+    o1 = torch.empty(B, 64, 64, C, device="cuda"); o2 = torch.empty(B, C, 64, 64, device="cuda")
+    ops.prep_image(x.cuda(), out_nhwc=o1, m1=m.cuda(), a1=0.9, b1=0.1, x2=x2.cuda(), alpha=al.cuda(), out_nchw=o2)
+    res = {"prep_nhwc": _rel(o1.permute(0, 3, 1, 2), want), "prep_nchw": _rel(o2, want)}
+    back = torch.empty(B, C, 64, 64, device="cuda")
+    ops.nhwc_to_nchw(o1, back)
+    res["nhwc_to_nchw"] = _rel(back, want)
+    y5 = _mk((B, 64, 64, C), torch.float32, 20).cuda()
+    fr, fm = torch.empty(B, C, 64, 64, device="cuda"), torch.empty(B, C, 64, 64, device="cuda")
+    mn = torch.empty(B, 64, 64, C, device="cuda")
+    ops.g_out_fwd(y5, m.cuda(), 0.9, 0.1, fr, fm, mn)
+    t = torch.tanh(y5.cpu().permute(0, 3, 1, 2))
+    res["g_out_raw"] = _rel(fr, t); res["g_out_mix"] = _rel(fm, 0.9 * t + 0.1 * m); res["g_out_mix_nhwc"] = _rel(mn.permute(0, 3, 1, 2), 0.9 * t + 0.1 * m)
+    dm = _mk((B, 64, 64, C), torch.float32, 21).cuda(); dy5 = torch.empty_like(dm)
+    ops.g_out_bwd(dm, fr, 0.9, dy5)
+    res["g_out_bwd"] = _rel(dy5.permute(0, 3, 1, 2), 0.9 * dm.cpu().permute(0, 3, 1, 2) * (1 - t * t))
+    sc = torch.zeros(2, device="cuda")
+    ops.gp_penalty(dm, sc)
+    wantgp = ((dm.cpu().reshape(B, -1).norm(2, dim=1) - 1) ** 2).mean()
+    res["gp"] = abs(float(sc[0]) - float(wantgp)) / float(wantgp)
+    # Adam, 3 steps against torch.optim.Adam
+    p0, g0 = _mk((1000,), torch.float32, 22), [_mk((1000,), torch.float32, 23 + i) for i in range(3)]
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=2e-4, betas=(0.5, 0.999))
+    pd, md, vd = p0.cuda(), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+    stepc = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for gi in g0:
+        pt.grad = gi.clone(); opt.step()
+        ops.adam(pd, gi.cuda(), md, vd, 2e-4, 0.5, 0.999, 1e-8, stepc); ops.adam_advance(stepc)
+    res["adam"] = _rel(pd - p0.cuda(), pt.detach() - p0)
+    # RNG moments
+    r = torch.empty(1 << 20, device="cuda"); ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ops.randn(r, 1234, 1, ctr)
+    res["randn_mean"] = abs(float(r.mean())); res["randn_std"] = abs(float(r.std()) - 1)
+    ops.rand(r, 1234, 2, ctr)
+    res["rand_mean"] = abs(float(r.mean()) - 0.5); res["rand_range"] = float((r.min() < 0) | (r.max() >= 1))
+    torch.cuda.synchronize()
+    return res
+
+
+def _alg(name):
+    from jck_generation_b200 import ops
+    return {"simt": ops.ALGO_SIMT, "tc": ops.ALGO_TC, "auto": ops.ALGO_AUTO}[name]
+
+
+def _dt(name):
+    return torch.float32 if name == "f32" else torch.bfloat16
+
+
+def all_cases():
+    cases = []
+    for op in ("down", "up", "wgrad"):
+        for shape in SHAPES:
+            cases.append((op, shape, "f32", "simt", 8))
+            cases.append((op, shape, "bf16", "simt", 8))
+            if shape != "edge":
+                cases.append((op, shape, "bf16", "tc", 8))
+                cases.append((op, shape, "bf16", "tc", 3))      # ragged: batch not a multiple of the tile
+    cases += [("down_groups", "c3", "bf16", "tc", 8), ("up_groups", "c4", "bf16", "tc", 16),
+              ("down_groups", "c4", "f32", "simt", 6)]
+    cases += [("bn", "-", "f32", "-", 8), ("bn", "-", "bf16", "-", 8), ("head", "-", "f32", "-", 8),
+              ("head", "-", "bf16", "-", 8), ("fc", "-", "f32", "-", 8), ("fc", "-", "bf16", "-", 8),
+              ("misc", "-", "f32", "-", 4)]
+    return cases
+
+
+def run_case(op, shape, dtype, algo, B):
+    if op == "down":
+        return check_down(shape, _dt(dtype), _alg(algo), B)
+    if op == "up":
+        return check_up(shape, _dt(dtype), _alg(algo), B)
+    if op == "wgrad":
+        return check_wgrad(shape, _dt(dtype), _alg(algo), B)
+    if op == "down_groups":
+        return check_down(shape, _dt(dtype), _alg(algo), B, groups=2)
+    if op == "up_groups":
+        return check_up(shape, _dt(dtype), _alg(algo), B, groups=2)
+    if op == "bn":
+        return check_bn(_dt(dtype))
+    if op == "head":
+        return check_head(_dt(dtype))
+    if op == "fc":
+        return check_fc(_dt(dtype))
+    if op == "misc":
+        return check_misc()
+    raise ValueError(op)
+
+
+def tolerance(op, dtype, key):
+    if key in ("nbt", "rand_range"):
+        return 0.5
+    if key.startswith("randn") or key.startswith("rand_"):
+        return 5e-3
+    if dtype == "f32":
+        return 2e-5 if key != "adam" else 1e-5
+    # bf16 storage: outputs are rounded to 8 bits of mantissa (2^-9 relative per element)
+    return {"dw": 2e-5, "dw5": 2e-5, "stats": 2e-4, "loss": 1e-3, "prob": 1e-3, "dgamma": 1e-2, "dbeta": 1e-2,
+            "running_mean": 1e-3, "running_var": 1e-3}.get(key, 4e-3)
+
+
+def main():
+    if "--one" in sys.argv:
+        spec = json.loads(sys.argv[sys.argv.index("--one") + 1])
+        print("RESULT " + json.dumps(run_case(*spec)))
+        return
+    bad = 0
+    cases = all_cases()
+    if "--only-tc" in sys.argv:
+        cases = [c for c in cases if c[3] == "tc"]
+    if "--no-tc" in sys.argv:
+        cases = [c for c in cases if c[3] != "tc"]
+    for spec in cases:
+        if "--isolate" in sys.argv:
+            try:
+                out = subprocess.run([sys.executable, "-m", "tests.kernel_checks", "--one", json.dumps(spec)],
+                                     capture_output=True, text=True, timeout=120)
+                line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+                res = json.loads(line[0][7:]) if line else {"error": (out.stderr or out.stdout)[-400:]}
+            except subprocess.TimeoutExpired:
+                res = {"error": "timeout"}
+        else:
+            res = run_case(*spec)
+        status = "ok"
+        for k, v in res.items():
+            if k == "error" or not (v <= tolerance(spec[0], spec[2], k)):
+                status = "FAIL"
+        bad += status != "ok"
+        print(status, spec, {k: (f"{v:.2e}" if isinstance(v, float) else v) for k, v in res.items()}, flush=True)
+    print("failures:", bad)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

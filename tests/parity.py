@@ -1,0 +1,124 @@
+"""Parity harness: the CUDA train step (through the public trainer / module API and the C ABI) against
+the CPU oracle on identical weights, inputs and injected random tensors.  Test infrastructure."""
+import types
+
+import torch
+
+from oracle import models as omodels
+from oracle import steps as osteps
+
+
+def rel_err(got, want):
+    got = got.detach().double().cpu()
+    want = want.detach().double().cpu()
+    denom = want.norm().item()
+    return (got - want).norm().item() / (denom if denom > 0 else 1.0)
+
+
+def nhwc_to_nchw(t):
+    return t.detach().float().permute(0, 3, 1, 2).contiguous()
+
+
+def make_pair(dtype, lr, seed=12345, nc=3):
+    """Oracle (CPU) and product (CUDA) networks with identical initial weights + optimizers."""
+    from jck_generation_b200 import parallel
+    from jck_generation_b200.model import DCGAN
+    from jck_generation_b200.train.dcgan_step import DCGANStep
+    from jck_generation_b200.train.optim import FusedAdam
+
+    g_o, d_o = omodels.build("DCGAN", seed=seed, nc=nc)
+    og, od = osteps.make_optimizers(g_o, d_o, lr)
+    g = DCGAN.Generator(nc=nc, dtype=dtype).cuda()
+    d = DCGAN.Discriminator(nc=nc, dtype=dtype).cuda()
+    g.load_state_dict(g_o.state_dict(), strict=True)
+    d.load_state_dict(d_o.state_dict(), strict=True)
+    comm = parallel.LocalComm()
+    fg, fd = parallel.FlatParams(g), parallel.FlatParams(d)
+    opt_g = FusedAdam(g.parameters(), lr=lr, betas=[0.5, 0.999], flat=fg)
+    opt_d = FusedAdam(d.parameters(), lr=lr, betas=[0.5, 0.999], flat=fd)
+    step = DCGANStep(g, d, opt_g, opt_d, fg, fd, comm)
+    return types.SimpleNamespace(g_o=g_o, d_o=d_o, og=og, od=od, g=g, d=d, fg=fg, fd=fd, opt_g=opt_g,
+                                 opt_d=opt_d, step=step)
+
+
+def to_cuda(rng):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in rng.items()}
+
+
+def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11):
+    """One step, everything compared.  Returns {name: relative error}."""
+    P = make_pair(dtype, lr, nc=nc)
+    real = osteps.make_real(batch, nc=nc, n_steps=1)[0]
+    rng = osteps.make_rng(batch, nc=nc, n_steps=1, seed=rng_seed)[0]
+    want = osteps.dcgan_step(P.g_o, P.d_o, P.og, P.od, real, rng, capture=True)
+    cap = want["capture"]
+
+    # D gradients are those of passes A+B (the G step does not recompute D's weight gradient)
+    scal = P.step.run(real.cuda(), to_cuda(rng))
+    torch.cuda.synchronize()
+    got = P.step.summarize(scal)
+    errs = {}
+    for k in ("loss_d", "loss_g", "x_d", "z1_gd", "z2_gd", "gp", "err_real", "err_fake"):
+        errs["scalar." + k] = abs(got[k] - want[k]) / max(abs(want[k]), 1e-6)
+
+    last = P.step.last
+    ctx, per = last["ctx"], batch
+    for gi, tag in enumerate("ABC"):
+        for k in range(1, 5):
+            errs[f"d_act.{tag}.conv{k}"] = rel_err(nhwc_to_nchw(ctx.y[k][gi * per:(gi + 1) * per]),
+                                                   cap["d_acts"][tag][f"conv{k}"])
+    for k in range(1, 5):
+        errs[f"d_act.D.conv{k}"] = rel_err(nhwc_to_nchw(last["ctx_d"].y[k]), cap["d_acts"]["D"][f"conv{k}"])
+    for k in range(1, 6):
+        errs[f"g_act.conv{k}"] = rel_err(nhwc_to_nchw(last["ctx_g"].y[k]), cap["g_acts"][f"conv{k}"])
+    errs["fake_raw"] = rel_err(last["fake_raw"], cap["fake_raw"])
+    errs["gp_grads"] = rel_err(nhwc_to_nchw(last["gp_grad_nhwc"]), cap["gp_grads"])
+    for (name, p) in P.d.named_parameters():
+        errs["d_grad." + name] = rel_err(p.grad, cap["d_grads"][name])
+    for (name, p) in P.g.named_parameters():
+        errs["g_grad." + name] = rel_err(p.grad, cap["g_grads"][name])
+    for name, v in P.d.state_dict().items():
+        if not name.endswith("num_batches_tracked"):
+            errs["d_state." + name] = rel_err(v, P.d_o.state_dict()[name])
+        else:
+            errs["d_state." + name] = float(abs(int(v) - int(P.d_o.state_dict()[name])))
+    for name, v in P.g.state_dict().items():
+        if not name.endswith("num_batches_tracked"):
+            errs["g_state." + name] = rel_err(v, P.g_o.state_dict()[name])
+    return errs
+
+
+def dcgan_trajectory(dtype, batch=8, steps=20, lr=2e-4, teacher_forced=False, real=None, rng=None):
+    """Loss trajectories of both sides.  teacher_forced: before every step the CUDA side is reset to the
+    oracle's weights / BN buffers / Adam moments, so per-step error does not compound chaotically."""
+    P = make_pair(dtype, lr)
+    real = real or osteps.make_real(batch, n_steps=steps)
+    rng = rng or osteps.make_rng(batch, n_steps=steps, seed=777)
+    got, want = [], []
+    for i in range(steps):
+        if teacher_forced and i > 0:
+            P.g.load_state_dict(P.g_o.state_dict())
+            P.d.load_state_dict(P.d_o.state_dict())
+            for opt_o, opt, flat in ((P.og, P.opt_g, P.fg), (P.od, P.opt_d, P.fd)):
+                sd = opt_o.state_dict()
+                for idx, (o, k) in enumerate(flat.offsets):
+                    flat.exp_avg[o:o + k].copy_(sd["state"][idx]["exp_avg"].reshape(-1))
+                    flat.exp_avg_sq[o:o + k].copy_(sd["state"][idx]["exp_avg_sq"].reshape(-1))
+            P.step.eg.refresh(force=True)
+            P.step.ed.refresh(force=True)
+        w = osteps.dcgan_step(P.g_o, P.d_o, P.og, P.od, real[i], rng[i])
+        s = P.step.summarize(P.step.run(real[i].cuda(), to_cuda(rng[i])))
+        got.append(s)
+        want.append(w)
+    return got, want, P
+
+
+def smoke_check():
+    """Used by __graft_entry__.smoke(): one tiny step in each arithmetic mode vs the oracle."""
+    e32 = dcgan_step_parity(torch.float32, batch=4)
+    worst32 = max(e32.items(), key=lambda kv: kv[1])
+    assert worst32[1] < 2e-3, f"fp32 path off the oracle: {worst32}"
+    e16 = dcgan_step_parity(torch.bfloat16, batch=8)
+    for k in ("scalar.loss_d", "scalar.loss_g", "g_act.conv3", "d_act.A.conv3", "fake_raw"):
+        assert e16[k] < 5e-2, f"bf16 path off the oracle: {k} {e16[k]}"
+    print("smoke ok: fp32 worst", worst32, "bf16 loss_d err", e16["scalar.loss_d"])
