@@ -91,8 +91,10 @@ def check_wgrad(shape, dtype, algo, B=8):
 def check_bn(dtype, C=128, B=8, H=16, groups=2):
     """stats -> finalize -> apply -> backward against F.batch_norm + leaky_relu autograd, per group."""
     from jck_generation_b200 import ops
-    y = _mk((B, C, H, H), dtype, 7) * 1.5 + 0.3
+    y = _mk((B, C, H, H), torch.float32, 7) * 1.5 + 0.3
     da = _mk((B, C, H, H), dtype, 8)
+    if dtype == torch.bfloat16:
+        y = y.to(dtype).float()
     gamma = 1 + 0.1 * _mk((C,), torch.float32, 9)
     beta = 0.1 * _mk((C,), torch.float32, 10)
     per = B // groups
@@ -274,7 +276,7 @@ def tolerance(op, dtype, key):
     if key.startswith("randn") or key.startswith("rand_"):
         return 5e-3
     if dtype == "f32":
-        return 2e-5 if key != "adam" else 1e-5
+        return 2e-5 if key != "adam" else 5e-5
     # bf16 storage: outputs are rounded to 8 bits of mantissa (2^-9 relative per element)
     return {"dw": 2e-5, "dw5": 2e-5, "stats": 2e-4, "loss": 1e-3, "prob": 1e-3, "dgamma": 1e-2, "dbeta": 1e-2,
             "running_mean": 1e-3, "running_var": 1e-3}.get(key, 4e-3)
