@@ -45,6 +45,14 @@ extern "C" {
 #define JCK_F32 0
 #define JCK_BF16 1
 
+/* activation-side layout of IMAGE tensors (the nc-channel 64x64 side of D.conv1 / G.conv5):
+ *   JCK_IMG_NHWC  dense [B][H][W][C]
+ *   JCK_IMG_P4    [B][H+2][W+2][4], zero border and zero pad channels (C <= 4): every 4x4 stride-2
+ *                 patch is then 4 runs of 32 contiguous bytes, which one TMA box fetches as a 128-byte
+ *                 GEMM row -- the layout of the tcgen05 image-edge kernels (jck_edge_*). */
+#define JCK_IMG_NHWC 0
+#define JCK_IMG_P4 1
+
 /* conv algorithm selector */
 #define JCK_ALGO_AUTO 0  /* tcgen05 where dtype/shape allow, else SIMT */
 #define JCK_ALGO_SIMT 1  /* CUDA-core fp32-FMA implicit GEMM (exact-fp32 parity mode; edge layers) */
@@ -63,11 +71,11 @@ unsigned long long jck_launch_count(void);
  * interpolation `alpha*real + (1-alpha)*fake` train/dcgan_trainer.py:112. */
 int jck_prep_image(const float* x1, const float* m1, float a1, float b1, const float* x2,
                    const float* alpha, void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W,
-                   int dtype, void* stream);
+                   int layout, int dtype, void* stream);
 
 /* NHWC activation-dtype tensor -> NCHW fp32 (e.g. the GP input-gradient handed back to the caller). */
-int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int dtype,
-                         void* stream);
+int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int layout,
+                         int dtype, void* stream);
 
 /* ---- weights ---------------------------------------------------------------------------------
  * w4[Ca][Cb][4][4] fp32 -> w_down[Ca][16][Cb] and w_up[4 phases][Cb][4 taps][Ca] (dtype).
@@ -87,6 +95,19 @@ int jck_conv_up(const void* in_small, const void* w_up, void* out_large, float* 
 size_t jck_conv_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo);
 int jck_conv_wgrad(const void* small, const void* large, float* dw4, void* workspace, size_t workspace_bytes,
                    int B, int Hs, int Ws, int Ca, int Cb, int accumulate, int dtype, int algo, void* stream);
+
+/* ---- image-edge layers on tensor cores (bf16, nc <= 4 image channels, JCK_IMG_P4 image layout) -----
+ * D.conv1 (model/DCGAN.py:10,30) and G.conv5 (model/DCGAN.py:58,66) have 3 channels on their large side:
+ * K = 48 or N = 3 in the GEMM view.  With the image stored as JCK_IMG_P4 the whole 4x4x4 patch is one
+ * 64-wide K step (down / wgrad), and the transposed direction is a 3x3-shift GEMM with N = 16
+ * (4 output parities x 4 channels).  w_down_e[Ca][64], w_up9[16][9*Ca] from jck_pack_weights_edge. */
+int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up9, int Ca, int nc, void* stream);
+int jck_edge_down(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
+                  int Ca, int imgs_per_group, void* stream);
+int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4, int B, int Hs, int Ws, int Ca, void* stream);
+size_t jck_edge_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca);
+int jck_edge_wgrad(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes,
+                   int B, int Hs, int Ws, int Ca, int nc, int accumulate, void* stream);
 
 /* ---- dense layers (G.conv1: a 1x1 -> 4x4 transposed conv is a matrix product) -----------------
  * out[m][n] = sum_k x[m][k] * w[n][k];  x fp32 [M][K]; w, out activation dtype; stats per channel
@@ -145,11 +166,11 @@ int jck_unpack_head_grad(const float* dw5, float* dw4, int C4, int accumulate, v
  * fake_raw = tanh(y5) (NCHW fp32); fake_mix = a*fake_raw + b*noise (NCHW fp32 and NHWC dtype).
  * Replaces nn.Tanh model/DCGAN.py:59,66 + train/dcgan_trainer.py:171.  Outputs nullable. */
 int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, float* fake_raw_nchw,
-                  float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int dtype,
+                  float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout, int dtype,
                   void* stream);
 /* dy5 = a * dmix * (1 - fake_raw^2)  (dmix NHWC dtype, fake_raw NCHW fp32, dy5 NHWC dtype) */
 int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, float a, void* dy5_nhwc, int B, int C,
-                  int H, int W, int dtype, void* stream);
+                  int H, int W, int layout, int dtype, void* stream);
 
 /* ---- gradient penalty --------------------------------------------------------------------------
  * scalars[0] += mean_n (||dx[n,:]||_2 - 1)^2.  Replaces train/dcgan_trainer.py:125-126. */

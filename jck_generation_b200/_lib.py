@@ -11,6 +11,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "jck_b200.h")
 
 JCK_F32, JCK_BF16 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+IMG_NHWC, IMG_P4 = 0, 1
 
 _lib = None
 
@@ -22,8 +23,13 @@ _SIGNATURES = {
     "jck_version": [],
     "jck_last_error_string": [],
     "jck_launch_count": [],
-    "jck_prep_image": [c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
-    "jck_nhwc_to_nchw_f32": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_prep_image": [c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_nhwc_to_nchw_f32": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_pack_weights_edge": [c_p, c_p, c_p, c_i, c_i, c_p],
+    "jck_edge_down": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_edge_up": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "jck_edge_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i],
+    "jck_edge_wgrad": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_weights": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_conv_down": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_conv_up": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -42,8 +48,8 @@ _SIGNATURES = {
     "jck_head_bwd": [c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_head": [c_p, c_p, c_i, c_i, c_p],
     "jck_unpack_head_grad": [c_p, c_p, c_i, c_i, c_p],
-    "jck_g_out_fwd": [c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
-    "jck_g_out_bwd": [c_p, c_p, c_f, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_g_out_fwd": [c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_g_out_bwd": [c_p, c_p, c_f, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_gp_penalty": [c_p, c_p, c_i, c_ll, c_i, c_p],
     "jck_adam": [c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_p, c_p],
     "jck_adam_advance": [c_p, c_p],
@@ -52,7 +58,7 @@ _SIGNATURES = {
     "jck_rng_advance": [c_p, c_ull, c_p],
 }
 _RESTYPES = {"jck_last_error_string": ctypes.c_char_p, "jck_launch_count": c_ull,
-             "jck_conv_wgrad_workspace_bytes": c_sz}
+             "jck_conv_wgrad_workspace_bytes": c_sz, "jck_edge_wgrad_workspace_bytes": c_sz}
 
 
 class JckError(RuntimeError):

@@ -84,6 +84,19 @@ int map_matrix(CUtensorMap* m, const void* p, int rows, int cols, int box_rows) 
     return encode(m, p, 2, dims, str, box);
 }
 
+// Patch view of a JCK_IMG_P4 image [B][H+2][W+2][4] (H = 2*Hs, W = 2*Ws): the 4x4 stride-2 patch of output
+// pixel (oy, ox) is rows 2*oy .. 2*oy+3 of the padded image, each a run of 16 contiguous elements starting at
+// padded column 2*ox.  As a 5-D tensor (16 | ky:4 | ox | oy | n) with OVERLAPPING strides (ox advances 8
+// elements, oy two rows) a box (16 | 4 | bw | bh | nb) lands in shared memory as [pixel][ky][16] = one
+// 128-byte im2col row per output pixel; the zero border supplies the convolution padding.
+int map_p4_patches(CUtensorMap* m, const void* p, int Hs, int Ws, int B, int bw, int bh, int nb) {
+    const cuuint64_t row = (cuuint64_t)(2 * Ws + 2) * 4 * 2, img = (cuuint64_t)(2 * Hs + 2) * row;
+    cuuint64_t dims[5] = {16, 4, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
+    cuuint64_t str[4] = {row, 16, 2 * row, img};
+    cuuint32_t box[5] = {16, 4, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)nb};
+    return encode(m, p, 5, dims, str, box);
+}
+
 struct PatchGeom { int bw, bh, nb; };
 // rows of a tile = bw x bh x nb output pixels (x fastest), bw*bh*nb == npix
 bool patch_geom(int Hs, int Ws, int npix, PatchGeom* g) {
@@ -119,10 +132,17 @@ struct ConvSmem {
     static constexpr int kTotal = kRedOff + 4 * 2 * BN_ * 4 + 1024;  // + alignment slack
 };
 
-template <int BN_, int STAGES, bool kUp>
+// MODE: which implicit GEMM the tile loop walks
+constexpr int kDown = 0;      // 16 taps x Cb/64 chunks, A through the parity view of the large tensor
+constexpr int kUpM = 1;       // one output parity (blockIdx.z): 4 taps x Ca/64 chunks, A = shifted small tensor
+constexpr int kEdgeDown = 2;  // image edge: ONE K step, A = whole 4x4x4 patches of a JCK_IMG_P4 image
+constexpr int kEdgeUp = 3;    // image edge: 9 input shifts x Ca/64, N = 16 (4 parities x 4 channels) -> P4 image
+
+template <int BN_, int STAGES, int MODE>
 __global__ void __launch_bounds__(kConvThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p) {
+    constexpr bool kUp = (MODE == kUpM);
     using L = ConvSmem<BN_, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,10 +162,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int nt = blockIdx.y;
     const int phase = kUp ? blockIdx.z : 0;
     const int py = phase >> 1, px = phase & 1;
-    const int Cin = kUp ? p.Ca : p.Cb;    // contraction channels
-    const int Cout = kUp ? p.Cb : p.Ca;
-    const int cchunks = Cin / kBK;
-    const int ksteps = (kUp ? 4 : 16) * cchunks;
+    const int Cin = (MODE == kUpM || MODE == kEdgeUp) ? p.Ca : p.Cb;    // contraction channels
+    const int Cout = (MODE == kUpM) ? p.Cb : p.Ca;
+    const int cchunks = MODE == kEdgeDown ? 1 : Cin / kBK;
+    const int ksteps = MODE == kEdgeDown ? 1 : (MODE == kUpM ? 4 : (MODE == kEdgeUp ? 9 : 16)) * cchunks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA);
@@ -171,7 +191,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint8_t* sb = sa + L::kABytes;
                 mbar_arrive_expect_tx(&full[s], L::kStage);
                 const int tap = ks / cchunks, cc = ks - tap * cchunks;
-                if (!kUp) {
+                if (MODE == kEdgeDown) {
+                    // (16 elems = 4 kx x 4 c | ky | ox | oy | n): every row of the tile is one whole patch
+                    tma_load_5d(sa, &mapA, &full[s], 0, 0, x0, y0, n0);
+                    tma_load_2d(sb, &mapB, &full[s], 0, nt * BN_);
+                } else if (MODE == kEdgeUp) {
+                    const int di = tap / 3 - 1, dj = tap % 3 - 1;
+                    tma_load_4d(sa, &mapA, &full[s], cc * kBK, x0 + dj, y0 + di, n0);
+                    tma_load_2d(sb, &mapB, &full[s], tap * p.Ca + cc * kBK, 0);
+                } else if (!kUp) {
                     const int ky = tap >> 2, kx = tap & 3;
                     const int dy = (ky - 1) >> 1, qy = (ky - 1) & 1;   // input row 2*oy + ky - 1 = 2*(oy+dy) + qy
                     const int dx = (kx - 1) >> 1, qx = (kx - 1) & 1;
@@ -220,6 +248,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
         mbar_wait(tmem_full, 0);
         fence_after_sync();
+        if constexpr (MODE == kEdgeUp) {
+            // 16 accumulator columns = (py, px, c4): two 16-byte stores into the padded 4-channel image
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16), v);
+            tmem_ld_wait();
+            if (valid) {
+                const int Wp = 2 * p.Ws + 2, Hp = 2 * p.Hs + 2;
+#pragma unroll
+                for (int qy = 0; qy < 2; ++qy) {
+                    // pixel (2i+qy, 2j) sits at padded column 2j+1: 8-byte aligned, so one 8-byte store per pixel
+                    const size_t o = (((size_t)n * Hp + 2 * (y0 + yl) + qy + 1) * Wp + 2 * (x0 + xl) + 1) * 4;
+                    uint2 u0, u1;
+                    u0.x = pack_bf16x2(v[qy * 8 + 0], v[qy * 8 + 1]);
+                    u0.y = pack_bf16x2(v[qy * 8 + 2], v[qy * 8 + 3]);
+                    u1.x = pack_bf16x2(v[qy * 8 + 4], v[qy * 8 + 5]);
+                    u1.y = pack_bf16x2(v[qy * 8 + 6], v[qy * 8 + 7]);
+                    *reinterpret_cast<uint2*>(out + o) = u0;
+                    *reinterpret_cast<uint2*>(out + o + 4) = u1;
+                }
+            }
+        } else {
 #pragma unroll 1
         for (int c = 0; c < BN_ / 32; ++c) {
             float v[32];
@@ -259,6 +308,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 atomicAdd(sp + which * Cout + cc, s);
             }
         }
+        }  // MODE != kEdgeUp
     }
 
     fence_before_sync();
@@ -269,21 +319,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
-template <int BN_, int STAGES, bool kUp>
-int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
-                   int m_tiles, int n_tiles, cudaStream_t st) {
+template <int BN_, int STAGES, int MODE>
+int launch_conv_tc_mode(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
+                        int m_tiles, int n_tiles, cudaStream_t st) {
     using L = ConvSmem<BN_, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, STAGES, kUp>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, STAGES, MODE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc smem attr: %s", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid(m_tiles, n_tiles, kUp ? 4 : 1);
-    conv_tc_kernel<BN_, STAGES, kUp><<<grid, kConvThreads, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats, p);
-    JCK_LAUNCH_CHECK(kUp ? "conv_up_tc" : "conv_down_tc");
+    dim3 grid(m_tiles, n_tiles, MODE == kUpM ? 4 : 1);
+    conv_tc_kernel<BN_, STAGES, MODE><<<grid, kConvThreads, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats, p);
+    JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc" : MODE == kDown ? "conv_down_tc" : MODE == kEdgeDown ? "edge_down_tc" : "edge_up_tc");
     return JCK_OK;
+}
+template <int BN_, int STAGES, bool kUp>
+int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
+                   int m_tiles, int n_tiles, cudaStream_t st) {
+    return launch_conv_tc_mode<BN_, STAGES, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, n_tiles, st);
 }
 
 bool tc_conv_supported(int B, int Hs, int Ws, int Ca, int Cb, int ipg, bool up, PatchGeom* g) {
@@ -509,6 +564,131 @@ int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan&
     return JCK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// image-edge wgrad: D[a][(ky,kx,c4)] = sum over pixels small[pix][a] * patch[pix][(ky,kx,c4)]
+// Ca = 64 -> M = 64: issued as an M = 128 MMA whose second 64-row atom aliases the first (LBO = 0);
+// TMEM lanes 64..127 then hold a copy that the epilogue ignores.  N = 64 = the whole patch, K = 64 pixels
+// per step, split over the grid; partials [split][64][64] are reduced by edge_wgrad_unpack.
+// ------------------------------------------------------------------------------------------------
+struct EdgeWgradParams { int B, Hs, Ws, rows_per_step, steps_per_img, total_steps, steps_per_split; };
+constexpr int kEdgeWStages = 4;
+constexpr int kEdgeWStage = 2 * kWgradKPix * 128;          // 8 KB small + 8 KB patches
+constexpr int kEdgeWSmem = kEdgeWStages * kEdgeWStage + 256 + 1024;
+
+__global__ void __launch_bounds__(kConvThreads)
+wgrad_edge_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapP,
+                     float* __restrict__ part, const EdgeWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kEdgeWStages * kEdgeWStage);
+    uint64_t* empty = full + kEdgeWStages;
+    uint64_t* tmem_full = empty + kEdgeWStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int step_beg = split * p.steps_per_split;
+    const int nsteps = max(0, min(p.total_steps, step_beg + p.steps_per_split) - step_beg);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapS);
+        prefetch_tmap(&mapP);
+        for (int s = 0; s < kEdgeWStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % kEdgeWStages;
+                mbar_wait(&empty[s], ((it / kEdgeWStages) & 1) ^ 1);
+                uint8_t* sa = smem + s * kEdgeWStage;
+                mbar_arrive_expect_tx(&full[s], kEdgeWStage);
+                const int st = step_beg + it;
+                const int n = st / p.steps_per_img, y = (st % p.steps_per_img) * p.rows_per_step;
+                tma_load_4d(sa, &mapS, &full[s], 0, 0, y, n);
+                tma_load_5d(sa + kWgradKPix * 128, &mapP, &full[s], 0, 0, 0, y, n);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(64, 1, 1);
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % kEdgeWStages;
+            mbar_wait(&full[s], (it / kEdgeWStages) & 1);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + s * kEdgeWStage);
+                const uint32_t b_addr = a_addr + kWgradKPix * 128;
+#pragma unroll
+                for (int k = 0; k < kWgradKPix / 16; ++k)
+                    umma_bf16(tmem_base, make_sdesc(a_addr + k * 2048, 0, 1024), make_sdesc(b_addr + k * 2048, 0, 1024),
+                              idesc, (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty[s]);
+                if (it == nsteps - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int wq = warp & 3;
+        if (wq < 2) {                                  // lanes 0..63 carry the 64 real rows
+            const int a = wq * 32 + lane;
+            if (nsteps > 0) { mbar_wait(tmem_full, 0); fence_after_sync(); }
+            float* dst = part + ((size_t)split * 64 + a) * 64;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float v[32];
+                if (nsteps > 0) {
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+                float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
+// dw4[a][c][ky][kx] (+)= sum_split part[split][a][ky*16 + kx*4 + c], c < nc
+__global__ void edge_wgrad_unpack_kernel(const float* __restrict__ part, float* __restrict__ dw4, int nc, int splits,
+                                         int accumulate) {
+    const int total = 64 * nc * 16;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int kx = idx & 3, ky = (idx >> 2) & 3, c = (idx >> 4) % nc, a = (idx >> 4) / nc;
+        const int col = ky * 16 + kx * 4 + c;
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[((size_t)z * 64 + a) * 64 + col];
+        dw4[idx] = accumulate ? dw4[idx] + s : s;
+    }
+}
+
+struct EdgePlan { bool ok; int splits, steps_per_split, total_steps, rows_per_step; };
+EdgePlan edge_wgrad_plan(int B, int Hs, int Ws) {
+    EdgePlan pl{};
+    pl.ok = (Ws <= kWgradKPix) && (kWgradKPix % Ws == 0) && (Hs % (kWgradKPix / Ws) == 0);
+    if (!pl.ok) return pl;
+    pl.rows_per_step = kWgradKPix / Ws;
+    pl.total_steps = B * (Hs / pl.rows_per_step);
+    int splits = kNumSMs < pl.total_steps ? kNumSMs : pl.total_steps;
+    pl.steps_per_split = (pl.total_steps + splits - 1) / splits;
+    pl.splits = (pl.total_steps + pl.steps_per_split - 1) / pl.steps_per_split;
+    return pl;
+}
+
 bool want_tc(int dtype, int algo) { return dtype == JCK_BF16 && algo != JCK_ALGO_SIMT; }
 
 }  // namespace
@@ -586,4 +766,67 @@ extern "C" int jck_conv_wgrad(const void* small, const void* large, float* dw4, 
     }
     if (rc) return rc;
     return launch_wgrad_unpack((const float*)workspace, dw4, Ca, Cb, splits, accumulate, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// image-edge entry points (bf16, JCK_IMG_P4 image layout)
+// ------------------------------------------------------------------------------------------------
+extern "C" int jck_edge_down(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
+                             int Ca, int imgs_per_group, void* stream) {
+    JCK_REQUIRE(img_p4 && w_down_e && out_small && B > 0 && Hs > 0 && Ws > 0, "edge_down: bad argument");
+    if (imgs_per_group <= 0) imgs_per_group = B;
+    PatchGeom g;
+    if (Ca != 64 || !patch_geom(Hs, Ws, kTileM, &g) || (imgs_per_group < B && imgs_per_group % g.nb != 0))
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_down: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
+    ConvTcParams p{B, Hs, Ws, Ca, 4, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, imgs_per_group};
+    const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = map_p4_patches(&mA, img_p4, Hs, Ws, B, g.bw, g.bh, g.nb))) return rc;
+    if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
+    return launch_conv_tc_mode<64, 2, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
+}
+
+extern "C" int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4, int B, int Hs, int Ws, int Ca, void* stream) {
+    JCK_REQUIRE(in_small && w_up9 && img_p4 && B > 0 && Hs > 0 && Ws > 0, "edge_up: bad argument");
+    PatchGeom g;
+    if (Ca % 64 != 0 || !patch_geom(Hs, Ws, kTileM, &g))
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_up: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
+    ConvTcParams p{B, Hs, Ws, Ca, 4, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, B};
+    const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = map_small(&mA, in_small, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
+    if ((rc = map_matrix(&mB, w_up9, 16, 9 * Ca, 16))) return rc;
+    return launch_conv_tc_mode<16, 4, kEdgeUp>(mA, mB, img_p4, nullptr, p, m_tiles, 1, as_stream(stream));
+}
+
+extern "C" size_t jck_edge_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca) {
+    EdgePlan pl = edge_wgrad_plan(B, Hs, Ws);
+    return pl.ok ? (size_t)pl.splits * 64 * 64 * sizeof(float) : 0;
+}
+
+extern "C" int jck_edge_wgrad(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes,
+                              int B, int Hs, int Ws, int Ca, int nc, int accumulate, void* stream) {
+    JCK_REQUIRE(small && img_p4 && dw4 && workspace && B > 0 && nc > 0 && nc <= 4, "edge_wgrad: bad argument");
+    EdgePlan pl = edge_wgrad_plan(B, Hs, Ws);
+    if (Ca != 64 || !pl.ok) return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_wgrad: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
+    JCK_REQUIRE(workspace_bytes >= (size_t)pl.splits * 64 * 64 * sizeof(float), "edge_wgrad: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    CUtensorMap mS, mP;
+    int rc;
+    if ((rc = map_small(&mS, small, 64, Ws, Hs, B, Ws, pl.rows_per_step, 1))) return rc;
+    if ((rc = map_p4_patches(&mP, img_p4, Hs, Ws, B, Ws, pl.rows_per_step, 1))) return rc;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeWSmem);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_wgrad smem attr: %s", cudaGetErrorString(e));
+        cfg = true;
+    }
+    EdgeWgradParams p{B, Hs, Ws, pl.rows_per_step, Hs / pl.rows_per_step, pl.total_steps, pl.steps_per_split};
+    wgrad_edge_tc_kernel<<<pl.splits, kConvThreads, kEdgeWSmem, st>>>(mS, mP, (float*)workspace, p);
+    JCK_LAUNCH_CHECK("edge_wgrad_tc");
+    edge_wgrad_unpack_kernel<<<(64 * nc * 16 + 255) / 256, 256, 0, st>>>((const float*)workspace, dw4, nc, pl.splits, accumulate);
+    JCK_LAUNCH_CHECK("edge_wgrad_unpack");
+    return JCK_OK;
 }

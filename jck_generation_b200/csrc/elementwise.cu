@@ -58,33 +58,49 @@ template <> struct Vec8<__nv_bfloat16> {
 };
 
 // ---- image edge ------------------------------------------------------------------------------
+// Activation-side image layouts.  JCK_IMG_NHWC: dense [B][H][W][C].  JCK_IMG_P4: [B][H+2][W+2][4] with a
+// zero border and zero pad channels -- the layout whose 4x4 patches are TMA-addressable (conv_tc.cu).
+struct ImgLayout {
+    int H, W, cs, pad;
+    __host__ __device__ ImgLayout(int H_, int W_, int C, int layout)
+        : H(H_), W(W_), cs(layout == JCK_IMG_P4 ? 4 : C), pad(layout == JCK_IMG_P4 ? 1 : 0) {}
+    __device__ __forceinline__ size_t off(int n, int hw) const {
+        const int h = hw / W, w = hw - h * W;
+        return (((size_t)n * (H + 2 * pad) + h + pad) * (W + 2 * pad) + w + pad) * cs;
+    }
+};
+
 template <typename T>
 __global__ void prep_image_kernel(const float* __restrict__ x1, const float* __restrict__ m1, float a1, float b1,
                                   const float* __restrict__ x2, const float* __restrict__ alpha,
-                                  T* __restrict__ out_nhwc, float* __restrict__ out_nchw, int B, int C, int HW) {
+                                  T* __restrict__ out_nhwc, float* __restrict__ out_nchw, int B, int C, int HW,
+                                  const ImgLayout lay) {
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(pix / HW), hw = (int)(pix % HW);
         const float al = alpha ? alpha[n] : 1.f;
+        const size_t o = lay.off(n, hw);
         for (int c = 0; c < C; ++c) {
             const size_t src = ((size_t)n * C + c) * HW + hw;
             float v = a1 * x1[src];
             if (m1) v += b1 * m1[src];
             if (alpha) v = al * v + (1.f - al) * x2[src];
-            if (out_nhwc) st_act(out_nhwc + pix * C + c, v);
+            if (out_nhwc) st_act(out_nhwc + o + c, v);
             if (out_nchw) out_nchw[src] = v;
         }
     }
 }
 
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int C, int HW) {
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int C, int HW,
+                                    const ImgLayout lay) {
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(pix / HW), hw = (int)(pix % HW);
-        for (int c = 0; c < C; ++c) out[((size_t)n * C + c) * HW + hw] = ld_act(in + pix * C + c);
+        const size_t o = lay.off(n, hw);
+        for (int c = 0; c < C; ++c) out[((size_t)n * C + c) * HW + hw] = ld_act(in + o + c);
     }
 }
 
@@ -107,6 +123,38 @@ __global__ void pack_weights_kernel(const float* __restrict__ w4, T* __restrict_
             const int px = (kx == 1 || kx == 3) ? 0 : 1, tx = (kx == 1 || kx == 2) ? 0 : 1;
             const int phase = py * 2 + px, t = ty * 2 + tx;
             st_act(w_up + (((size_t)phase * Cb + b) * 4 + t) * Ca + a, v);
+        }
+    }
+}
+
+// Image-edge layers (Cb = nc <= 4 image channels) for the tcgen05 path:
+//   w_down_e[a][ky*16 + kx*4 + c]                 one 64-wide K step = the whole 4x4x(4) patch
+//   w_up9[(py*2+px)*4 + c][s*Ca + a], s = 3x3 input shift (di+1)*3+(dj+1); zero where output parity
+//   (py,px) does not read that shift (see up_k / up_d in common.cuh)
+__device__ __forceinline__ int edge_k_of(int parity, int d) {   // kernel index for (output parity, input shift) or -1
+    if (parity == 0) return d == 0 ? 1 : (d == -1 ? 3 : -1);
+    return d == 0 ? 2 : (d == 1 ? 0 : -1);
+}
+__global__ void pack_weights_edge_kernel(const float* __restrict__ w4, __nv_bfloat16* __restrict__ w_down_e,
+                                         __nv_bfloat16* __restrict__ w_up9, int Ca, int nc) {
+    const int n_down = Ca * 64, n_up = 16 * 9 * Ca;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_down + n_up; idx += gridDim.x * blockDim.x) {
+        if (idx < n_down) {
+            if (!w_down_e) continue;
+            const int k = idx % 64, a = idx / 64;
+            const int ky = k >> 4, kx = (k >> 2) & 3, c = k & 3;
+            const float v = c < nc ? w4[(((size_t)a * nc + c) * 4 + ky) * 4 + kx] : 0.f;
+            w_down_e[idx] = __float2bfloat16_rn(v);
+        } else {
+            if (!w_up9) continue;
+            const int j = idx - n_down;
+            const int k = j % (9 * Ca), n = j / (9 * Ca);
+            const int a = k % Ca, s = k / Ca;
+            const int di = s / 3 - 1, dj = s % 3 - 1;
+            const int c = n & 3, px = (n >> 2) & 1, py = n >> 3;
+            const int ky = edge_k_of(py, di), kx = edge_k_of(px, dj);
+            const float v = (c < nc && ky >= 0 && kx >= 0) ? w4[(((size_t)a * nc + c) * 4 + ky) * 4 + kx] : 0.f;
+            w_up9[j] = __float2bfloat16_rn(v);
         }
     }
 }
@@ -364,31 +412,33 @@ head_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob,
 template <typename T>
 __global__ void g_out_fwd_kernel(const T* __restrict__ y5, const float* __restrict__ noise, float a, float b,
                                  float* __restrict__ fake_raw, float* __restrict__ fake_mix, T* __restrict__ mix_nhwc,
-                                 int B, int C, int HW) {
+                                 int B, int C, int HW, const ImgLayout lay) {
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        const size_t o = lay.off(n, hw);
         for (int c = 0; c < C; ++c) {
             const size_t dst = ((size_t)n * C + c) * HW + hw;
-            const float t = tanhf(ld_act(y5 + pix * C + c));
+            const float t = tanhf(ld_act(y5 + o + c));
             if (fake_raw) fake_raw[dst] = t;
             const float m = noise ? a * t + b * noise[dst] : a * t;
             if (fake_mix) fake_mix[dst] = m;
-            if (mix_nhwc) st_act(mix_nhwc + pix * C + c, m);
+            if (mix_nhwc) st_act(mix_nhwc + o + c, m);
         }
     }
 }
 template <typename T>
 __global__ void g_out_bwd_kernel(const T* __restrict__ dmix, const float* __restrict__ fake_raw, float a,
-                                 T* __restrict__ dy5, int B, int C, int HW) {
+                                 T* __restrict__ dy5, int B, int C, int HW, const ImgLayout lay) {
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        const size_t o = lay.off(n, hw);
         for (int c = 0; c < C; ++c) {
             const float t = fake_raw[((size_t)n * C + c) * HW + hw];
-            st_act(dy5 + pix * C + c, a * ld_act(dmix + pix * C + c) * (1.f - t * t));
+            st_act(dy5 + o + c, a * ld_act(dmix + o + c) * (1.f - t * t));
         }
     }
 }
@@ -488,22 +538,28 @@ extern "C" const char* jck_last_error_string(void) { return g_err; }
 extern "C" unsigned long long jck_launch_count(void) { return g_launches.load(); }
 
 extern "C" int jck_prep_image(const float* x1, const float* m1, float a1, float b1, const float* x2, const float* alpha,
-                              void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W, int dtype, void* stream) {
+                              void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W, int layout, int dtype,
+                              void* stream) {
     JCK_REQUIRE(x1 && (out_nhwc || out_nchw_f32) && B > 0 && C > 0 && H > 0 && W > 0, "prep_image: bad argument");
     JCK_REQUIRE(!alpha || x2, "prep_image: alpha needs x2");
+    JCK_REQUIRE(layout == JCK_IMG_NHWC || (layout == JCK_IMG_P4 && C <= 4), "prep_image: bad layout");
     const long long total = (long long)B * H * W;
+    const ImgLayout lay(H, W, C, layout);
     DISPATCH_DTYPE(dtype, "prep_image",
         prep_image_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x1, m1, a1, b1, x2, alpha, (T*)out_nhwc,
-                                                                                  out_nchw_f32, B, C, H * W);)
+                                                                                  out_nchw_f32, B, C, H * W, lay);)
     JCK_LAUNCH_CHECK("prep_image");
     return JCK_OK;
 }
 
-extern "C" int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int dtype, void* stream) {
+extern "C" int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int layout, int dtype,
+                                    void* stream) {
     JCK_REQUIRE(in_nhwc && out_nchw && B > 0 && C > 0, "nhwc_to_nchw: bad argument");
+    JCK_REQUIRE(layout == JCK_IMG_NHWC || (layout == JCK_IMG_P4 && C <= 4), "nhwc_to_nchw: bad layout");
     const long long total = (long long)B * H * W;
+    const ImgLayout lay(H, W, C, layout);
     DISPATCH_DTYPE(dtype, "nhwc_to_nchw",
-        nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)in_nhwc, out_nchw, B, C, H * W);)
+        nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)in_nhwc, out_nchw, B, C, H * W, lay);)
     JCK_LAUNCH_CHECK("nhwc_to_nchw");
     return JCK_OK;
 }
@@ -514,6 +570,14 @@ extern "C" int jck_pack_weights(const float* w4, void* w_down, void* w_up, int C
     DISPATCH_DTYPE(dtype, "pack_weights",
         pack_weights_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w_down, (T*)w_up, Ca, Cb);)
     JCK_LAUNCH_CHECK("pack_weights");
+    return JCK_OK;
+}
+
+extern "C" int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up9, int Ca, int nc, void* stream) {
+    JCK_REQUIRE(w4 && (w_down_e || w_up9) && Ca > 0 && nc > 0 && nc <= 4, "pack_weights_edge: bad argument");
+    pack_weights_edge_kernel<<<grid_for((long long)Ca * 64 + 144LL * Ca, 256), 256, 0, as_stream(stream)>>>(
+        w4, (__nv_bfloat16*)w_down_e, (__nv_bfloat16*)w_up9, Ca, nc);
+    JCK_LAUNCH_CHECK("pack_weights_edge");
     return JCK_OK;
 }
 
@@ -639,22 +703,27 @@ extern "C" int jck_head_bwd(const float* prob, const float* dprob, float target,
 }
 
 extern "C" int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, float* fake_raw_nchw,
-                             float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int dtype, void* stream) {
+                             float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout, int dtype,
+                             void* stream) {
     JCK_REQUIRE(y5_nhwc && B > 0 && C > 0 && H > 0 && W > 0, "g_out_fwd: bad argument");
+    JCK_REQUIRE(layout == JCK_IMG_NHWC || (layout == JCK_IMG_P4 && C <= 4), "g_out_fwd: bad layout");
     const long long total = (long long)B * H * W;
+    const ImgLayout lay(H, W, C, layout);
     DISPATCH_DTYPE(dtype, "g_out_fwd",
         g_out_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)y5_nhwc, noise, a, b, fake_raw_nchw,
-                                                                               fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W);)
+                                                                               fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W, lay);)
     JCK_LAUNCH_CHECK("g_out_fwd");
     return JCK_OK;
 }
 extern "C" int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, float a, void* dy5_nhwc, int B, int C, int H,
-                             int W, int dtype, void* stream) {
+                             int W, int layout, int dtype, void* stream) {
     JCK_REQUIRE(dmix_nhwc && fake_raw_nchw && dy5_nhwc && B > 0 && C > 0, "g_out_bwd: bad argument");
+    JCK_REQUIRE(layout == JCK_IMG_NHWC || (layout == JCK_IMG_P4 && C <= 4), "g_out_bwd: bad layout");
     const long long total = (long long)B * H * W;
+    const ImgLayout lay(H, W, C, layout);
     DISPATCH_DTYPE(dtype, "g_out_bwd",
         g_out_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)dmix_nhwc, fake_raw_nchw, a,
-                                                                               (T*)dy5_nhwc, B, C, H * W);)
+                                                                               (T*)dy5_nhwc, B, C, H * W, lay);)
     JCK_LAUNCH_CHECK("g_out_bwd");
     return JCK_OK;
 }

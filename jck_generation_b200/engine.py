@@ -28,20 +28,33 @@ BN_MOM = 0.1
 class _Conv:
     """One 4x4 stride-2 layer: weight w4[Ca][Cb][4][4] + packed operand caches."""
 
-    def __init__(self, weight, Hs, dtype):
+    def __init__(self, weight, Hs, dtype, edge=False):
         self.weight = weight
         self.Ca, self.Cb = int(weight.shape[0]), int(weight.shape[1])
         self.Hs = self.Ws = Hs
+        self.edge = edge          # image-side layer on the tcgen05 edge kernels (JCK_IMG_P4 image layout)
         dev = weight.device
-        self.w_down = torch.empty(self.Ca * 16 * self.Cb, dtype=dtype, device=dev)
-        self.w_up = torch.empty(16 * self.Cb * self.Ca, dtype=dtype, device=dev)
+        if edge:
+            self.w_down_e = torch.empty(self.Ca * 64, dtype=dtype, device=dev)
+            self.w_up9 = torch.empty(16 * 9 * self.Ca, dtype=dtype, device=dev)
+        else:
+            self.w_down = torch.empty(self.Ca * 16 * self.Cb, dtype=dtype, device=dev)
+            self.w_up = torch.empty(16 * self.Cb * self.Ca, dtype=dtype, device=dev)
         self._seen = None
 
     def refresh(self, force=False):
         key = (self.weight._version, self.weight.data_ptr())
         if force or key != self._seen:
-            ops.pack_weights(self.weight.detach(), self.w_down, self.w_up)
+            if self.edge:
+                ops.pack_weights_edge(self.weight.detach(), self.w_down_e, self.w_up9)
+            else:
+                ops.pack_weights(self.weight.detach(), self.w_down, self.w_up)
             self._seen = key
+
+
+def use_edge_kernels(dtype, algo, Ca, nc):
+    """The image-side layers (nc <= 4 channels) run on tcgen05 when the arithmetic is bf16."""
+    return dtype == torch.bfloat16 and algo != ops.ALGO_SIMT and Ca == 64 and nc <= 4
 
 
 class _Norm:
@@ -123,8 +136,11 @@ class DiscriminatorEngine(_GradTarget):
         self.comm = comm or LocalComm()
         dev = module.conv1.weight.device
         self.dev = dev
-        self.nc = module.conv1.weight.shape[1]
-        self.convs = {k: _Conv(getattr(module, f"conv{k}").weight, 64 >> k, dtype) for k in range(1, 5)}
+        self.nc = int(module.conv1.weight.shape[1])
+        edge = use_edge_kernels(dtype, algo, int(module.conv1.weight.shape[0]), self.nc)
+        self.img_layout = ops.IMG_P4 if edge else ops.IMG_NHWC
+        self.convs = {k: _Conv(getattr(module, f"conv{k}").weight, 64 >> k, dtype, edge=(edge and k == 1))
+                      for k in range(1, 5)}
         self.norms = {k: _Norm(getattr(module, f"norm{k}")) for k in range(1, 5)}
         self.has_head = hasattr(module, "conv5")
         if self.has_head:
@@ -157,7 +173,10 @@ class DiscriminatorEngine(_GradTarget):
             cv, nm = self.convs[k], self.norms[k]
             y = torch.empty(B, cv.Hs, cv.Ws, cv.Ca, dtype=self.dtype, device=self.dev)
             stats = torch.zeros(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
-            ops.conv_down(cur, cv.w_down, y, stats, cv.Ca, cv.Cb, ipg=B // groups, algo=self.algo)
+            if cv.edge:
+                ops.edge_down(cur, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)
+            else:
+                ops.conv_down(cur, cv.w_down, y, stats, cv.Ca, cv.Cb, ipg=B // groups, algo=self.algo)
             self.comm.allreduce_sum_(stats)                                  # SyncBN: global batch statistics
             ss = torch.empty(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
             mr = torch.empty(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
@@ -222,12 +241,20 @@ class DiscriminatorEngine(_GradTarget):
             ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count, LRELU)
             inp = ctx.a[k - 1] if k > 1 else ctx.x
             if wgrad:
-                nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
-                ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
-                               algo=self.algo)
+                if cv.edge:
+                    nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
+                    ops.edge_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                else:
+                    nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
+                    ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
+                                   algo=self.algo)
             if k > 1 or input_grad:
-                da = torch.empty_like(inp)
-                ops.conv_up(dy, cv.w_up, da, None, cv.Ca, cv.Cb, algo=self.algo)
+                if cv.edge:
+                    da = torch.zeros_like(inp)          # border / pad channel of the P4 image stay zero
+                    ops.edge_up(dy, cv.w_up9, da, cv.Ca)
+                else:
+                    da = torch.empty_like(inp)
+                    ops.conv_up(dy, cv.w_up, da, None, cv.Ca, cv.Cb, algo=self.algo)
             else:
                 da = None
         return da
@@ -248,9 +275,13 @@ class GeneratorEngine(_GradTarget):
         self.w_fc = torch.empty(16 * self.C1, self.K1, dtype=dtype, device=dev)
         self.dw_fc = torch.empty(16 * self.C1, self.K1, dtype=torch.float32, device=dev)
         self._w1_seen = None
-        self.convs = {k: _Conv(getattr(module, f"conv{k}").weight, 2 << (k - 1), dtype) for k in range(2, 6)}
+        w5 = module.conv5.weight
+        self.nc = int(w5.shape[1])
+        edge = use_edge_kernels(dtype, algo, int(w5.shape[0]), self.nc)
+        self.img_layout = ops.IMG_P4 if edge else ops.IMG_NHWC
+        self.convs = {k: _Conv(getattr(module, f"conv{k}").weight, 2 << (k - 1), dtype, edge=(edge and k == 5))
+                      for k in range(2, 6)}
         self.norms = {k: _Norm(getattr(module, f"norm{k}")) for k in range(1, 5)}
-        self.nc = self.convs[5].Cb
         self.ws = _Workspace(dev)
 
     def refresh(self, force=False):
@@ -293,6 +324,11 @@ class GeneratorEngine(_GradTarget):
         cur = self._bn_relu(ctx, 1, y1, stats, 1, update_running)
         for k in range(2, 6):
             cv = self.convs[k]
+            if cv.edge:
+                y = ops.img_alloc(B, self.nc, 2 * cv.Hs, 2 * cv.Ws, self.dtype, self.dev, ops.IMG_P4)
+                ops.edge_up(cur, cv.w_up9, y, cv.Ca)
+                ctx.y[5] = y
+                continue
             y = torch.empty(B, 2 * cv.Hs, 2 * cv.Ws, cv.Cb, dtype=self.dtype, device=self.dev)
             if k < 5:
                 stats = torch.zeros(1, 2 * cv.Cb, dtype=torch.float32, device=self.dev)
@@ -310,11 +346,16 @@ class GeneratorEngine(_GradTarget):
         d_large = dy5
         for k in range(5, 1, -1):
             cv = self.convs[k]
-            nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
-            ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,
-                           accumulate, algo=self.algo)
             da = torch.empty_like(ctx.a[k - 1])
-            ops.conv_down(d_large, cv.w_down, da, None, cv.Ca, cv.Cb, algo=self.algo)
+            if cv.edge:
+                nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
+                ops.edge_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                ops.edge_down(d_large, cv.w_down_e, da, None, cv.Ca)
+            else:
+                nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
+                ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,
+                               accumulate, algo=self.algo)
+                ops.conv_down(d_large, cv.w_down, da, None, cv.Ca, cv.Cb, algo=self.algo)
             nm = self.norms[k - 1]
             C = nm.C
             sums = torch.zeros(1, 2 * C, dtype=torch.float32, device=self.dev)

@@ -29,8 +29,8 @@ class _DForward(torch.autograd.Function):
     def forward(ctx, x, module, *params):
         eng = module.engine()
         B = x.shape[0]
-        x_nhwc = torch.empty(B, x.shape[2], x.shape[3], x.shape[1], dtype=eng.dtype, device=x.device)
-        ops.prep_image(x.detach().contiguous().float(), out_nhwc=x_nhwc)
+        x_nhwc = ops.img_alloc(B, x.shape[1], x.shape[2], x.shape[3], eng.dtype, x.device, eng.img_layout)
+        ops.prep_image(x.detach().contiguous().float(), out_nhwc=x_nhwc, layout=eng.img_layout)
         c = eng.trunk_forward(x_nhwc, groups=1, update_running=module.training)
         prob = eng.head_forward(c)
         ctx.c, ctx.module = c, module
@@ -56,7 +56,7 @@ class _DForward(torch.autograd.Function):
         dx = None
         if need_x:
             dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dprob.device)
-            ops.nhwc_to_nchw(dx_nhwc, dx)
+            ops.nhwc_to_nchw(dx_nhwc, dx, layout=eng.img_layout)
         grads = [sink.get(id(p)) if need_w else None for p in params]
         return (dx, None, *grads)
 
@@ -105,7 +105,7 @@ class _GForward(torch.autograd.Function):
         z2d = z.detach().reshape(B, -1).contiguous().float()
         c = eng.forward(z2d, update_running=module.training)
         out = torch.empty(B, eng.nc, 64, 64, dtype=torch.float32, device=z.device)
-        ops.g_out_fwd(c.y[5], None, 1.0, 0.0, out, None, None)
+        ops.g_out_fwd(c.y[5], None, 1.0, 0.0, out, None, None, (B, eng.nc, 64, 64), layout=eng.img_layout)
         ctx.c, ctx.module, ctx.out = c, module, out
         return out
 
@@ -116,10 +116,11 @@ class _GForward(torch.autograd.Function):
         eng = module.engine()
         params = list(module.parameters())
         B = dout.shape[0]
-        d_nhwc = torch.empty(B, 64, 64, eng.nc, dtype=eng.dtype, device=dout.device)
-        ops.prep_image(dout.detach().contiguous().float(), out_nhwc=d_nhwc)
-        dy5 = torch.empty_like(d_nhwc)
-        ops.g_out_bwd(d_nhwc, ctx.out, 1.0, dy5)
+        lay = eng.img_layout
+        d_nhwc = ops.img_alloc(B, eng.nc, 64, 64, eng.dtype, dout.device, lay)
+        ops.prep_image(dout.detach().contiguous().float(), out_nhwc=d_nhwc, layout=lay)
+        dy5 = torch.zeros_like(d_nhwc) if lay == ops.IMG_P4 else torch.empty_like(d_nhwc)
+        ops.g_out_bwd(d_nhwc, ctx.out, 1.0, dy5, layout=lay)
         eng.sink = {}
         try:
             eng.backward(c, dy5, accumulate=False)

@@ -4,7 +4,7 @@ the CPU or through torch operators."""
 import torch
 
 from . import _lib
-from ._lib import JCK_BF16, JCK_F32, ALGO_AUTO, ALGO_SIMT, ALGO_TC, check  # noqa: F401
+from ._lib import JCK_BF16, JCK_F32, ALGO_AUTO, ALGO_SIMT, ALGO_TC, IMG_NHWC, IMG_P4, check  # noqa: F401
 
 _DT = {torch.float32: JCK_F32, torch.bfloat16: JCK_BF16}
 
@@ -30,16 +30,23 @@ def L():
 
 
 # ---- image edge ----------------------------------------------------------------------------------
-def prep_image(x1, out_nhwc=None, m1=None, a1=1.0, b1=0.0, x2=None, alpha=None, out_nchw=None):
+def img_alloc(B, C, H, W, dtype, device, layout):
+    """Activation-side image tensor: dense NHWC, or the zero-bordered 4-channel JCK_IMG_P4 layout."""
+    if layout == IMG_P4:
+        return torch.zeros(B, H + 2, W + 2, 4, dtype=dtype, device=device)
+    return torch.empty(B, H, W, C, dtype=dtype, device=device)
+
+
+def prep_image(x1, out_nhwc=None, m1=None, a1=1.0, b1=0.0, x2=None, alpha=None, out_nchw=None, layout=IMG_NHWC):
     B, C, H, W = x1.shape
     d = dt(out_nhwc) if out_nhwc is not None else JCK_F32
     check(L().jck_prep_image(_p(x1), _p(m1), a1, b1, _p(x2), _p(alpha), _p(out_nhwc), _p(out_nchw),
-                             B, C, H, W, d, _s()), "prep_image")
+                             B, C, H, W, layout, d, _s()), "prep_image")
 
 
-def nhwc_to_nchw(x_nhwc, out_nchw):
+def nhwc_to_nchw(x_nhwc, out_nchw, layout=IMG_NHWC):
     B, C, H, W = out_nchw.shape
-    check(L().jck_nhwc_to_nchw_f32(_p(x_nhwc), _p(out_nchw), B, C, H, W, dt(x_nhwc), _s()), "nhwc_to_nchw")
+    check(L().jck_nhwc_to_nchw_f32(_p(x_nhwc), _p(out_nchw), B, C, H, W, layout, dt(x_nhwc), _s()), "nhwc_to_nchw")
 
 
 # ---- weights ---------------------------------------------------------------------------------------
@@ -47,6 +54,30 @@ def pack_weights(w4, w_down, w_up):
     Ca, Cb = w4.shape[0], w4.shape[1]
     d = dt(w_down if w_down is not None else w_up)
     check(L().jck_pack_weights(_p(w4), _p(w_down), _p(w_up), Ca, Cb, d, _s()), "pack_weights")
+
+
+def pack_weights_edge(w4, w_down_e, w_up9):
+    check(L().jck_pack_weights_edge(_p(w4), _p(w_down_e), _p(w_up9), w4.shape[0], w4.shape[1], _s()), "pack_weights_edge")
+
+
+def edge_down(img_p4, w_down_e, out_small, stats, Ca, ipg=0):
+    B, Hs, Ws = out_small.shape[0], out_small.shape[1], out_small.shape[2]
+    check(L().jck_edge_down(_p(img_p4), _p(w_down_e), _p(out_small), _p(stats), B, Hs, Ws, Ca, ipg, _s()), "edge_down")
+
+
+def edge_up(x_small, w_up9, img_p4, Ca):
+    B, Hs, Ws = x_small.shape[0], x_small.shape[1], x_small.shape[2]
+    check(L().jck_edge_up(_p(x_small), _p(w_up9), _p(img_p4), B, Hs, Ws, Ca, _s()), "edge_up")
+
+
+def edge_wgrad_workspace_bytes(B, Hs, Ws, Ca):
+    return int(L().jck_edge_wgrad_workspace_bytes(B, Hs, Ws, Ca))
+
+
+def edge_wgrad(small, img_p4, dw4, workspace, Ca, nc, accumulate):
+    B, Hs, Ws = small.shape[0], small.shape[1], small.shape[2]
+    check(L().jck_edge_wgrad(_p(small), _p(img_p4), _p(dw4), _p(workspace), workspace.numel() * workspace.element_size(),
+                             B, Hs, Ws, Ca, nc, int(accumulate), _s()), "edge_wgrad")
 
 
 def pack_fc(w4, w_fc):
@@ -146,15 +177,16 @@ def head_bwd(prob, target, w5, a4, da4, dw5, mode, accumulate, dprob=None):
 
 
 # ---- generator output, GP, Adam, RNG ---------------------------------------------------------------------------
-def g_out_fwd(y5, noise, a, b, fake_raw, fake_mix, mix_nhwc):
-    B, H, W, C = y5.shape
-    check(L().jck_g_out_fwd(_p(y5), _p(noise), a, b, _p(fake_raw), _p(fake_mix), _p(mix_nhwc), B, C, H, W, dt(y5),
-                            _s()), "g_out_fwd")
+def g_out_fwd(y5, noise, a, b, fake_raw, fake_mix, mix_nhwc, shape, layout=IMG_NHWC):
+    """shape = (B, C, H, W) of the image (y5 may be in the padded JCK_IMG_P4 layout)."""
+    B, C, H, W = shape
+    check(L().jck_g_out_fwd(_p(y5), _p(noise), a, b, _p(fake_raw), _p(fake_mix), _p(mix_nhwc), B, C, H, W, layout,
+                            dt(y5), _s()), "g_out_fwd")
 
 
-def g_out_bwd(dmix, fake_raw, a, dy5):
-    B, H, W, C = dmix.shape
-    check(L().jck_g_out_bwd(_p(dmix), _p(fake_raw), a, _p(dy5), B, C, H, W, dt(dmix), _s()), "g_out_bwd")
+def g_out_bwd(dmix, fake_raw, a, dy5, layout=IMG_NHWC):
+    B, C, H, W = fake_raw.shape
+    check(L().jck_g_out_bwd(_p(dmix), _p(fake_raw), a, _p(dy5), B, C, H, W, layout, dt(dmix), _s()), "g_out_bwd")
 
 
 def gp_penalty(dx, scalars):

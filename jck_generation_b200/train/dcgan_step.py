@@ -68,15 +68,18 @@ class DCGANStep:
         self.flat_d.rebind()
         self.flat_g.rebind()
 
-        X = torch.empty(3 * B, 64, 64, self.nc, dtype=dt, device=dev)         # [real_n | fake_n | x_hat]
+        lay = ed.img_layout
+        X = ops.img_alloc(3 * B, self.nc, 64, 64, dt, dev, lay)                 # [real_n | fake_n | x_hat]
         real_n = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
-        ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n)       # :160
+        ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n, layout=lay)  # :160
 
         gctx = eg.forward(r["z"].reshape(B, self.nz))                                                      # :169
         fake_raw = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
         fake_n = torch.empty_like(fake_raw)
-        ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B])                  # :171
-        ops.prep_image(real_n, out_nhwc=X[2 * B:3 * B], a1=1.0, x2=fake_n, alpha=r["alpha"].reshape(B))    # :112
+        ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B],
+                      (B, self.nc, 64, 64), layout=lay)                                                    # :171
+        ops.prep_image(real_n, out_nhwc=X[2 * B:3 * B], a1=1.0, x2=fake_n, alpha=r["alpha"].reshape(B),
+                       layout=lay)                                                                         # :112
 
         scal = torch.zeros(4, 2, dtype=torch.float32, device=dev)
         ctx = ed.trunk_forward(X, groups=3)                                                                # :162,173,114
@@ -99,8 +102,8 @@ class DCGANStep:
         ed.head_forward(ctx2, targets=[LABEL_REAL], scalars=scal[S_G:S_G + 1])
         da4 = ed.head_backward(ctx2, mode=0, targets=[LABEL_REAL], wgrad=False)                            # :187
         dmix = ed.trunk_backward(ctx2, da4, wgrad=False, input_grad=True)
-        dy5 = torch.empty_like(dmix)
-        ops.g_out_bwd(dmix, fake_raw, 0.9, dy5)
+        dy5 = torch.zeros_like(dmix) if lay == ops.IMG_P4 else torch.empty_like(dmix)
+        ops.g_out_bwd(dmix, fake_raw, 0.9, dy5, layout=lay)
         eg.backward(gctx, dy5, accumulate=False)
         self.comm.allreduce_mean_(self.flat_g.grad)
         self.opt_g.step()                                                                                  # :189

@@ -119,9 +119,10 @@ class DCGANTrainer(Trainer):
         if alpha is None:
             alpha = torch.empty(B, 1, 1, 1, device=self.device)
             ops.rand(alpha, self.step.seed, 99, self.step.rng_counter)
-        x_hat = torch.empty(B, 64, 64, ed.nc, dtype=ed.dtype, device=self.device)
+        x_hat = ops.img_alloc(B, ed.nc, 64, 64, ed.dtype, self.device, ed.img_layout)
         ops.prep_image(real_data.detach().contiguous().float(), out_nhwc=x_hat, a1=1.0,
-                       x2=fake_data.detach().contiguous().float(), alpha=alpha.reshape(B).contiguous())
+                       x2=fake_data.detach().contiguous().float(), alpha=alpha.reshape(B).contiguous(),
+                       layout=ed.img_layout)
         ctx = ed.trunk_forward(x_hat, groups=1)
         ed.head_forward(ctx)
         da4 = ed.head_backward(ctx, mode=1, wgrad=False)

@@ -88,6 +88,52 @@ def check_wgrad(shape, dtype, algo, B=8):
     return {"dw": _rel(dw, 2 * want)}
 
 
+def _to_p4(x_nchw):
+    """NCHW fp32 -> zero-bordered 4-channel bf16 image layout [B][H+2][W+2][4] on the GPU."""
+    B, C, H, W = x_nchw.shape
+    out = torch.zeros(B, H + 2, W + 2, 4, dtype=torch.bfloat16, device="cuda")
+    out[:, 1:-1, 1:-1, :C] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    return out
+
+
+def check_edge(which, B=8, nc=3):
+    """tcgen05 image-edge kernels (Ca = 64, nc image channels, Hs = 32) against torch CPU convolutions."""
+    from jck_generation_b200 import ops
+    Ca, Hs = 64, 32
+    dt = torch.bfloat16
+    w4 = _mk((Ca, nc, 4, 4), dt, 31, 0.05)
+    wde = torch.empty(Ca * 64, dtype=dt, device="cuda"); wu9 = torch.empty(16 * 9 * Ca, dtype=dt, device="cuda")
+    ops.pack_weights_edge(w4.cuda().contiguous(), wde, wu9)
+    if which == "down":
+        x = _mk((B, nc, 64, 64), dt, 32)
+        want = F.conv2d(x, w4, stride=2, padding=1)
+        out = torch.full((B, Hs, Hs, Ca), float("nan"), dtype=dt, device="cuda")
+        stats = torch.zeros(1, 2 * Ca, device="cuda")
+        ops.edge_down(_to_p4(x), wde, out, stats, Ca)
+        torch.cuda.synchronize()
+        ws = torch.cat([want.sum((0, 2, 3)), (want ** 2).sum((0, 2, 3))])
+        return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats.view(-1), ws)}
+    if which == "up":
+        x = _mk((B, Ca, Hs, Hs), dt, 33)
+        want = F.conv_transpose2d(x, w4, stride=2, padding=1)
+        img = torch.zeros(B, 66, 66, 4, dtype=dt, device="cuda")
+        ops.edge_up(x.permute(0, 2, 3, 1).contiguous().to(dt).cuda(), wu9, img, Ca)
+        torch.cuda.synchronize()
+        border = float(img[:, 0].abs().sum() + img[:, -1].abs().sum() + img[:, :, 0].abs().sum() + img[:, :, -1].abs().sum()
+                       + img[..., nc:].abs().sum())
+        return {"out": _rel(img[:, 1:-1, 1:-1, :nc].float().permute(0, 3, 1, 2), want), "border": border}
+    small = _mk((B, Ca, Hs, Hs), dt, 34)
+    large = _mk((B, nc, 64, 64), dt, 35)
+    want = torch.nn.grad.conv2d_weight(large, (Ca, nc, 4, 4), small, stride=2, padding=1)
+    ws = torch.empty(ops.edge_wgrad_workspace_bytes(B, Hs, Hs, Ca) // 4, device="cuda")
+    dw = torch.full((Ca, nc, 4, 4), float("nan"), device="cuda")
+    s = small.permute(0, 2, 3, 1).contiguous().to(dt).cuda()
+    ops.edge_wgrad(s, _to_p4(large), dw, ws, Ca, nc, False)
+    ops.edge_wgrad(s, _to_p4(large), dw, ws, Ca, nc, True)
+    torch.cuda.synchronize()
+    return {"dw": _rel(dw, 2 * want)}
+
+
 def check_bn(dtype, C=128, B=8, H=16, groups=2):
     """stats -> finalize -> apply -> backward against F.batch_norm + leaky_relu autograd, per group."""
     from jck_generation_b200 import ops
@@ -242,6 +288,9 @@ def all_cases():
                 cases.append((op, shape, "bf16", "tc", 3))      # ragged: batch not a multiple of the tile
     cases += [("down_groups", "c3", "bf16", "tc", 8), ("up_groups", "c4", "bf16", "tc", 16),
               ("down_groups", "c4", "f32", "simt", 6)]
+    cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_up", "-", "bf16", "tc", 8),
+              ("edge_up", "-", "bf16", "tc", 5), ("edge_wgrad", "-", "bf16", "tc", 8), ("edge_wgrad", "-", "bf16", "tc", 3),
+              ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
     cases += [("bn", "-", "f32", "-", 8), ("bn", "-", "bf16", "-", 8), ("head", "-", "f32", "-", 8),
               ("head", "-", "bf16", "-", 8), ("fc", "-", "f32", "-", 8), ("fc", "-", "bf16", "-", 8),
               ("misc", "-", "f32", "-", 4)]
@@ -259,6 +308,8 @@ def run_case(op, shape, dtype, algo, B):
         return check_down(shape, _dt(dtype), _alg(algo), B, groups=2)
     if op == "up_groups":
         return check_up(shape, _dt(dtype), _alg(algo), B, groups=2)
+    if op.startswith("edge_"):
+        return check_edge(op[5:].rstrip("1"), B, nc=1 if op.endswith("1") else 3)
     if op == "bn":
         return check_bn(_dt(dtype))
     if op == "head":
@@ -271,7 +322,7 @@ def run_case(op, shape, dtype, algo, B):
 
 
 def tolerance(op, dtype, key):
-    if key in ("nbt", "rand_range"):
+    if key in ("nbt", "rand_range", "border"):
         return 0.5
     if key.startswith("randn") or key.startswith("rand_"):
         return 5e-3

@@ -15,8 +15,12 @@ def rel_err(got, want):
     return (got - want).norm().item() / (denom if denom > 0 else 1.0)
 
 
-def nhwc_to_nchw(t):
-    return t.detach().float().permute(0, 3, 1, 2).contiguous()
+def nhwc_to_nchw(t, nc=None):
+    """NHWC (or, when it carries the 1-pixel border of the padded 4-channel image layout, P4) -> NCHW."""
+    t = t.detach().float()
+    if nc is not None and t.shape[1] == 66 and t.shape[-1] == 4:
+        t = t[:, 1:-1, 1:-1, :nc]
+    return t.permute(0, 3, 1, 2).contiguous()
 
 
 def make_pair(dtype, lr, seed=12345, nc=3):
@@ -70,9 +74,9 @@ def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11):
     for k in range(1, 5):
         errs[f"d_act.D.conv{k}"] = rel_err(nhwc_to_nchw(last["ctx_d"].y[k]), cap["d_acts"]["D"][f"conv{k}"])
     for k in range(1, 6):
-        errs[f"g_act.conv{k}"] = rel_err(nhwc_to_nchw(last["ctx_g"].y[k]), cap["g_acts"][f"conv{k}"])
+        errs[f"g_act.conv{k}"] = rel_err(nhwc_to_nchw(last["ctx_g"].y[k], nc), cap["g_acts"][f"conv{k}"])
     errs["fake_raw"] = rel_err(last["fake_raw"], cap["fake_raw"])
-    errs["gp_grads"] = rel_err(nhwc_to_nchw(last["gp_grad_nhwc"]), cap["gp_grads"])
+    errs["gp_grads"] = rel_err(nhwc_to_nchw(last["gp_grad_nhwc"], nc), cap["gp_grads"])
     for (name, p) in P.d.named_parameters():
         errs["d_grad." + name] = rel_err(p.grad, cap["d_grads"][name])
     for (name, p) in P.g.named_parameters():

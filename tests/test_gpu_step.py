@@ -34,10 +34,17 @@ def bf16_errs():
     return parity.dcgan_step_parity(torch.bfloat16, batch=8)
 
 
+# Quantities computed AFTER optimizer_d.step() inside the same step (pass D: z2_gd, loss_g and what
+# follows from them).  Adam's first update is lr*g/(|g|+eps), i.e. sign-like: the ~1e-5 of elements whose
+# gradient is below rounding noise flip by 2*lr, which moves the updated D by ~5e-5 relative and these
+# scalars by ~2e-4 -- the oracle itself shows the same spread across CPU kernels.
+POST_UPDATE = ("scalar.z2_gd", "scalar.loss_g")
+
+
 def test_fp32_activations_and_gradients(fp32_errs):
     for k, v in fp32_errs.items():
         if k.startswith(("d_act", "g_act", "d_grad", "g_grad", "gp_grads", "fake_raw", "scalar")):
-            assert v <= 1e-4, f"{k}: {v}"
+            assert v <= (1e-3 if k in POST_UPDATE else 1e-4), f"{k}: {v}"
 
 
 def test_fp32_post_step_state(fp32_errs):
@@ -69,7 +76,7 @@ def test_nc1_restatement_fp32():
     errs = parity.dcgan_step_parity(torch.float32, batch=4, nc=1)
     for k, v in errs.items():
         if k.startswith(("d_act", "g_act", "d_grad", "g_grad", "gp_grads", "scalar")):
-            assert v <= 1e-4, f"{k}: {v}"
+            assert v <= (1e-3 if k in POST_UPDATE else 1e-4), f"{k}: {v}"
 
 
 def test_fp32_trajectory_matches_golden_and_oracle(golden_dir):
