@@ -102,11 +102,13 @@ int jck_conv_wgrad(const void* small, const void* large, float* dw4, void* works
  * 64-wide K step (down / wgrad), and the transposed direction is a 3x3-shift GEMM with N = 16
  * (4 output parities x 4 channels).  w_down_e[Ca][64], w_up9[16][9*Ca] from jck_pack_weights_edge. */
 int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up9, int Ca, int nc, void* stream);
-int jck_edge_down(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
+/* patches[B*Hs*Ws][64] bf16: row = output pixel, columns (ky, kx, c4) = its 4x4 patch of the P4 image */
+int jck_p4_to_patches(const void* img_p4, void* patches, int B, int Hs, int Ws, void* stream);
+int jck_edge_down(const void* patches, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
                   int Ca, int imgs_per_group, void* stream);
 int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4, int B, int Hs, int Ws, int Ca, void* stream);
 size_t jck_edge_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca);
-int jck_edge_wgrad(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes,
+int jck_edge_wgrad(const void* small, const void* patches, float* dw4, void* workspace, size_t workspace_bytes,
                    int B, int Hs, int Ws, int Ca, int nc, int accumulate, void* stream);
 
 /* ---- dense layers (G.conv1: a 1x1 -> 4x4 transposed conv is a matrix product) -----------------

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "jck_prep_image": [c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_nhwc_to_nchw_f32": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_weights_edge": [c_p, c_p, c_p, c_i, c_i, c_p],
+    "jck_p4_to_patches": [c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_edge_down": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_up": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i],

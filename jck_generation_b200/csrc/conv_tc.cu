@@ -84,17 +84,14 @@ int map_matrix(CUtensorMap* m, const void* p, int rows, int cols, int box_rows) 
     return encode(m, p, 2, dims, str, box);
 }
 
-// Patch view of a JCK_IMG_P4 image [B][H+2][W+2][4] (H = 2*Hs, W = 2*Ws): the 4x4 stride-2 patch of output
-// pixel (oy, ox) is rows 2*oy .. 2*oy+3 of the padded image, each a run of 16 contiguous elements starting at
-// padded column 2*ox.  As a 5-D tensor (16 | ky:4 | ox | oy | n) with OVERLAPPING strides (ox advances 8
-// elements, oy two rows) a box (16 | 4 | bw | bh | nb) lands in shared memory as [pixel][ky][16] = one
-// 128-byte im2col row per output pixel; the zero border supplies the convolution padding.
-int map_p4_patches(CUtensorMap* m, const void* p, int Hs, int Ws, int B, int bw, int bh, int nb) {
-    const cuuint64_t row = (cuuint64_t)(2 * Ws + 2) * 4 * 2, img = (cuuint64_t)(2 * Hs + 2) * row;
-    cuuint64_t dims[5] = {16, 4, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
-    cuuint64_t str[4] = {row, 16, 2 * row, img};
-    cuuint32_t box[5] = {16, 4, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)nb};
-    return encode(m, p, 5, dims, str, box);
+// Patch matrix [B*Hs*Ws][64] bf16 made by jck_p4_to_patches: row = output pixel, 64 = (ky, kx, c4).
+// (A 5-D tensor map with overlapping strides over the P4 image itself would avoid materialising it, but
+// cuTensorMapEncodeTiled-built maps of that shape faulted on sm_100a / driver 580 -- see DESIGN.md.)
+int map_rows64(CUtensorMap* m, const void* p, long long rows, int box_rows) {
+    cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    cuuint64_t str[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    return encode(m, p, 2, dims, str, box);
 }
 
 struct PatchGeom { int bw, bh, nb; };
@@ -135,7 +132,7 @@ struct ConvSmem {
 // MODE: which implicit GEMM the tile loop walks
 constexpr int kDown = 0;      // 16 taps x Cb/64 chunks, A through the parity view of the large tensor
 constexpr int kUpM = 1;       // one output parity (blockIdx.z): 4 taps x Ca/64 chunks, A = shifted small tensor
-constexpr int kEdgeDown = 2;  // image edge: ONE K step, A = whole 4x4x4 patches of a JCK_IMG_P4 image
+constexpr int kEdgeDown = 2;  // image edge: ONE K step, A = 128 rows of the patch matrix (whole 4x4x4 patches)
 constexpr int kEdgeUp = 3;    // image edge: 9 input shifts x Ca/64, N = 16 (4 parities x 4 channels) -> P4 image
 
 template <int BN_, int STAGES, int MODE>
@@ -192,8 +189,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_arrive_expect_tx(&full[s], L::kStage);
                 const int tap = ks / cchunks, cc = ks - tap * cchunks;
                 if (MODE == kEdgeDown) {
-                    // (16 elems = 4 kx x 4 c | ky | ox | oy | n): every row of the tile is one whole patch
-                    tma_load_5d(sa, &mapA, &full[s], 0, 0, x0, y0, n0);
+                    // every row of the tile is one whole patch; tiles are 128 consecutive output pixels
+                    tma_load_2d(sa, &mapA, &full[s], 0, mt * kTileM);
                     tma_load_2d(sb, &mapB, &full[s], 0, nt * BN_);
                 } else if (MODE == kEdgeUp) {
                     const int di = tap / 3 - 1, dj = tap % 3 - 1;
@@ -570,17 +567,19 @@ int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan&
 // TMEM lanes 64..127 then hold a copy that the epilogue ignores.  N = 64 = the whole patch, K = 64 pixels
 // per step, split over the grid; partials [split][64][64] are reduced by edge_wgrad_unpack.
 // ------------------------------------------------------------------------------------------------
-struct EdgeWgradParams { int B, Hs, Ws, rows_per_step, steps_per_img, total_steps, steps_per_split; };
+struct EdgeWgradParams { int total_steps, steps_per_split; };
 constexpr int kEdgeWStages = 4;
 constexpr int kEdgeWStage = 2 * kWgradKPix * 128;          // 8 KB small + 8 KB patches
-constexpr int kEdgeWSmem = kEdgeWStages * kEdgeWStage + 256 + 1024;
+constexpr int kEdgeWZeroOff = kEdgeWStages * kEdgeWStage;  // 8 KB of zeros: the upper 64-row atom of the M = 128 MMA
+constexpr int kEdgeWBarOff = kEdgeWZeroOff + kWgradKPix * 128;
+constexpr int kEdgeWSmem = kEdgeWBarOff + 256 + 1024;
 
 __global__ void __launch_bounds__(kConvThreads)
 wgrad_edge_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapP,
                      float* __restrict__ part, const EdgeWgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kEdgeWStages * kEdgeWStage);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kEdgeWBarOff);
     uint64_t* empty = full + kEdgeWStages;
     uint64_t* tmem_full = empty + kEdgeWStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -588,6 +587,9 @@ wgrad_edge_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
     const int split = blockIdx.x;
     const int step_beg = split * p.steps_per_split;
     const int nsteps = max(0, min(p.total_steps, step_beg + p.steps_per_split) - step_beg);
+    for (int i = threadIdx.x; i < kWgradKPix * 128 / 16; i += kConvThreads)
+        reinterpret_cast<uint4*>(smem + kEdgeWZeroOff)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> visible to the MMA
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapS);
@@ -609,10 +611,9 @@ wgrad_edge_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
                 mbar_wait(&empty[s], ((it / kEdgeWStages) & 1) ^ 1);
                 uint8_t* sa = smem + s * kEdgeWStage;
                 mbar_arrive_expect_tx(&full[s], kEdgeWStage);
-                const int st = step_beg + it;
-                const int n = st / p.steps_per_img, y = (st % p.steps_per_img) * p.rows_per_step;
-                tma_load_4d(sa, &mapS, &full[s], 0, 0, y, n);
-                tma_load_5d(sa + kWgradKPix * 128, &mapP, &full[s], 0, 0, 0, y, n);
+                const int row0 = (step_beg + it) * kWgradKPix;
+                tma_load_2d(sa, &mapS, &full[s], 0, row0);
+                tma_load_2d(sa + kWgradKPix * 128, &mapP, &full[s], 0, row0);
             }
         }
     } else if (warp == 1) {
@@ -624,9 +625,10 @@ wgrad_edge_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
             if (lane == 0) {
                 const uint32_t a_addr = smem_u32(smem + s * kEdgeWStage);
                 const uint32_t b_addr = a_addr + kWgradKPix * 128;
+                const uint32_t lbo = smem_u32(smem + kEdgeWZeroOff) - a_addr;   // second M atom = the zero block
 #pragma unroll
                 for (int k = 0; k < kWgradKPix / 16; ++k)
-                    umma_bf16(tmem_base, make_sdesc(a_addr + k * 2048, 0, 1024), make_sdesc(b_addr + k * 2048, 0, 1024),
+                    umma_bf16(tmem_base, make_sdesc(a_addr + k * 2048, lbo, 1024), make_sdesc(b_addr + k * 2048, 0, 1024),
                               idesc, (it > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&empty[s]);
                 if (it == nsteps - 1) umma_commit(tmem_full);
@@ -676,13 +678,12 @@ __global__ void edge_wgrad_unpack_kernel(const float* __restrict__ part, float* 
     }
 }
 
-struct EdgePlan { bool ok; int splits, steps_per_split, total_steps, rows_per_step; };
+struct EdgePlan { bool ok; int splits, steps_per_split, total_steps; };
 EdgePlan edge_wgrad_plan(int B, int Hs, int Ws) {
     EdgePlan pl{};
-    pl.ok = (Ws <= kWgradKPix) && (kWgradKPix % Ws == 0) && (Hs % (kWgradKPix / Ws) == 0);
+    pl.ok = ((long long)B * Hs * Ws) % kWgradKPix == 0;
     if (!pl.ok) return pl;
-    pl.rows_per_step = kWgradKPix / Ws;
-    pl.total_steps = B * (Hs / pl.rows_per_step);
+    pl.total_steps = (int)((long long)B * Hs * Ws / kWgradKPix);
     int splits = kNumSMs < pl.total_steps ? kNumSMs : pl.total_steps;
     pl.steps_per_split = (pl.total_steps + splits - 1) / splits;
     pl.splits = (pl.total_steps + pl.steps_per_split - 1) / pl.steps_per_split;
@@ -771,9 +772,9 @@ extern "C" int jck_conv_wgrad(const void* small, const void* large, float* dw4, 
 // ------------------------------------------------------------------------------------------------
 // image-edge entry points (bf16, JCK_IMG_P4 image layout)
 // ------------------------------------------------------------------------------------------------
-extern "C" int jck_edge_down(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
+extern "C" int jck_edge_down(const void* patches, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
                              int Ca, int imgs_per_group, void* stream) {
-    JCK_REQUIRE(img_p4 && w_down_e && out_small && B > 0 && Hs > 0 && Ws > 0, "edge_down: bad argument");
+    JCK_REQUIRE(patches && w_down_e && out_small && B > 0 && Hs > 0 && Ws > 0, "edge_down: bad argument");
     if (imgs_per_group <= 0) imgs_per_group = B;
     PatchGeom g;
     if (Ca != 64 || !patch_geom(Hs, Ws, kTileM, &g) || (imgs_per_group < B && imgs_per_group % g.nb != 0))
@@ -782,7 +783,7 @@ extern "C" int jck_edge_down(const void* img_p4, const void* w_down_e, void* out
     const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
     CUtensorMap mA, mB;
     int rc;
-    if ((rc = map_p4_patches(&mA, img_p4, Hs, Ws, B, g.bw, g.bh, g.nb))) return rc;
+    if ((rc = map_rows64(&mA, patches, (long long)B * Hs * Ws, kTileM))) return rc;
     if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
     return launch_conv_tc_mode<64, 2, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
 }
@@ -806,24 +807,24 @@ extern "C" size_t jck_edge_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca) 
     return pl.ok ? (size_t)pl.splits * 64 * 64 * sizeof(float) : 0;
 }
 
-extern "C" int jck_edge_wgrad(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes,
+extern "C" int jck_edge_wgrad(const void* small, const void* patches, float* dw4, void* workspace, size_t workspace_bytes,
                               int B, int Hs, int Ws, int Ca, int nc, int accumulate, void* stream) {
-    JCK_REQUIRE(small && img_p4 && dw4 && workspace && B > 0 && nc > 0 && nc <= 4, "edge_wgrad: bad argument");
+    JCK_REQUIRE(small && patches && dw4 && workspace && B > 0 && nc > 0 && nc <= 4, "edge_wgrad: bad argument");
     EdgePlan pl = edge_wgrad_plan(B, Hs, Ws);
     if (Ca != 64 || !pl.ok) return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_wgrad: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
     JCK_REQUIRE(workspace_bytes >= (size_t)pl.splits * 64 * 64 * sizeof(float), "edge_wgrad: workspace too small");
     cudaStream_t st = as_stream(stream);
     CUtensorMap mS, mP;
     int rc;
-    if ((rc = map_small(&mS, small, 64, Ws, Hs, B, Ws, pl.rows_per_step, 1))) return rc;
-    if ((rc = map_p4_patches(&mP, img_p4, Hs, Ws, B, Ws, pl.rows_per_step, 1))) return rc;
+    if ((rc = map_rows64(&mS, small, (long long)B * Hs * Ws, kWgradKPix))) return rc;
+    if ((rc = map_rows64(&mP, patches, (long long)B * Hs * Ws, kWgradKPix))) return rc;
     static bool cfg = false;
     if (!cfg) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeWSmem);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_wgrad smem attr: %s", cudaGetErrorString(e));
         cfg = true;
     }
-    EdgeWgradParams p{B, Hs, Ws, pl.rows_per_step, Hs / pl.rows_per_step, pl.total_steps, pl.steps_per_split};
+    EdgeWgradParams p{pl.total_steps, pl.steps_per_split};
     wgrad_edge_tc_kernel<<<pl.splits, kConvThreads, kEdgeWSmem, st>>>(mS, mP, (float*)workspace, p);
     JCK_LAUNCH_CHECK("edge_wgrad_tc");
     edge_wgrad_unpack_kernel<<<(64 * nc * 16 + 255) / 256, 256, 0, st>>>((const float*)workspace, dw4, nc, pl.splits, accumulate);

@@ -159,6 +159,23 @@ __global__ void pack_weights_edge_kernel(const float* __restrict__ w4, __nv_bflo
     }
 }
 
+// patches[pix][ky*16 + kx*4 + c] = P4 image row 2*oy+ky, columns 2*ox .. 2*ox+3 (4 channels each): one thread
+// moves one 32-byte run (two 128-bit loads / stores, both sides coalesced).
+__global__ void p4_to_patches_kernel(const uint4* __restrict__ img, uint4* __restrict__ patches, int B, int Hs, int Ws) {
+    const long long total = (long long)B * Hs * Ws * 4;
+    const int Wp = 2 * Ws + 2, Hp = 2 * Hs + 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ky = (int)(i & 3);
+        const long long pix = i >> 2;
+        const int ox = (int)(pix % Ws);
+        const long long t = pix / Ws;
+        const int oy = (int)(t % Hs), n = (int)(t / Hs);
+        const size_t src = (((size_t)n * Hp + 2 * oy + ky) * Wp + 2 * ox) * 8 / 16;   // uint4 units (8 B per pixel)
+        patches[i * 2] = img[src];
+        patches[i * 2 + 1] = img[src + 1];
+    }
+}
+
 template <typename T>
 __global__ void pack_fc_kernel(const float* __restrict__ w4, T* __restrict__ w_fc, int K, int C) {
     const long long total = (long long)K * C * 16;
@@ -578,6 +595,14 @@ extern "C" int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up
     pack_weights_edge_kernel<<<grid_for((long long)Ca * 64 + 144LL * Ca, 256), 256, 0, as_stream(stream)>>>(
         w4, (__nv_bfloat16*)w_down_e, (__nv_bfloat16*)w_up9, Ca, nc);
     JCK_LAUNCH_CHECK("pack_weights_edge");
+    return JCK_OK;
+}
+
+extern "C" int jck_p4_to_patches(const void* img_p4, void* patches, int B, int Hs, int Ws, void* stream) {
+    JCK_REQUIRE(img_p4 && patches && B > 0 && Hs > 0 && Ws > 0, "p4_to_patches: bad argument");
+    p4_to_patches_kernel<<<grid_for((long long)B * Hs * Ws * 4, 256), 256, 0, as_stream(stream)>>>(
+        (const uint4*)img_p4, (uint4*)patches, B, Hs, Ws);
+    JCK_LAUNCH_CHECK("p4_to_patches");
     return JCK_OK;
 }
 

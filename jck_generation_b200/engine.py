@@ -76,6 +76,7 @@ class Ctx:
 
     def __init__(self):
         self.x = None          # network input (NHWC)
+        self.x_patches = None  # its 4x4 patch matrix (tcgen05 image-edge path only)
         self.y = {}            # raw conv outputs per layer
         self.a = {}            # activations per layer
         self.ss = {}           # BN scale/shift [groups][2C]
@@ -91,6 +92,9 @@ class Ctx:
         s.groups, s.B = g1 - g0, per * (g1 - g0)
         lo, hi = per * g0, per * g1
         s.x = self.x[lo:hi]
+        if self.x_patches is not None:
+            rows = self.x_patches.shape[0] // self.B
+            s.x_patches = self.x_patches[lo * rows:hi * rows]
         s.y = {k: v[lo:hi] for k, v in self.y.items()}
         s.a = {k: v[lo:hi] for k, v in self.a.items()}
         s.ss = {k: v[g0:g1] for k, v in self.ss.items()}
@@ -174,7 +178,8 @@ class DiscriminatorEngine(_GradTarget):
             y = torch.empty(B, cv.Hs, cv.Ws, cv.Ca, dtype=self.dtype, device=self.dev)
             stats = torch.zeros(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
             if cv.edge:
-                ops.edge_down(cur, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)
+                ctx.x_patches = ops.p4_to_patches(cur)
+                ops.edge_down(ctx.x_patches, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)
             else:
                 ops.conv_down(cur, cv.w_down, y, stats, cv.Ca, cv.Cb, ipg=B // groups, algo=self.algo)
             self.comm.allreduce_sum_(stats)                                  # SyncBN: global batch statistics
@@ -243,7 +248,7 @@ class DiscriminatorEngine(_GradTarget):
             if wgrad:
                 if cv.edge:
                     nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
-                    ops.edge_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                    ops.edge_wgrad(dy, ctx.x_patches, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
                 else:
                     nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
                     ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
@@ -349,8 +354,9 @@ class GeneratorEngine(_GradTarget):
             da = torch.empty_like(ctx.a[k - 1])
             if cv.edge:
                 nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
-                ops.edge_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
-                ops.edge_down(d_large, cv.w_down_e, da, None, cv.Ca)
+                patches = ops.p4_to_patches(d_large)
+                ops.edge_wgrad(ctx.a[k - 1], patches, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                ops.edge_down(patches, cv.w_down_e, da, None, cv.Ca)
             else:
                 nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
                 ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,

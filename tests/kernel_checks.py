@@ -109,7 +109,7 @@ def check_edge(which, B=8, nc=3):
         want = F.conv2d(x, w4, stride=2, padding=1)
         out = torch.full((B, Hs, Hs, Ca), float("nan"), dtype=dt, device="cuda")
         stats = torch.zeros(1, 2 * Ca, device="cuda")
-        ops.edge_down(_to_p4(x), wde, out, stats, Ca)
+        ops.edge_down(ops.p4_to_patches(_to_p4(x)), wde, out, stats, Ca)
         torch.cuda.synchronize()
         ws = torch.cat([want.sum((0, 2, 3)), (want ** 2).sum((0, 2, 3))])
         return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats.view(-1), ws)}
@@ -128,8 +128,9 @@ def check_edge(which, B=8, nc=3):
     ws = torch.empty(ops.edge_wgrad_workspace_bytes(B, Hs, Hs, Ca) // 4, device="cuda")
     dw = torch.full((Ca, nc, 4, 4), float("nan"), device="cuda")
     s = small.permute(0, 2, 3, 1).contiguous().to(dt).cuda()
-    ops.edge_wgrad(s, _to_p4(large), dw, ws, Ca, nc, False)
-    ops.edge_wgrad(s, _to_p4(large), dw, ws, Ca, nc, True)
+    patches = ops.p4_to_patches(_to_p4(large))
+    ops.edge_wgrad(s, patches, dw, ws, Ca, nc, False)
+    ops.edge_wgrad(s, patches, dw, ws, Ca, nc, True)
     torch.cuda.synchronize()
     return {"dw": _rel(dw, 2 * want)}
 
