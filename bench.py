@@ -142,7 +142,7 @@ class OpTimer:
 
     def __enter__(self):
         names = [n for n in dir(self.ops) if callable(getattr(self.ops, n)) and not n.startswith("_") and
-                 n not in ("dt", "L", "check", "wgrad_workspace_bytes")]
+                 n not in ("dt", "L", "check", "wgrad_workspace_bytes", "edge_wgrad_workspace_bytes", "img_alloc")]
         for n in names:
             fn = getattr(self.ops, n)
             if getattr(fn, "__module__", "") != self.ops.__name__:

@@ -162,17 +162,16 @@ __global__ void pack_weights_edge_kernel(const float* __restrict__ w4, __nv_bflo
 // patches[pix][ky*16 + kx*4 + c] = P4 image row 2*oy+ky, columns 2*ox .. 2*ox+3 (4 channels each): one thread
 // moves one 32-byte run (two 128-bit loads / stores, both sides coalesced).
 __global__ void p4_to_patches_kernel(const uint4* __restrict__ img, uint4* __restrict__ patches, int B, int Hs, int Ws) {
-    const long long total = (long long)B * Hs * Ws * 4;
-    const int Wp = 2 * Ws + 2, Hp = 2 * Hs + 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ky = (int)(i & 3);
-        const long long pix = i >> 2;
-        const int ox = (int)(pix % Ws);
-        const long long t = pix / Ws;
-        const int oy = (int)(t % Hs), n = (int)(t / Hs);
-        const size_t src = (((size_t)n * Hp + 2 * oy + ky) * Wp + 2 * ox) * 8 / 16;   // uint4 units (8 B per pixel)
-        patches[i * 2] = img[src];
-        patches[i * 2 + 1] = img[src + 1];
+    const unsigned total = (unsigned)B * Hs * Ws * 4;          // host guarantees < 2^31
+    const unsigned Wp = 2 * Ws + 2, Hp = 2 * Hs + 2;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned ky = i & 3, pix = i >> 2;
+        const unsigned ox = pix % Ws, t = pix / Ws;
+        const unsigned oy = t % Hs, n = t / Hs;
+        const size_t src = (((size_t)n * Hp + 2 * oy + ky) * Wp + 2 * ox) / 2;   // uint4 units (8 B per pixel)
+        const uint4 v0 = img[src], v1 = img[src + 1];
+        patches[(size_t)i * 2] = v0;
+        patches[(size_t)i * 2 + 1] = v1;
     }
 }
 
@@ -246,13 +245,13 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
 
 template <typename T>
 __global__ void bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift, T* __restrict__ a,
-                                  long long nvec, int C, long long vec_per_group, float slope) {
-    const int cv = C / 8;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+                                  unsigned nvec, int C, unsigned vec_per_group, float slope) {
+    const unsigned cv = C / 8;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
         const int c0 = (int)(i % cv) * 8;
         const float* ss = scale_shift + (size_t)(i / vec_per_group) * 2 * C;
         float v[8], sc[8], sh[8];
-        Vec8<T>::load(y + i * 8, v);
+        Vec8<T>::load(y + (size_t)i * 8, v);
         Vec8<float>::load(ss + c0, sc);
         Vec8<float>::load(ss + C + c0, sh);
 #pragma unroll
@@ -260,7 +259,7 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ y, const float* __restri
             const float pre = fmaf(v[j], sc[j], sh[j]);
             v[j] = pre > 0.f ? pre : pre * slope;
         }
-        Vec8<T>::store(a + i * 8, v);
+        Vec8<T>::store(a + (size_t)i * 8, v);
     }
 }
 
@@ -316,15 +315,15 @@ template <typename T>
 __global__ void bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                         const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
                                         const float* __restrict__ gamma, const float* __restrict__ sums,
-                                        T* __restrict__ dy, long long nvec, int C, long long vec_per_group,
+                                        T* __restrict__ dy, unsigned nvec, int C, unsigned vec_per_group,
                                         float inv_count, float slope) {
-    const int cv = C / 8;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned cv = C / 8;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
         const int c0 = (int)(i % cv) * 8;
         const size_t gofs = (size_t)(i / vec_per_group) * 2 * C;
         float d[8], v[8], sc[8], sh[8], mu[8], rs[8], ga[8], sg[8], sgx[8];
-        Vec8<T>::load(da + i * 8, d);
-        Vec8<T>::load(y + i * 8, v);
+        Vec8<T>::load(da + (size_t)i * 8, d);
+        Vec8<T>::load(y + (size_t)i * 8, v);
         Vec8<float>::load(scale_shift + gofs + c0, sc);
         Vec8<float>::load(scale_shift + gofs + C + c0, sh);
         Vec8<float>::load(mean_rstd + gofs + c0, mu);
@@ -339,7 +338,7 @@ __global__ void bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __res
             const float xh = (v[j] - mu[j]) * rs[j];
             d[j] = ga[j] * rs[j] * (gg - sg[j] * inv_count - xh * sgx[j] * inv_count);
         }
-        Vec8<T>::store(dy + i * 8, d);
+        Vec8<T>::store(dy + (size_t)i * 8, d);
     }
 }
 
@@ -599,7 +598,8 @@ extern "C" int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up
 }
 
 extern "C" int jck_p4_to_patches(const void* img_p4, void* patches, int B, int Hs, int Ws, void* stream) {
-    JCK_REQUIRE(img_p4 && patches && B > 0 && Hs > 0 && Ws > 0, "p4_to_patches: bad argument");
+    JCK_REQUIRE(img_p4 && patches && B > 0 && Hs > 0 && Ws > 0 && (long long)B * Hs * Ws * 4 < (1LL << 31),
+                "p4_to_patches: bad argument");
     p4_to_patches_kernel<<<grid_for((long long)B * Hs * Ws * 4, 256), 256, 0, as_stream(stream)>>>(
         (const uint4*)img_p4, (uint4*)patches, B, Hs, Ws);
     JCK_LAUNCH_CHECK("p4_to_patches");
@@ -650,9 +650,10 @@ extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, 
                               float slope, int dtype, void* stream) {
     JCK_REQUIRE(y && scale_shift && a && npix > 0 && C % 8 == 0 && pix_per_group > 0, "bn_act_fwd: bad argument");
     const long long nvec = npix * (C / 8);
+    JCK_REQUIRE(nvec < (1LL << 31), "bn_act_fwd: tensor too large for 32-bit indexing");
     DISPATCH_DTYPE(dtype, "bn_act_fwd",
-        bn_act_fwd_kernel<T><<<grid_for(nvec, 256), 256, 0, as_stream(stream)>>>((const T*)y, scale_shift, (T*)a, nvec, C,
-                                                                               pix_per_group * (C / 8), slope);)
+        bn_act_fwd_kernel<T><<<grid_for(nvec, 256, 16), 256, 0, as_stream(stream)>>>((const T*)y, scale_shift, (T*)a, (unsigned)nvec, C,
+                                                                               (unsigned)(pix_per_group * (C / 8)), slope);)
     JCK_LAUNCH_CHECK("bn_act_fwd");
     return JCK_OK;
 }
@@ -684,10 +685,11 @@ extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* 
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && gamma && sums && dy && npix > 0 && C % 8 == 0 && count > 0,
                 "bn_act_bwd_apply: bad argument");
     const long long nvec = npix * (C / 8);
+    JCK_REQUIRE(nvec < (1LL << 31), "bn_act_bwd_apply: tensor too large for 32-bit indexing");
     DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
-        bn_act_bwd_apply_kernel<T><<<grid_for(nvec, 256), 256, 0, as_stream(stream)>>>(
-            (const T*)da, (const T*)y, scale_shift, mean_rstd, gamma, sums, (T*)dy, nvec, C, pix_per_group * (C / 8),
-            1.f / count, slope);)
+        bn_act_bwd_apply_kernel<T><<<grid_for(nvec, 256, 16), 256, 0, as_stream(stream)>>>(
+            (const T*)da, (const T*)y, scale_shift, mean_rstd, gamma, sums, (T*)dy, (unsigned)nvec, C,
+            (unsigned)(pix_per_group * (C / 8)), 1.f / count, slope);)
     JCK_LAUNCH_CHECK("bn_act_bwd_apply");
     return JCK_OK;
 }
