@@ -243,23 +243,39 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
     if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += groups;
 }
 
+// The three streaming BatchNorm passes share one thread mapping: a thread owns ONE 8-channel vector
+// (cvi = tid % (C/8)) and walks pixels of one statistics group (blockIdx.y), so every per-channel
+// coefficient lives in registers for the whole kernel; four independent 128-bit loads per tensor are in
+// flight per thread (the passes are pure HBM streams, MLP is what keeps them near the copy bandwidth).
+constexpr int kBnUnroll = 4;
+
 template <typename T>
-__global__ void bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift, T* __restrict__ a,
-                                  unsigned nvec, int C, unsigned vec_per_group, float slope) {
-    const unsigned cv = C / 8;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cv) * 8;
-        const float* ss = scale_shift + (size_t)(i / vec_per_group) * 2 * C;
-        float v[8], sc[8], sh[8];
-        Vec8<T>::load(y + (size_t)i * 8, v);
-        Vec8<float>::load(ss + c0, sc);
-        Vec8<float>::load(ss + C + c0, sh);
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift, T* __restrict__ a, int C,
+                  unsigned pix_per_group, unsigned slab, float slope) {
+    const unsigned cv = C / 8, rows = 256 / cv;
+    const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
+    const unsigned g = blockIdx.y, c0 = myc * 8;
+    const unsigned p_beg = blockIdx.x * slab, p_end = min(pix_per_group, p_beg + slab);
+    float sc[8], sh[8];
+    Vec8<float>::load(scale_shift + (size_t)g * 2 * C + c0, sc);
+    Vec8<float>::load(scale_shift + (size_t)g * 2 * C + C + c0, sh);
+    const size_t base = (size_t)g * pix_per_group * C + c0;
+    for (unsigned pp = p_beg + myr; pp < p_end; pp += rows * kBnUnroll) {
+        float v[kBnUnroll][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float pre = fmaf(v[j], sc[j], sh[j]);
-            v[j] = pre > 0.f ? pre : pre * slope;
+        for (int u = 0; u < kBnUnroll; ++u)
+            if (pp + u * rows < p_end) Vec8<T>::load(y + base + (size_t)(pp + u * rows) * C, v[u]);
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            if (pp + u * rows >= p_end) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float pre = fmaf(v[u][j], sc[j], sh[j]);
+                v[u][j] = pre > 0.f ? pre : pre * slope;
+            }
+            Vec8<T>::store(a + base + (size_t)(pp + u * rows) * C, v[u]);
         }
-        Vec8<T>::store(a + (size_t)i * 8, v);
     }
 }
 
@@ -267,16 +283,13 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ y, const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
-                         const float* __restrict__ mean_rstd, float* __restrict__ sums, int C, long long pix_per_group,
-                         long long slab, float slope) {
+                         const float* __restrict__ mean_rstd, float* __restrict__ sums, int C, unsigned pix_per_group,
+                         unsigned slab, float slope) {
     __shared__ float red[256][17];
-    const int cv = C / 8;              // channel vectors per pixel; 256 % cv == 0
-    const int rows = 256 / cv;
-    const int myc = threadIdx.x % cv, myr = threadIdx.x / cv;
-    const int g = blockIdx.y;
-    const long long p_beg = (long long)blockIdx.x * slab;
-    const long long p_end = min(pix_per_group, p_beg + slab);
-    const int c0 = myc * 8;
+    const unsigned cv = C / 8, rows = 256 / cv;
+    const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
+    const unsigned g = blockIdx.y, c0 = myc * 8;
+    const unsigned p_beg = blockIdx.x * slab, p_end = min(pix_per_group, p_beg + slab);
     float sc[8], sh[8], mu[8], rs[8];
     Vec8<float>::load(scale_shift + (size_t)g * 2 * C + c0, sc);
     Vec8<float>::load(scale_shift + (size_t)g * 2 * C + C + c0, sh);
@@ -285,45 +298,54 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, cons
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-    for (long long pp = p_beg + myr; pp < p_end; pp += rows) {
-        const size_t off = ((size_t)(g * pix_per_group + pp)) * C + c0;
-        float d[8], v[8];
-        Vec8<T>::load(da + off, d);
-        Vec8<T>::load(y + off, v);
+    const size_t base = (size_t)g * pix_per_group * C + c0;
+    for (unsigned pp = p_beg + myr; pp < p_end; pp += rows * kBnUnroll) {
+        float d[kBnUnroll][8], v[kBnUnroll][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float pre = fmaf(v[j], sc[j], sh[j]);
-            const float gg = pre > 0.f ? d[j] : d[j] * slope;
-            s1[j] += gg;
-            s2[j] += gg * (v[j] - mu[j]) * rs[j];
+        for (int u = 0; u < kBnUnroll; ++u)
+            if (pp + u * rows < p_end) {
+                Vec8<T>::load(da + base + (size_t)(pp + u * rows) * C, d[u]);
+                Vec8<T>::load(y + base + (size_t)(pp + u * rows) * C, v[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            if (pp + u * rows >= p_end) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float pre = fmaf(v[u][j], sc[j], sh[j]);
+                const float gg = pre > 0.f ? d[u][j] : d[u][j] * slope;
+                s1[j] += gg;
+                s2[j] += gg * (v[u][j] - mu[j]) * rs[j];
+            }
         }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
     __syncthreads();
-    // thread t < 2*C: column (which, channel) summed over `rows` partials
     for (int col = threadIdx.x; col < 2 * C; col += 256) {
         const int which = col / C, ch = col % C;
         const int vc = ch / 8, j = ch % 8;
         float s = 0.f;
-        for (int r = 0; r < rows; ++r) s += red[r * cv + vc][which * 8 + j];
+        for (unsigned r = 0; r < rows; ++r) s += red[r * cv + vc][which * 8 + j];
         atomicAdd(sums + (size_t)g * 2 * C + which * C + ch, s);
     }
 }
 
+// dy = gamma*rstd*(g - sum_g/N - xhat*sum_gx/N) = k1*g - k2 - k3*(y - mean)
 template <typename T>
-__global__ void bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y,
-                                        const float* __restrict__ scale_shift, const float* __restrict__ mean_rstd,
-                                        const float* __restrict__ gamma, const float* __restrict__ sums,
-                                        T* __restrict__ dy, unsigned nvec, int C, unsigned vec_per_group,
-                                        float inv_count, float slope) {
-    const unsigned cv = C / 8;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cv) * 8;
-        const size_t gofs = (size_t)(i / vec_per_group) * 2 * C;
-        float d[8], v[8], sc[8], sh[8], mu[8], rs[8], ga[8], sg[8], sgx[8];
-        Vec8<T>::load(da + (size_t)i * 8, d);
-        Vec8<T>::load(y + (size_t)i * 8, v);
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
+                        const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                        const float* __restrict__ sums, T* __restrict__ dy, int C, unsigned pix_per_group,
+                        unsigned slab, float inv_count, float slope) {
+    const unsigned cv = C / 8, rows = 256 / cv;
+    const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
+    const unsigned g = blockIdx.y, c0 = myc * 8;
+    const unsigned p_beg = blockIdx.x * slab, p_end = min(pix_per_group, p_beg + slab);
+    float sc[8], sh[8], mu[8], k1[8], k2[8], k3[8];
+    {
+        float rs[8], ga[8], sg[8], sgx[8];
+        const size_t gofs = (size_t)g * 2 * C;
         Vec8<float>::load(scale_shift + gofs + c0, sc);
         Vec8<float>::load(scale_shift + gofs + C + c0, sh);
         Vec8<float>::load(mean_rstd + gofs + c0, mu);
@@ -333,12 +355,31 @@ __global__ void bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __res
         Vec8<float>::load(sums + gofs + C + c0, sgx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float pre = fmaf(v[j], sc[j], sh[j]);
-            const float gg = pre > 0.f ? d[j] : d[j] * slope;
-            const float xh = (v[j] - mu[j]) * rs[j];
-            d[j] = ga[j] * rs[j] * (gg - sg[j] * inv_count - xh * sgx[j] * inv_count);
+            k1[j] = ga[j] * rs[j];
+            k2[j] = k1[j] * sg[j] * inv_count;
+            k3[j] = k1[j] * rs[j] * sgx[j] * inv_count;
         }
-        Vec8<T>::store(dy + (size_t)i * 8, d);
+    }
+    const size_t base = (size_t)g * pix_per_group * C + c0;
+    for (unsigned pp = p_beg + myr; pp < p_end; pp += rows * kBnUnroll) {
+        float d[kBnUnroll][8], v[kBnUnroll][8];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u)
+            if (pp + u * rows < p_end) {
+                Vec8<T>::load(da + base + (size_t)(pp + u * rows) * C, d[u]);
+                Vec8<T>::load(y + base + (size_t)(pp + u * rows) * C, v[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            if (pp + u * rows >= p_end) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float pre = fmaf(v[u][j], sc[j], sh[j]);
+                const float gg = pre > 0.f ? d[u][j] : d[u][j] * slope;
+                d[u][j] = k1[j] * gg - k2[j] - k3[j] * (v[u][j] - mu[j]);
+            }
+            Vec8<T>::store(dy + base + (size_t)(pp + u * rows) * C, d[u]);
+        }
     }
 }
 
@@ -646,14 +687,30 @@ extern "C" int jck_bn_finalize(const float* stats, const float* gamma, const flo
 
 static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (256 % (C / 8)) == 0; }
 
+// grid (blocks per group, groups): ~`waves` waves of 256-thread blocks, each thread row gets >= 4 pixels
+static dim3 bn_grid(long long pix_per_group, int groups, int C, int waves, unsigned* slab) {
+    const int rows = 256 / (C / 8);
+    long long bpg = ((long long)waves * kNumSMs + groups - 1) / groups;
+    const long long max_b = (pix_per_group + rows * 4 - 1) / (rows * 4);
+    if (bpg > max_b) bpg = max_b;
+    if (bpg < 1) bpg = 1;
+    *slab = (unsigned)((pix_per_group + bpg - 1) / bpg);
+    return dim3((unsigned)bpg, (unsigned)groups);
+}
+
+#define BN_COMMON_CHECKS(name)                                                                                   \
+    JCK_REQUIRE(npix > 0 && pix_per_group > 0 && npix % pix_per_group == 0 && npix < (1LL << 31), name ": bad size"); \
+    if (!bn_c_ok(C)) return set_error(JCK_E_UNSUPPORTED_SHAPE, name ": C=%d (need C/8 dividing 256)", C);
+
 extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, long long npix, int C, long long pix_per_group,
                               float slope, int dtype, void* stream) {
-    JCK_REQUIRE(y && scale_shift && a && npix > 0 && C % 8 == 0 && pix_per_group > 0, "bn_act_fwd: bad argument");
-    const long long nvec = npix * (C / 8);
-    JCK_REQUIRE(nvec < (1LL << 31), "bn_act_fwd: tensor too large for 32-bit indexing");
+    JCK_REQUIRE(y && scale_shift && a, "bn_act_fwd: bad argument");
+    BN_COMMON_CHECKS("bn_act_fwd")
+    unsigned slab;
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 8, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_fwd",
-        bn_act_fwd_kernel<T><<<grid_for(nvec, 256, 16), 256, 0, as_stream(stream)>>>((const T*)y, scale_shift, (T*)a, (unsigned)nvec, C,
-                                                                               (unsigned)(pix_per_group * (C / 8)), slope);)
+        bn_act_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)y, scale_shift, (T*)a, C, (unsigned)pix_per_group,
+                                                                slab, slope);)
     JCK_LAUNCH_CHECK("bn_act_fwd");
     return JCK_OK;
 }
@@ -661,20 +718,13 @@ extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, 
 extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
                                      float* sums, long long npix, int C, long long pix_per_group, float slope, int dtype,
                                      void* stream) {
-    JCK_REQUIRE(da && y && scale_shift && mean_rstd && sums && npix > 0 && pix_per_group > 0 && npix % pix_per_group == 0,
-                "bn_act_bwd_reduce: bad argument");
-    if (!bn_c_ok(C)) return set_error(JCK_E_UNSUPPORTED_SHAPE, "bn_act_bwd_reduce: C=%d (need C/8 dividing 256)", C);
-    const int groups = (int)(npix / pix_per_group);
-    const int rows = 256 / (C / 8);
-    long long bpg = (2LL * kNumSMs + groups - 1) / groups;                    // blocks per group: ~2 waves total
-    const long long max_b = (pix_per_group + rows * 4 - 1) / (rows * 4);      // at least 4 pixels per thread row
-    if (bpg > max_b) bpg = max_b;
-    if (bpg < 1) bpg = 1;
-    const long long slab = (pix_per_group + bpg - 1) / bpg;
-    dim3 grid((unsigned)bpg, (unsigned)groups);
+    JCK_REQUIRE(da && y && scale_shift && mean_rstd && sums, "bn_act_bwd_reduce: bad argument");
+    BN_COMMON_CHECKS("bn_act_bwd_reduce")
+    unsigned slab;
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 4, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
         bn_act_bwd_reduce_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)da, (const T*)y, scale_shift, mean_rstd,
-                                                                       sums, C, pix_per_group, slab, slope);)
+                                                                       sums, C, (unsigned)pix_per_group, slab, slope);)
     JCK_LAUNCH_CHECK("bn_act_bwd_reduce");
     return JCK_OK;
 }
@@ -682,14 +732,14 @@ extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float*
 extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
                                     const float* gamma, const float* sums, void* dy, long long npix, int C,
                                     long long pix_per_group, float count, float slope, int dtype, void* stream) {
-    JCK_REQUIRE(da && y && scale_shift && mean_rstd && gamma && sums && dy && npix > 0 && C % 8 == 0 && count > 0,
-                "bn_act_bwd_apply: bad argument");
-    const long long nvec = npix * (C / 8);
-    JCK_REQUIRE(nvec < (1LL << 31), "bn_act_bwd_apply: tensor too large for 32-bit indexing");
+    JCK_REQUIRE(da && y && scale_shift && mean_rstd && gamma && sums && dy && count > 0, "bn_act_bwd_apply: bad argument");
+    BN_COMMON_CHECKS("bn_act_bwd_apply")
+    unsigned slab;
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 8, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
-        bn_act_bwd_apply_kernel<T><<<grid_for(nvec, 256, 16), 256, 0, as_stream(stream)>>>(
-            (const T*)da, (const T*)y, scale_shift, mean_rstd, gamma, sums, (T*)dy, (unsigned)nvec, C,
-            (unsigned)(pix_per_group * (C / 8)), 1.f / count, slope);)
+        bn_act_bwd_apply_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)da, (const T*)y, scale_shift, mean_rstd,
+                                                                      gamma, sums, (T*)dy, C, (unsigned)pix_per_group, slab,
+                                                                      1.f / count, slope);)
     JCK_LAUNCH_CHECK("bn_act_bwd_apply");
     return JCK_OK;
 }

@@ -103,6 +103,17 @@ class Ctx:
         return s
 
 
+def _zero_blocks(groups, channels, device):
+    """One memset for all the [groups][2C] fp32 accumulators of a pass (stats / backward sums)."""
+    total = sum(groups * 2 * c for c in channels)
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    out, off = [], 0
+    for c in channels:
+        out.append(flat[off:off + groups * 2 * c].view(groups, 2 * c))
+        off += groups * 2 * c
+    return out
+
+
 class _Workspace:
     def __init__(self, device):
         self.device = device
@@ -173,10 +184,11 @@ class DiscriminatorEngine(_GradTarget):
         ctx.x, ctx.groups, ctx.B = x_nhwc, groups, B
         cur = x_nhwc
         world = self.comm.world_size
+        zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev)
         for k in range(1, 5):
             cv, nm = self.convs[k], self.norms[k]
             y = torch.empty(B, cv.Hs, cv.Ws, cv.Ca, dtype=self.dtype, device=self.dev)
-            stats = torch.zeros(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
+            stats = zeros[k - 1]
             if cv.edge:
                 ctx.x_patches = ops.p4_to_patches(cur)
                 ops.edge_down(ctx.x_patches, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)
@@ -233,10 +245,11 @@ class DiscriminatorEngine(_GradTarget):
         B, groups = ctx.B, ctx.groups
         world = self.comm.world_size
         da = da4
+        zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev)
         for k in range(4, 0, -1):
             cv, nm = self.convs[k], self.norms[k]
             C = cv.Ca
-            sums = torch.zeros(groups, 2 * C, dtype=torch.float32, device=self.dev)
+            sums = zeros[k - 1]
             ops.bn_act_bwd_reduce(da, ctx.y[k], ctx.ss[k], ctx.mr[k], sums, C, groups, LRELU)
             if wgrad:   # parameter gradients are this rank's contribution; ranks are averaged later
                 ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, groups, accumulate)
@@ -324,7 +337,8 @@ class GeneratorEngine(_GradTarget):
         ctx = Ctx()
         ctx.x, ctx.B, ctx.groups = z2d, B, 1
         y1 = torch.empty(B, 4, 4, self.C1, dtype=self.dtype, device=self.dev)
-        stats = torch.zeros(1, 2 * self.C1, dtype=torch.float32, device=self.dev)
+        zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev)
+        stats = zeros[0]
         ops.fc_fwd(z2d, self.w_fc, y1, stats, self.C1)
         cur = self._bn_relu(ctx, 1, y1, stats, 1, update_running)
         for k in range(2, 6):
@@ -336,7 +350,7 @@ class GeneratorEngine(_GradTarget):
                 continue
             y = torch.empty(B, 2 * cv.Hs, 2 * cv.Ws, cv.Cb, dtype=self.dtype, device=self.dev)
             if k < 5:
-                stats = torch.zeros(1, 2 * cv.Cb, dtype=torch.float32, device=self.dev)
+                stats = zeros[k - 1]
                 ops.conv_up(cur, cv.w_up, y, stats, cv.Ca, cv.Cb, algo=self.algo)
                 cur = self._bn_relu(ctx, k, y, stats, 1, update_running)
             else:
@@ -349,6 +363,7 @@ class GeneratorEngine(_GradTarget):
         B = ctx.B
         world = self.comm.world_size
         d_large = dy5
+        zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev)
         for k in range(5, 1, -1):
             cv = self.convs[k]
             da = torch.empty_like(ctx.a[k - 1])
@@ -364,7 +379,7 @@ class GeneratorEngine(_GradTarget):
                 ops.conv_down(d_large, cv.w_down, da, None, cv.Ca, cv.Cb, algo=self.algo)
             nm = self.norms[k - 1]
             C = nm.C
-            sums = torch.zeros(1, 2 * C, dtype=torch.float32, device=self.dev)
+            sums = zeros[k - 2]
             ops.bn_act_bwd_reduce(da, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], sums, C, 1, 0.0)
             ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, 1, accumulate)
             self.comm.allreduce_sum_(sums)
