@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device time table")
+    ap.add_argument("--kernel-table", action="store_true", help="print per-kernel device time (CUPTI via torch.profiler)")
     return ap.parse_args()
 
 
@@ -289,6 +290,19 @@ def run_b200(args):
                 "avg_launch_ms": tv["ms"] / tv["calls"], "share_of_step": tv["ms"] / tot,
                 "step_tensor_frac": FLOP_PER_IMAGE * value / (comm.world_size * pk["tf_sustained"] * 1e12),
                 "families": {k: {"share": f["ms"] / tot, "tflops": f["flop"] / (f["ms"] * 1e-3) / 1e12} for k, f in fam.items()}}
+    if args.kernel_table and rank == 0:
+        # per-kernel device time from CUPTI (torch.profiler), warm caches, eager launches
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step.run(real)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot_us = sum(e.device_time_total for e in rows)
+        print(f"# kernel table: {tot_us / 3e3:.3f} ms/step of device time over 3 eager steps", file=sys.stderr)
+        for e in rows[:45]:
+            print(f"# {e.device_time_total / 3e3:8.3f} ms/step {e.count // 3:4d} calls {e.device_time_total / max(e.count, 1):8.1f} us  "
+                  f"{e.key[:100]}", file=sys.stderr)
     if args.profile_ops and rank == 0:
         for k, t in sorted(tab.items(), key=lambda kv: -kv[1]["ms"]):
             print(f"# {t['ms'] / 2:9.3f} ms/step  {t['calls'] // 2:4d} calls  {k}", file=sys.stderr)

@@ -239,7 +239,7 @@ def check_misc():
     y5 = _mk((B, 64, 64, C), torch.float32, 20).cuda()
     fr, fm = torch.empty(B, C, 64, 64, device="cuda"), torch.empty(B, C, 64, 64, device="cuda")
     mn = torch.empty(B, 64, 64, C, device="cuda")
-    ops.g_out_fwd(y5, m.cuda(), 0.9, 0.1, fr, fm, mn)
+    ops.g_out_fwd(y5, m.cuda(), 0.9, 0.1, fr, fm, mn, (B, C, 64, 64))
     t = torch.tanh(y5.cpu().permute(0, 3, 1, 2))
     res["g_out_raw"] = _rel(fr, t); res["g_out_mix"] = _rel(fm, 0.9 * t + 0.1 * m); res["g_out_mix_nhwc"] = _rel(mn.permute(0, 3, 1, 2), 0.9 * t + 0.1 * m)
     dm = _mk((B, 64, 64, C), torch.float32, 21).cuda(); dy5 = torch.empty_like(dm)
