@@ -84,6 +84,7 @@ class Ctx:
         self.prob = None
         self.groups = 1
         self.B = 0
+        self.dy = {}           # gradients w.r.t. the raw conv outputs, filled by the backward sweep
 
     def slice(self, g0, g1):
         """View of groups [g0, g1) of a grouped pass."""
@@ -257,6 +258,7 @@ class DiscriminatorEngine(_GradTarget):
             dy = torch.empty_like(ctx.y[k])
             count = (B // groups) * cv.Hs * cv.Ws * world
             ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count, LRELU)
+            ctx.dy[k] = dy
             inp = ctx.a[k - 1] if k > 1 else ctx.x
             if wgrad:
                 if cv.edge:
@@ -386,6 +388,7 @@ class GeneratorEngine(_GradTarget):
             dy = torch.empty_like(ctx.y[k - 1])
             count = (ctx.y[k - 1].numel() // C) * world
             ops.bn_act_bwd_apply(da, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], nm.gamma, sums, dy, C, 1, count, 0.0)
+            ctx.dy[k - 1] = dy
             d_large = dy
         ops.fc_wgrad(d_large.view(B, 16 * self.C1), ctx.x, self.dw_fc, accumulate=False)
         ops.unpack_fc_grad(self.dw_fc, self._gb(self.m.conv1.weight), accumulate)

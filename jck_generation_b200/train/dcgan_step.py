@@ -108,7 +108,8 @@ class DCGANStep:
         self.comm.allreduce_mean_(self.flat_g.grad)
         self.opt_g.step()                                                                                  # :189
         eg.refresh(force=True)
-        self.last = {"fake_raw": fake_raw, "gp_grad_nhwc": dx, "ctx": ctx, "ctx_g": gctx, "ctx_d": ctx2}
+        self.last = {"fake_raw": fake_raw, "gp_grad_nhwc": dx, "ctx": ctx, "ctx_g": gctx, "ctx_d": ctx2,
+                     "dmix": dmix, "dy5": dy5}
         return scal
 
     # ---- CUDA graph ---------------------------------------------------------------------------------
