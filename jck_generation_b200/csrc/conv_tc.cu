@@ -14,6 +14,7 @@
 // Kernel anatomy (one output tile per CTA): warp 0 = TMA producer, warp 1 = TMEM allocator + single
 // thread MMA issuer, warps 2..5 = epilogue (tcgen05.ld -> BatchNorm partial sums by warp shuffles ->
 // bf16 -> global).  smem ring: full/empty mbarriers; accumulator handed over by tcgen05.commit.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace jck {
@@ -316,6 +317,254 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem
+// ring keeps streaming across tile boundaries and the accumulator is double-buffered in TMEM, so the
+// epilogue of tile i (tcgen05.ld, BatchNorm partial sums, stores) overlaps the MMAs of tile i+1 and the
+// per-CTA set-up (TMEM alloc, barrier init, descriptor prefetch) is paid once per SM instead of per tile.
+// Tile order: n fastest, so CTAs running side by side share the activation tile in L2.
+// ------------------------------------------------------------------------------------------------
+template <int BN_, int STAGES>
+struct PersistSmem {
+    static constexpr int kABytes = kTileM * kBK * 2;
+    static constexpr int kBBytes = BN_ * kBK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kBarOff = STAGES * kStage;
+    static constexpr int kRedOff = kBarOff + 512;
+    static constexpr int kTotal = kRedOff + 2 * 4 * 2 * BN_ * 4 + 1024;
+};
+
+template <int BN_, int STAGES, int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p,
+                       const int n_tiles, const int total_tiles) {
+    constexpr bool kUp = (MODE == kUpM);
+    constexpr int kAccCols = BN_ < 32 ? 32 : BN_;
+    using L = PersistSmem<BN_, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;     // [2] accumulator ready
+    uint64_t* tempty = tfull + 2;         // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* red = reinterpret_cast<float*>(smem + L::kRedOff);  // [2][4 warps][2][BN_]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cin = (MODE == kUpM || MODE == kEdgeUp) ? p.Ca : p.Cb;
+    const int Cout = (MODE == kUpM) ? p.Cb : p.Ca;
+    const int cchunks = MODE == kEdgeDown ? 1 : Cin / kBK;
+    const int ksteps = MODE == kEdgeDown ? 1 : (MODE == kUpM ? 4 : (MODE == kEdgeUp ? 9 : 16)) * cchunks;
+    const int tiles_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = t % n_tiles;
+                int rest = t / n_tiles;
+                const int phase = kUp ? (rest & 3) : 0;
+                if (kUp) rest >>= 2;
+                const int mt = rest;
+                const int x0 = (mt % p.tiles_x) * p.bw, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+                const int n0 = (mt / tiles_img) * p.nb;
+                const int py = phase >> 1, px = phase & 1;
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* sa = smem + s * L::kStage;
+                    uint8_t* sb = sa + L::kABytes;
+                    mbar_arrive_expect_tx(&full[s], L::kStage);
+                    const int tap = ks / cchunks, cc = ks - tap * cchunks;
+                    if (MODE == kEdgeDown) {
+                        tma_load_2d(sa, &mapA, &full[s], 0, mt * kTileM);
+                        tma_load_2d(sb, &mapB, &full[s], 0, nt * BN_);
+                    } else if (MODE == kEdgeUp) {
+                        const int di = tap / 3 - 1, dj = tap % 3 - 1;
+                        tma_load_4d(sa, &mapA, &full[s], cc * kBK, x0 + dj, y0 + di, n0);
+                        tma_load_2d(sb, &mapB, &full[s], tap * p.Ca + cc * kBK, 0);
+                    } else if (!kUp) {
+                        const int ky = tap >> 2, kx = tap & 3;
+                        const int dy = (ky - 1) >> 1, qy = (ky - 1) & 1;
+                        const int dx = (kx - 1) >> 1, qx = (kx - 1) & 1;
+                        tma_load_5d(sa, &mapA, &full[s], qx * p.Cb + cc * kBK, x0 + dx, qy, y0 + dy, n0);
+                        tma_load_2d(sb, &mapB, &full[s], tap * p.Cb + cc * kBK, nt * BN_);
+                    } else {
+                        const int dy = up_d(py, tap >> 1), dx = up_d(px, tap & 1);
+                        tma_load_4d(sa, &mapA, &full[s], cc * kBK, x0 + dx, y0 + dy, n0);
+                        tma_load_2d(sb, &mapB, &full[s], tap * p.Ca + cc * kBK, phase * p.Cb + nt * BN_);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc = make_idesc(BN_, 0, 0);
+        int it = 0, lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);
+            fence_after_sync();
+            const uint32_t tmem_d = tmem_base + acc * kAccCols;
+            for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem + s * L::kStage);
+                    const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16(tmem_d, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024), idesc,
+                                  (ks > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                    if (ks == ksteps - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------- epilogue (warps 2..5) ----------------
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;
+        const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+        int lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int nt = t % n_tiles;
+            int rest = t / n_tiles;
+            const int phase = kUp ? (rest & 3) : 0;
+            if (kUp) rest >>= 2;
+            const int mt = rest;
+            const int x0 = (mt % p.tiles_x) * p.bw, y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+            const int n0 = (mt / tiles_img) * p.nb;
+            const int py = phase >> 1, px = phase & 1;
+            const int n = n0 + nl;
+            const bool valid = n < p.B;
+            const int acc = lt & 1;
+            const uint32_t tmem_d = tmem_base + acc * kAccCols + ((uint32_t)(wq * 32) << 16);
+            mbar_wait(&tfull[acc], (lt >> 1) & 1);
+            fence_after_sync();
+            if constexpr (MODE == kEdgeUp) {
+                float v[16];
+                tmem_ld16(tmem_d, v);
+                tmem_ld_wait();
+                fence_before_sync();
+                mbar_arrive(&tempty[acc]);
+                if (valid) {
+                    const int Wp = 2 * p.Ws + 2, Hp = 2 * p.Hs + 2;
+#pragma unroll
+                    for (int qy = 0; qy < 2; ++qy) {
+                        const size_t o = (((size_t)n * Hp + 2 * (y0 + yl) + qy + 1) * Wp + 2 * (x0 + xl) + 1) * 4;
+                        uint2 u0, u1;
+                        u0.x = pack_bf16x2(v[qy * 8 + 0], v[qy * 8 + 1]);
+                        u0.y = pack_bf16x2(v[qy * 8 + 2], v[qy * 8 + 3]);
+                        u1.x = pack_bf16x2(v[qy * 8 + 4], v[qy * 8 + 5]);
+                        u1.y = pack_bf16x2(v[qy * 8 + 6], v[qy * 8 + 7]);
+                        *reinterpret_cast<uint2*>(out + o) = u0;
+                        *reinterpret_cast<uint2*>(out + o + 4) = u1;
+                    }
+                }
+            } else {
+                size_t pix;
+                if (!kUp) pix = ((size_t)n * p.Hs + (y0 + yl)) * p.Ws + (x0 + xl);
+                else pix = ((size_t)n * 2 * p.Hs + 2 * (y0 + yl) + py) * (2 * p.Ws) + 2 * (x0 + xl) + px;
+                __nv_bfloat16* orow = out + pix * Cout + nt * BN_;
+                float* rbuf = red + (lt & 1) * (4 * 2 * BN_);
+#pragma unroll 1
+                for (int c = 0; c < BN_ / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(tmem_d + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == BN_ / 32 - 1) {            // accumulator fully read: hand the TMEM buffer back
+                        fence_before_sync();
+                        mbar_arrive(&tempty[acc]);
+                    }
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u;
+                            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                            dst[q] = u;
+                        }
+                    }
+                    if (stats != nullptr) {
+                        float sq[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+                        const float s1 = warp_transpose_sum(v, lane);
+                        const float s2 = warp_transpose_sum(sq, lane);
+                        rbuf[(wq * 2 + 0) * BN_ + c * 32 + lane] = s1;
+                        rbuf[(wq * 2 + 1) * BN_ + c * 32 + lane] = s2;
+                    }
+                }
+                if (stats != nullptr) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+                    const int e = threadIdx.x - 64;
+                    float* sp = stats + (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
+                    for (int col = e; col < 2 * BN_; col += 128) {
+                        const int which = col / BN_, cc = col % BN_;
+                        const float s = rbuf[(0 * 2 + which) * BN_ + cc] + rbuf[(1 * 2 + which) * BN_ + cc] +
+                                        rbuf[(2 * 2 + which) * BN_ + cc] + rbuf[(3 * 2 + which) * BN_ + cc];
+                        atomicAdd(sp + which * Cout + cc, s);
+                    }
+                }
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 2 * kAccCols);
+    }
+}
+
+static bool use_persistent() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("JCK_CONV_PERSIST"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+template <int BN_, int STAGES, int MODE>
+int launch_conv_tc_persist(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
+                           int m_tiles, int n_tiles, cudaStream_t st) {
+    using L = PersistSmem<BN_, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, STAGES, MODE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_persist smem attr: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int total = m_tiles * n_tiles * (MODE == kUpM ? 4 : 1);
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    conv_tc_persist_kernel<BN_, STAGES, MODE><<<grid, kConvThreads, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats, p,
+                                                                                     n_tiles, total);
+    JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc_persist" : MODE == kDown ? "conv_down_tc_persist"
+                                                        : MODE == kEdgeDown ? "edge_down_tc_persist" : "edge_up_tc_persist");
+    return JCK_OK;
+}
+
 template <int BN_, int STAGES, int MODE>
 int launch_conv_tc_mode(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
                         int m_tiles, int n_tiles, cudaStream_t st) {
@@ -364,6 +613,10 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
     } else {
         if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
         if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn))) return rc;
+    }
+    if (use_persistent()) {
+        if (bn == 128) return launch_conv_tc_persist<128, 6, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 128, st);
+        return launch_conv_tc_persist<64, 8, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 64, st);
     }
     if (bn == 128) return launch_conv_tc<128, 3, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 128, st);
     return launch_conv_tc<64, 4, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 64, st);
@@ -785,6 +1038,7 @@ extern "C" int jck_edge_down(const void* patches, const void* w_down_e, void* ou
     int rc;
     if ((rc = map_rows64(&mA, patches, (long long)B * Hs * Ws, kTileM))) return rc;
     if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
+    if (use_persistent()) return launch_conv_tc_persist<64, 6, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
     return launch_conv_tc_mode<64, 2, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
 }
 
@@ -799,6 +1053,7 @@ extern "C" int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4
     int rc;
     if ((rc = map_small(&mA, in_small, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
     if ((rc = map_matrix(&mB, w_up9, 16, 9 * Ca, 16))) return rc;
+    if (use_persistent()) return launch_conv_tc_persist<16, 8, kEdgeUp>(mA, mB, img_p4, nullptr, p, m_tiles, 1, as_stream(stream));
     return launch_conv_tc_mode<16, 4, kEdgeUp>(mA, mB, img_p4, nullptr, p, m_tiles, 1, as_stream(stream));
 }
 
