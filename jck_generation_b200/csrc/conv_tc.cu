@@ -334,8 +334,8 @@ struct PersistSmem {
     static constexpr int kTotal = kRedOff + 2 * 4 * 2 * BN_ * 4 + 1024;
 };
 
-template <int BN_, int STAGES, int MODE>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN_, int STAGES, int MODE, int EPI>   // EPI = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two, splitting the columns)
+__global__ void __launch_bounds__(64 + 32 * EPI, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                        __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p,
                        const int n_tiles, const int total_tiles) {
@@ -362,7 +362,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * EPI); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccCols);
@@ -439,8 +439,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             }
         }
     } else {
-        // ---------------- epilogue (warps 2..5) ----------------
-        const int wq = warp & 3;
+        // ---------------- epilogue (warps 2..) ----------------
+        const int wq = warp & 3;                     // TMEM lane quarter
+        const int half = (warp - 2) >> 2;            // with 8 warps: which half of the 32-column chunks
+        constexpr int kChunkStep = EPI / 4;
         const int r = wq * 32 + lane;
         const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
         int lt = 0;
@@ -461,11 +463,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             fence_after_sync();
             if constexpr (MODE == kEdgeUp) {
                 float v[16];
-                tmem_ld16(tmem_d, v);
-                tmem_ld_wait();
+                if (half == 0) { tmem_ld16(tmem_d, v); tmem_ld_wait(); }
                 fence_before_sync();
                 mbar_arrive(&tempty[acc]);
-                if (valid) {
+                if (valid && half == 0) {
                     const int Wp = 2 * p.Ws + 2, Hp = 2 * p.Hs + 2;
 #pragma unroll
                     for (int qy = 0; qy < 2; ++qy) {
@@ -485,12 +486,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 else pix = ((size_t)n * 2 * p.Hs + 2 * (y0 + yl) + py) * (2 * p.Ws) + 2 * (x0 + xl) + px;
                 __nv_bfloat16* orow = out + pix * Cout + nt * BN_;
                 float* rbuf = red + (lt & 1) * (4 * 2 * BN_);
+                constexpr int kChunks = BN_ / 32;
 #pragma unroll 1
-                for (int c = 0; c < BN_ / 32; ++c) {
+                for (int c = half; c < kChunks; c += kChunkStep) {
                     float v[32];
                     tmem_ld32(tmem_d + c * 32, v);
                     tmem_ld_wait();
-                    if (c == BN_ / 32 - 1) {            // accumulator fully read: hand the TMEM buffer back
+                    if (c + kChunkStep >= kChunks) {    // this warp's share of the accumulator is read: hand it back
                         fence_before_sync();
                         mbar_arrive(&tempty[acc]);
                     }
@@ -517,10 +519,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                     }
                 }
                 if (stats != nullptr) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");   // epilogue warps only
                     const int e = threadIdx.x - 64;
                     float* sp = stats + (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
-                    for (int col = e; col < 2 * BN_; col += 128) {
+                    for (int col = e; col < 2 * BN_; col += 32 * EPI) {
                         const int which = col / BN_, cc = col % BN_;
                         const float s = rbuf[(0 * 2 + which) * BN_ + cc] + rbuf[(1 * 2 + which) * BN_ + cc] +
                                         rbuf[(2 * 2 + which) * BN_ + cc] + rbuf[(3 * 2 + which) * BN_ + cc];
@@ -539,27 +541,42 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     }
 }
 
-static bool use_persistent() {
+// JCK_CONV_PERSIST: 0 = one tile per CTA (2 CTAs/SM); 1 = persistent, 1 CTA/SM, 8 epilogue warps;
+// 2 = persistent, 2 CTAs/SM, 4 epilogue warps each (default: measured 3.91 ms/step vs 4.27 (0) and 4.52 (1) --
+// two co-resident CTAs hide each other's TMA and epilogue latency, persistence removes the per-tile set-up)
+static int persist_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("JCK_CONV_PERSIST"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
+    if (v < 0) { const char* e = getenv("JCK_CONV_PERSIST"); v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    return v;
 }
+static bool use_persistent() { return persist_mode() != 0; }
 
-template <int BN_, int STAGES, int MODE>
-int launch_conv_tc_persist(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
-                           int m_tiles, int n_tiles, cudaStream_t st) {
+template <int BN_, int STAGES, int MODE, int EPI, int CTAS_PER_SM>
+int launch_persist_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
+                       int m_tiles, int n_tiles, cudaStream_t st) {
     using L = PersistSmem<BN_, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, STAGES, MODE>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, STAGES, MODE, EPI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_persist smem attr: %s", cudaGetErrorString(e));
         configured = true;
     }
     const int total = m_tiles * n_tiles * (MODE == kUpM ? 4 : 1);
-    const int grid = total < kNumSMs ? total : kNumSMs;
-    conv_tc_persist_kernel<BN_, STAGES, MODE><<<grid, kConvThreads, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats, p,
-                                                                                     n_tiles, total);
+    const int cap = kNumSMs * CTAS_PER_SM;
+    const int grid = total < cap ? total : cap;
+    conv_tc_persist_kernel<BN_, STAGES, MODE, EPI><<<grid, 64 + 32 * EPI, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats,
+                                                                                        p, n_tiles, total);
+    return JCK_OK;
+}
+
+template <int BN_, int STAGES, int MODE>
+int launch_conv_tc_persist(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
+                           int m_tiles, int n_tiles, cudaStream_t st) {
+    int rc;
+    if (persist_mode() == 2) rc = launch_persist_cfg<BN_, STAGES / 2, MODE, 4, 2>(mA, mB, out, stats, p, m_tiles, n_tiles, st);
+    else rc = launch_persist_cfg<BN_, STAGES, MODE, 8, 1>(mA, mB, out, stats, p, m_tiles, n_tiles, st);
+    if (rc) return rc;
     JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc_persist" : MODE == kDown ? "conv_down_tc_persist"
                                                         : MODE == kEdgeDown ? "edge_down_tc_persist" : "edge_up_tc_persist");
     return JCK_OK;
