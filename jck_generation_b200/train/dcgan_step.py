@@ -115,8 +115,8 @@ class DCGANStep:
     # ---- CUDA graph ---------------------------------------------------------------------------------
     def capture(self, batch):
         """Capture one step (device-drawn random tensors) into a CUDA graph; replay() then costs one
-        launch.  Single-process only: collectives stay outside graphs in this round."""
-        assert self.comm.world_size == 1, "graph capture is single-GPU in this round"
+        launch.  Under data parallelism the NCCL all-reduces (SyncBN statistics, gradient buckets) are
+        captured with it: every rank replays the same sequence, so the collectives still pair up."""
         self._static = torch.zeros(batch, self.nc, 64, 64, dtype=torch.float32, device=self.dev)
         # warm-up steps really train; put the training state back afterwards
         bufs = [b for m in (self.g, self.d) for b in m.buffers()]

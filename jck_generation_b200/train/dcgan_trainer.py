@@ -75,7 +75,8 @@ class DCGANTrainer(Trainer):
         self.criterion = nn.BCELoss()
         self.step = DCGANStep(self.model_g, self.model_d, self.optimizer_g, self.optimizer_d, self.flat_g,
                               self.flat_d, self.comm, self.lambda_gp, seed=int(getattr(args, "seed", 12345)))
-        self.use_graph = bool(getattr(args, "cuda_graph", 0)) and self.comm.world_size == 1
+        self.use_graph = bool(getattr(args, "cuda_graph", 0)) and (
+            self.comm.world_size == 1 or bool(int(os.environ.get("JCK_DP_GRAPH", "1"))))
         self.max_iters = int(getattr(args, "max_iters", 0))
 
         datetime_now = args.model_path if getattr(args, "model_path", "") != "" else datetime.now().strftime("%Y%m%d_%H%M%S")
