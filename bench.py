@@ -322,7 +322,13 @@ def run_b200(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if comm.world_size > 1:
-        torch.distributed.destroy_process_group()
+        # tearing down a NCCL communicator that captured CUDA graphs still reference can block for minutes;
+        # everything is measured and printed, so leave without the collective teardown
+        comm.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
