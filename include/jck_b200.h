@@ -174,6 +174,35 @@ int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, flo
 int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, float a, void* dy5_nhwc, int B, int C,
                   int H, int W, int layout, int dtype, void* stream);
 
+/* ---- CGAN discriminator head and the second-order (gradient-penalty) sweep ---------------------------
+ * model/CGAN.py:83-84,103-107,112-122 (label_embedding + LeakyReLU, flatten, cat, linear1, drop1, linear2,
+ * sigmoid) and train/cgan_trainer.py:200-204 (error_d.backward() through the gradient penalty).
+ * jck_dense: C[m][n] (+)= sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk]; dtypes JCK_F32 / JCK_BF16 per operand. */
+int jck_dense(const void* A, int a_dt, long long sam, long long sak, const void* B, int b_dt, long long sbn,
+              long long sbk, void* C, int c_dt, long long ldc, int M, int N, int K, int accumulate, void* stream);
+/* fp32 [M][N] helpers.  op 0: out = act(x + y[n]) (act slope s, y nullable); 1: out = x*y*s; 2: out = x*(y>0 ? 1 : s);
+ * 3: out[m] = x[m] + y[m % rows_y]; 4: out[r] = sum_g x[g*rows_y + r]; 5: out[m][n] = x[m]*y[n]; 6: out[m][n] = x[m][n]*y[m]; 7: out = (x >= s) ? 1 : 0 */
+int jck_rowop(int op, const float* x, const float* y, float* out, int M, int N, int rows_y, float s, void* stream);
+/* prob = sigmoid(logit); scalars (nullable): [0] += BCE mean vs target, [1] += mean(prob) */
+int jck_sigmoid_bce(const float* logit, float* prob, float target, float* scalars, int B, void* stream);
+/* d/d(logit): mode 0 BCE-mean, 1 ones on prob, 2 up*p(1-p), 3 second order up*p(1-p)(1-2p); all times `scale` */
+int jck_logit_grad(const float* prob, const float* up, float target, float* out, int B, int mode, float scale, void* stream);
+int jck_i64_to_f32(const long long* in, float* out, long long n, void* stream);
+int jck_axpy(const void* x, void* y, float a, long long n, int dtype, void* stream);   /* y += a*x */
+/* per sample b: norm = ||v_b||; scalars[0] += (norm-1)^2/B; u_b = scale*(1 - 1/norm)*v_b (u nullable) */
+int jck_gp_seed(const void* v, void* u, float* scalars, int B, long long per_sample, float scale, int dtype, void* stream);
+/* linear1.weight [O][C*HW + E] (NCHW flatten order) <-> w_a [O][HW*C] (NHWC order, dtype), w_b [O][E] fp32 */
+int jck_pack_linear(const float* w, void* w_a, float* w_b, int O, int C, int HW, int E, int dtype, void* stream);
+int jck_unpack_linear_grad(const float* dwa, const float* dwb, float* dw, int O, int C, int HW, int E, int accumulate,
+                           void* stream);
+/* adjoint of the BatchNorm backward pass (formulas in csrc/cgan.cu): asums [3C] += {S1,S2,S3} (caller zeroes) */
+int jck_bn_adj_reduce(const void* dbar, const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
+                      const float* sums1, float* asums, long long npix, int C, float count, float slope, int dtype, void* stream);
+int jck_bn_adj_apply(const void* dbar, const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
+                     const float* gamma, const float* sums1, const float* asums, void* gbar_a, void* ybar, long long npix,
+                     int C, float count, float slope, int dtype, void* stream);
+int jck_bn_adj_param(const float* asums, const float* mean_rstd, float* dgamma, int C, float scale, void* stream);
+
 /* ---- gradient penalty --------------------------------------------------------------------------
  * scalars[0] += mean_n (||dx[n,:]||_2 - 1)^2.  Replaces train/dcgan_trainer.py:125-126. */
 int jck_gp_penalty(const void* dx, float* scalars, int B, long long per_sample, int dtype, void* stream);

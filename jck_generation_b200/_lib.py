@@ -36,6 +36,18 @@ _SIGNATURES = {
     "jck_conv_up": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_conv_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i, c_i, c_i, c_i],
     "jck_conv_wgrad": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_dense": [c_p, c_i, c_ll, c_ll, c_p, c_i, c_ll, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p],
+    "jck_rowop": [c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
+    "jck_sigmoid_bce": [c_p, c_p, c_f, c_p, c_i, c_p],
+    "jck_logit_grad": [c_p, c_p, c_f, c_p, c_i, c_i, c_f, c_p],
+    "jck_i64_to_f32": [c_p, c_p, c_ll, c_p],
+    "jck_axpy": [c_p, c_p, c_f, c_ll, c_i, c_p],
+    "jck_gp_seed": [c_p, c_p, c_p, c_i, c_ll, c_f, c_i, c_p],
+    "jck_pack_linear": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_unpack_linear_grad": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_bn_adj_reduce": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_f, c_i, c_p],
+    "jck_bn_adj_apply": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_f, c_f, c_i, c_p],
+    "jck_bn_adj_param": [c_p, c_p, c_p, c_i, c_f, c_p],
     "jck_fc_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_fc_wgrad": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_fc": [c_p, c_p, c_i, c_i, c_i, c_p],

@@ -158,6 +158,48 @@ struct FcWgradProblem {  // dw[n][k] = sum_m dy[m][n] x[m][k]:  M' = N, N' = K, 
     __device__ bool uniform_group() const { return true; }
 };
 
+// Generic strided dense product C[m][n] (+)= sum_k A(m,k) * B(n,k), A(m,k) = A[m*sam + k*sak],
+// B(n,k) = B[n*sbn + k*sbk]; operand / result dtypes chosen at run time (JCK_F32 / JCK_BF16).  The CGAN
+// discriminator head (label embedding, Linear 8392 -> 256 -> 1 and every first / second order product
+// around them) is built from this one kernel.
+__device__ __forceinline__ float ld_any(const void* p, size_t i, int dt) {
+    return dt == JCK_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                          : reinterpret_cast<const float*>(p)[i];
+}
+template <bool KCONTIG>
+struct DenseProblem {
+    static constexpr bool kKContigLoad = KCONTIG;
+    const void* A; const void* B; void* C;
+    int a_dt, b_dt, c_dt;
+    long long sam, sak, sbn, sbk, ldc;
+    int Mm, Nn, Kk, accumulate;
+    __device__ int M() const { return Mm; }
+    __device__ int N() const { return Nn; }
+    __device__ int K() const { return Kk; }
+    struct Row { int m; bool ok; };
+    __device__ Row rowA(int m, int) const { return Row{m, m < Mm}; }
+    __device__ float loadA(const Row& r, int k, int) const {
+        return (r.ok && k < Kk) ? ld_any(A, (size_t)(r.m * sam + k * sak), a_dt) : 0.f;
+    }
+    __device__ float loadB(int n, int k, int) const {
+        return (n < Nn && k < Kk) ? ld_any(B, (size_t)(n * sbn + k * sbk), b_dt) : 0.f;
+    }
+    __device__ void store(int m, int n, float v, int) const {
+        if (m >= Mm || n >= Nn) return;
+        const size_t i = (size_t)m * ldc + n;
+        if (c_dt == JCK_BF16) {
+            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(C) + i;
+            *p = __float2bfloat16_rn(accumulate ? __bfloat162float(*p) + v : v);
+        } else {
+            float* p = reinterpret_cast<float*>(C) + i;
+            *p = accumulate ? *p + v : v;
+        }
+    }
+    __device__ float* stats_ptr(int, int) const { return nullptr; }
+    __device__ int stats_channels() const { return 0; }
+    __device__ bool uniform_group() const { return true; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------------------------
@@ -362,4 +404,16 @@ extern "C" int jck_fc_wgrad(const void* dy, const float* x, float* dw, int M, in
         return launch(p, N, K, 1, 0, as_stream(stream), "fc_wgrad");
     }
     return set_error(JCK_E_BADARG, "fc_wgrad: dtype %d", dtype);
+}
+
+extern "C" int jck_dense(const void* A, int a_dt, long long sam, long long sak, const void* B, int b_dt, long long sbn,
+                         long long sbk, void* C, int c_dt, long long ldc, int M, int N, int K, int accumulate, void* stream) {
+    JCK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "dense: bad argument");
+    JCK_REQUIRE((a_dt | 1) == 1 && (b_dt | 1) == 1 && (c_dt | 1) == 1, "dense: bad dtype");
+    if (sak == 1) {
+        DenseProblem<true> p{A, B, C, a_dt, b_dt, c_dt, sam, sak, sbn, sbk, ldc, M, N, K, accumulate};
+        return launch(p, M, N, 1, 0, as_stream(stream), "dense");
+    }
+    DenseProblem<false> p{A, B, C, a_dt, b_dt, c_dt, sam, sak, sbn, sbk, ldc, M, N, K, accumulate};
+    return launch(p, M, N, 1, 0, as_stream(stream), "dense");
 }

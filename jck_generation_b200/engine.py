@@ -85,6 +85,9 @@ class Ctx:
         self.groups = 1
         self.B = 0
         self.dy = {}           # gradients w.r.t. the raw conv outputs, filled by the backward sweep
+        self.da = {}           # gradients w.r.t. the activations (inputs of the BatchNorm backward)
+        self.bsum = {}         # BatchNorm backward sums [groups][2C]
+        self.head = {}         # CGAN head intermediates
 
     def slice(self, g0, g1):
         """View of groups [g0, g1) of a grouped pass."""
@@ -241,8 +244,11 @@ class DiscriminatorEngine(_GradTarget):
             ops.unpack_head_grad(self.dw5, self._gb(self.m.conv5.weight), accumulate)
         return da4.view(B, 4, 4, self.convs[4].Ca)
 
-    def trunk_backward(self, ctx, da4, wgrad=True, input_grad=False, accumulate=False):
-        """Backward through conv4..conv1 given d/d(a4).  Returns d/d(input) (NHWC) when asked."""
+    def trunk_backward(self, ctx, da4, wgrad=True, input_grad=False, accumulate=False, inject=None, inject_rows=None):
+        """Backward through conv4..conv1 given d/d(a4).  Returns d/d(input) (NHWC) when asked.
+        `inject[k]` (rows `inject_rows` of the batch) is added to the gradient of the raw conv-k output
+        before it is used: the second-order terms of the CGAN gradient penalty enter here.  The sweep
+        records ctx.da[k] (gradient w.r.t. the activation) and ctx.bsum[k] (BatchNorm backward sums)."""
         B, groups = ctx.B, ctx.groups
         world = self.comm.world_size
         da = da4
@@ -258,7 +264,10 @@ class DiscriminatorEngine(_GradTarget):
             dy = torch.empty_like(ctx.y[k])
             count = (B // groups) * cv.Hs * cv.Ws * world
             ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count, LRELU)
-            ctx.dy[k] = dy
+            ctx.dy[k], ctx.da[k], ctx.bsum[k] = dy, da, sums
+            if inject is not None:
+                lo, hi = inject_rows
+                ops.axpy(inject[k], dy[lo:hi], 1.0)
             inp = ctx.a[k - 1] if k > 1 else ctx.x
             if wgrad:
                 if cv.edge:

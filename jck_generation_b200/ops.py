@@ -222,3 +222,71 @@ def rand(out, seed, stream_id, counter):
 
 def rng_advance(counter, by):
     check(L().jck_rng_advance(_p(counter), by, _s()), "rng_advance")
+
+
+# ---- CGAN head / second-order helpers -----------------------------------------------------------------------
+def dense(A, sam, sak, B, sbn, sbk, C, M, N, K, accumulate=False):
+    """C[m][n] (+)= sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk]; C row-major with leading dimension C.shape[-1]."""
+    ldc = C.shape[-1] if C.dim() > 1 else N
+    check(L().jck_dense(_p(A), dt(A), sam, sak, _p(B), dt(B), sbn, sbk, _p(C), dt(C), ldc, M, N, K, int(accumulate), _s()),
+          "dense")
+
+
+ROW_BIAS_ACT, ROW_MUL, ROW_ACT_BWD, ROW_ADD_BCAST, ROW_SUM_GROUPS, ROW_OUTER, ROW_SCALE_ROWS, ROW_THRESH = range(8)
+
+
+def dropout_mask(out, p_drop, seed, stream_id, counter):
+    """keep-mask (1 with probability 1 - p_drop) from our Philox stream; advances `counter`."""
+    rand(out, seed, stream_id, counter)
+    rng_advance(counter, (out.numel() + 3) // 4)
+    rowop(ROW_THRESH, out, None, out, out.shape[0], out.shape[1], s=p_drop)
+    return out
+
+
+def rowop(op, x, y, out, M, N, rows_y=0, s=1.0):
+    check(L().jck_rowop(op, _p(x), _p(y), _p(out), M, N, rows_y, float(s), _s()), "rowop")
+
+
+def sigmoid_bce(logit, prob, target, scalars):
+    check(L().jck_sigmoid_bce(_p(logit), _p(prob), float(target), _p(scalars), prob.numel(), _s()), "sigmoid_bce")
+
+
+def logit_grad(prob, out, mode, target=0.0, scale=1.0, up=None):
+    check(L().jck_logit_grad(_p(prob), _p(up), float(target), _p(out), prob.numel(), mode, float(scale), _s()), "logit_grad")
+
+
+def i64_to_f32(x, out):
+    check(L().jck_i64_to_f32(_p(x), _p(out), x.numel(), _s()), "i64_to_f32")
+
+
+def axpy(x, y, a=1.0):
+    check(L().jck_axpy(_p(x), _p(y), float(a), x.numel(), dt(x), _s()), "axpy")
+
+
+def gp_seed(v, u, scalars, scale):
+    B = v.shape[0]
+    check(L().jck_gp_seed(_p(v), _p(u), _p(scalars), B, v.numel() // B, float(scale), dt(v), _s()), "gp_seed")
+
+
+def pack_linear(w, w_a, w_b, C, HW):
+    O, E = w.shape[0], w.shape[1] - C * HW
+    check(L().jck_pack_linear(_p(w), _p(w_a), _p(w_b), O, C, HW, E, dt(w_a), _s()), "pack_linear")
+
+
+def unpack_linear_grad(dwa, dwb, dw, C, HW, accumulate):
+    O, E = dw.shape[0], dw.shape[1] - C * HW
+    check(L().jck_unpack_linear_grad(_p(dwa), _p(dwb), _p(dw), O, C, HW, E, int(accumulate), _s()), "unpack_linear_grad")
+
+
+def bn_adj_reduce(dbar, da, y, ss, mr, sums1, asums, C, count, slope):
+    check(L().jck_bn_adj_reduce(_p(dbar), _p(da), _p(y), _p(ss), _p(mr), _p(sums1), _p(asums), y.numel() // C, C,
+                                float(count), slope, dt(y), _s()), "bn_adj_reduce")
+
+
+def bn_adj_apply(dbar, da, y, ss, mr, gamma, sums1, asums, gbar_a, ybar, C, count, slope):
+    check(L().jck_bn_adj_apply(_p(dbar), _p(da), _p(y), _p(ss), _p(mr), _p(gamma), _p(sums1), _p(asums), _p(gbar_a),
+                               _p(ybar), y.numel() // C, C, float(count), slope, dt(y), _s()), "bn_adj_apply")
+
+
+def bn_adj_param(asums, mr, dgamma, C, scale=1.0):
+    check(L().jck_bn_adj_param(_p(asums), _p(mr), _p(dgamma), C, float(scale), _s()), "bn_adj_param")

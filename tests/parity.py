@@ -156,3 +156,52 @@ def autocast_envelope(batch, nc=3, seed=12345, rng_seed=11):
 
     a, b = grads(False), grads(True)
     return {k: rel_err(b[k], a[k]) for k in a}
+
+
+def make_cgan_pair(dtype, lr, seed=12345):
+    from jck_generation_b200 import parallel
+    from jck_generation_b200.model import CGAN
+    from jck_generation_b200.train.cgan_step import CGANStep
+    from jck_generation_b200.train.optim import FusedAdam
+    g_o, d_o = omodels.build("CGAN", seed=seed)
+    osteps.inject_dropout(d_o)
+    og, od = osteps.make_optimizers(g_o, d_o, lr)
+    g = CGAN.Generator(dtype=dtype).cuda()
+    d = CGAN.Discriminator(dtype=dtype).cuda()
+    g.load_state_dict(g_o.state_dict(), strict=True)
+    d.load_state_dict(d_o.state_dict(), strict=True)
+    comm = parallel.LocalComm()
+    fg, fd = parallel.FlatParams(g), parallel.FlatParams(d)
+    opt_g = FusedAdam(g.parameters(), lr=lr, betas=[0.5, 0.999], flat=fg)
+    opt_d = FusedAdam(d.parameters(), lr=lr, betas=[0.5, 0.999], flat=fd)
+    step = CGANStep(g, d, opt_g, opt_d, fg, fd, comm)
+    return types.SimpleNamespace(g_o=g_o, d_o=d_o, og=og, od=od, g=g, d=d, fg=fg, fd=fd, opt_g=opt_g, opt_d=opt_d, step=step)
+
+
+def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11):
+    """One CGAN step (incl. the back-propagated gradient penalty) vs the oracle.  Returns {name: rel err}."""
+    P = make_cgan_pair(dtype, lr)
+    real = osteps.make_real(batch, n_steps=1)[0]
+    rng = osteps.make_rng(batch, n_steps=1, seed=rng_seed, dropout_dim=256)[0]
+    labels = osteps.one_hot(torch.randint(0, 100, (batch,), generator=torch.Generator().manual_seed(3)), 100)
+    want = osteps.cgan_step(P.g_o, P.d_o, P.og, P.od, real, labels, rng, capture=True)
+    cap = want["capture"]
+    r = to_cuda({k: v for k, v in rng.items() if k != "drop"})
+    r["drop"] = [m.cuda() for m in rng["drop"]]
+    scal = P.step.run(real.cuda(), labels.cuda(), r)
+    torch.cuda.synchronize()
+    got = P.step.summarize(scal)
+    errs = {}
+    for k in ("loss_d", "loss_g", "x_d", "z1_gd", "z2_gd", "gp", "err_real", "err_fake"):
+        errs["scalar." + k] = abs(got[k] - want[k]) / max(abs(want[k]), 1e-6)
+    errs["fake_raw"] = rel_err(P.step.last["fake_raw"], cap["fake_raw"])
+    errs["gp_grads"] = rel_err(nhwc_to_nchw(P.step.last["gp_grad_nhwc"], 3), cap["gp_grads"])
+    for (name, p) in P.d.named_parameters():
+        errs["d_grad." + name] = rel_err(p.grad, cap["d_grads"][name])
+    for (name, p) in P.g.named_parameters():
+        errs["g_grad." + name] = rel_err(p.grad, cap["g_grads"][name])
+    for tag, m, mo in (("d_state.", P.d, P.d_o), ("g_state.", P.g, P.g_o)):
+        for name, v in m.state_dict().items():
+            if not name.endswith("num_batches_tracked"):
+                errs[tag + name] = rel_err(v, mo.state_dict()[name])
+    return errs
