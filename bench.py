@@ -38,8 +38,8 @@ WORKLOAD = ("DCGAN 3x64x64 nz=100 ngf=ndf=64, 512 images/GPU/step (BASELINE conf
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
@@ -61,33 +61,70 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled every 2 ms (the timed
+    region of a default run is well under a second, shorter than one `nvidia-smi` process start); when the NVML
+    binding is missing the `nvidia-smi --query-gpu` line of B200_PROFILING.md is used instead."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.mx, self.seen, self.stop_flag, self.how = index, [], [], set(), False, "none"
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            self.nv, self.how = pynvml, "nvml, 2 ms poll"
+        except Exception:
+            self.nv = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for n, b in bits.items():
+            if r & b:
+                self.seen.add(n)
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [t.strip() for t in out.split(",")]
+        if len(c) >= 6 and c[0].isdigit():
+            self.sm.append(int(c[0]))
+            if c[1].isdigit():
+                self.mx.append(int(c[1]))
+            for i, n in enumerate(self.NAMES):
+                if c[2 + i].lower().startswith("active"):
+                    self.seen.add(n)
+            self.how = "nvidia-smi"
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nv is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002 if self.nv is not None else 0.05)
 
     def summary(self):
         self.stop_flag = True
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        self.join(timeout=6)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": [n for n in self.NAMES if n in self.seen], "samples": len(sm), "how": self.how}
 
 
 # -------------------------------------------------------------------------------------------------------

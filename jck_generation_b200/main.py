@@ -64,8 +64,12 @@ def main(args):
         data_pre.transform_data()
         trainer = DCGANTrainer(args, DCGAN.Generator(), DCGAN.Discriminator(), data_pre)
     else:
-        raise NotImplementedError("CGAN on the B200 kernels needs the second-order gradient-penalty sweep "
-                                  "(train/cgan_trainer.py:200-204); see DESIGN.md section 7")
+        from .model import CGAN
+        from .preprocess.cgan_data_preprocessor import CGANDataPreprocessor
+        from .train.cgan_trainer import CGANTrainer
+        data_pre = CGANDataPreprocessor(args)
+        data_pre.transform_data()
+        trainer = CGANTrainer(args, CGAN.Generator(), CGAN.Discriminator(), data_pre)
     trainer.train()
 
 

@@ -71,7 +71,7 @@ class CGANStep(DCGANStep):
         v = ed.trunk_backward(cc, g_a4, wgrad=False, input_grad=True)                                             # :120-127
         u = torch.zeros_like(v) if lay == ops.IMG_P4 else torch.empty_like(v)
         world_b = B * self.comm.world_size
-        ops.gp_seed(v, u, scal[S_GP], B, self.lambda_gp * 2.0 / B)                                                # :130, 201
+        ops.gp_seed(v, u, scal[S_GP], self.lambda_gp * 2.0 / B)                                                # :130, 201
         sbar, ybar = ed.adjoint_sweep(cc, u)
         dls = torch.empty(3 * B, dtype=torch.float32, device=dev)
         ops.logit_grad(ctx.prob[0:B], dls[0:B], mode=0, target=LABEL_REAL, scale=1.0 / B)

@@ -205,3 +205,31 @@ def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11):
             if not name.endswith("num_batches_tracked"):
                 errs[tag + name] = rel_err(v, mo.state_dict()[name])
     return errs
+
+
+def cgan_trajectory(dtype, batch=8, steps=12, lr=2e-4, real=None, labels=None, rng=None, teacher_forced=False):
+    """Loss trajectories of the CGAN step on both sides (see dcgan_trajectory)."""
+    P = make_cgan_pair(dtype, lr)
+    real = real or osteps.make_real(batch, n_steps=steps)
+    rng = rng or osteps.make_rng(batch, n_steps=steps, seed=777, dropout_dim=256)
+    if labels is None:
+        gen = torch.Generator().manual_seed(31337)
+        labels = [osteps.one_hot(torch.randint(0, 100, (batch,), generator=gen), 100) for _ in range(steps)]
+    got, want = [], []
+    for i in range(steps):
+        if teacher_forced and i > 0:
+            P.g.load_state_dict(P.g_o.state_dict())
+            P.d.load_state_dict(P.d_o.state_dict())
+            for opt_o, flat in ((P.og, P.fg), (P.od, P.fd)):
+                sd = opt_o.state_dict()
+                for idx, (o, k) in enumerate(flat.offsets):
+                    flat.exp_avg[o:o + k].copy_(sd["state"][idx]["exp_avg"].reshape(-1))
+                    flat.exp_avg_sq[o:o + k].copy_(sd["state"][idx]["exp_avg_sq"].reshape(-1))
+            P.step.eg.refresh(force=True)
+            P.step.ed.refresh(force=True)
+        w = osteps.cgan_step(P.g_o, P.d_o, P.og, P.od, real[i], labels[i], rng[i])
+        r = to_cuda({k: v for k, v in rng[i].items() if k != "drop"})
+        r["drop"] = [m.cuda() for m in rng[i]["drop"]]
+        got.append(P.step.summarize(P.step.run(real[i].cuda(), labels[i].cuda(), r)))
+        want.append(w)
+    return got, want, P

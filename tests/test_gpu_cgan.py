@@ -1,0 +1,103 @@
+"""Parity of the CGAN G+D train step (reference train/cgan_trainer.py:173-213, model/CGAN.py:79-162) on the
+GPU against the CPU oracle.  The discriminator update back-propagates the gradient penalty, so D's gradients
+contain second-order terms (conv / BatchNorm / LeakyReLU / Linear / Dropout / Sigmoid double backward): the
+fp32 tests pin every one of them to <= 1e-4, through the same C ABI the trainer uses."""
+import argparse
+import json
+import os
+
+import pytest
+import torch
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+POST_UPDATE = ("scalar.z2_gd", "scalar.loss_g")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as entry
+    entry.build()
+
+
+@pytest.fixture(scope="module")
+def fp32_errs():
+    return parity.cgan_step_parity(torch.float32, batch=8)
+
+
+def test_fp32_losses_penalty_and_gradients(fp32_errs):
+    for k, v in fp32_errs.items():
+        if k.startswith(("d_grad", "g_grad", "gp_grads", "fake_raw", "scalar")):
+            assert v <= (1e-3 if k in POST_UPDATE else 1e-4), f"{k}: {v}"
+
+
+def test_fp32_post_step_state(fp32_errs):
+    for k, v in fp32_errs.items():
+        if k.startswith(("d_state", "g_state")):
+            assert v <= 2e-4, f"{k}: {v}"
+
+
+def test_fp32_trajectory_matches_reference_golden(golden_dir):
+    """12 free-running steps at lr 2e-4 on the golden inputs: against the live oracle and against the losses
+    frozen from the unmodified reference trainer (tests/golden/cgan_b8_lr2e-4.json)."""
+    from oracle import make_golden
+    with open(os.path.join(golden_dir, "cgan_b8_lr2e-4.json")) as f:
+        gold = json.load(f)
+    n = gold["case"]["steps"]
+    real, labels, rng, _, _ = make_golden.cgan_inputs(gold["case"]["batch"], n)
+    got, want, _ = parity.cgan_trajectory(torch.float32, batch=8, steps=n, lr=gold["case"]["lr"], real=real, labels=labels, rng=rng)
+    for i in range(n):
+        assert got[i]["loss_d"] == pytest.approx(want[i]["loss_d"], rel=5e-3, abs=5e-3), i
+        assert got[i]["loss_g"] == pytest.approx(want[i]["loss_g"], rel=5e-3, abs=5e-3), i
+        assert got[i]["loss_d"] == pytest.approx(gold["losses_d"][i], rel=5e-3, abs=5e-3), i
+        assert got[i]["loss_g"] == pytest.approx(gold["losses_g"][i], rel=5e-3, abs=5e-3), i
+
+
+def test_bf16_step_scalars():
+    """tcgen05 mode: forward-side quantities of the step (losses, D outputs, the generated image)."""
+    e = parity.cgan_step_parity(torch.bfloat16, batch=8)
+    assert e["fake_raw"] <= 2e-2, e["fake_raw"]
+    for k in ("scalar.err_real", "scalar.err_fake", "scalar.loss_g", "scalar.x_d", "scalar.z1_gd"):
+        assert e[k] <= 3e-2, f"{k}: {e[k]}"
+    assert e["scalar.gp"] <= 1e-1, e["scalar.gp"]
+
+
+def test_module_api_forward_matches_oracle():
+    """Reference-style calls: G(z, labels), D(x, labels) in eval-free train mode with an injected dropout mask."""
+    from jck_generation_b200.model import CGAN
+    from oracle import models as omodels
+    g_o, d_o = omodels.build("CGAN", seed=12345)
+    g = CGAN.Generator(dtype=torch.float32).cuda()
+    g.load_state_dict(g_o.state_dict())
+    B = 4
+    z = torch.randn(B, 100, 1, 1, generator=torch.Generator().manual_seed(3))
+    lab = torch.nn.functional.one_hot(torch.tensor([3, 14, 15, 92]), 100)
+    want = g_o(z, lab)
+    got = g(z.cuda(), lab.cuda())
+    assert parity.rel_err(got, want) < 1e-4
+    d = CGAN.Discriminator(dtype=torch.float32).cuda()
+    assert list(d.state_dict()) == list(d_o.state_dict())
+    out = d(got.detach(), lab.cuda())
+    assert out.shape == (B, 1) and bool(((out > 0) & (out < 1)).all())
+
+
+def test_trainer_runs_and_checkpoints(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from jck_generation_b200.model import CGAN
+    from jck_generation_b200.preprocess.cgan_data_preprocessor import CGANDataPreprocessor
+    from jck_generation_b200.train.cgan_trainer import CGANTrainer
+    args = argparse.Namespace(epoch=1, max_learning_rate=2e-4, model_path="t", log_file=0, batch_size=16, num_worker=0,
+                              synthetic=1, synthetic_batches=4, dtype="fp32", cuda_graph=0, metrics=0, save_path=str(tmp_path))
+    data = CGANDataPreprocessor(args); data.transform_data()
+    tr = CGANTrainer(args, CGAN.Generator(), CGAN.Discriminator(), data)
+    losses_d, losses_g = tr.train()
+    assert len(losses_d) == 4 and all(map(lambda v: v == v and abs(v) < 200, losses_d + losses_g))
+    tr.save_model("fid", 4, 1.0, 2.0, 3.0, torch.zeros(4, 3, 64, 64))
+    ck = torch.load(os.path.join(tr.model_save_path, "fid", "4_1.0000_2.0000_3.0000.pt"))
+    assert set(ck) == {"model_g", "model_d", "optimizer_g", "optimizer_d"}
+    assert "linear1.weight" in ck["model_d"] and "label_embedding.weight" in ck["model_d"]
+    x = torch.rand(8, 3, 64, 64, device="cuda")
+    lab = torch.nn.functional.one_hot(torch.arange(8), 100).cuda()
+    assert tr.compute_gradient_penalty(x, x.flip(0), lab).item() >= 0
