@@ -178,12 +178,13 @@ def make_cgan_pair(dtype, lr, seed=12345):
     return types.SimpleNamespace(g_o=g_o, d_o=d_o, og=og, od=od, g=g, d=d, fg=fg, fd=fd, opt_g=opt_g, opt_d=opt_d, step=step)
 
 
-def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11):
+def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11, real=None, labels=None, rng=None):
     """One CGAN step (incl. the back-propagated gradient penalty) vs the oracle.  Returns {name: rel err}."""
     P = make_cgan_pair(dtype, lr)
-    real = osteps.make_real(batch, n_steps=1)[0]
-    rng = osteps.make_rng(batch, n_steps=1, seed=rng_seed, dropout_dim=256)[0]
-    labels = osteps.one_hot(torch.randint(0, 100, (batch,), generator=torch.Generator().manual_seed(3)), 100)
+    real = real if real is not None else osteps.make_real(batch, n_steps=1)[0]
+    rng = rng if rng is not None else osteps.make_rng(batch, n_steps=1, seed=rng_seed, dropout_dim=256)[0]
+    if labels is None:
+        labels = osteps.one_hot(torch.randint(0, 100, (batch,), generator=torch.Generator().manual_seed(3)), 100)
     want = osteps.cgan_step(P.g_o, P.d_o, P.og, P.od, real, labels, rng, capture=True)
     cap = want["capture"]
     r = to_cuda({k: v for k, v in rng.items() if k != "drop"})

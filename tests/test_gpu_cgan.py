@@ -40,19 +40,31 @@ def test_fp32_post_step_state(fp32_errs):
 
 
 def test_fp32_trajectory_matches_reference_golden(golden_dir):
-    """12 free-running steps at lr 2e-4 on the golden inputs: against the live oracle and against the losses
-    frozen from the unmodified reference trainer (tests/golden/cgan_b8_lr2e-4.json)."""
+    """12 steps at lr 2e-4 on the golden inputs (tests/golden/cgan_b8_lr2e-4.json, frozen from the unmodified
+    reference trainer).  The CGAN trajectory is chaotic: a 1e-6 relative perturbation of the real batch moves
+    the ORACLE's own D gradients by 5e-3 and its G gradients by 4e-2 within one step (LeakyReLU masks of
+    near-zero pre-activations flip, Adam's first updates are sign-like), and the oracle run on another CPU is
+    1.5 % off the frozen losses by step 11.  So: teacher-forced (every step starts from the oracle's state) all
+    12 steps are tight; free-running the first steps are tight and the rest stay within the chaos envelope."""
     from oracle import make_golden
     with open(os.path.join(golden_dir, "cgan_b8_lr2e-4.json")) as f:
         gold = json.load(f)
     n = gold["case"]["steps"]
     real, labels, rng, _, _ = make_golden.cgan_inputs(gold["case"]["batch"], n)
-    got, want, _ = parity.cgan_trajectory(torch.float32, batch=8, steps=n, lr=gold["case"]["lr"], real=real, labels=labels, rng=rng)
+    kw = dict(batch=8, steps=n, lr=gold["case"]["lr"], real=real, labels=labels, rng=rng)
+    got, want, _ = parity.cgan_trajectory(torch.float32, teacher_forced=True, **kw)
     for i in range(n):
-        assert got[i]["loss_d"] == pytest.approx(want[i]["loss_d"], rel=5e-3, abs=5e-3), i
-        assert got[i]["loss_g"] == pytest.approx(want[i]["loss_g"], rel=5e-3, abs=5e-3), i
-        assert got[i]["loss_d"] == pytest.approx(gold["losses_d"][i], rel=5e-3, abs=5e-3), i
-        assert got[i]["loss_g"] == pytest.approx(gold["losses_g"][i], rel=5e-3, abs=5e-3), i
+        for k in ("loss_d", "loss_g", "gp", "err_real", "err_fake", "x_d", "z1_gd"):
+            assert got[i][k] == pytest.approx(want[i][k], rel=1e-3, abs=1e-4), (i, k)
+    assert got[0]["loss_d"] == pytest.approx(gold["losses_d"][0], rel=1e-3)
+    assert got[0]["loss_g"] == pytest.approx(gold["losses_g"][0], rel=1e-3)
+    got, want, _ = parity.cgan_trajectory(torch.float32, **kw)
+    for i in range(n):
+        tol = 5e-3 if i < 4 else 6e-2
+        assert got[i]["loss_d"] == pytest.approx(want[i]["loss_d"], rel=tol, abs=tol), i
+        assert got[i]["loss_g"] == pytest.approx(want[i]["loss_g"], rel=tol, abs=tol), i
+        assert got[i]["loss_d"] == pytest.approx(gold["losses_d"][i], rel=tol, abs=tol), i
+        assert got[i]["loss_g"] == pytest.approx(gold["losses_g"][i], rel=tol, abs=tol), i
 
 
 def test_bf16_step_scalars():
