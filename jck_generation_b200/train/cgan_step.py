@@ -31,8 +31,9 @@ class CGANStep(DCGANStep):
         r["drop_abc"] = masks[:3 * B]
         return r
 
-    def run(self, real, labels, rng=None):
-        """real [B,nc,64,64] fp32, labels [B,n_classes] one-hot (int64 or fp32) on the device."""
+    def run(self, real, labels, rng=None, after_d_update=None):
+        """real [B,nc,64,64] fp32, labels [B,n_classes] one-hot (int64 or fp32) on the device.
+        `after_d_update` (parity tests only) is called right after optimizer_d.step()."""
         ed, eg = self.ed, self.eg
         B = real.shape[0]
         dev, dt = self.dev, self.dtype
@@ -82,6 +83,8 @@ class CGANStep(DCGANStep):
         ed.trunk_backward(ctx, da4, wgrad=True, input_grad=False, accumulate=True, inject=ybar, inject_rows=(2 * B, 3 * B))  # :203
         self.comm.allreduce_mean_(self.flat_d.grad)
         self.opt_d.step()                                                                                         # :204
+        if after_d_update is not None:
+            after_d_update()
         ed.refresh(force=True)
 
         # ---- G update ---------------------------------------------------------------------------------------------

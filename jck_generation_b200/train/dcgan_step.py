@@ -58,9 +58,10 @@ class DCGANStep:
         return r
 
     # ---- the step ------------------------------------------------------------------------------------
-    def run(self, real, rng=None):
+    def run(self, real, rng=None, after_d_update=None):
         """real: [B,nc,64,64] fp32 on the device (this rank's rows).  Returns a [4,2] fp32 device tensor:
-        rows (real, fake, gp, g), columns (BCE mean | GP value, mean D output) -- local-batch means."""
+        rows (real, fake, gp, g), columns (BCE mean | GP value, mean D output) -- local-batch means.
+        `after_d_update` (parity tests only) is called right after optimizer_d.step()."""
         ed, eg = self.ed, self.eg
         B = real.shape[0]
         dev, dt = self.dev, self.dtype
@@ -96,6 +97,8 @@ class DCGANStep:
 
         self.comm.allreduce_mean_(self.flat_d.grad)
         self.opt_d.step()                                                                                  # :180
+        if after_d_update is not None:
+            after_d_update()
         ed.refresh(force=True)
 
         ctx2 = ed.trunk_forward(X[B:2 * B], groups=1)                                                      # :185

@@ -30,6 +30,15 @@ def _tap(taps, name, y):
         taps[name] = y
 
 
+def _bn_act(taps, name, norm, act, y):
+    """BatchNorm then the (in-place) activation; with taps, also records the BatchNorm output -- the
+    pre-activation whose sign decides the LeakyReLU / ReLU branch -- under ``name + ".pre"``."""
+    pre = norm(y)
+    if taps is not None:
+        taps[name + ".pre"] = pre.detach().clone()
+    return act(pre)
+
+
 class DcganDiscriminator(nn.Module):
     """DCGAN.py:6-35 -- 4x (Conv k4 s2 p1 -> BN -> LeakyReLU .2), Conv k4 s1 p0, Sigmoid."""
 
@@ -48,7 +57,7 @@ class DcganDiscriminator(nn.Module):
         for c, n, r in _stack_names(4):
             y = getattr(self, c)(h)
             _tap(taps, c, y)
-            h = getattr(self, r)(getattr(self, n)(y))
+            h = _bn_act(taps, c, getattr(self, n), getattr(self, r), y)
         return h
 
     def forward(self, x, taps=None):
@@ -74,7 +83,7 @@ class DcganGenerator(nn.Module):
         for c, n, r in _stack_names(4):
             y = getattr(self, c)(h)
             _tap(taps, c, y)
-            h = getattr(self, r)(getattr(self, n)(y))
+            h = _bn_act(taps, c, getattr(self, n), getattr(self, r), y)
         y = self.conv5(h)
         _tap(taps, "conv5", y)
         return self.tanh(y)
@@ -105,7 +114,7 @@ class CganDiscriminator(nn.Module):
         for c, n, r in _stack_names(4):
             y = getattr(self, c)(h)
             _tap(taps, c, y)
-            h = getattr(self, r)(getattr(self, n)(y))
+            h = _bn_act(taps, c, getattr(self, n), getattr(self, r), y)
         joined = torch.cat([self.flatten(h), lab], dim=1)
         return self.sigmoid(self.linear2(self.drop1(self.linear1(joined))))
 

@@ -107,16 +107,16 @@ def dcgan_step(g, d, opt_g, opt_d, real, rng, capture=False):
     err_d = err_real + err_fake + LAMBDA_GP * gp
     if capture:
         cap["d_grads"] = _param_grads(d)
-        cap["d_acts"] = {"A": {k: v.detach().clone() for k, v in taps_a.items()},
-                         "B": {k: v.detach().clone() for k, v in taps_b.items()},
-                         "C": {k: v.detach().clone() for k, v in taps_c.items()}}
-        cap["d_act_grads"] = {"A": {k: v.grad.detach().clone() for k, v in taps_a.items()},
-                              "B": {k: v.grad.detach().clone() for k, v in taps_b.items()}}
+        cap["d_acts"] = {"A": {k: v.detach().clone() for k, v in taps_a.items() if not k.endswith('.pre')},
+                         "B": {k: v.detach().clone() for k, v in taps_b.items() if not k.endswith('.pre')},
+                         "C": {k: v.detach().clone() for k, v in taps_c.items() if not k.endswith('.pre')}}
+        cap["d_act_grads"] = {"A": {k: v.grad.detach().clone() for k, v in taps_a.items() if not k.endswith('.pre')},
+                              "B": {k: v.grad.detach().clone() for k, v in taps_b.items() if not k.endswith('.pre')}}
         cap["p_real"], cap["p_fake"], cap["p_hat"] = (p_real.detach().clone(), p_fake.detach().clone(),
                                                       p_hat.detach().view(-1).clone())
         cap["gp_grads"] = gp_grads.detach().clone()
         cap["fake_raw"] = fake_raw.detach().clone()
-        cap["g_acts"] = {k: v.detach().clone() for k, v in taps_g.items()}
+        cap["g_acts"] = {k: v.detach().clone() for k, v in taps_g.items() if not k.endswith('.pre')}
     opt_d.step()
 
     # ---- G step (D) :182-189
@@ -129,10 +129,12 @@ def dcgan_step(g, d, opt_g, opt_d, real, rng, capture=False):
     out["z2_gd"] = p_g.mean().item()
     if capture:
         cap["g_grads"] = _param_grads(g)
-        cap["g_act_grads"] = {k: v.grad.detach().clone() for k, v in taps_g.items()}
-        cap["d_acts"]["D"] = {k: v.detach().clone() for k, v in taps_d.items()}
-        cap["d_act_grads"]["D"] = {k: v.grad.detach().clone() for k, v in taps_d.items()}
+        cap["g_act_grads"] = {k: v.grad.detach().clone() for k, v in taps_g.items() if not k.endswith('.pre')}
+        cap["d_acts"]["D"] = {k: v.detach().clone() for k, v in taps_d.items() if not k.endswith('.pre')}
+        cap["d_act_grads"]["D"] = {k: v.grad.detach().clone() for k, v in taps_d.items() if not k.endswith('.pre')}
         cap["p_g"] = p_g.detach().clone()
+        cap["pre"] = {tag: {k[:-4]: v for k, v in t.items() if k.endswith('.pre')}
+                      for tag, t in (("A", taps_a), ("B", taps_b), ("C", taps_c), ("D", taps_d), ("G", taps_g))}
     opt_g.step()
 
     out.update(loss_d=err_d.item(), loss_g=err_g.item(), gp=gp.item(),
@@ -181,21 +183,22 @@ def cgan_step(g, d, opt_g, opt_d, real, labels, rng, capture=False):
     label = torch.full((b,), LABEL_REAL, dtype=torch.float32)
     real_n = 0.9 * real + 0.1 * rng["noise_real"]                       # :182
     set_mask(0)
-    p_real = d(real_n, labels.detach()).view(-1)                        # :184
+    taps = {t: ({} if capture else None) for t in "ABCDG"}
+    p_real = d(real_n, labels.detach(), taps=taps["A"]).view(-1)        # :184
     err_real = bce(p_real, label)
     out["x_d"] = p_real.mean().item()
 
-    fake_raw = g(rng["z"], labels.detach())                             # :190
+    fake_raw = g(rng["z"], labels.detach(), taps=taps["G"])             # :190
     label = torch.full((b,), LABEL_FAKE, dtype=torch.float32)           # :191
     fake = 0.9 * fake_raw + 0.1 * rng["noise_fake"]
     set_mask(1)
-    p_fake = d(fake.detach(), labels.detach()).view(-1)                 # :194
+    p_fake = d(fake.detach(), labels.detach(), taps=taps["B"]).view(-1)  # :194
     err_fake = bce(p_fake, label)
     out["z1_gd"] = p_fake.mean().item()
 
     set_mask(2)
     gp, x_hat, p_hat, gp_grads = gradient_penalty(d, real_n.detach(), fake.detach(), rng["alpha"],
-                                                  d_args=(labels.detach(),))   # :200
+                                                  d_args=(labels.detach(),), taps=taps["C"])   # :200
     err_d = err_real.mean() + err_fake.mean() + LAMBDA_GP * gp          # :201
     err_d.backward()                                                    # :203 -- second order through D
     if capture:
@@ -209,13 +212,14 @@ def cgan_step(g, d, opt_g, opt_d, real, labels, rng, capture=False):
     g.zero_grad()
     label.fill_(LABEL_REAL)
     set_mask(3)
-    p_g = d(fake, labels).view(-1)                                      # :209
+    p_g = d(fake, labels, taps=taps["D"]).view(-1)                      # :209
     err_g = bce(p_g, label)
     err_g.backward()
     out["z2_gd"] = p_g.mean().item()
     if capture:
         cap["g_grads"] = _param_grads(g)
         cap["p_g"] = p_g.detach().clone()
+        cap["pre"] = {tag: {k[:-4]: v for k, v in t.items() if k.endswith('.pre')} for tag, t in taps.items()}
     opt_g.step()
 
     out.update(loss_d=err_d.item(), loss_g=err_g.item(), gp=gp.item(),

@@ -49,8 +49,54 @@ def to_cuda(rng):
     return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in rng.items()}
 
 
-def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11):
-    """One step, everything compared.  Returns {name: relative error}."""
+def _d_update_sync(P, errs):
+    """Callback for `after_d_update`: record the error of D's freshly updated parameters, then overwrite them
+    with the oracle's.  Adam's first update is lr*sign(g)-like, so the handful of weights whose gradient is
+    below rounding noise move by 2*lr the other way; everything computed afterwards in the same step (pass D,
+    the generator's gradients) would then measure that coin toss instead of the kernels.  With D synchronised
+    here the rest of the step is compared tightly."""
+    def cb():
+        for (name, p), po in zip(P.d.named_parameters(), P.d_o.parameters()):
+            errs["d_state." + name] = rel_err(p.detach(), po.detach())
+            p.data.copy_(po.detach().to(p.device))
+    return cb
+
+
+def _kink_flips(last, pre, batch, errs):
+    """Elements whose LeakyReLU / ReLU branch differs between the two sides.  A pre-activation within rounding
+    distance of zero takes either branch depending on the summation order of the convolution before it (the
+    oracle itself differs here from one CPU model to the next); ONE flipped element moves the gradients of a
+    whole step by ~1/sqrt(N) ~ 1e-3.  errs["kink.flips"] counts them, errs["kink.worst_pre"] is the largest
+    |pre-activation| among them (it must be rounding-small, else it is a bug, not a coin toss)."""
+    n, worst = 0, 0.0
+    ctx = last["ctx"]
+    sides = [(tag, {k: ctx.a[k][gi * batch:(gi + 1) * batch] for k in range(1, 5)}) for gi, tag in enumerate("ABC")]
+    sides.append(("D", last["ctx_d"].a))
+    sides.append(("G", last["ctx_g"].a))
+    for tag, acts in sides:
+        for k in range(1, 5):
+            want = pre[tag][f"conv{k}"]
+            m = (nhwc_to_nchw(acts[k]).cpu() > 0) != (want > 0)
+            if bool(m.any()):
+                n += int(m.sum())
+                worst = max(worst, float(want[m].abs().max()))
+    errs["kink.flips"], errs["kink.worst_pre"] = float(n), worst
+
+
+def first_clean(fn, seeds=(11, 12, 13, 14, 15, 16, 17, 18), **kw):
+    """Run a *_step_parity function over `seeds` until a draw has no kink flip (see _kink_flips); every skipped
+    draw must only have flipped rounding-small pre-activations."""
+    for s in seeds:
+        errs = fn(rng_seed=s, **kw)
+        if errs["kink.flips"] == 0:
+            errs["kink.seed"] = float(s)
+            return errs
+        assert errs["kink.worst_pre"] < 1e-4, f"seed {s}: activation branch differs at |pre| = {errs['kink.worst_pre']}"
+    raise AssertionError(f"no draw without a LeakyReLU/ReLU kink flip among seeds {seeds}")
+
+
+def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11, sync_d=True):
+    """One step, everything compared.  Returns {name: relative error}.  `sync_d`: see _d_update_sync."""
     P = make_pair(dtype, lr, nc=nc)
     real = osteps.make_real(batch, nc=nc, n_steps=1)[0]
     rng = osteps.make_rng(batch, nc=nc, n_steps=1, seed=rng_seed)[0]
@@ -58,10 +104,10 @@ def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11):
     cap = want["capture"]
 
     # D gradients are those of passes A+B (the G step does not recompute D's weight gradient)
-    scal = P.step.run(real.cuda(), to_cuda(rng))
+    errs = {}
+    scal = P.step.run(real.cuda(), to_cuda(rng), after_d_update=_d_update_sync(P, errs) if sync_d else None)
     torch.cuda.synchronize()
     got = P.step.summarize(scal)
-    errs = {}
     for k in ("loss_d", "loss_g", "x_d", "z1_gd", "z2_gd", "gp", "err_real", "err_fake"):
         errs["scalar." + k] = abs(got[k] - want[k]) / max(abs(want[k]), 1e-6)
 
@@ -77,15 +123,16 @@ def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11):
         errs[f"g_act.conv{k}"] = rel_err(nhwc_to_nchw(last["ctx_g"].y[k], nc), cap["g_acts"][f"conv{k}"])
     errs["fake_raw"] = rel_err(last["fake_raw"], cap["fake_raw"])
     errs["gp_grads"] = rel_err(nhwc_to_nchw(last["gp_grad_nhwc"], nc), cap["gp_grads"])
+    _kink_flips(last, cap["pre"], batch, errs)
     for (name, p) in P.d.named_parameters():
         errs["d_grad." + name] = rel_err(p.grad, cap["d_grads"][name])
     for (name, p) in P.g.named_parameters():
         errs["g_grad." + name] = rel_err(p.grad, cap["g_grads"][name])
     for name, v in P.d.state_dict().items():
-        if not name.endswith("num_batches_tracked"):
-            errs["d_state." + name] = rel_err(v, P.d_o.state_dict()[name])
-        else:
+        if name.endswith("num_batches_tracked"):
             errs["d_state." + name] = float(abs(int(v) - int(P.d_o.state_dict()[name])))
+        elif "d_state." + name not in errs:         # parameters were compared inside the callback
+            errs["d_state." + name] = rel_err(v, P.d_o.state_dict()[name])
     for name, v in P.g.state_dict().items():
         if not name.endswith("num_batches_tracked"):
             errs["g_state." + name] = rel_err(v, P.g_o.state_dict()[name])
@@ -119,8 +166,8 @@ def dcgan_trajectory(dtype, batch=8, steps=20, lr=2e-4, teacher_forced=False, re
 
 def smoke_check():
     """Used by __graft_entry__.smoke(): one tiny step in each arithmetic mode vs the oracle."""
-    e32 = dcgan_step_parity(torch.float32, batch=4)
-    worst32 = max(e32.items(), key=lambda kv: kv[1])
+    e32 = first_clean(dcgan_step_parity, dtype=torch.float32, batch=4)
+    worst32 = max(((k, v) for k, v in e32.items() if not k.startswith("kink.")), key=lambda kv: kv[1])
     assert worst32[1] < 2e-3, f"fp32 path off the oracle: {worst32}"
     e16 = dcgan_step_parity(torch.bfloat16, batch=8)
     for k in ("scalar.loss_d", "scalar.loss_g", "g_act.conv3", "d_act.A.conv3", "fake_raw"):
@@ -178,7 +225,7 @@ def make_cgan_pair(dtype, lr, seed=12345):
     return types.SimpleNamespace(g_o=g_o, d_o=d_o, og=og, od=od, g=g, d=d, fg=fg, fd=fd, opt_g=opt_g, opt_d=opt_d, step=step)
 
 
-def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11, real=None, labels=None, rng=None):
+def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11, real=None, labels=None, rng=None, sync_d=True):
     """One CGAN step (incl. the back-propagated gradient penalty) vs the oracle.  Returns {name: rel err}."""
     P = make_cgan_pair(dtype, lr)
     real = real if real is not None else osteps.make_real(batch, n_steps=1)[0]
@@ -189,21 +236,22 @@ def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11, real=None, labels=Non
     cap = want["capture"]
     r = to_cuda({k: v for k, v in rng.items() if k != "drop"})
     r["drop"] = [m.cuda() for m in rng["drop"]]
-    scal = P.step.run(real.cuda(), labels.cuda(), r)
+    errs = {}
+    scal = P.step.run(real.cuda(), labels.cuda(), r, after_d_update=_d_update_sync(P, errs) if sync_d else None)
     torch.cuda.synchronize()
     got = P.step.summarize(scal)
-    errs = {}
     for k in ("loss_d", "loss_g", "x_d", "z1_gd", "z2_gd", "gp", "err_real", "err_fake"):
         errs["scalar." + k] = abs(got[k] - want[k]) / max(abs(want[k]), 1e-6)
     errs["fake_raw"] = rel_err(P.step.last["fake_raw"], cap["fake_raw"])
     errs["gp_grads"] = rel_err(nhwc_to_nchw(P.step.last["gp_grad_nhwc"], 3), cap["gp_grads"])
+    _kink_flips(P.step.last, cap["pre"], batch, errs)
     for (name, p) in P.d.named_parameters():
         errs["d_grad." + name] = rel_err(p.grad, cap["d_grads"][name])
     for (name, p) in P.g.named_parameters():
         errs["g_grad." + name] = rel_err(p.grad, cap["g_grads"][name])
     for tag, m, mo in (("d_state.", P.d, P.d_o), ("g_state.", P.g, P.g_o)):
         for name, v in m.state_dict().items():
-            if not name.endswith("num_batches_tracked"):
+            if not name.endswith("num_batches_tracked") and tag + name not in errs:
                 errs[tag + name] = rel_err(v, mo.state_dict()[name])
     return errs
 
