@@ -35,8 +35,10 @@ def test_fp32_losses_penalty_and_gradients(fp32_errs):
 
 def test_fp32_post_step_state(fp32_errs):
     for k, v in fp32_errs.items():
-        if k.startswith(("d_state", "g_state")):
-            assert v <= 2e-4, f"{k}: {v}"
+        if k.startswith(("d_state", "g_state")):      # see tests/parity.py:_adam_dev
+            assert v <= 2e-3, f"{k}: {v}"
+        elif k.startswith("updmax."):
+            assert v <= 2.01, f"{k}: {v}"
 
 
 def test_fp32_trajectory_matches_reference_golden(golden_dir):

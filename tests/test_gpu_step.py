@@ -53,9 +53,11 @@ def test_fp32_post_step_state(fp32_errs):
         if k.endswith("num_batches_tracked"):
             assert v == 0, k
         elif k.startswith(("d_state", "g_state")):
-            # weights after one Adam step: the update is lr*sign-like, so tiny gradient errors on
-            # near-zero gradients show up at the 1e-4 level of the *weights' change*, not the weights
-            assert v <= 2e-4, f"{k}: {v}"
+            # parameters: fraction of elements further than 2 % of lr from the oracle's (Adam's sign-like first
+            # update on gradients below rounding noise, tests/parity.py:_adam_dev); BN running buffers: rel err
+            assert v <= 2e-3, f"{k}: {v}"
+        elif k.startswith("updmax."):
+            assert v <= 2.01, f"{k}: {v}"
 
 
 def test_bf16_activations(bf16_errs):
