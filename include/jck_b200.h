@@ -91,6 +91,24 @@ int jck_conv_down(const void* in_large, const void* w_down, void* out_small, flo
                   int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
 int jck_conv_up(const void* in_small, const void* w_up, void* out_large, float* stats, int B, int Hs,
                 int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
+/* Input-gradient convolution with the BatchNorm-backward REDUCTION of the layer below fused into its epilogue
+ * (bf16 / tcgen05 only; returns JCK_E_UNSUPPORTED_SHAPE otherwise -- callers then use jck_conv_up / jck_conv_down
+ * followed by jck_bn_act_bwd_reduce).  With y_saved = that layer's raw conv output (same shape as the result) and
+ * its statistics, the epilogue forms, from the fp32 accumulators,
+ *     g = acc * act'(y*scale + shift),   sums[group][0:C] += sum g,   sums[group][C:2C] += sum g * xhat
+ * and stores g (out_g), i.e. what jck_bn_act_bwd_apply consumes with slope = 1.
+ * Replaces: autograd of nn.Conv2d / nn.ConvTranspose2d followed by native_batch_norm_backward's reduction
+ * (model/DCGAN.py:30-33 and :62-65 under loss.backward(), train/dcgan_trainer.py:164,175,187). */
+int jck_conv_up_bnbwd(const void* in_small, const void* w_up, const void* y_saved, const float* scale_shift,
+                      const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws, int Ca,
+                      int Cb, int imgs_per_group, int dtype, void* stream);
+int jck_conv_down_bnbwd(const void* in_large, const void* w_down, const void* y_saved, const float* scale_shift,
+                        const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws, int Ca,
+                        int Cb, int imgs_per_group, int dtype, void* stream);
+int jck_edge_down_bnbwd(const void* patches, const void* w_down_e, const void* y_saved, const float* scale_shift,
+                        const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws, int Ca,
+                        int imgs_per_group, void* stream);
+
 /* dw4[Ca][Cb][4][4] (+)= sum over pixels small (x) large.  workspace: jck_conv_wgrad_workspace_bytes. */
 size_t jck_conv_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo);
 int jck_conv_wgrad(const void* small, const void* large, float* dw4, void* workspace, size_t workspace_bytes,

@@ -331,14 +331,26 @@ struct PersistSmem {
     static constexpr int kStage = kABytes + kBBytes;
     static constexpr int kBarOff = STAGES * kStage;
     static constexpr int kRedOff = kBarOff + 512;
-    static constexpr int kTotal = kRedOff + 2 * 4 * 2 * BN_ * 4 + 1024;
+    static constexpr int kCoefOff = kRedOff + 2 * 4 * 2 * BN_ * 4;
+    static constexpr int kTotal = kCoefOff + 2 * 4 * BN_ * 4 + 1024;
 };
 
-template <int BN_, int STAGES, int MODE, int EPI>   // EPI = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two, splitting the columns)
-__global__ void __launch_bounds__(64 + 32 * EPI, 1)
+// Epilogue mode 1 = BatchNorm-backward reduction fused into the input-gradient convolution that produces
+// d/d(activation): with the layer's saved raw output y and its statistics, the epilogue forms
+//   g = acc * act'(y*scale + shift),   sums += (sum g, sum g * xhat),   xhat = (y - mean) * rstd
+// from the fp32 accumulators and stores g, so the separate reduce pass over (da, y) disappears.
+struct BnBwdEpi {
+    const __nv_bfloat16* y;   // saved raw conv output, same shape as `out`
+    const float* ss;          // [groups][2C] scale | shift
+    const float* mr;          // [groups][2C] mean | rstd
+    float slope;              // LeakyReLU slope (0 = ReLU)
+};
+
+template <int BN_, int STAGES, int MODE, int EPI, int EPIM>   // EPI = epilogue warps: 4 (one per TMEM lane quarter) or 8 (two, splitting the columns)
+__global__ void __launch_bounds__(64 + 32 * EPI, EPI == 4 ? 2 : 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                        __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p,
-                       const int n_tiles, const int total_tiles) {
+                       const int n_tiles, const int total_tiles, const BnBwdEpi bb) {
     constexpr bool kUp = (MODE == kUpM);
     constexpr int kAccCols = BN_ < 32 ? 32 : BN_;
     using L = PersistSmem<BN_, STAGES>;
@@ -350,6 +362,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     uint64_t* tempty = tfull + 2;         // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* red = reinterpret_cast<float*>(smem + L::kRedOff);  // [2][4 warps][2][BN_]
+    float* coef = reinterpret_cast<float*>(smem + L::kCoefOff); // [2][scale|shift|mean|rstd][BN_]  (EPIM == 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Cin = (MODE == kUpM || MODE == kEdgeUp) ? p.Ca : p.Cb;
@@ -459,6 +472,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             const bool valid = n < p.B;
             const int acc = lt & 1;
             const uint32_t tmem_d = tmem_base + acc * kAccCols + ((uint32_t)(wq * 32) << 16);
+            float* cf = coef + (lt & 1) * (4 * BN_);
+            if constexpr (EPIM == 1) {
+                // this tile's BatchNorm coefficients -> smem while the MMAs of the tile are still running
+                const size_t gofs = (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
+                for (int i = threadIdx.x - 64; i < 4 * BN_; i += 32 * EPI) {
+                    const int which = i / BN_, cc = i - which * BN_;
+                    cf[i] = ((which < 2) ? bb.ss : bb.mr)[gofs + (which & 1) * Cout + cc];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+            }
             mbar_wait(&tfull[acc], (lt >> 1) & 1);
             fence_after_sync();
             if constexpr (MODE == kEdgeUp) {
@@ -496,6 +519,28 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                         fence_before_sync();
                         mbar_arrive(&tempty[acc]);
                     }
+                    float sq[32];
+                    if constexpr (EPIM == 1) {
+                        uint4 yr[4];
+                        if (valid) {
+                            const uint4* ys = reinterpret_cast<const uint4*>(bb.y + pix * Cout + nt * BN_ + c * 32);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) yr[q] = __ldg(ys + q);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) yr[q] = make_uint4(0, 0, 0, 0);
+                        }
+                        const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(yr);
+                        const float* c0 = cf + c * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float yv = __bfloat162float(yb[i]);
+                            const float pre = fmaf(yv, c0[i], c0[BN_ + i]);
+                            const float gg = pre > 0.f ? v[i] : v[i] * bb.slope;
+                            v[i] = gg;
+                            sq[i] = gg * (yv - c0[2 * BN_ + i]) * c0[3 * BN_ + i];
+                        }
+                    }
                     if (valid) {
                         uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
@@ -509,9 +554,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                         }
                     }
                     if (stats != nullptr) {
-                        float sq[32];
+                        if constexpr (EPIM == 0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+                            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+                        }
                         const float s1 = warp_transpose_sum(v, lane);
                         const float s2 = warp_transpose_sum(sq, lane);
                         rbuf[(wq * 2 + 0) * BN_ + c * 32 + lane] = s1;
@@ -551,13 +597,13 @@ static int persist_mode() {
 }
 static bool use_persistent() { return persist_mode() != 0; }
 
-template <int BN_, int STAGES, int MODE, int EPI, int CTAS_PER_SM>
+template <int BN_, int STAGES, int MODE, int EPI, int CTAS_PER_SM, int EPIM>
 int launch_persist_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
-                       int m_tiles, int n_tiles, cudaStream_t st) {
+                       int m_tiles, int n_tiles, const BnBwdEpi& bb, cudaStream_t st) {
     using L = PersistSmem<BN_, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, STAGES, MODE, EPI>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, STAGES, MODE, EPI, EPIM>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_persist smem attr: %s", cudaGetErrorString(e));
         configured = true;
@@ -565,17 +611,27 @@ int launch_persist_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, 
     const int total = m_tiles * n_tiles * (MODE == kUpM ? 4 : 1);
     const int cap = kNumSMs * CTAS_PER_SM;
     const int grid = total < cap ? total : cap;
-    conv_tc_persist_kernel<BN_, STAGES, MODE, EPI><<<grid, 64 + 32 * EPI, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats,
-                                                                                        p, n_tiles, total);
+    conv_tc_persist_kernel<BN_, STAGES, MODE, EPI, EPIM><<<grid, 64 + 32 * EPI, L::kTotal, st>>>(
+        mA, mB, (__nv_bfloat16*)out, stats, p, n_tiles, total, bb);
     return JCK_OK;
 }
 
 template <int BN_, int STAGES, int MODE>
 int launch_conv_tc_persist(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
-                           int m_tiles, int n_tiles, cudaStream_t st) {
+                           int m_tiles, int n_tiles, cudaStream_t st, const BnBwdEpi* bb = nullptr) {
     int rc;
-    if (persist_mode() == 2) rc = launch_persist_cfg<BN_, STAGES / 2, MODE, 4, 2>(mA, mB, out, stats, p, m_tiles, n_tiles, st);
-    else rc = launch_persist_cfg<BN_, STAGES, MODE, 8, 1>(mA, mB, out, stats, p, m_tiles, n_tiles, st);
+    const BnBwdEpi none{nullptr, nullptr, nullptr, 0.f};
+    if constexpr (MODE != kEdgeUp) {
+        if (bb != nullptr) {
+            if (persist_mode() == 1) rc = launch_persist_cfg<BN_, STAGES, MODE, 8, 1, 1>(mA, mB, out, stats, p, m_tiles, n_tiles, *bb, st);
+            else rc = launch_persist_cfg<BN_, STAGES / 2, MODE, 4, 2, 1>(mA, mB, out, stats, p, m_tiles, n_tiles, *bb, st);
+            if (rc) return rc;
+            JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_bnbwd_tc" : MODE == kDown ? "conv_down_bnbwd_tc" : "edge_down_bnbwd_tc");
+            return JCK_OK;
+        }
+    }
+    if (persist_mode() == 2) rc = launch_persist_cfg<BN_, STAGES / 2, MODE, 4, 2, 0>(mA, mB, out, stats, p, m_tiles, n_tiles, none, st);
+    else rc = launch_persist_cfg<BN_, STAGES, MODE, 8, 1, 0>(mA, mB, out, stats, p, m_tiles, n_tiles, none, st);
     if (rc) return rc;
     JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc_persist" : MODE == kDown ? "conv_down_tc_persist"
                                                         : MODE == kEdgeDown ? "edge_down_tc_persist" : "edge_up_tc_persist");
@@ -614,7 +670,7 @@ bool tc_conv_supported(int B, int Hs, int Ws, int Ca, int Cb, int ipg, bool up, 
 
 template <bool kUp>
 int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int Hs, int Ws, int Ca, int Cb, int ipg,
-            cudaStream_t st) {
+            cudaStream_t st, const BnBwdEpi* bb = nullptr) {
     PatchGeom g;
     if (!tc_conv_supported(B, Hs, Ws, Ca, Cb, ipg, kUp, &g))
         return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv tc: unsupported shape B=%d Hs=%d Ws=%d Ca=%d Cb=%d", B, Hs, Ws, Ca, Cb);
@@ -631,9 +687,9 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
         if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
         if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn))) return rc;
     }
-    if (use_persistent()) {
-        if (bn == 128) return launch_conv_tc_persist<128, 6, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 128, st);
-        return launch_conv_tc_persist<64, 8, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 64, st);
+    if (use_persistent() || bb != nullptr) {
+        if (bn == 128) return launch_conv_tc_persist<128, 6, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 128, st, bb);
+        return launch_conv_tc_persist<64, 8, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 64, st, bb);
     }
     if (bn == 128) return launch_conv_tc<128, 3, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 128, st);
     return launch_conv_tc<64, 4, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 64, st);
@@ -1005,6 +1061,32 @@ extern "C" int jck_conv_up(const void* in_small, const void* w_up, void* out_lar
     return set_error(JCK_E_BADARG, "conv_up: dtype %d", dtype);
 }
 
+// Input-gradient convolutions with the BatchNorm-backward reduction of the layer BELOW fused into the epilogue
+// (tcgen05 / bf16 only; the fp32 parity mode keeps the separate jck_bn_act_bwd_reduce pass).
+extern "C" int jck_conv_up_bnbwd(const void* in_small, const void* w_up, const void* y_saved, const float* scale_shift,
+                                 const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws,
+                                 int Ca, int Cb, int imgs_per_group, int dtype, void* stream) {
+    JCK_REQUIRE(in_small && w_up && y_saved && scale_shift && mean_rstd && out_g && sums && B > 0, "conv_up_bnbwd: bad argument");
+    if (imgs_per_group <= 0) imgs_per_group = B;
+    PatchGeom g;
+    if (dtype != JCK_BF16 || !tc_conv_supported(B, Hs, Ws, Ca, Cb, imgs_per_group, true, &g))
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_up_bnbwd: bf16 tcgen05 shapes only (Ca=%d Cb=%d Hs=%d)", Ca, Cb, Hs);
+    const BnBwdEpi bb{(const __nv_bfloat16*)y_saved, scale_shift, mean_rstd, slope};
+    return conv_tc<true>(in_small, w_up, out_g, sums, B, Hs, Ws, Ca, Cb, imgs_per_group, as_stream(stream), &bb);
+}
+
+extern "C" int jck_conv_down_bnbwd(const void* in_large, const void* w_down, const void* y_saved, const float* scale_shift,
+                                   const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws,
+                                   int Ca, int Cb, int imgs_per_group, int dtype, void* stream) {
+    JCK_REQUIRE(in_large && w_down && y_saved && scale_shift && mean_rstd && out_g && sums && B > 0, "conv_down_bnbwd: bad argument");
+    if (imgs_per_group <= 0) imgs_per_group = B;
+    PatchGeom g;
+    if (dtype != JCK_BF16 || !tc_conv_supported(B, Hs, Ws, Ca, Cb, imgs_per_group, false, &g))
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_down_bnbwd: bf16 tcgen05 shapes only (Ca=%d Cb=%d Hs=%d)", Ca, Cb, Hs);
+    const BnBwdEpi bb{(const __nv_bfloat16*)y_saved, scale_shift, mean_rstd, slope};
+    return conv_tc<false>(in_large, w_down, out_g, sums, B, Hs, Ws, Ca, Cb, imgs_per_group, as_stream(stream), &bb);
+}
+
 static bool wgrad_uses_tc(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo, WgradPlan* pl) {
     if (!want_tc(dtype, algo)) return false;
     *pl = wgrad_plan(B, Hs, Ws, Ca, Cb);
@@ -1057,6 +1139,24 @@ extern "C" int jck_edge_down(const void* patches, const void* w_down_e, void* ou
     if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
     if (use_persistent()) return launch_conv_tc_persist<64, 6, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
     return launch_conv_tc_mode<64, 2, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
+}
+
+extern "C" int jck_edge_down_bnbwd(const void* patches, const void* w_down_e, const void* y_saved, const float* scale_shift,
+                                   const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws,
+                                   int Ca, int imgs_per_group, void* stream) {
+    JCK_REQUIRE(patches && w_down_e && y_saved && scale_shift && mean_rstd && out_g && sums && B > 0, "edge_down_bnbwd: bad argument");
+    if (imgs_per_group <= 0) imgs_per_group = B;
+    PatchGeom g;
+    if (Ca != 64 || !patch_geom(Hs, Ws, kTileM, &g) || (imgs_per_group < B && imgs_per_group % g.nb != 0))
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_down_bnbwd: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
+    ConvTcParams p{B, Hs, Ws, Ca, 4, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, imgs_per_group};
+    const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = map_rows64(&mA, patches, (long long)B * Hs * Ws, kTileM))) return rc;
+    if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
+    const BnBwdEpi bb{(const __nv_bfloat16*)y_saved, scale_shift, mean_rstd, slope};
+    return launch_conv_tc_persist<64, 6, kEdgeDown>(mA, mB, out_g, sums, p, m_tiles, 1, as_stream(stream), &bb);
 }
 
 extern "C" int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4, int B, int Hs, int Ws, int Ca, void* stream) {

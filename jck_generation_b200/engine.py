@@ -21,6 +21,11 @@ from . import ops
 from .parallel import LocalComm
 
 LRELU = 0.2
+# The input-gradient convolution can do the next BatchNorm-backward reduction in its epilogue (jck_conv_*_bnbwd).
+# Measured at 512 images (tests/notes/conv_bench.py): the thread-per-row epilogue re-reads y under an L2 that the
+# TMA stream already saturates, so it only beats the separate streaming pass where the K loop is long -- layers
+# whose output has >= 256 channels (+3..6 us vs a 8..14 us reduce pass); at 64 / 128 channels it loses (+18..46 us).
+FUSE_MIN_C = 256
 BN_EPS = 1e-5
 BN_MOM = 0.1
 
@@ -161,6 +166,7 @@ class DiscriminatorEngine(_GradTarget):
         self.convs = {k: _Conv(getattr(module, f"conv{k}").weight, 64 >> k, dtype, edge=(edge and k == 1))
                       for k in range(1, 5)}
         self.norms = {k: _Norm(getattr(module, f"norm{k}")) for k in range(1, 5)}
+        self.fused_bn_bwd = dtype == torch.bfloat16 and algo != ops.ALGO_SIMT
         self.has_head = hasattr(module, "conv5")
         if self.has_head:
             self.K5 = 16 * self.convs[4].Ca
@@ -244,27 +250,36 @@ class DiscriminatorEngine(_GradTarget):
             ops.unpack_head_grad(self.dw5, self._gb(self.m.conv5.weight), accumulate)
         return da4.view(B, 4, 4, self.convs[4].Ca)
 
-    def trunk_backward(self, ctx, da4, wgrad=True, input_grad=False, accumulate=False, inject=None, inject_rows=None):
+    def trunk_backward(self, ctx, da4, wgrad=True, input_grad=False, accumulate=False, inject=None, inject_rows=None,
+                       fuse=True):
         """Backward through conv4..conv1 given d/d(a4).  Returns d/d(input) (NHWC) when asked.
         `inject[k]` (rows `inject_rows` of the batch) is added to the gradient of the raw conv-k output
         before it is used: the second-order terms of the CGAN gradient penalty enter here.  The sweep
-        records ctx.da[k] (gradient w.r.t. the activation) and ctx.bsum[k] (BatchNorm backward sums)."""
+        records ctx.dy[k] and ctx.bsum[k] (BatchNorm backward sums).
+        `fuse` (bf16 / tcgen05): the input-gradient convolution of layer k also performs the BatchNorm-backward
+        reduction of layer k-1 in its epilogue and hands down g = da * act'(pre) instead of da; with
+        fuse=False every layer runs the separate reduce pass and ctx.da[k] keeps d/d(activation) (the CGAN
+        penalty sweep needs it)."""
         B, groups = ctx.B, ctx.groups
         world = self.comm.world_size
-        da = da4
+        fuse = fuse and self.fused_bn_bwd
+        da, reduced = da4, False
         zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev)
         for k in range(4, 0, -1):
             cv, nm = self.convs[k], self.norms[k]
             C = cv.Ca
             sums = zeros[k - 1]
-            ops.bn_act_bwd_reduce(da, ctx.y[k], ctx.ss[k], ctx.mr[k], sums, C, groups, LRELU)
+            if not reduced:
+                ops.bn_act_bwd_reduce(da, ctx.y[k], ctx.ss[k], ctx.mr[k], sums, C, groups, LRELU)
             if wgrad:   # parameter gradients are this rank's contribution; ranks are averaged later
                 ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, groups, accumulate)
             self.comm.allreduce_sum_(sums)
             dy = torch.empty_like(ctx.y[k])
             count = (B // groups) * cv.Hs * cv.Ws * world
-            ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count, LRELU)
-            ctx.dy[k], ctx.da[k], ctx.bsum[k] = dy, da, sums
+            ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count,
+                                 1.0 if reduced else LRELU)     # a fused producer already applied act'
+            ctx.dy[k], ctx.bsum[k] = dy, sums
+            ctx.da[k] = None if reduced else da
             if inject is not None:
                 lo, hi = inject_rows
                 ops.axpy(inject[k], dy[lo:hi], 1.0)
@@ -277,10 +292,16 @@ class DiscriminatorEngine(_GradTarget):
                     nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
                     ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
                                    algo=self.algo)
+            reduced = False
             if k > 1 or input_grad:
                 if cv.edge:
                     da = torch.zeros_like(inp)          # border / pad channel of the P4 image stay zero
                     ops.edge_up(dy, cv.w_up9, da, cv.Ca)
+                elif fuse and k > 1 and cv.Cb >= FUSE_MIN_C:
+                    da = torch.empty_like(inp)
+                    ops.conv_up_bnbwd(dy, cv.w_up, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], LRELU, da, zeros[k - 2],
+                                      cv.Ca, cv.Cb, ipg=B // groups)
+                    reduced = True
                 else:
                     da = torch.empty_like(inp)
                     ops.conv_up(dy, cv.w_up, da, None, cv.Ca, cv.Cb, algo=self.algo)
@@ -375,28 +396,37 @@ class GeneratorEngine(_GradTarget):
         world = self.comm.world_size
         d_large = dy5
         zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev)
+        fuse = self.dtype == torch.bfloat16 and self.algo != ops.ALGO_SIMT
         for k in range(5, 1, -1):
             cv = self.convs[k]
+            nm = self.norms[k - 1]
+            C = nm.C
+            sums = zeros[k - 2]
+            yk, ssk, mrk = ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1]
             da = torch.empty_like(ctx.a[k - 1])
             if cv.edge:
                 nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
                 patches = ops.p4_to_patches(d_large)
                 ops.edge_wgrad(ctx.a[k - 1], patches, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
                 ops.edge_down(patches, cv.w_down_e, da, None, cv.Ca)
+                reduced = False
             else:
                 nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
                 ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,
                                accumulate, algo=self.algo)
-                ops.conv_down(d_large, cv.w_down, da, None, cv.Ca, cv.Cb, algo=self.algo)
-            nm = self.norms[k - 1]
-            C = nm.C
-            sums = zeros[k - 2]
-            ops.bn_act_bwd_reduce(da, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], sums, C, 1, 0.0)
+                reduced = fuse and cv.Ca >= FUSE_MIN_C
+                if reduced:
+                    ops.conv_down_bnbwd(d_large, cv.w_down, yk, ssk, mrk, 0.0, da, sums, cv.Ca, cv.Cb)
+                else:
+                    ops.conv_down(d_large, cv.w_down, da, None, cv.Ca, cv.Cb, algo=self.algo)
+            if not reduced:
+                ops.bn_act_bwd_reduce(da, yk, ssk, mrk, sums, C, 1, 0.0)
             ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, 1, accumulate)
             self.comm.allreduce_sum_(sums)
-            dy = torch.empty_like(ctx.y[k - 1])
-            count = (ctx.y[k - 1].numel() // C) * world
-            ops.bn_act_bwd_apply(da, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], nm.gamma, sums, dy, C, 1, count, 0.0)
+            dy = torch.empty_like(yk)
+            count = (yk.numel() // C) * world
+            # a fused producer already applied relu': slope 1 leaves g untouched
+            ops.bn_act_bwd_apply(da, yk, ssk, mrk, nm.gamma, sums, dy, C, 1, count, 1.0 if reduced else 0.0)
             ctx.dy[k - 1] = dy
             d_large = dy
         ops.fc_wgrad(d_large.view(B, 16 * self.C1), ctx.x, self.dw_fc, accumulate=False)

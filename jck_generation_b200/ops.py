@@ -120,6 +120,25 @@ def conv_up(x_small, w_up, out_large, stats, Ca, Cb, ipg=0, algo=ALGO_AUTO):
                           dt(x_small), algo, _s()), "conv_up")
 
 
+def conv_up_bnbwd(x_small, w_up, y_saved, scale_shift, mean_rstd, slope, out_g, sums, Ca, Cb, ipg=0):
+    """conv_up whose epilogue also does the BatchNorm-backward reduction of the layer below (bf16 / tcgen05)."""
+    B, Hs, Ws = x_small.shape[0], x_small.shape[1], x_small.shape[2]
+    check(L().jck_conv_up_bnbwd(_p(x_small), _p(w_up), _p(y_saved), _p(scale_shift), _p(mean_rstd), float(slope), _p(out_g),
+                                _p(sums), B, Hs, Ws, Ca, Cb, ipg, dt(x_small), _s()), "conv_up_bnbwd")
+
+
+def conv_down_bnbwd(x_large, w_down, y_saved, scale_shift, mean_rstd, slope, out_g, sums, Ca, Cb, ipg=0):
+    B, Hs, Ws = out_g.shape[0], out_g.shape[1], out_g.shape[2]
+    check(L().jck_conv_down_bnbwd(_p(x_large), _p(w_down), _p(y_saved), _p(scale_shift), _p(mean_rstd), float(slope),
+                                  _p(out_g), _p(sums), B, Hs, Ws, Ca, Cb, ipg, dt(x_large), _s()), "conv_down_bnbwd")
+
+
+def edge_down_bnbwd(patches, w_down_e, y_saved, scale_shift, mean_rstd, slope, out_g, sums, Ca, ipg=0):
+    B, Hs, Ws = out_g.shape[0], out_g.shape[1], out_g.shape[2]
+    check(L().jck_edge_down_bnbwd(_p(patches), _p(w_down_e), _p(y_saved), _p(scale_shift), _p(mean_rstd), float(slope),
+                                  _p(out_g), _p(sums), B, Hs, Ws, Ca, ipg, _s()), "edge_down_bnbwd")
+
+
 def wgrad_workspace_bytes(B, Hs, Ws, Ca, Cb, dtype, algo=ALGO_AUTO):
     return int(L().jck_conv_wgrad_workspace_bytes(B, Hs, Ws, Ca, Cb, dt(dtype), algo))
 

@@ -69,7 +69,7 @@ class CGANStep(DCGANStep):
         cc = ctx.slice(2, 3)
         cc.head = {k: (v[2 * B:3 * B] if (torch.is_tensor(v) and v.shape[0] == 3 * B) else v) for k, v in ctx.head.items()}
         g_a4 = ed.head_gp_seed(cc)
-        v = ed.trunk_backward(cc, g_a4, wgrad=False, input_grad=True)                                             # :120-127
+        v = ed.trunk_backward(cc, g_a4, wgrad=False, input_grad=True, fuse=False)                                          # :120-127
         u = torch.zeros_like(v) if lay == ops.IMG_P4 else torch.empty_like(v)
         world_b = B * self.comm.world_size
         ops.gp_seed(v, u, scal[S_GP], self.lambda_gp * 2.0 / B)                                                # :130, 201

@@ -22,6 +22,7 @@ from .cgan_step import CGANStep
 from .dcgan_step import DCGANStep
 from .dcgan_trainer import _dtype_of
 from .optim import FusedAdam
+from .prefetch import DevicePrefetcher
 from .trainer import Trainer
 
 try:
@@ -156,10 +157,9 @@ class CGANTrainer(Trainer):
 
         done = False
         for epoch in range(self.epoch):
-            for i, data in enumerate(real_images_loader):
+            for i, data in enumerate(DevicePrefetcher(real_images_loader, self.device)):
                 real_data, labels_data = data
-                real_data = real_data.to(self.device, non_blocking=True).contiguous().float()
-                labels_data = labels_data.to(self.device, non_blocking=True)
+                real_data = real_data.contiguous().float()
                 pending.append((epoch, i, self.train_step(real_data, labels_data)))
                 if len(pending) >= 100:
                     flush()

@@ -23,6 +23,7 @@ from ..utils import get_default_device
 from .. import ops, parallel
 from .dcgan_step import DCGANStep
 from .optim import FusedAdam
+from .prefetch import DevicePrefetcher
 from .trainer import Trainer
 
 try:  # optional, as in the reference's environment
@@ -170,8 +171,8 @@ class DCGANTrainer(Trainer):
 
         done = False
         for epoch in range(self.epoch):
-            for i, data in enumerate(real_images_loader):
-                real_data = data[0].to(self.device, non_blocking=True)
+            for i, data in enumerate(DevicePrefetcher(real_images_loader, self.device)):
+                real_data = data[0]
                 real_data = parallel.shard_rows(real_data, self.comm) if getattr(self.data_pre, "global_batches", False) else real_data
                 scal = self.train_step(real_data.contiguous().float())
                 pending.append((epoch, i, scal if not self.use_graph else scal.clone()))

@@ -71,6 +71,73 @@ def check_up(shape, dtype, algo, B=8, groups=1):
     return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats, ws)}
 
 
+def _bnbwd_want(da, y, C, groups, slope):
+    """torch fp32 restatement of the fused epilogue: g = da * act'(pre), sums = (sum g, sum g * xhat) per group.
+    da, y: NCHW fp32.  Returns (g, sums[groups][2C], scale_shift, mean_rstd) with gamma / beta drawn here."""
+    per = da.shape[0] // groups
+    gamma = 1.0 + 0.1 * _mk((C,), torch.float32, 31)
+    beta = 0.1 * _mk((C,), torch.float32, 32)
+    gs, sums, ss, mr = [], [], [], []
+    for g in range(groups):
+        yy, dd = y[g * per:(g + 1) * per], da[g * per:(g + 1) * per]
+        mean, var = yy.mean((0, 2, 3)), yy.var((0, 2, 3), unbiased=False)
+        rstd = (var + 1e-5).rsqrt()
+        sc, sh = gamma * rstd, beta - mean * gamma * rstd
+        pre = yy * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+        gg = torch.where(pre > 0, dd, dd * slope)
+        xhat = (yy - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
+        gs.append(gg)
+        sums.append(torch.cat([gg.sum((0, 2, 3)), (gg * xhat).sum((0, 2, 3))]))
+        ss.append(torch.cat([sc, sh]))
+        mr.append(torch.cat([mean, rstd]))
+    return torch.cat(gs), torch.stack(sums), torch.stack(ss), torch.stack(mr)
+
+
+def check_bnbwd(kind, shape, B=8, groups=1, slope=0.2):
+    """jck_conv_up_bnbwd / jck_conv_down_bnbwd / jck_edge_down_bnbwd vs conv + torch BatchNorm-backward reduction."""
+    from jck_generation_b200 import ops
+    dtype = torch.bfloat16
+    if kind == "up":
+        Ca, Cb, Hs = SHAPES[shape]
+        x = _mk((B, Ca, Hs, Hs), dtype, 3)
+        w4 = _mk((Ca, Cb, 4, 4), dtype, 4, 0.05)
+        da = F.conv_transpose2d(x, w4, stride=2, padding=1)
+        C, Ho = Cb, 2 * Hs
+    elif kind == "down":
+        Ca, Cb, Hs = SHAPES[shape]
+        x = _mk((B, Cb, 2 * Hs, 2 * Hs), dtype, 1)
+        w4 = _mk((Ca, Cb, 4, 4), dtype, 2, 0.05)
+        da = F.conv2d(x, w4, stride=2, padding=1)
+        C, Ho = Ca, Hs
+    else:   # image edge: 3-channel 64x64 gradient image -> 64 channels at 32x32
+        Ca, Cb, Hs = 64, 3, 32
+        x = _mk((B, Cb, 64, 64), dtype, 1)
+        w4 = _mk((Ca, Cb, 4, 4), dtype, 2, 0.05)
+        da = F.conv2d(x, w4, stride=2, padding=1)
+        C, Ho = Ca, Hs
+    y = _mk((B, C, Ho, Ho), dtype, 7)
+    g_want, s_want, ss, mr = _bnbwd_want(da, y, C, groups, slope)
+    out = torch.full((B, Ho, Ho, C), float("nan"), dtype=dtype, device="cuda")
+    sums = torch.zeros(groups, 2 * C, device="cuda")
+    y_dev = y.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    ss, mr = ss.cuda().contiguous(), mr.cuda().contiguous()
+    if kind == "edge":
+        wde = torch.empty(Ca * 64, dtype=dtype, device="cuda")
+        wu9 = torch.empty(16 * 9 * Ca, dtype=dtype, device="cuda")
+        ops.pack_weights_edge(w4.cuda().contiguous(), wde, wu9)
+        patches = ops.p4_to_patches(_to_p4(x))
+        ops.edge_down_bnbwd(patches, wde, y_dev, ss, mr, slope, out, sums, Ca, ipg=B // groups)
+    else:
+        wd, wu = _packed(w4, dtype)
+        xin = x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+        if kind == "up":
+            ops.conv_up_bnbwd(xin, wu, y_dev, ss, mr, slope, out, sums, Ca, Cb, ipg=B // groups)
+        else:
+            ops.conv_down_bnbwd(xin, wd, y_dev, ss, mr, slope, out, sums, Ca, Cb, ipg=B // groups)
+    torch.cuda.synchronize()
+    return {"out": _rel(out.float().permute(0, 3, 1, 2), g_want), "stats": _rel(sums, s_want)}
+
+
 def check_wgrad(shape, dtype, algo, B=8):
     from jck_generation_b200 import ops
     Ca, Cb, Hs = SHAPES[shape]
@@ -292,6 +359,9 @@ def all_cases():
     cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_up", "-", "bf16", "tc", 8),
               ("edge_up", "-", "bf16", "tc", 5), ("edge_wgrad", "-", "bf16", "tc", 8), ("edge_wgrad", "-", "bf16", "tc", 3),
               ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
+    cases += [("bnbwd_up", "c2", "bf16", "tc", 8), ("bnbwd_up", "c3", "bf16", "tc", 8), ("bnbwd_up", "c4", "bf16", "tc", 3),
+              ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16),
+              ("bnbwd_edge", "-", "bf16", "tc", 8), ("bnbwd_edge", "-", "bf16", "tc", 3)]
     cases += [("bn", "-", "f32", "-", 8), ("bn", "-", "bf16", "-", 8), ("head", "-", "f32", "-", 8),
               ("head", "-", "bf16", "-", 8), ("fc", "-", "f32", "-", 8), ("fc", "-", "bf16", "-", 8),
               ("misc", "-", "f32", "-", 4)]
@@ -309,6 +379,10 @@ def run_case(op, shape, dtype, algo, B):
         return check_down(shape, _dt(dtype), _alg(algo), B, groups=2)
     if op == "up_groups":
         return check_up(shape, _dt(dtype), _alg(algo), B, groups=2)
+    if op.startswith("bnbwd_"):
+        kind = op[6:]
+        groups = 2 if (B % 2 == 0 and shape in ("c3", "c4")) else 1
+        return check_bnbwd(kind, shape, B, groups=groups, slope=0.0 if kind != "up" else 0.2)
     if op.startswith("edge_"):
         return check_edge(op[5:].rstrip("1"), B, nc=1 if op.endswith("1") else 3)
     if op == "bn":
