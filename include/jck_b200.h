@@ -53,6 +53,10 @@ extern "C" {
 #define JCK_IMG_NHWC 0
 #define JCK_IMG_P4 1
 
+/* peer-memory communicator (jck_comm_*) */
+#define JCK_COMM_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
+#define JCK_COMM_MAX_N 3072      /* floats per small all-reduce: 3 groups x 2C, C <= 512 */
+
 /* conv algorithm selector */
 #define JCK_ALGO_AUTO 0  /* tcgen05 where dtype/shape allow, else SIMT */
 #define JCK_ALGO_SIMT 1  /* CUDA-core fp32-FMA implicit GEMM (exact-fp32 parity mode; edge layers) */
@@ -241,6 +245,28 @@ int jck_randn(float* out, long long n, unsigned long long seed, unsigned long lo
 int jck_rand(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
              const unsigned long long* counter_base, void* stream);
 int jck_rng_advance(unsigned long long* counter_base, unsigned long long by, void* stream);
+
+/* ---- data-parallel exchange over NVLink peer memory -------------------------------------------
+ * The reference is single-GPU: these entry points have no reference counterpart.  They make
+ * an N-GPU run equal the reference at the global batch: nn.BatchNorm2d's batch statistics (model/DCGAN.py:
+ * 11,15,19,23,43,47,51,55) are taken over ALL ranks' rows.  One process per GPU; each rank creates a
+ * communicator, the 64-byte IPC handles are exchanged by the host (torch.distributed all_gather) and
+ * connected.  A small all-reduce is then one single-CTA kernel per rank that stores (value, sequence) words
+ * into every peer's mailbox and spins on its own -- no host call, no NCCL launch, CUDA-graph capturable.
+ * All ranks must issue the same sequence of jck_comm_* / *_sync calls. */
+int jck_comm_create(int rank, int world, void** comm_out, void* ipc_handle_out /* JCK_COMM_HANDLE_BYTES */);
+int jck_comm_connect(void* comm, const void* all_handles /* world x JCK_COMM_HANDLE_BYTES, rank order */);
+int jck_comm_destroy(void* comm);
+/* data[0..n) <- sum over ranks, in place, n <= JCK_COMM_MAX_N; identical bits on every rank */
+int jck_comm_allreduce_small(void* comm, float* data, int n, void* stream);
+/* SyncBN forward: all-reduce stats[groups][2C] in place, then exactly jck_bn_finalize (count = GLOBAL samples) */
+int jck_bn_finalize_sync(void* comm, float* stats, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_rstd, int C,
+                         int groups, float count, float eps, float momentum, void* stream);
+/* SyncBN backward: jck_bn_param_grad on the LOCAL sums (skipped when dgamma == dbeta == NULL), then all-reduce
+ * sums[groups][2C] in place for jck_bn_act_bwd_apply */
+int jck_bn_bwd_sums_sync(void* comm, float* sums, float* dgamma, float* dbeta, int C, int groups, int accumulate,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,12 @@ _SIGNATURES = {
     "jck_randn": [c_p, c_ll, c_ull, c_ull, c_p, c_p],
     "jck_rand": [c_p, c_ll, c_ull, c_ull, c_p, c_p],
     "jck_rng_advance": [c_p, c_ull, c_p],
+    "jck_comm_create": [c_i, c_i, ctypes.POINTER(c_p), c_p],
+    "jck_comm_connect": [c_p, c_p],
+    "jck_comm_destroy": [c_p],
+    "jck_comm_allreduce_small": [c_p, c_p, c_i, c_p],
+    "jck_bn_finalize_sync": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_f, c_p],
+    "jck_bn_bwd_sums_sync": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"jck_last_error_string": ctypes.c_char_p, "jck_launch_count": c_ull,
              "jck_conv_wgrad_workspace_bytes": c_sz, "jck_edge_wgrad_workspace_bytes": c_sz}

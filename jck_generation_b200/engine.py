@@ -123,6 +123,28 @@ def _zero_blocks(groups, channels, device):
     return out
 
 
+def _bn_finalize(comm, stats, nm, update_running, ss, mr, C, groups, count):
+    """Batch statistics over the GLOBAL batch -> scale/shift, mean/rstd, running-buffer update.  With a peer
+    communicator the exchange happens inside the finalize kernel (one launch, no NCCL call)."""
+    bn = nm.bn
+    run = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if update_running else (None, None, None)
+    if comm.peer is not None and stats.numel() <= ops.COMM_MAX_N:
+        ops.bn_finalize_sync(comm.peer, stats, nm.gamma, nm.beta, *run, ss, mr, C, groups, count, BN_EPS, BN_MOM)
+    else:
+        comm.allreduce_sum_(stats)
+        ops.bn_finalize(stats, nm.gamma, nm.beta, *run, ss, mr, C, groups, count, BN_EPS, BN_MOM)
+
+
+def _bn_bwd_sums(comm, sums, dgamma, dbeta, C, groups, accumulate):
+    """BatchNorm-backward sums: local dgamma / dbeta (when asked), then the sums over the global batch."""
+    if comm.peer is not None and sums.numel() <= ops.COMM_MAX_N:
+        ops.bn_bwd_sums_sync(comm.peer, sums, dgamma, dbeta, C, groups, accumulate)
+    else:
+        if dgamma is not None:
+            ops.bn_param_grad(sums, dgamma, dbeta, C, groups, accumulate)
+        comm.allreduce_sum_(sums)
+
+
 class _Workspace:
     def __init__(self, device):
         self.device = device
@@ -204,16 +226,10 @@ class DiscriminatorEngine(_GradTarget):
                 ops.edge_down(ctx.x_patches, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)
             else:
                 ops.conv_down(cur, cv.w_down, y, stats, cv.Ca, cv.Cb, ipg=B // groups, algo=self.algo)
-            self.comm.allreduce_sum_(stats)                                  # SyncBN: global batch statistics
             ss = torch.empty(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
             mr = torch.empty(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
             count = (B // groups) * cv.Hs * cv.Ws * world
-            bn = nm.bn
-            ops.bn_finalize(stats, nm.gamma, nm.beta,
-                            bn.running_mean if update_running else None,
-                            bn.running_var if update_running else None,
-                            bn.num_batches_tracked if update_running else None,
-                            ss, mr, cv.Ca, groups, count, BN_EPS, BN_MOM)
+            _bn_finalize(self.comm, stats, nm, update_running, ss, mr, cv.Ca, groups, count)   # SyncBN: global batch statistics
             a = torch.empty_like(y)
             ops.bn_act_fwd(y, ss, a, cv.Ca, groups, LRELU)
             ctx.y[k], ctx.a[k], ctx.ss[k], ctx.mr[k] = y, a, ss, mr
@@ -271,9 +287,9 @@ class DiscriminatorEngine(_GradTarget):
             sums = zeros[k - 1]
             if not reduced:
                 ops.bn_act_bwd_reduce(da, ctx.y[k], ctx.ss[k], ctx.mr[k], sums, C, groups, LRELU)
-            if wgrad:   # parameter gradients are this rank's contribution; ranks are averaged later
-                ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, groups, accumulate)
-            self.comm.allreduce_sum_(sums)
+            # parameter gradients are this rank's contribution (ranks are averaged later); then the global sums
+            _bn_bwd_sums(self.comm, sums, self._gb(nm.bn.weight) if wgrad else None, self._gb(nm.bn.bias) if wgrad else None,
+                         C, groups, accumulate)
             dy = torch.empty_like(ctx.y[k])
             count = (B // groups) * cv.Hs * cv.Ws * world
             ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count,
@@ -346,16 +362,10 @@ class GeneratorEngine(_GradTarget):
     def _bn_relu(self, ctx, k, y, stats, groups, update_running):
         nm = self.norms[k]
         C = nm.C
-        self.comm.allreduce_sum_(stats)
         ss = torch.empty(groups, 2 * C, dtype=torch.float32, device=self.dev)
         mr = torch.empty(groups, 2 * C, dtype=torch.float32, device=self.dev)
         count = (y.numel() // C // groups) * self.comm.world_size
-        bn = nm.bn
-        ops.bn_finalize(stats, nm.gamma, nm.beta,
-                        bn.running_mean if update_running else None,
-                        bn.running_var if update_running else None,
-                        bn.num_batches_tracked if update_running else None,
-                        ss, mr, C, groups, count, BN_EPS, BN_MOM)
+        _bn_finalize(self.comm, stats, nm, update_running, ss, mr, C, groups, count)
         a = torch.empty_like(y)
         ops.bn_act_fwd(y, ss, a, C, groups, 0.0)
         ctx.y[k], ctx.a[k], ctx.ss[k], ctx.mr[k] = y, a, ss, mr
@@ -421,8 +431,7 @@ class GeneratorEngine(_GradTarget):
                     ops.conv_down(d_large, cv.w_down, da, None, cv.Ca, cv.Cb, algo=self.algo)
             if not reduced:
                 ops.bn_act_bwd_reduce(da, yk, ssk, mrk, sums, C, 1, 0.0)
-            ops.bn_param_grad(sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, 1, accumulate)
-            self.comm.allreduce_sum_(sums)
+            _bn_bwd_sums(self.comm, sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, 1, accumulate)
             dy = torch.empty_like(yk)
             count = (yk.numel() // C) * world
             # a fused producer already applied relu': slope 1 leaves g untouched

@@ -169,6 +169,45 @@ def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale_shift,
           "bn_finalize")
 
 
+# ---- peer-memory communicator (SyncBN exchanges) ---------------------------------------------------------------
+COMM_MAX_N = 3072
+COMM_HANDLE_BYTES = 64
+
+
+def comm_create(rank, world):
+    """-> (opaque communicator, 64-byte CUDA IPC handle of this rank's mailbox)"""
+    import ctypes
+    comm = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(COMM_HANDLE_BYTES)
+    check(L().jck_comm_create(rank, world, ctypes.byref(comm), handle), "comm_create")
+    return comm, handle.raw
+
+
+def comm_connect(comm, all_handles):
+    check(L().jck_comm_connect(comm, all_handles), "comm_connect")
+
+
+def comm_destroy(comm):
+    check(L().jck_comm_destroy(comm), "comm_destroy")
+
+
+def comm_allreduce_small(comm, t):
+    assert t.dtype == torch.float32 and t.numel() <= COMM_MAX_N
+    check(L().jck_comm_allreduce_small(comm, _p(t), t.numel(), _s()), "comm_allreduce_small")
+
+
+def bn_finalize_sync(comm, stats, gamma, beta, running_mean, running_var, nbt, scale_shift, mean_rstd, C, groups, count,
+                     eps=1e-5, momentum=0.1):
+    check(L().jck_bn_finalize_sync(comm, _p(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt),
+                                   _p(scale_shift), _p(mean_rstd), C, groups, float(count), eps, momentum, _s()),
+          "bn_finalize_sync")
+
+
+def bn_bwd_sums_sync(comm, sums, dgamma, dbeta, C, groups, accumulate):
+    check(L().jck_bn_bwd_sums_sync(comm, _p(sums), _p(dgamma), _p(dbeta), C, groups, int(accumulate), _s()),
+          "bn_bwd_sums_sync")
+
+
 def bn_act_fwd(y, scale_shift, a, C, groups, slope):
     npix = y.numel() // C
     check(L().jck_bn_act_fwd(_p(y), _p(scale_shift), _p(a), npix, C, npix // groups, slope, dt(y), _s()), "bn_act_fwd")

@@ -14,10 +14,14 @@ import torch
 import torch.distributed as dist
 
 
+_PEER_MAX_N = 3072       # JCK_COMM_MAX_N
+
+
 class LocalComm:
     """World of one: every collective is the identity."""
     world_size = 1
     rank = 0
+    peer = None
 
     def allreduce_sum_(self, t):
         return t
@@ -33,15 +37,40 @@ class TorchComm:
     """Collectives through an initialised torch.distributed process group (nccl on GPUs, gloo in the
     CPU tests)."""
 
+    peer = None      # opaque libjck_b200 communicator (NVLink peer-memory mailboxes) once open_peer() succeeded
+
     def __init__(self, group=None):
         assert dist.is_initialized(), "init the process group first (see init_from_env)"
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
+    def open_peer(self):
+        """Open the peer-memory communicator of csrc/comm.cu: every rank exports its mailbox with CUDA IPC, the
+        handles travel through one torch.distributed all_gather, every rank maps its peers.  From then on the
+        SyncBN exchanges (2C floats, 40+ per step) are single-CTA kernels storing straight into the peers' HBM
+        instead of host-launched NCCL calls.  Large buffers (the gradient buckets) stay on NCCL."""
+        from . import ops
+        if self.peer is not None or self.world_size == 1 or self.world_size > 8 or not torch.cuda.is_available():
+            return self
+        comm, handle = ops.comm_create(self.rank, self.world_size)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+        gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
+        dist.all_gather(gathered, mine, group=self.group)
+        ops.comm_connect(comm, b"".join(bytes(g.cpu().tolist()) for g in gathered))
+        dist.barrier(group=self.group)            # every mailbox is zeroed and mapped before the first store
+        self.peer = comm
+        return self
+
     def allreduce_sum_(self, t):
         if self.world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if self.peer is not None and t.is_cuda and t.dtype == torch.float32 and t.numel() <= _PEER_MAX_N \
+                    and t.is_contiguous():
+                from . import ops
+                ops.comm_allreduce_small(self.peer, t)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
     def allreduce_mean_(self, t):
@@ -67,7 +96,10 @@ def init_from_env(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group(backend=backend)
-    return TorchComm()
+    comm = TorchComm()
+    if dist.get_backend() == "nccl" and os.environ.get("JCK_SYNCBN", "p2p") == "p2p":
+        comm.open_peer()
+    return comm
 
 
 def shard_rows(t, comm):

@@ -10,7 +10,12 @@ The tight comparison runs with lr = 0: Adam's first update is lr*g/(|g|+eps), i.
 ~1e-6 of D's gradient elements that sit below fp32 summation-order noise flip by 2*lr between ANY two
 runs; pass D then sees a D that differs by ~1e-4 and BatchNorm backward (which cancels the batch-common
 part of the gradient, almost all of it at initialisation) amplifies that to ~1e-2 in G's gradients.  That
-is optimiser chaos, not a collective bug, and lr = 0 removes it so every gradient must agree to 1e-4."""
+is optimiser chaos, not a collective bug, and lr = 0 removes it so every gradient must agree to 1e-4.
+
+bf16: the two runs differ in fp32 summation order of the batch statistics (1e-7), which re-rounds a random
+subset of the bf16 activations by one ulp (2^-9); BatchNorm backward amplifies that to the same 3-7 % on D's
+gradients that separates ANY two bf16 evaluations of this network (tests/parity.py:autocast_envelope), so the
+bf16 bound is that envelope (1e-1), not a collective tolerance."""
 import sys
 
 import torch
@@ -44,7 +49,7 @@ def main():
     real = osteps.make_real(B, n_steps=1)[0].cuda()
     rng = {k: v.cuda() for k, v in osteps.make_rng(B, n_steps=1, seed=5)[0].items()}
     worst = {}
-    for dtype, tol, lr in ((torch.float32, 1e-4, 0.0), (torch.bfloat16, 6e-2, 0.0), (torch.float32, 5e-2, 2e-4)):
+    for dtype, tol, lr in ((torch.float32, 1e-4, 0.0), (torch.bfloat16, 1e-1, 0.0), (torch.float32, 5e-2, 2e-4)):
         g, d, step = build(dtype, comm, lr)
         shard = {k: parallel.shard_rows(v, comm).contiguous() for k, v in rng.items()}
         scal = step.run(parallel.shard_rows(real, comm).contiguous(), shard).clone()
