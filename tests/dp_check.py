@@ -91,7 +91,7 @@ def main():
             # pass-D-derived gradients: at N(0,.02) initial weights D(x) is almost constant over the batch, so
             # BatchNorm backward cancels nearly all of the gradient and fp32 summation-order noise (1e-6) is
             # amplified ~1000x (measured 1.3e-3 at lr = 0; 1.3e-2 once Adam's sign-like first update is in)
-            assert w[1] <= (2e-2 if lr == 0 else 1e-1), loose
+            assert w[1] <= (0.2 if dtype == torch.bfloat16 else 2e-2 if lr == 0 else 1e-1), loose
         comm.barrier()
     if comm.rank == 0:
         print("dp_check OK", worst, flush=True)
