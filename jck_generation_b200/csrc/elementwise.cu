@@ -32,6 +32,16 @@ inline int grid_for(long long work_items, int threads, int max_waves = 8) {
 // ---- 8-wide channel vectors ------------------------------------------------------------------
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw load_raw(const float* p) {
+        Raw r;
+        r.a = __ldg(reinterpret_cast<const float4*>(p));
+        r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        return r;
+    }
+    static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+        v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+    }
     static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
         const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -42,6 +52,13 @@ template <> struct Vec8<float> {
     }
 };
 template <> struct Vec8<__nv_bfloat16> {
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    static __device__ __forceinline__ void unpack(const Raw& u, float (&v)[8]) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
     static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
         const uint4 u = *reinterpret_cast<const uint4*>(p);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -245,14 +262,19 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
 
 // The three streaming BatchNorm passes share one thread mapping: a thread owns ONE 8-channel vector
 // (cvi = tid % (C/8)) and walks pixels of one statistics group (blockIdx.y), so every per-channel
-// coefficient lives in registers for the whole kernel; four independent 128-bit loads per tensor are in
-// flight per thread (the passes are pure HBM streams, MLP is what keeps them near the copy bandwidth).
+// coefficient lives in registers for the whole kernel.  The passes are pure HBM streams, so what matters is
+// memory-level parallelism: the main loop issues ALL 128-bit loads of kBnUnroll rows (both tensors, raw,
+// unconverted) before touching any of them -- no bounds test, no conversion between the loads -- and a
+// separate tail loop takes the last < kBnUnroll rows.  Rows of one thread are 256/(C/8) pixels apart, i.e.
+// always 2048 elements, so the unrolled addresses are immediates off one running pointer.
 constexpr int kBnUnroll = 4;
+constexpr int kBnRowElems = 2048;    // (256 / (C/8)) * C
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift, T* __restrict__ a, int C,
                   unsigned pix_per_group, unsigned slab, float slope) {
+    typedef typename Vec8<T>::Raw Raw;
     const unsigned cv = C / 8, rows = 256 / cv;
     const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
     const unsigned g = blockIdx.y, c0 = myc * 8;
@@ -260,23 +282,28 @@ bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift
     float sc[8], sh[8];
     Vec8<float>::load(scale_shift + (size_t)g * 2 * C + c0, sc);
     Vec8<float>::load(scale_shift + (size_t)g * 2 * C + C + c0, sh);
-    const size_t base = (size_t)g * pix_per_group * C + c0;
-    for (unsigned pp = p_beg + myr; pp < p_end; pp += rows * kBnUnroll) {
-        float v[kBnUnroll][8];
+    unsigned pp = p_beg + myr;
+    const size_t off = ((size_t)g * pix_per_group + pp) * C + c0;
+    const T* py = y + off;
+    T* pa = a + off;
+    auto one = [&](const Raw& r, T* dst) {
+        float v[8];
+        Vec8<T>::unpack(r, v);
 #pragma unroll
-        for (int u = 0; u < kBnUnroll; ++u)
-            if (pp + u * rows < p_end) Vec8<T>::load(y + base + (size_t)(pp + u * rows) * C, v[u]);
-#pragma unroll
-        for (int u = 0; u < kBnUnroll; ++u) {
-            if (pp + u * rows >= p_end) continue;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float pre = fmaf(v[u][j], sc[j], sh[j]);
-                v[u][j] = pre > 0.f ? pre : pre * slope;
-            }
-            Vec8<T>::store(a + base + (size_t)(pp + u * rows) * C, v[u]);
+        for (int j = 0; j < 8; ++j) {
+            const float pre = fmaf(v[j], sc[j], sh[j]);
+            v[j] = pre > 0.f ? pre : pre * slope;
         }
+        Vec8<T>::store(dst, v);
+    };
+    for (; pp + (kBnUnroll - 1) * rows < p_end; pp += kBnUnroll * rows, py += kBnUnroll * kBnRowElems, pa += kBnUnroll * kBnRowElems) {
+        Raw r[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) r[u] = Vec8<T>::load_raw(py + u * kBnRowElems);
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) one(r[u], pa + u * kBnRowElems);
     }
+    for (; pp < p_end; pp += rows, py += kBnRowElems, pa += kBnRowElems) one(Vec8<T>::load_raw(py), pa);
 }
 
 // sums[g][0:C] += sum g,  sums[g][C:2C] += sum g*xhat, g = da * act'(pre)
@@ -285,42 +312,52 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
                          const float* __restrict__ mean_rstd, float* __restrict__ sums, int C, unsigned pix_per_group,
                          unsigned slab, float slope) {
+    typedef typename Vec8<T>::Raw Raw;
     __shared__ float red[256][17];
     const unsigned cv = C / 8, rows = 256 / cv;
     const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
     const unsigned g = blockIdx.y, c0 = myc * 8;
     const unsigned p_beg = blockIdx.x * slab, p_end = min(pix_per_group, p_beg + slab);
-    float sc[8], sh[8], mu[8], rs[8];
+    float sc[8], sh[8], mu[8];
     Vec8<float>::load(scale_shift + (size_t)g * 2 * C + c0, sc);
     Vec8<float>::load(scale_shift + (size_t)g * 2 * C + C + c0, sh);
     Vec8<float>::load(mean_rstd + (size_t)g * 2 * C + c0, mu);
-    Vec8<float>::load(mean_rstd + (size_t)g * 2 * C + C + c0, rs);
-    float s1[8], s2[8];
+    float s1[8], s2[8];                    // s2 accumulates g * (y - mean); rstd is applied once at the end
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-    const size_t base = (size_t)g * pix_per_group * C + c0;
-    for (unsigned pp = p_beg + myr; pp < p_end; pp += rows * kBnUnroll) {
-        float d[kBnUnroll][8], v[kBnUnroll][8];
+    unsigned pp = p_beg + myr;
+    const size_t off = ((size_t)g * pix_per_group + pp) * C + c0;
+    const T* pd = da + off;
+    const T* py = y + off;
+    auto one = [&](const Raw& rd, const Raw& ry) {
+        float d[8], v[8];
+        Vec8<T>::unpack(rd, d);
+        Vec8<T>::unpack(ry, v);
 #pragma unroll
-        for (int u = 0; u < kBnUnroll; ++u)
-            if (pp + u * rows < p_end) {
-                Vec8<T>::load(da + base + (size_t)(pp + u * rows) * C, d[u]);
-                Vec8<T>::load(y + base + (size_t)(pp + u * rows) * C, v[u]);
-            }
+        for (int j = 0; j < 8; ++j) {
+            const float pre = fmaf(v[j], sc[j], sh[j]);
+            const float gg = pre > 0.f ? d[j] : d[j] * slope;
+            s1[j] += gg;
+            s2[j] = fmaf(gg, v[j] - mu[j], s2[j]);
+        }
+    };
+    for (; pp + (kBnUnroll - 1) * rows < p_end; pp += kBnUnroll * rows, pd += kBnUnroll * kBnRowElems, py += kBnUnroll * kBnRowElems) {
+        Raw rd[kBnUnroll], ry[kBnUnroll];
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
-            if (pp + u * rows >= p_end) continue;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float pre = fmaf(v[u][j], sc[j], sh[j]);
-                const float gg = pre > 0.f ? d[u][j] : d[u][j] * slope;
-                s1[j] += gg;
-                s2[j] += gg * (v[u][j] - mu[j]) * rs[j];
-            }
+            rd[u] = Vec8<T>::load_raw(pd + u * kBnRowElems);
+            ry[u] = Vec8<T>::load_raw(py + u * kBnRowElems);
         }
-    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j]; }
+        for (int u = 0; u < kBnUnroll; ++u) one(rd[u], ry[u]);
+    }
+    for (; pp < p_end; pp += rows, pd += kBnRowElems, py += kBnRowElems) one(Vec8<T>::load_raw(pd), Vec8<T>::load_raw(py));
+    {
+        float rs[8];
+        Vec8<float>::load(mean_rstd + (size_t)g * 2 * C + C + c0, rs);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j] * rs[j]; }
+    }
     __syncthreads();
     for (int col = threadIdx.x; col < 2 * C; col += 256) {
         const int which = col / C, ch = col % C;
@@ -331,20 +368,22 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, cons
     }
 }
 
-// dy = gamma*rstd*(g - sum_g/N - xhat*sum_gx/N) = k1*g - k2 - k3*(y - mean)
+// dy = gamma*rstd*(g - sum_g/N - xhat*sum_gx/N) = k1*g - k3*y + k4,  k1 = gamma*rstd, k3 = k1*rstd*sum_gx/N,
+// k4 = k3*mean - k1*sum_g/N
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
                         const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                         const float* __restrict__ sums, T* __restrict__ dy, int C, unsigned pix_per_group,
                         unsigned slab, float inv_count, float slope) {
+    typedef typename Vec8<T>::Raw Raw;
     const unsigned cv = C / 8, rows = 256 / cv;
     const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
     const unsigned g = blockIdx.y, c0 = myc * 8;
     const unsigned p_beg = blockIdx.x * slab, p_end = min(pix_per_group, p_beg + slab);
-    float sc[8], sh[8], mu[8], k1[8], k2[8], k3[8];
+    float sc[8], sh[8], k1[8], k3[8], k4[8];
     {
-        float rs[8], ga[8], sg[8], sgx[8];
+        float mu[8], rs[8], ga[8], sg[8], sgx[8];
         const size_t gofs = (size_t)g * 2 * C;
         Vec8<float>::load(scale_shift + gofs + c0, sc);
         Vec8<float>::load(scale_shift + gofs + C + c0, sh);
@@ -356,31 +395,40 @@ bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y, const
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             k1[j] = ga[j] * rs[j];
-            k2[j] = k1[j] * sg[j] * inv_count;
             k3[j] = k1[j] * rs[j] * sgx[j] * inv_count;
+            k4[j] = k3[j] * mu[j] - k1[j] * sg[j] * inv_count;
         }
     }
-    const size_t base = (size_t)g * pix_per_group * C + c0;
-    for (unsigned pp = p_beg + myr; pp < p_end; pp += rows * kBnUnroll) {
-        float d[kBnUnroll][8], v[kBnUnroll][8];
+    unsigned pp = p_beg + myr;
+    const size_t off = ((size_t)g * pix_per_group + pp) * C + c0;
+    const T* pd = da + off;
+    const T* py = y + off;
+    T* po = dy + off;
+    auto one = [&](const Raw& rd, const Raw& ry, T* dst) {
+        float d[8], v[8];
+        Vec8<T>::unpack(rd, d);
+        Vec8<T>::unpack(ry, v);
 #pragma unroll
-        for (int u = 0; u < kBnUnroll; ++u)
-            if (pp + u * rows < p_end) {
-                Vec8<T>::load(da + base + (size_t)(pp + u * rows) * C, d[u]);
-                Vec8<T>::load(y + base + (size_t)(pp + u * rows) * C, v[u]);
-            }
+        for (int j = 0; j < 8; ++j) {
+            const float pre = fmaf(v[j], sc[j], sh[j]);
+            const float gg = pre > 0.f ? d[j] : d[j] * slope;
+            d[j] = fmaf(k1[j], gg, fmaf(-k3[j], v[j], k4[j]));
+        }
+        Vec8<T>::store(dst, d);
+    };
+    for (; pp + (kBnUnroll - 1) * rows < p_end;
+         pp += kBnUnroll * rows, pd += kBnUnroll * kBnRowElems, py += kBnUnroll * kBnRowElems, po += kBnUnroll * kBnRowElems) {
+        Raw rd[kBnUnroll], ry[kBnUnroll];
 #pragma unroll
         for (int u = 0; u < kBnUnroll; ++u) {
-            if (pp + u * rows >= p_end) continue;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float pre = fmaf(v[u][j], sc[j], sh[j]);
-                const float gg = pre > 0.f ? d[u][j] : d[u][j] * slope;
-                d[u][j] = k1[j] * gg - k2[j] - k3[j] * (v[u][j] - mu[j]);
-            }
-            Vec8<T>::store(dy + base + (size_t)(pp + u * rows) * C, d[u]);
+            rd[u] = Vec8<T>::load_raw(pd + u * kBnRowElems);
+            ry[u] = Vec8<T>::load_raw(py + u * kBnRowElems);
         }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) one(rd[u], ry[u], po + u * kBnRowElems);
     }
+    for (; pp < p_end; pp += rows, pd += kBnRowElems, py += kBnRowElems, po += kBnRowElems)
+        one(Vec8<T>::load_raw(pd), Vec8<T>::load_raw(py), po);
 }
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -687,7 +735,9 @@ extern "C" int jck_bn_finalize(const float* stats, const float* gamma, const flo
 
 static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (256 % (C / 8)) == 0; }
 
-// grid (blocks per group, groups): ~`waves` waves of 256-thread blocks, each thread row gets >= 4 pixels
+// grid (blocks per group, groups): `waves` x 148 blocks of 256 threads in total, each thread row gets >= 4 pixels.
+// `waves` is chosen per kernel as a multiple of the blocks of that kernel that fit on one SM (registers:
+// fwd 40 -> 6, reduce 66 -> 3, apply 70 -> 3), so the grid is a whole number of resident waves (no ragged tail)
 static dim3 bn_grid(long long pix_per_group, int groups, int C, int waves, unsigned* slab) {
     const int rows = 256 / (C / 8);
     long long bpg = ((long long)waves * kNumSMs + groups - 1) / groups;
@@ -707,7 +757,7 @@ extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, 
     JCK_REQUIRE(y && scale_shift && a, "bn_act_fwd: bad argument");
     BN_COMMON_CHECKS("bn_act_fwd")
     unsigned slab;
-    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 8, &slab);
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 6, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_fwd",
         bn_act_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)y, scale_shift, (T*)a, C, (unsigned)pix_per_group,
                                                                 slab, slope);)
@@ -721,7 +771,7 @@ extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float*
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && sums, "bn_act_bwd_reduce: bad argument");
     BN_COMMON_CHECKS("bn_act_bwd_reduce")
     unsigned slab;
-    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 4, &slab);
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 3, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
         bn_act_bwd_reduce_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)da, (const T*)y, scale_shift, mean_rstd,
                                                                        sums, C, (unsigned)pix_per_group, slab, slope);)
@@ -735,7 +785,7 @@ extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* 
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && gamma && sums && dy && count > 0, "bn_act_bwd_apply: bad argument");
     BN_COMMON_CHECKS("bn_act_bwd_apply")
     unsigned slab;
-    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 8, &slab);
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 6, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
         bn_act_bwd_apply_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)da, (const T*)y, scale_shift, mean_rstd,
                                                                       gamma, sums, (T*)dy, C, (unsigned)pix_per_group, slab,

@@ -29,6 +29,12 @@ class LocalComm:
     def allreduce_mean_(self, t):
         return t
 
+    def allreduce_mean_begin(self, t):
+        return None
+
+    def allreduce_mean_end(self, handle, t):
+        return t
+
     def barrier(self):
         pass
 
@@ -76,6 +82,19 @@ class TorchComm:
     def allreduce_mean_(self, t):
         if self.world_size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world_size)
+        return t
+
+    def allreduce_mean_begin(self, t):
+        """Start averaging a gradient bucket; kernels launched before allreduce_mean_end() overlap the exchange
+        (the collective runs on the process group's own stream, ordered after everything queued so far)."""
+        if self.world_size == 1:
+            return None
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def allreduce_mean_end(self, handle, t):
+        if handle is not None:
+            handle.wait()                       # stream-ordered: the current stream waits, the host does not
             t.div_(self.world_size)
         return t
 

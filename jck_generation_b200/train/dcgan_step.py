@@ -89,13 +89,14 @@ class DCGANStep:
         cab = ctx.slice(0, 2)                                                                              # :164,175
         da4 = ed.head_backward(cab, mode=0, targets=[LABEL_REAL, LABEL_FAKE], wgrad=True, accumulate=False)
         ed.trunk_backward(cab, da4, wgrad=True, input_grad=False, accumulate=False)
+        pending = self.comm.allreduce_mean_begin(self.flat_d.grad)      # D's gradients are final: exchange them ...
 
         cc = ctx.slice(2, 3)                                                                               # :116-126
         da4 = ed.head_backward(cc, mode=1, wgrad=False)
-        dx = ed.trunk_backward(cc, da4, wgrad=False, input_grad=True)
+        dx = ed.trunk_backward(cc, da4, wgrad=False, input_grad=True)   # ... while the penalty's input-gradient sweep runs
         ops.gp_penalty(dx, scal[S_GP])
 
-        self.comm.allreduce_mean_(self.flat_d.grad)
+        self.comm.allreduce_mean_end(pending, self.flat_d.grad)
         self.opt_d.step()                                                                                  # :180
         if after_d_update is not None:
             after_d_update()
