@@ -587,6 +587,287 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the measured bound of the kernels above is the L2 -> shared-memory
+// stream (~6300 B/clk chip-wide, 128x128 tiles move 32 KB per 2.1 MFLOP).  Here two CTAs of a 2-CTA cluster,
+// on the two SMs of one TPC, compute a 256-pixel x BN tile with ONE MMA of M = 256: each CTA stages its own 128
+// pixel rows of A but only HALF of the weight tile (the tensor core reads both halves across the pair), so the
+// bytes per flop drop by 25 % (BN = 128) / 17 % (BN = 64) at the same shared-memory footprint -- which buys a
+// fourth pipeline stage.  The leader (cluster rank 0) issues the MMAs and owns the `full` and `tempty`
+// barriers; TMA completions of both CTAs land on the leader's `full`, tcgen05.commit multicasts `empty` /
+// `tfull` to both CTAs, both CTAs' epilogue warps release the accumulator on the leader's `tempty`.
+// ------------------------------------------------------------------------------------------------
+template <int BN_, int STAGES>
+struct PairSmem {
+    static constexpr int kABytes = kTileM * kBK * 2;
+    static constexpr int kBBytes = (BN_ / 2) * kBK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kBarOff = STAGES * kStage;
+    static constexpr int kRedOff = kBarOff + 512;
+    static constexpr int kCoefOff = kRedOff + 2 * 4 * 2 * BN_ * 4;
+    static constexpr int kTotal = kCoefOff + 2 * 4 * BN_ * 4 + 1024;
+};
+
+template <int BN_, int STAGES, int MODE, int EPIM>
+__global__ void __launch_bounds__(192, 2)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p,
+                    const int n_tiles, const int total_pairs, const BnBwdEpi bb) {
+    static_assert(MODE == kDown || MODE == kUpM, "pair kernel: trunk layers only");
+    constexpr bool kUp = (MODE == kUpM);
+    constexpr int kAccCols = BN_;
+    constexpr int EPI = 4;
+    using L = PairSmem<BN_, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* red = reinterpret_cast<float*>(smem + L::kRedOff);
+    float* coef = reinterpret_cast<float*>(smem + L::kCoefOff);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int Cin = kUp ? p.Ca : p.Cb;
+    const int Cout = kUp ? p.Cb : p.Ca;
+    const int cchunks = Cin / kBK;
+    const int ksteps = (kUp ? 4 : 16) * cchunks;
+    const int tiles_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * 32 * EPI); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2cta(tmem_slot, 2 * kAccCols);
+    fence_before_sync();
+    cluster_sync_all();                    // barriers of BOTH CTAs are initialised before anyone signals across
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int tp, int& nt, int& phase, int& x0, int& y0, int& n0) {
+        nt = tp % n_tiles;
+        int rest = tp / n_tiles;
+        phase = kUp ? (rest & 3) : 0;
+        if (kUp) rest >>= 2;
+        const int mt = 2 * rest + rank;
+        x0 = (mt % p.tiles_x) * p.bw;
+        y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+        n0 = (mt / tiles_img) * p.nb;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer (both CTAs) ----------------
+            int it = 0;
+            for (int tp = cid; tp < total_pairs; tp += ncl) {
+                int nt, phase, x0, y0, n0;
+                decode(tp, nt, phase, x0, y0, n0);
+                const int py = phase >> 1, px = phase & 1;
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* sa = smem + s * L::kStage;
+                    uint8_t* sb = sa + L::kABytes;
+                    if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * L::kStage);   // both CTAs' bytes
+                    const int tap = ks / cchunks, cc = ks - tap * cchunks;
+                    if (!kUp) {
+                        const int ky = tap >> 2, kx = tap & 3;
+                        const int dy = (ky - 1) >> 1, qy = (ky - 1) & 1;
+                        const int dx = (kx - 1) >> 1, qx = (kx - 1) & 1;
+                        tma_load_5d_2cta(sa, &mapA, &full[s], qx * p.Cb + cc * kBK, x0 + dx, qy, y0 + dy, n0);
+                        tma_load_2d_2cta(sb, &mapB, &full[s], tap * p.Cb + cc * kBK, nt * BN_ + rank * (BN_ / 2));
+                    } else {
+                        const int dy = up_d(py, tap >> 1), dx = up_d(px, tap & 1);
+                        tma_load_4d_2cta(sa, &mapA, &full[s], cc * kBK, x0 + dx, y0 + dy, n0);
+                        tma_load_2d_2cta(sb, &mapB, &full[s], tap * p.Ca + cc * kBK, phase * p.Cb + nt * BN_ + rank * (BN_ / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---------------- MMA issuer (leader CTA only) ----------------
+            constexpr uint32_t idesc = make_idesc(BN_, 0, 0, 256);
+            int it = 0, lt = 0;
+            for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);
+                fence_after_sync();
+                const uint32_t tmem_d = tmem_base + acc * kAccCols;
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    fence_after_sync();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(smem + s * L::kStage);
+                        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_bf16_2cta(tmem_d, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024),
+                                           idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_2cta(&empty[s], 3);
+                        if (ks == ksteps - 1) umma_commit_2cta(&tfull[acc], 3);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue (warps 2..5 of both CTAs: this CTA's 128 rows) ----------------
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;
+        const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+        int lt = 0;
+        for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
+            int nt, phase, x0, y0, n0;
+            decode(tp, nt, phase, x0, y0, n0);
+            const int py = phase >> 1, px = phase & 1;
+            const int n = n0 + nl;
+            const bool valid = n < p.B;
+            const bool tile_live = n0 < p.B;            // the odd pair member past the last tile holds zeros only
+            const int acc = lt & 1;
+            const uint32_t tmem_d = tmem_base + acc * kAccCols + ((uint32_t)(wq * 32) << 16);
+            float* cf = coef + (lt & 1) * (4 * BN_);
+            if constexpr (EPIM == 1) {
+                if (tile_live) {
+                    const size_t gofs = (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
+                    for (int i = threadIdx.x - 64; i < 4 * BN_; i += 32 * EPI) {
+                        const int which = i / BN_, cc = i - which * BN_;
+                        cf[i] = ((which < 2) ? bb.ss : bb.mr)[gofs + (which & 1) * Cout + cc];
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+            }
+            mbar_wait(&tfull[acc], (lt >> 1) & 1);
+            fence_after_sync();
+            size_t pix;
+            if (!kUp) pix = ((size_t)n * p.Hs + (y0 + yl)) * p.Ws + (x0 + xl);
+            else pix = ((size_t)n * 2 * p.Hs + 2 * (y0 + yl) + py) * (2 * p.Ws) + 2 * (x0 + xl) + px;
+            __nv_bfloat16* orow = out + pix * Cout + nt * BN_;
+            float* rbuf = red + (lt & 1) * (4 * 2 * BN_);
+            constexpr int kChunks = BN_ / 32;
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c) {
+                float v[32];
+                tmem_ld32(tmem_d + c * 32, v);
+                tmem_ld_wait();
+                if (c == kChunks - 1) {                 // accumulator read: hand it back to the leader's MMA warp
+                    fence_before_sync();
+                    mbar_arrive_leader(&tempty[acc]);
+                }
+                float sq[32];
+                if constexpr (EPIM == 1) {
+                    uint4 yr[4];
+                    if (valid) {
+                        const uint4* ys = reinterpret_cast<const uint4*>(bb.y + pix * Cout + nt * BN_ + c * 32);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) yr[q] = __ldg(ys + q);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) yr[q] = make_uint4(0, 0, 0, 0);
+                    }
+                    const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(yr);
+                    const float* c0 = cf + c * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float yv = __bfloat162float(yb[i]);
+                        const float pre = fmaf(yv, c0[i], c0[BN_ + i]);
+                        const float gg = pre > 0.f ? v[i] : v[i] * bb.slope;
+                        v[i] = gg;
+                        sq[i] = gg * (yv - c0[2 * BN_ + i]) * c0[3 * BN_ + i];
+                    }
+                }
+                if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                        u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                        u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                        u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                        dst[q] = u;
+                    }
+                }
+                if (stats != nullptr) {
+                    if constexpr (EPIM == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+                    }
+                    const float s1 = warp_transpose_sum(v, lane);
+                    const float s2 = warp_transpose_sum(sq, lane);
+                    rbuf[(wq * 2 + 0) * BN_ + c * 32 + lane] = s1;
+                    rbuf[(wq * 2 + 1) * BN_ + c * 32 + lane] = s2;
+                }
+            }
+            if (stats != nullptr) {
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+                if (tile_live) {
+                    const int e = threadIdx.x - 64;
+                    float* sp = stats + (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
+                    for (int col = e; col < 2 * BN_; col += 32 * EPI) {
+                        const int which = col / BN_, cc = col % BN_;
+                        const float sv = rbuf[(0 * 2 + which) * BN_ + cc] + rbuf[(1 * 2 + which) * BN_ + cc] +
+                                         rbuf[(2 * 2 + which) * BN_ + cc] + rbuf[(3 * 2 + which) * BN_ + cc];
+                        atomicAdd(sp + which * Cout + cc, sv);
+                    }
+                }
+            }
+        }
+    }
+
+    fence_before_sync();
+    cluster_sync_all();                    // the peer may still be signalling this CTA's barriers / reading its smem
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc_2cta(tmem_base, 2 * kAccCols);
+    }
+}
+
+// JCK_CONV_PAIR=0 disables the cta_group::2 kernels (default on)
+static bool use_pair() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("JCK_CONV_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
+template <int BN_, int STAGES, int MODE, int EPIM>
+int launch_pair_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
+                    int m_tiles, int n_tiles, const BnBwdEpi& bb, cudaStream_t st) {
+    using L = PairSmem<BN_, STAGES>;
+    static bool configured = false;
+    auto kern = conv_tc_pair_kernel<BN_, STAGES, MODE, EPIM>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_pair smem attr: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int total_pairs = ((m_tiles + 1) / 2) * n_tiles * (MODE == kUpM ? 4 : 1);
+    const int clusters = total_pairs < kNumSMs ? total_pairs : kNumSMs;     // 2 co-resident CTAs per SM
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA, mB, (__nv_bfloat16*)out, stats, p, n_tiles, total_pairs, bb);
+    if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_pair launch: %s", cudaGetErrorString(e));
+    JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc_pair" : "conv_down_tc_pair");
+    return JCK_OK;
+}
+
 // JCK_CONV_PERSIST: 0 = one tile per CTA (2 CTAs/SM); 1 = persistent, 1 CTA/SM, 8 epilogue warps;
 // 2 = persistent, 2 CTAs/SM, 4 epilogue warps each (default: measured 3.91 ms/step vs 4.27 (0) and 4.52 (1) --
 // two co-resident CTAs hide each other's TMA and epilogue latency, persistence removes the per-tile set-up)
@@ -686,6 +967,19 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
     } else {
         if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
         if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn))) return rc;
+    }
+    if (use_pair()) {
+        // cta_group::2: every CTA of a pair stages half of the weight tile -> B box of bn / 2 rows
+        if (!kUp) { if ((rc = map_matrix(&mB, w, Ca, 16 * Cb, bn / 2))) return rc; }
+        else { if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn / 2))) return rc; }
+        const BnBwdEpi none{nullptr, nullptr, nullptr, 0.f};
+        constexpr int M_ = kUp ? kUpM : kDown;
+        if (bn == 128) {
+            if (bb) return launch_pair_cfg<128, 4, M_, 1>(mA, mB, out, stats, p, m_tiles, Cout / 128, *bb, st);
+            return launch_pair_cfg<128, 4, M_, 0>(mA, mB, out, stats, p, m_tiles, Cout / 128, none, st);
+        }
+        if (bb) return launch_pair_cfg<64, 4, M_, 1>(mA, mB, out, stats, p, m_tiles, Cout / 64, *bb, st);
+        return launch_pair_cfg<64, 4, M_, 0>(mA, mB, out, stats, p, m_tiles, Cout / 64, none, st);
     }
     if (use_persistent() || bb != nullptr) {
         if (bn == 128) return launch_conv_tc_persist<128, 6, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 128, st, bb);
