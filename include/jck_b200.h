@@ -95,6 +95,12 @@ int jck_conv_down(const void* in_large, const void* w_down, void* out_small, flo
                   int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
 int jck_conv_up(const void* in_small, const void* w_up, void* out_large, float* stats, int B, int Hs,
                 int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
+/* Image-edge down conv (D.conv1 forward, model/DCGAN.py:10 / G.conv5 input-gradient, :58) straight from the padded
+ * 4-channel image -- no patch matrix: each CTA bulk-copies the 2*bh+2 image rows of a 128-pixel tile into shared
+ * memory and re-packs them into the swizzled MMA operand there.  Same result as jck_p4_to_patches + jck_edge_down. */
+int jck_edge_down_img(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws, int Ca,
+                      int imgs_per_group, void* stream);
+
 /* Input-gradient convolution with the BatchNorm-backward REDUCTION of the layer below fused into its epilogue
  * (bf16 / tcgen05 only; returns JCK_E_UNSUPPORTED_SHAPE otherwise -- callers then use jck_conv_up / jck_conv_down
  * followed by jck_bn_act_bwd_reduce).  With y_saved = that layer's raw conv output (same shape as the result) and

@@ -1298,6 +1298,172 @@ __global__ void edge_wgrad_unpack_kernel(const float* __restrict__ part, float* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// image-edge down conv straight from the padded 4-channel image (no patch matrix in HBM).
+// A 128-pixel output tile (bh rows x Ws columns of one image) needs 2*bh + 2 CONSECUTIVE rows of the P4 image:
+// one contiguous run of (2*bh + 2) * (2*Ws + 2) * 8 bytes (5280 B for a 4 x 32 tile vs the 16 KB patch tile), so
+//   warp 0     : one 1-D bulk copy per tile into a small raw ring (runs ahead of the consumers),
+//   warps 2..5 : thread r re-packs the four 32-byte runs of ITS output pixel from the raw rows into row r of the
+//                128B-swizzled K-major A tile (conflict-free 16-byte shared loads / stores), fences the async proxy,
+//   warp 1     : ONE K = 64 step of tcgen05.mma against the weight tile (loaded once per CTA),
+//   warps 2..5 : epilogue (tcgen05.ld, BatchNorm partial sums, bf16 rows) -- then the next tile.
+// The per-tile chain is serial inside a CTA (the MMA is 4 instructions); three co-resident CTAs per SM overlap it.
+// HBM traffic per output pixel: 8 B of image (L2-shared between neighbouring tiles) + 128 B written, instead of
+// 128 B (patches written) + 128 B (patches read) + 128 B.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEdgeRawStages = 3;
+struct EdgeDirectParams {
+    int B, Hs, Ws, bh, tiles_y, ipg, raw_bytes, raw_stride;
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(192, 3)
+edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfloat16* __restrict__ img,
+                        __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const EdgeDirectParams p,
+                        const int total_tiles) {
+    constexpr int BN_ = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                                   // [128][64] bf16, 128B swizzle
+    uint8_t* sB = smem + kTileM * 128;                    // [64][64] bf16, 128B swizzle
+    uint8_t* sRaw = sB + BN_ * 128;                       // kEdgeRawStages x raw_stride
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(sRaw + kEdgeRawStages * p.raw_stride);
+    uint64_t* raw_empty = raw_full + kEdgeRawStages;
+    uint64_t* b_full = raw_empty + kEdgeRawStages;
+    uint64_t* a_ready = b_full + 1;
+    uint64_t* tfull = a_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    float* red = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][2][64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Wp = 2 * p.Ws + 2, Hp = 2 * p.Hs + 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < kEdgeRawStages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
+        mbar_init(b_full, 1);
+        mbar_init(a_ready, 128);
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN_);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(b_full, BN_ * 128);
+            tma_load_2d(sB, &mapB, b_full, 0, 0);
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int s = it % kEdgeRawStages;
+                mbar_wait(&raw_empty[s], ((it / kEdgeRawStages) & 1) ^ 1);
+                const int n = t / p.tiles_y, oy0 = (t - n * p.tiles_y) * p.bh;
+                const __nv_bfloat16* src = img + ((size_t)n * Hp + 2 * oy0) * Wp * 4;
+                mbar_arrive_expect_tx(&raw_full[s], p.raw_bytes);
+                bulk_load_1d(sRaw + s * p.raw_stride, src, p.raw_bytes, &raw_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BN_, 0, 0);
+        mbar_wait(b_full, 0);
+        int lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            mbar_wait(a_ready, lt & 1);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                    umma_bf16(tmem_base, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024), idesc,
+                              k > 0 ? 1u : 0u);
+                umma_commit(tfull);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;                      // tile row = output pixel = TMEM lane
+        const int ox = r % p.Ws, oyl = r / p.Ws;
+        int lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int s = lt % kEdgeRawStages;
+            const int n = t / p.tiles_y, oy0 = (t - n * p.tiles_y) * p.bh;
+            // ---- re-pack this pixel's 4x4x4 patch: raw rows -> swizzled K-major row r of A ----
+            mbar_wait(&raw_full[s], (lt / kEdgeRawStages) & 1);
+            const uint8_t* raw = sRaw + s * p.raw_stride;
+            uint4 q[8];
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                const uint4* src = reinterpret_cast<const uint4*>(raw + ((size_t)(2 * oyl + ky) * Wp + 2 * ox) * 8);
+                q[2 * ky] = src[0];
+                q[2 * ky + 1] = src[1];
+            }
+            mbar_arrive(&raw_empty[s]);                    // raw slot read into registers
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(sA + r * 128 + ((c ^ (r & 7)) << 4)) = q[c];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+            fence_before_sync();                           // orders this thread's earlier tcgen05.ld before the next MMA
+            mbar_arrive(a_ready);
+            // ---- epilogue ----
+            mbar_wait(tfull, lt & 1);
+            fence_after_sync();
+            const size_t pix = ((size_t)n * p.Hs + oy0 + oyl) * p.Ws + ox;
+            __nv_bfloat16* orow = out + pix * BN_;
+            const uint32_t tmem_d = tmem_base + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN_ / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_d + c * 32, v);
+                tmem_ld_wait();
+                uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint4 u;
+                    u.x = pack_bf16x2(v[qq * 8 + 0], v[qq * 8 + 1]);
+                    u.y = pack_bf16x2(v[qq * 8 + 2], v[qq * 8 + 3]);
+                    u.z = pack_bf16x2(v[qq * 8 + 4], v[qq * 8 + 5]);
+                    u.w = pack_bf16x2(v[qq * 8 + 6], v[qq * 8 + 7]);
+                    dst[qq] = u;
+                }
+                if (stats != nullptr) {
+                    float sq[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+                    const float s1 = warp_transpose_sum(v, lane);
+                    const float s2 = warp_transpose_sum(sq, lane);
+                    red[(wq * 2 + 0) * BN_ + c * 32 + lane] = s1;
+                    red[(wq * 2 + 1) * BN_ + c * 32 + lane] = s2;
+                }
+            }
+            if (stats != nullptr) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int e = threadIdx.x - 64;            // 128 threads = 2 * BN_ columns
+                const int which = e / BN_, cc = e % BN_;
+                const float sv = red[(0 * 2 + which) * BN_ + cc] + red[(1 * 2 + which) * BN_ + cc] +
+                                 red[(2 * 2 + which) * BN_ + cc] + red[(3 * 2 + which) * BN_ + cc];
+                atomicAdd(stats + (size_t)(n / p.ipg) * 2 * BN_ + which * BN_ + cc, sv);
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // red[] is rewritten by the next tile
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, BN_);
+    }
+}
+
 struct EdgePlan { bool ok; int splits, steps_per_split, total_steps; };
 EdgePlan edge_wgrad_plan(int B, int Hs, int Ws) {
     EdgePlan pl{};
@@ -1433,6 +1599,34 @@ extern "C" int jck_edge_down(const void* patches, const void* w_down_e, void* ou
     if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
     if (use_persistent()) return launch_conv_tc_persist<64, 6, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
     return launch_conv_tc_mode<64, 2, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
+}
+
+extern "C" int jck_edge_down_img(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
+                                 int Ca, int imgs_per_group, void* stream) {
+    JCK_REQUIRE(img_p4 && w_down_e && out_small && B > 0 && Hs > 0 && Ws > 0, "edge_down_img: bad argument");
+    if (imgs_per_group <= 0) imgs_per_group = B;
+    PatchGeom g;
+    if (Ca != 64 || !patch_geom(Hs, Ws, kTileM, &g) || g.bw != Ws || g.nb != 1)
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_down_img: Ca=%d Hs=%d Ws=%d (needs Ca = 64, Ws <= 128, Hs*Ws >= 128)", Ca, Hs, Ws);
+    EdgeDirectParams p{B, Hs, Ws, g.bh, Hs / g.bh, imgs_per_group, (2 * g.bh + 2) * (2 * Ws + 2) * 8, 0};
+    p.raw_stride = (p.raw_bytes + 127) & ~127;
+    const int smem = kTileM * 128 + 64 * 128 + kEdgeRawStages * p.raw_stride + 256 + 4 * 2 * 64 * 4 + 1024;
+    JCK_REQUIRE(smem <= 72 * 1024, "edge_down_img: tile too large for the raw ring (%d bytes)", smem);
+    CUtensorMap mB;
+    int rc;
+    if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(edge_down_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_down_img smem attr: %s", cudaGetErrorString(e));
+        cfg = true;
+    }
+    const int total = B * p.tiles_y;
+    const int grid = total < 3 * kNumSMs ? total : 3 * kNumSMs;
+    edge_down_direct_kernel<<<grid, 192, smem, as_stream(stream)>>>(mB, (const __nv_bfloat16*)img_p4, (__nv_bfloat16*)out_small,
+                                                                  stats, p, total);
+    JCK_LAUNCH_CHECK("edge_down_img");
+    return JCK_OK;
 }
 
 extern "C" int jck_edge_down_bnbwd(const void* patches, const void* w_down_e, const void* y_saved, const float* scale_shift,

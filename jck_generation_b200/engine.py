@@ -222,8 +222,7 @@ class DiscriminatorEngine(_GradTarget):
             y = torch.empty(B, cv.Hs, cv.Ws, cv.Ca, dtype=self.dtype, device=self.dev)
             stats = zeros[k - 1]
             if cv.edge:
-                ctx.x_patches = ops.p4_to_patches(cur)
-                ops.edge_down(ctx.x_patches, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)
+                ops.edge_down_img(cur, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)   # patch matrix only if wgrad needs it
             else:
                 ops.conv_down(cur, cv.w_down, y, stats, cv.Ca, cv.Cb, ipg=B // groups, algo=self.algo)
             ss = torch.empty(groups, 2 * cv.Ca, dtype=torch.float32, device=self.dev)
@@ -302,6 +301,8 @@ class DiscriminatorEngine(_GradTarget):
             inp = ctx.a[k - 1] if k > 1 else ctx.x
             if wgrad:
                 if cv.edge:
+                    if ctx.x_patches is None:
+                        ctx.x_patches = ops.p4_to_patches(ctx.x)
                     nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
                     ops.edge_wgrad(dy, ctx.x_patches, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
                 else:
@@ -418,7 +419,7 @@ class GeneratorEngine(_GradTarget):
                 nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
                 patches = ops.p4_to_patches(d_large)
                 ops.edge_wgrad(ctx.a[k - 1], patches, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
-                ops.edge_down(patches, cv.w_down_e, da, None, cv.Ca)
+                ops.edge_down_img(d_large, cv.w_down_e, da, None, cv.Ca)
                 reduced = False
             else:
                 nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)

@@ -74,6 +74,12 @@ def edge_down(patches, w_down_e, out_small, stats, Ca, ipg=0):
     check(L().jck_edge_down(_p(patches), _p(w_down_e), _p(out_small), _p(stats), B, Hs, Ws, Ca, ipg, _s()), "edge_down")
 
 
+def edge_down_img(img_p4, w_down_e, out_small, stats, Ca, ipg=0):
+    """edge_down reading the JCK_IMG_P4 image itself (no patch matrix)."""
+    B, Hs, Ws = out_small.shape[0], out_small.shape[1], out_small.shape[2]
+    check(L().jck_edge_down_img(_p(img_p4), _p(w_down_e), _p(out_small), _p(stats), B, Hs, Ws, Ca, ipg, _s()), "edge_down_img")
+
+
 def edge_up(x_small, w_up9, img_p4, Ca):
     B, Hs, Ws = x_small.shape[0], x_small.shape[1], x_small.shape[2]
     check(L().jck_edge_up(_p(x_small), _p(w_up9), _p(img_p4), B, Hs, Ws, Ca, _s()), "edge_up")

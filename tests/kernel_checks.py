@@ -171,15 +171,21 @@ def check_edge(which, B=8, nc=3):
     w4 = _mk((Ca, nc, 4, 4), dt, 31, 0.05)
     wde = torch.empty(Ca * 64, dtype=dt, device="cuda"); wu9 = torch.empty(16 * 9 * Ca, dtype=dt, device="cuda")
     ops.pack_weights_edge(w4.cuda().contiguous(), wde, wu9)
-    if which == "down":
+    if which in ("down", "downimg"):
         x = _mk((B, nc, 64, 64), dt, 32)
         want = F.conv2d(x, w4, stride=2, padding=1)
         out = torch.full((B, Hs, Hs, Ca), float("nan"), dtype=dt, device="cuda")
-        stats = torch.zeros(1, 2 * Ca, device="cuda")
-        ops.edge_down(ops.p4_to_patches(_to_p4(x)), wde, out, stats, Ca)
+        groups = 2 if (which == "downimg" and B % 2 == 0) else 1
+        stats = torch.zeros(groups, 2 * Ca, device="cuda")
+        if which == "down":
+            ops.edge_down(ops.p4_to_patches(_to_p4(x)), wde, out, stats, Ca)
+        else:                                   # straight from the padded image, two BatchNorm groups
+            ops.edge_down_img(_to_p4(x), wde, out, stats, Ca, ipg=B // groups)
         torch.cuda.synchronize()
-        ws = torch.cat([want.sum((0, 2, 3)), (want ** 2).sum((0, 2, 3))])
-        return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats.view(-1), ws)}
+        per = B // groups
+        ws = torch.stack([torch.cat([want[g * per:(g + 1) * per].sum((0, 2, 3)), (want[g * per:(g + 1) * per] ** 2).sum((0, 2, 3))])
+                          for g in range(groups)])
+        return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats, ws)}
     if which == "up":
         x = _mk((B, Ca, Hs, Hs), dt, 33)
         want = F.conv_transpose2d(x, w4, stride=2, padding=1)
@@ -358,7 +364,8 @@ def all_cases():
               ("down_groups", "c4", "f32", "simt", 6)]
     cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_up", "-", "bf16", "tc", 8),
               ("edge_up", "-", "bf16", "tc", 5), ("edge_wgrad", "-", "bf16", "tc", 8), ("edge_wgrad", "-", "bf16", "tc", 3),
-              ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
+              ("edge_downimg", "-", "bf16", "tc", 8), ("edge_downimg", "-", "bf16", "tc", 3), ("edge_downimg", "-", "bf16", "tc", 150),
+              ("edge_downimg1", "-", "bf16", "tc", 4), ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
     cases += [("bnbwd_up", "c2", "bf16", "tc", 8), ("bnbwd_up", "c3", "bf16", "tc", 8), ("bnbwd_up", "c4", "bf16", "tc", 3),
               ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16),
               ("bnbwd_edge", "-", "bf16", "tc", 8), ("bnbwd_edge", "-", "bf16", "tc", 3)]
