@@ -98,6 +98,8 @@ int jck_conv_up(const void* in_small, const void* w_up, void* out_large, float* 
 /* Image-edge down conv (D.conv1 forward, model/DCGAN.py:10 / G.conv5 input-gradient, :58) straight from the padded
  * 4-channel image -- no patch matrix: each CTA bulk-copies the 2*bh+2 image rows of a 128-pixel tile into shared
  * memory and re-packs them into the swizzled MMA operand there.  Same result as jck_p4_to_patches + jck_edge_down. */
+int jck_edge_wgrad_img(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes, int B,
+                       int Hs, int Ws, int Ca, int nc, int accumulate, void* stream);   /* = p4_to_patches + edge_wgrad */
 int jck_edge_down_img(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws, int Ca,
                       int imgs_per_group, void* stream);
 

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "jck_pack_weights_edge": [c_p, c_p, c_p, c_i, c_i, c_p],
     "jck_p4_to_patches": [c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_edge_down": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_edge_wgrad_img": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_down_img": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_up": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i],

@@ -1285,6 +1285,136 @@ wgrad_edge_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
     }
 }
 
+// Same weight gradient with the patch operand built in shared memory from the padded image itself (see
+// edge_down_direct_kernel): per 64-pixel K step the producer bulk-copies the 2*rps + 2 image rows next to the TMA
+// box of `small`, warps 2..5 re-pack them into the swizzled [64 pixels][64] tile (half a pixel row per thread),
+// and the MMA warp consumes the stage once both the TMA bytes and the re-pack have landed.
+struct EdgeWgradDirectParams { int total_steps, steps_per_split, Hs, Ws, rps, raw_bytes, raw_stride; };
+constexpr int kEdgeWDStages = 4;
+
+__global__ void __launch_bounds__(kConvThreads)
+wgrad_edge_direct_kernel(const __grid_constant__ CUtensorMap mapS, const __nv_bfloat16* __restrict__ img,
+                         float* __restrict__ part, const EdgeWgradDirectParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kTile = kWgradKPix * 128;                        // 8 KB
+    uint8_t* sSmall = smem;                                        // [stages][8 KB]
+    uint8_t* sPatch = sSmall + kEdgeWDStages * kTile;              // [stages][8 KB]
+    uint8_t* sZero = sPatch + kEdgeWDStages * kTile;               // 8 KB of zeros (upper 64-row atom of the M = 128 MMA)
+    uint8_t* sRaw = sZero + kTile;                                 // [stages][raw_stride]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRaw + kEdgeWDStages * p.raw_stride);
+    uint64_t* empty = full + kEdgeWDStages;
+    uint64_t* ready = empty + kEdgeWDStages;
+    uint64_t* tmem_full = ready + kEdgeWDStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int step_beg = split * p.steps_per_split;
+    const int nsteps = max(0, min(p.total_steps, step_beg + p.steps_per_split) - step_beg);
+    const int Wp = 2 * p.Ws + 2, Hp = 2 * p.Hs + 2;
+    for (int i = threadIdx.x; i < kTile / 16; i += kConvThreads) reinterpret_cast<uint4*>(sZero)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapS);
+        for (int s = 0; s < kEdgeWDStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % kEdgeWDStages;
+                mbar_wait(&empty[s], ((it / kEdgeWDStages) & 1) ^ 1);
+                const int st = step_beg + it;
+                const int row = st * p.rps;                         // global output row index (n * Hs + oy0)
+                const int n = row / p.Hs, oy0 = row - n * p.Hs;
+                mbar_arrive_expect_tx(&full[s], kTile + p.raw_bytes);
+                tma_load_2d(sSmall + s * kTile, &mapS, &full[s], 0, st * kWgradKPix);
+                bulk_load_1d(sRaw + s * p.raw_stride, img + ((size_t)n * Hp + 2 * oy0) * Wp * 4, p.raw_bytes, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(64, 1, 1);
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % kEdgeWDStages;
+            const uint32_t ph = (it / kEdgeWDStages) & 1;
+            mbar_wait(&full[s], ph);                               // TMA bytes of `small`
+            mbar_wait(&ready[s], ph);                              // re-packed patches
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(sSmall + s * kTile);
+                const uint32_t b_addr = smem_u32(sPatch + s * kTile);
+                const uint32_t lbo = smem_u32(sZero) - a_addr;
+#pragma unroll
+                for (int k = 0; k < kWgradKPix / 16; ++k)
+                    umma_bf16(tmem_base, make_sdesc(a_addr + k * 2048, lbo, 1024), make_sdesc(b_addr + k * 2048, 0, 1024),
+                              idesc, (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty[s]);
+                if (it == nsteps - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int e = threadIdx.x - 64;                            // 0..127
+        const int r = e >> 1, half = e & 1;                        // pixel row of the K step, which two filter rows
+        const int ox = r % p.Ws, oyl = r / p.Ws;
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % kEdgeWDStages;
+            mbar_wait(&full[s], (it / kEdgeWDStages) & 1);
+            const uint8_t* raw = sRaw + s * p.raw_stride;
+            uint8_t* dst = sPatch + s * kTile + r * 128;
+            uint4 q[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int ky = 2 * half + j;
+                const uint4* src = reinterpret_cast<const uint4*>(raw + ((size_t)(2 * oyl + ky) * Wp + 2 * ox) * 8);
+                q[2 * j] = src[0];
+                q[2 * j + 1] = src[1];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 4 * half + j;
+                *reinterpret_cast<uint4*>(dst + ((c ^ (r & 7)) << 4)) = q[j];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&ready[s]);
+        }
+        const int wq = warp & 3;
+        if (wq < 2) {                                              // TMEM lanes 0..63 carry the 64 real rows
+            const int a = wq * 32 + lane;
+            if (nsteps > 0) { mbar_wait(tmem_full, 0); fence_after_sync(); }
+            float* drow = part + ((size_t)split * 64 + a) * 64;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float v[32];
+                if (nsteps > 0) {
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+                float4* d4 = reinterpret_cast<float4*>(drow + c * 32);
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) d4[qq] = make_float4(v[qq * 4], v[qq * 4 + 1], v[qq * 4 + 2], v[qq * 4 + 3]);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
 // dw4[a][c][ky][kx] (+)= sum_split part[split][a][ky*16 + kx*4 + c], c < nc
 __global__ void edge_wgrad_unpack_kernel(const float* __restrict__ part, float* __restrict__ dw4, int nc, int splits,
                                          int accumulate) {
@@ -1315,12 +1445,6 @@ constexpr int kEdgeRawStages = 3;
 struct EdgeDirectParams {
     int B, Hs, Ws, bh, tiles_y, ipg, raw_bytes, raw_stride;
 };
-
-__device__ __forceinline__ void bulk_load_1d(void* smem, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 __global__ void __launch_bounds__(192, 3)
 edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfloat16* __restrict__ img,
@@ -1687,6 +1811,35 @@ extern "C" int jck_edge_wgrad(const void* small, const void* patches, float* dw4
     EdgeWgradParams p{pl.total_steps, pl.steps_per_split};
     wgrad_edge_tc_kernel<<<pl.splits, kConvThreads, kEdgeWSmem, st>>>(mS, mP, (float*)workspace, p);
     JCK_LAUNCH_CHECK("edge_wgrad_tc");
+    edge_wgrad_unpack_kernel<<<(64 * nc * 16 + 255) / 256, 256, 0, st>>>((const float*)workspace, dw4, nc, pl.splits, accumulate);
+    JCK_LAUNCH_CHECK("edge_wgrad_unpack");
+    return JCK_OK;
+}
+
+extern "C" int jck_edge_wgrad_img(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes,
+                                  int B, int Hs, int Ws, int Ca, int nc, int accumulate, void* stream) {
+    JCK_REQUIRE(small && img_p4 && dw4 && workspace && B > 0 && nc > 0 && nc <= 4, "edge_wgrad_img: bad argument");
+    EdgePlan pl = edge_wgrad_plan(B, Hs, Ws);
+    if (Ca != 64 || !pl.ok || Ws > kWgradKPix || kWgradKPix % Ws != 0 || Hs % (kWgradKPix / Ws) != 0)
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_wgrad_img: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
+    JCK_REQUIRE(workspace_bytes >= (size_t)pl.splits * 64 * 64 * sizeof(float), "edge_wgrad_img: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    CUtensorMap mS;
+    int rc;
+    if ((rc = map_rows64(&mS, small, (long long)B * Hs * Ws, kWgradKPix))) return rc;
+    const int rps = kWgradKPix / Ws;
+    EdgeWgradDirectParams p{pl.total_steps, pl.steps_per_split, Hs, Ws, rps, (2 * rps + 2) * (2 * Ws + 2) * 8, 0};
+    p.raw_stride = (p.raw_bytes + 127) & ~127;
+    const int smem = (2 * kEdgeWDStages + 1) * kWgradKPix * 128 + kEdgeWDStages * p.raw_stride + 256 + 1024;
+    JCK_REQUIRE(smem <= 100 * 1024, "edge_wgrad_img: raw ring too large (%d bytes)", smem);
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_edge_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_wgrad_img smem attr: %s", cudaGetErrorString(e));
+        cfg = true;
+    }
+    wgrad_edge_direct_kernel<<<pl.splits, kConvThreads, smem, st>>>(mS, (const __nv_bfloat16*)img_p4, (float*)workspace, p);
+    JCK_LAUNCH_CHECK("edge_wgrad_img");
     edge_wgrad_unpack_kernel<<<(64 * nc * 16 + 255) / 256, 256, 0, st>>>((const float*)workspace, dw4, nc, pl.splits, accumulate);
     JCK_LAUNCH_CHECK("edge_wgrad_unpack");
     return JCK_OK;

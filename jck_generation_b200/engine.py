@@ -81,7 +81,6 @@ class Ctx:
 
     def __init__(self):
         self.x = None          # network input (NHWC)
-        self.x_patches = None  # its 4x4 patch matrix (tcgen05 image-edge path only)
         self.y = {}            # raw conv outputs per layer
         self.a = {}            # activations per layer
         self.ss = {}           # BN scale/shift [groups][2C]
@@ -101,9 +100,6 @@ class Ctx:
         s.groups, s.B = g1 - g0, per * (g1 - g0)
         lo, hi = per * g0, per * g1
         s.x = self.x[lo:hi]
-        if self.x_patches is not None:
-            rows = self.x_patches.shape[0] // self.B
-            s.x_patches = self.x_patches[lo * rows:hi * rows]
         s.y = {k: v[lo:hi] for k, v in self.y.items()}
         s.a = {k: v[lo:hi] for k, v in self.a.items()}
         s.ss = {k: v[g0:g1] for k, v in self.ss.items()}
@@ -301,10 +297,8 @@ class DiscriminatorEngine(_GradTarget):
             inp = ctx.a[k - 1] if k > 1 else ctx.x
             if wgrad:
                 if cv.edge:
-                    if ctx.x_patches is None:
-                        ctx.x_patches = ops.p4_to_patches(ctx.x)
                     nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
-                    ops.edge_wgrad(dy, ctx.x_patches, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                    ops.edge_wgrad_img(dy, ctx.x, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
                 else:
                     nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
                     ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
@@ -417,8 +411,7 @@ class GeneratorEngine(_GradTarget):
             da = torch.empty_like(ctx.a[k - 1])
             if cv.edge:
                 nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
-                patches = ops.p4_to_patches(d_large)
-                ops.edge_wgrad(ctx.a[k - 1], patches, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                ops.edge_wgrad_img(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
                 ops.edge_down_img(d_large, cv.w_down_e, da, None, cv.Ca)
                 reduced = False
             else:

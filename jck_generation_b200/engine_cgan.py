@@ -170,10 +170,9 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
             C = cv.Ca
             dbar = torch.empty_like(ctx.y[k])
             if cv.edge:
-                patches = ops.p4_to_patches(abar)
-                ops.edge_down(patches, cv.w_down_e, dbar, None, C)
+                ops.edge_down_img(abar, cv.w_down_e, dbar, None, C)
                 nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, C)
-                ops.edge_wgrad(ctx.dy[k], patches, self._gb(cv.weight), self.ws.get(nbytes), C, self.nc, True)
+                ops.edge_wgrad_img(ctx.dy[k], abar, self._gb(cv.weight), self.ws.get(nbytes), C, self.nc, True)
             else:
                 ops.conv_down(abar, cv.w_down, dbar, None, C, cv.Cb, algo=self.algo)
                 nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, C, cv.Cb, self.dtype, self.algo)

@@ -74,6 +74,13 @@ def edge_down(patches, w_down_e, out_small, stats, Ca, ipg=0):
     check(L().jck_edge_down(_p(patches), _p(w_down_e), _p(out_small), _p(stats), B, Hs, Ws, Ca, ipg, _s()), "edge_down")
 
 
+def edge_wgrad_img(small, img_p4, dw4, workspace, Ca, nc, accumulate):
+    """edge_wgrad reading the JCK_IMG_P4 image itself (no patch matrix)."""
+    B, Hs, Ws = small.shape[0], small.shape[1], small.shape[2]
+    check(L().jck_edge_wgrad_img(_p(small), _p(img_p4), _p(dw4), _p(workspace), workspace.numel() * workspace.element_size(),
+                                 B, Hs, Ws, Ca, nc, int(accumulate), _s()), "edge_wgrad_img")
+
+
 def edge_down_img(img_p4, w_down_e, out_small, stats, Ca, ipg=0):
     """edge_down reading the JCK_IMG_P4 image itself (no patch matrix)."""
     B, Hs, Ws = out_small.shape[0], out_small.shape[1], out_small.shape[2]

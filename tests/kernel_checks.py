@@ -201,9 +201,14 @@ def check_edge(which, B=8, nc=3):
     ws = torch.empty(ops.edge_wgrad_workspace_bytes(B, Hs, Hs, Ca) // 4, device="cuda")
     dw = torch.full((Ca, nc, 4, 4), float("nan"), device="cuda")
     s = small.permute(0, 2, 3, 1).contiguous().to(dt).cuda()
-    patches = ops.p4_to_patches(_to_p4(large))
-    ops.edge_wgrad(s, patches, dw, ws, Ca, nc, False)
-    ops.edge_wgrad(s, patches, dw, ws, Ca, nc, True)
+    if which == "wgradimg":                      # straight from the padded image
+        img = _to_p4(large)
+        ops.edge_wgrad_img(s, img, dw, ws, Ca, nc, False)
+        ops.edge_wgrad_img(s, img, dw, ws, Ca, nc, True)
+    else:
+        patches = ops.p4_to_patches(_to_p4(large))
+        ops.edge_wgrad(s, patches, dw, ws, Ca, nc, False)
+        ops.edge_wgrad(s, patches, dw, ws, Ca, nc, True)
     torch.cuda.synchronize()
     return {"dw": _rel(dw, 2 * want)}
 
@@ -365,7 +370,8 @@ def all_cases():
     cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_up", "-", "bf16", "tc", 8),
               ("edge_up", "-", "bf16", "tc", 5), ("edge_wgrad", "-", "bf16", "tc", 8), ("edge_wgrad", "-", "bf16", "tc", 3),
               ("edge_downimg", "-", "bf16", "tc", 8), ("edge_downimg", "-", "bf16", "tc", 3), ("edge_downimg", "-", "bf16", "tc", 150),
-              ("edge_downimg1", "-", "bf16", "tc", 4), ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
+              ("edge_downimg1", "-", "bf16", "tc", 4), ("edge_wgradimg", "-", "bf16", "tc", 8), ("edge_wgradimg", "-", "bf16", "tc", 3),
+              ("edge_wgradimg", "-", "bf16", "tc", 150), ("edge_wgradimg1", "-", "bf16", "tc", 4), ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
     cases += [("bnbwd_up", "c2", "bf16", "tc", 8), ("bnbwd_up", "c3", "bf16", "tc", 8), ("bnbwd_up", "c4", "bf16", "tc", 3),
               ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16),
               ("bnbwd_edge", "-", "bf16", "tc", 8), ("bnbwd_edge", "-", "bf16", "tc", 3)]
