@@ -95,14 +95,6 @@ int jck_conv_down(const void* in_large, const void* w_down, void* out_small, flo
                   int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
 int jck_conv_up(const void* in_small, const void* w_up, void* out_large, float* stats, int B, int Hs,
                 int Ws, int Ca, int Cb, int imgs_per_group, int dtype, int algo, void* stream);
-/* Image-edge down conv (D.conv1 forward, model/DCGAN.py:10 / G.conv5 input-gradient, :58) straight from the padded
- * 4-channel image -- no patch matrix: each CTA bulk-copies the 2*bh+2 image rows of a 128-pixel tile into shared
- * memory and re-packs them into the swizzled MMA operand there.  Same result as jck_p4_to_patches + jck_edge_down. */
-int jck_edge_wgrad_img(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes, int B,
-                       int Hs, int Ws, int Ca, int nc, int accumulate, void* stream);   /* = p4_to_patches + edge_wgrad */
-int jck_edge_down_img(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws, int Ca,
-                      int imgs_per_group, void* stream);
-
 /* Input-gradient convolution with the BatchNorm-backward REDUCTION of the layer below fused into its epilogue
  * (bf16 / tcgen05 only; returns JCK_E_UNSUPPORTED_SHAPE otherwise -- callers then use jck_conv_up / jck_conv_down
  * followed by jck_bn_act_bwd_reduce).  With y_saved = that layer's raw conv output (same shape as the result) and
@@ -117,9 +109,6 @@ int jck_conv_up_bnbwd(const void* in_small, const void* w_up, const void* y_save
 int jck_conv_down_bnbwd(const void* in_large, const void* w_down, const void* y_saved, const float* scale_shift,
                         const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws, int Ca,
                         int Cb, int imgs_per_group, int dtype, void* stream);
-int jck_edge_down_bnbwd(const void* patches, const void* w_down_e, const void* y_saved, const float* scale_shift,
-                        const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws, int Ca,
-                        int imgs_per_group, void* stream);
 
 /* dw4[Ca][Cb][4][4] (+)= sum over pixels small (x) large.  workspace: jck_conv_wgrad_workspace_bytes. */
 size_t jck_conv_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo);
@@ -128,18 +117,21 @@ int jck_conv_wgrad(const void* small, const void* large, float* dw4, void* works
 
 /* ---- image-edge layers on tensor cores (bf16, nc <= 4 image channels, JCK_IMG_P4 image layout) -----
  * D.conv1 (model/DCGAN.py:10,30) and G.conv5 (model/DCGAN.py:58,66) have 3 channels on their large side:
- * K = 48 or N = 3 in the GEMM view.  With the image stored as JCK_IMG_P4 the whole 4x4x4 patch is one
- * 64-wide K step (down / wgrad), and the transposed direction is a 3x3-shift GEMM with N = 16
- * (4 output parities x 4 channels).  w_down_e[Ca][64], w_up9[16][9*Ca] from jck_pack_weights_edge. */
+ * K = 48 or N = 3 in the GEMM view.  With the image stored as JCK_IMG_P4 the whole 4x4x4 patch of an output
+ * pixel is one 64-wide K step (down / wgrad): the kernels bulk-copy the 2*rows+2 image rows a tile needs into
+ * shared memory and re-pack them there into the swizzled MMA operand -- no im2col / patch matrix ever exists in
+ * HBM.  The transposed direction is a 3x3-shift GEMM with N = 16 (4 output parities x 4 channels).
+ * w_down_e[Ca][64], w_up9[16][9*Ca] from jck_pack_weights_edge. */
 int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up9, int Ca, int nc, void* stream);
-/* patches[B*Hs*Ws][64] bf16: row = output pixel, columns (ky, kx, c4) = its 4x4 patch of the P4 image */
-int jck_p4_to_patches(const void* img_p4, void* patches, int B, int Hs, int Ws, void* stream);
-int jck_edge_down(const void* patches, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
-                  int Ca, int imgs_per_group, void* stream);
+/* D.conv1 forward (nn.Conv2d(nc,64,4,2,1) model/DCGAN.py:10,30) / G.conv5 input-gradient (:58 under backward) */
+int jck_edge_down_img(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws, int Ca,
+                      int imgs_per_group, void* stream);
+/* G.conv5 forward (nn.ConvTranspose2d(64,nc,4,2,1) model/DCGAN.py:58,66) / D.conv1 input-gradient (GP sweep, pass D) */
 int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4, int B, int Hs, int Ws, int Ca, void* stream);
+/* weight gradient of either (small = the 64-channel side, img_p4 = the image side) */
 size_t jck_edge_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca);
-int jck_edge_wgrad(const void* small, const void* patches, float* dw4, void* workspace, size_t workspace_bytes,
-                   int B, int Hs, int Ws, int Ca, int nc, int accumulate, void* stream);
+int jck_edge_wgrad_img(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes, int B,
+                       int Hs, int Ws, int Ca, int nc, int accumulate, void* stream);
 
 /* ---- dense layers (G.conv1: a 1x1 -> 4x4 transposed conv is a matrix product) -----------------
  * out[m][n] = sum_k x[m][k] * w[n][k];  x fp32 [M][K]; w, out activation dtype; stats per channel

@@ -26,19 +26,15 @@ _SIGNATURES = {
     "jck_prep_image": [c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_nhwc_to_nchw_f32": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_weights_edge": [c_p, c_p, c_p, c_i, c_i, c_p],
-    "jck_p4_to_patches": [c_p, c_p, c_i, c_i, c_i, c_p],
-    "jck_edge_down": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_wgrad_img": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_down_img": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_up": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i],
-    "jck_edge_wgrad": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_weights": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_conv_down": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_conv_up": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_conv_up_bnbwd": [c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_conv_down_bnbwd": [c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
-    "jck_edge_down_bnbwd": [c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_conv_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i, c_i, c_i, c_i],
     "jck_conv_wgrad": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_dense": [c_p, c_i, c_ll, c_ll, c_p, c_i, c_ll, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p],

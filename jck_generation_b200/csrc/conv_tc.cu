@@ -120,205 +120,15 @@ constexpr int kConvThreads = 192;
 constexpr int kTileM = 128;
 constexpr int kBK = 64;  // bf16 elements per K step = one 128-byte swizzle row
 
-template <int BN_, int STAGES>
-struct ConvSmem {
-    static constexpr int kABytes = kTileM * kBK * 2;
-    static constexpr int kBBytes = BN_ * kBK * 2;
-    static constexpr int kStage = kABytes + kBBytes;
-    static constexpr int kBarOff = STAGES * kStage;
-    static constexpr int kRedOff = kBarOff + 256;
-    static constexpr int kTotal = kRedOff + 4 * 2 * BN_ * 4 + 1024;  // + alignment slack
-};
-
 // MODE: which implicit GEMM the tile loop walks
 constexpr int kDown = 0;      // 16 taps x Cb/64 chunks, A through the parity view of the large tensor
-constexpr int kUpM = 1;       // one output parity (blockIdx.z): 4 taps x Ca/64 chunks, A = shifted small tensor
-constexpr int kEdgeDown = 2;  // image edge: ONE K step, A = 128 rows of the patch matrix (whole 4x4x4 patches)
+constexpr int kUpM = 1;       // one output parity: 4 taps x Ca/64 chunks, A = shifted small tensor
+constexpr int kEdgeDown = 2;  // (patch-matrix image edge; superseded by edge_down_direct_kernel, kept for the generic tile walker)
 constexpr int kEdgeUp = 3;    // image edge: 9 input shifts x Ca/64, N = 16 (4 parities x 4 channels) -> P4 image
 
-template <int BN_, int STAGES, int MODE>
-__global__ void __launch_bounds__(kConvThreads)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p) {
-    constexpr bool kUp = (MODE == kUpM);
-    using L = ConvSmem<BN_, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* red = reinterpret_cast<float*>(smem + L::kRedOff);  // [4 warps][2][BN_]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates
-    const int mt = blockIdx.x;
-    const int x0 = (mt % p.tiles_x) * p.bw;
-    const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
-    const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.nb;
-    const int nt = blockIdx.y;
-    const int phase = kUp ? blockIdx.z : 0;
-    const int py = phase >> 1, px = phase & 1;
-    const int Cin = (MODE == kUpM || MODE == kEdgeUp) ? p.Ca : p.Cb;    // contraction channels
-    const int Cout = (MODE == kUpM) ? p.Cb : p.Ca;
-    const int cchunks = MODE == kEdgeDown ? 1 : Cin / kBK;
-    const int ksteps = MODE == kEdgeDown ? 1 : (MODE == kUpM ? 4 : (MODE == kEdgeUp ? 9 : 16)) * cchunks;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&mapA);
-        prefetch_tmap(&mapB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, BN_ < 32 ? 32 : BN_);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer ----------------
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int s = ks % STAGES;
-                const uint32_t ph = (ks / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* sa = smem + s * L::kStage;
-                uint8_t* sb = sa + L::kABytes;
-                mbar_arrive_expect_tx(&full[s], L::kStage);
-                const int tap = ks / cchunks, cc = ks - tap * cchunks;
-                if (MODE == kEdgeDown) {
-                    // every row of the tile is one whole patch; tiles are 128 consecutive output pixels
-                    tma_load_2d(sa, &mapA, &full[s], 0, mt * kTileM);
-                    tma_load_2d(sb, &mapB, &full[s], 0, nt * BN_);
-                } else if (MODE == kEdgeUp) {
-                    const int di = tap / 3 - 1, dj = tap % 3 - 1;
-                    tma_load_4d(sa, &mapA, &full[s], cc * kBK, x0 + dj, y0 + di, n0);
-                    tma_load_2d(sb, &mapB, &full[s], tap * p.Ca + cc * kBK, 0);
-                } else if (!kUp) {
-                    const int ky = tap >> 2, kx = tap & 3;
-                    const int dy = (ky - 1) >> 1, qy = (ky - 1) & 1;   // input row 2*oy + ky - 1 = 2*(oy+dy) + qy
-                    const int dx = (kx - 1) >> 1, qx = (kx - 1) & 1;
-                    tma_load_5d(sa, &mapA, &full[s], qx * p.Cb + cc * kBK, x0 + dx, qy, y0 + dy, n0);
-                    tma_load_2d(sb, &mapB, &full[s], tap * p.Cb + cc * kBK, nt * BN_);
-                } else {
-                    const int dy = up_d(py, tap >> 1), dx = up_d(px, tap & 1);
-                    tma_load_4d(sa, &mapA, &full[s], cc * kBK, x0 + dx, y0 + dy, n0);
-                    tma_load_2d(sb, &mapB, &full[s], tap * p.Ca + cc * kBK, phase * p.Cb + nt * BN_);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        constexpr uint32_t idesc = make_idesc(BN_, 0, 0);
-        for (int ks = 0; ks < ksteps; ++ks) {
-            const int s = ks % STAGES;
-            const uint32_t ph = (ks / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            fence_after_sync();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + s * L::kStage);
-                const uint32_t b_addr = a_addr + L::kABytes;
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                    const uint64_t da = make_sdesc(a_addr + k * 32, 0, 1024);
-                    const uint64_t db = make_sdesc(b_addr + k * 32, 0, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
-                if (ks == ksteps - 1) umma_commit(tmem_full); // accumulator complete
-            }
-            __syncwarp();
-        }
-    } else {
-        // ---------------- epilogue (warps 2..5) ----------------
-        const int wq = warp & 3;                 // TMEM lane quarter this warp may read
-        const int r = wq * 32 + lane;            // tile row = output pixel
-        const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
-        const int n = n0 + nl;
-        const bool valid = n < p.B;
-        size_t pix;
-        if (!kUp) pix = ((size_t)n * p.Hs + (y0 + yl)) * p.Ws + (x0 + xl);
-        else pix = ((size_t)n * 2 * p.Hs + 2 * (y0 + yl) + py) * (2 * p.Ws) + 2 * (x0 + xl) + px;
-        __nv_bfloat16* orow = out + pix * Cout + nt * BN_;
-
-        mbar_wait(tmem_full, 0);
-        fence_after_sync();
-        if constexpr (MODE == kEdgeUp) {
-            // 16 accumulator columns = (py, px, c4): two 16-byte stores into the padded 4-channel image
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16), v);
-            tmem_ld_wait();
-            if (valid) {
-                const int Wp = 2 * p.Ws + 2, Hp = 2 * p.Hs + 2;
-#pragma unroll
-                for (int qy = 0; qy < 2; ++qy) {
-                    // pixel (2i+qy, 2j) sits at padded column 2j+1: 8-byte aligned, so one 8-byte store per pixel
-                    const size_t o = (((size_t)n * Hp + 2 * (y0 + yl) + qy + 1) * Wp + 2 * (x0 + xl) + 1) * 4;
-                    uint2 u0, u1;
-                    u0.x = pack_bf16x2(v[qy * 8 + 0], v[qy * 8 + 1]);
-                    u0.y = pack_bf16x2(v[qy * 8 + 2], v[qy * 8 + 3]);
-                    u1.x = pack_bf16x2(v[qy * 8 + 4], v[qy * 8 + 5]);
-                    u1.y = pack_bf16x2(v[qy * 8 + 6], v[qy * 8 + 7]);
-                    *reinterpret_cast<uint2*>(out + o) = u0;
-                    *reinterpret_cast<uint2*>(out + o + 4) = u1;
-                }
-            }
-        } else {
-#pragma unroll 1
-        for (int c = 0; c < BN_ / 32; ++c) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
-            tmem_ld_wait();
-            if (valid) {
-                uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 u;
-                    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                    dst[q] = u;
-                }
-            }
-            if (stats != nullptr) {
-                // rows past the batch hold exact zeros (TMA zero fill), so no masking is needed
-                float sq[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-                const float s1 = warp_transpose_sum(v, lane);
-                const float s2 = warp_transpose_sum(sq, lane);
-                red[(wq * 2 + 0) * BN_ + c * 32 + lane] = s1;
-                red[(wq * 2 + 1) * BN_ + c * 32 + lane] = s2;
-            }
-        }
-        if (stats != nullptr) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
-            const int e = threadIdx.x - 64;                  // 0..127
-            float* sp = stats + (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
-            for (int col = e; col < 2 * BN_; col += 128) {
-                const int which = col / BN_, cc = col % BN_;
-                const float s = red[(0 * 2 + which) * BN_ + cc] + red[(1 * 2 + which) * BN_ + cc] +
-                                red[(2 * 2 + which) * BN_ + cc] + red[(3 * 2 + which) * BN_ + cc];
-                atomicAdd(sp + which * Cout + cc, s);
-            }
-        }
-        }  // MODE != kEdgeUp
-    }
-
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 1) {
-        fence_after_sync();
-        tmem_dealloc(tmem_base, BN_ < 32 ? 32 : BN_);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem
+// Single-CTA persistent tile walker (used for the image-edge up conv; the trunk layers run on the CTA-pair kernel
+// below): a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem
 // ring keeps streaming across tile boundaries and the accumulator is double-buffered in TMEM, so the
 // epilogue of tile i (tcgen05.ld, BatchNorm partial sums, stores) overlaps the MMAs of tile i+1 and the
 // per-CTA set-up (TMEM alloc, barrier init, descriptor prefetch) is paid once per SM instead of per tile.
@@ -830,13 +640,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
 }
 
-// JCK_CONV_PAIR=0 disables the cta_group::2 kernels (default on)
-static bool use_pair() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("JCK_CONV_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
-}
-
 template <int BN_, int STAGES, int MODE, int EPIM>
 int launch_pair_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
                     int m_tiles, int n_tiles, const BnBwdEpi& bb, cudaStream_t st) {
@@ -868,16 +671,6 @@ int launch_pair_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, flo
     return JCK_OK;
 }
 
-// JCK_CONV_PERSIST: 0 = one tile per CTA (2 CTAs/SM); 1 = persistent, 1 CTA/SM, 8 epilogue warps;
-// 2 = persistent, 2 CTAs/SM, 4 epilogue warps each (default: measured 3.91 ms/step vs 4.27 (0) and 4.52 (1) --
-// two co-resident CTAs hide each other's TMA and epilogue latency, persistence removes the per-tile set-up)
-static int persist_mode() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("JCK_CONV_PERSIST"); v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
-    return v;
-}
-static bool use_persistent() { return persist_mode() != 0; }
-
 template <int BN_, int STAGES, int MODE, int EPI, int CTAS_PER_SM, int EPIM>
 int launch_persist_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
                        int m_tiles, int n_tiles, const BnBwdEpi& bb, cudaStream_t st) {
@@ -897,48 +690,15 @@ int launch_persist_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, 
     return JCK_OK;
 }
 
+// two co-resident CTAs per SM, four epilogue warps each: one CTA's epilogue and TMA latency hide behind the other's MMAs
 template <int BN_, int STAGES, int MODE>
 int launch_conv_tc_persist(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
-                           int m_tiles, int n_tiles, cudaStream_t st, const BnBwdEpi* bb = nullptr) {
-    int rc;
+                           int m_tiles, int n_tiles, cudaStream_t st) {
     const BnBwdEpi none{nullptr, nullptr, nullptr, 0.f};
-    if constexpr (MODE != kEdgeUp) {
-        if (bb != nullptr) {
-            if (persist_mode() == 1) rc = launch_persist_cfg<BN_, STAGES, MODE, 8, 1, 1>(mA, mB, out, stats, p, m_tiles, n_tiles, *bb, st);
-            else rc = launch_persist_cfg<BN_, STAGES / 2, MODE, 4, 2, 1>(mA, mB, out, stats, p, m_tiles, n_tiles, *bb, st);
-            if (rc) return rc;
-            JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_bnbwd_tc" : MODE == kDown ? "conv_down_bnbwd_tc" : "edge_down_bnbwd_tc");
-            return JCK_OK;
-        }
-    }
-    if (persist_mode() == 2) rc = launch_persist_cfg<BN_, STAGES / 2, MODE, 4, 2, 0>(mA, mB, out, stats, p, m_tiles, n_tiles, none, st);
-    else rc = launch_persist_cfg<BN_, STAGES, MODE, 8, 1, 0>(mA, mB, out, stats, p, m_tiles, n_tiles, none, st);
+    int rc = launch_persist_cfg<BN_, STAGES, MODE, 4, 2, 0>(mA, mB, out, stats, p, m_tiles, n_tiles, none, st);
     if (rc) return rc;
-    JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc_persist" : MODE == kDown ? "conv_down_tc_persist"
-                                                        : MODE == kEdgeDown ? "edge_down_tc_persist" : "edge_up_tc_persist");
+    JCK_LAUNCH_CHECK("edge_up_tc_persist");
     return JCK_OK;
-}
-
-template <int BN_, int STAGES, int MODE>
-int launch_conv_tc_mode(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
-                        int m_tiles, int n_tiles, cudaStream_t st) {
-    using L = ConvSmem<BN_, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, STAGES, MODE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc smem attr: %s", cudaGetErrorString(e));
-        configured = true;
-    }
-    dim3 grid(m_tiles, n_tiles, MODE == kUpM ? 4 : 1);
-    conv_tc_kernel<BN_, STAGES, MODE><<<grid, kConvThreads, L::kTotal, st>>>(mA, mB, (__nv_bfloat16*)out, stats, p);
-    JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc" : MODE == kDown ? "conv_down_tc" : MODE == kEdgeDown ? "edge_down_tc" : "edge_up_tc");
-    return JCK_OK;
-}
-template <int BN_, int STAGES, bool kUp>
-int launch_conv_tc(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
-                   int m_tiles, int n_tiles, cudaStream_t st) {
-    return launch_conv_tc_mode<BN_, STAGES, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, n_tiles, st);
 }
 
 bool tc_conv_supported(int B, int Hs, int Ws, int Ca, int Cb, int ipg, bool up, PatchGeom* g) {
@@ -961,32 +721,22 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
     const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
     CUtensorMap mA, mB;
     int rc;
+    // cta_group::2: every CTA of a pair stages half of the weight tile -> B box of bn / 2 rows
     if (!kUp) {
         if ((rc = map_large(&mA, in, Cb, 2 * Ws, 2 * Hs, B, g.bw, g.bh, g.nb))) return rc;
-        if ((rc = map_matrix(&mB, w, Ca, 16 * Cb, bn))) return rc;
+        if ((rc = map_matrix(&mB, w, Ca, 16 * Cb, bn / 2))) return rc;
     } else {
         if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
-        if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn))) return rc;
+        if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn / 2))) return rc;
     }
-    if (use_pair()) {
-        // cta_group::2: every CTA of a pair stages half of the weight tile -> B box of bn / 2 rows
-        if (!kUp) { if ((rc = map_matrix(&mB, w, Ca, 16 * Cb, bn / 2))) return rc; }
-        else { if ((rc = map_matrix(&mB, w, 4 * Cb, 4 * Ca, bn / 2))) return rc; }
-        const BnBwdEpi none{nullptr, nullptr, nullptr, 0.f};
-        constexpr int M_ = kUp ? kUpM : kDown;
-        if (bn == 128) {
-            if (bb) return launch_pair_cfg<128, 4, M_, 1>(mA, mB, out, stats, p, m_tiles, Cout / 128, *bb, st);
-            return launch_pair_cfg<128, 4, M_, 0>(mA, mB, out, stats, p, m_tiles, Cout / 128, none, st);
-        }
-        if (bb) return launch_pair_cfg<64, 4, M_, 1>(mA, mB, out, stats, p, m_tiles, Cout / 64, *bb, st);
-        return launch_pair_cfg<64, 4, M_, 0>(mA, mB, out, stats, p, m_tiles, Cout / 64, none, st);
+    const BnBwdEpi none{nullptr, nullptr, nullptr, 0.f};
+    constexpr int M_ = kUp ? kUpM : kDown;
+    if (bn == 128) {
+        if (bb) return launch_pair_cfg<128, 4, M_, 1>(mA, mB, out, stats, p, m_tiles, Cout / 128, *bb, st);
+        return launch_pair_cfg<128, 4, M_, 0>(mA, mB, out, stats, p, m_tiles, Cout / 128, none, st);
     }
-    if (use_persistent() || bb != nullptr) {
-        if (bn == 128) return launch_conv_tc_persist<128, 6, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 128, st, bb);
-        return launch_conv_tc_persist<64, 8, kUp ? kUpM : kDown>(mA, mB, out, stats, p, m_tiles, Cout / 64, st, bb);
-    }
-    if (bn == 128) return launch_conv_tc<128, 3, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 128, st);
-    return launch_conv_tc<64, 4, kUp>(mA, mB, out, stats, p, m_tiles, Cout / 64, st);
+    if (bb) return launch_pair_cfg<64, 4, M_, 1>(mA, mB, out, stats, p, m_tiles, Cout / 64, *bb, st);
+    return launch_pair_cfg<64, 4, M_, 0>(mA, mB, out, stats, p, m_tiles, Cout / 64, none, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1183,109 +933,10 @@ int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan&
 
 // ------------------------------------------------------------------------------------------------
 // image-edge wgrad: D[a][(ky,kx,c4)] = sum over pixels small[pix][a] * patch[pix][(ky,kx,c4)]
-// Ca = 64 -> M = 64: issued as an M = 128 MMA whose second 64-row atom aliases the first (LBO = 0);
-// TMEM lanes 64..127 then hold a copy that the epilogue ignores.  N = 64 = the whole patch, K = 64 pixels
+// Ca = 64 -> M = 64: issued as an M = 128 MMA whose second 64-row atom is a block of zeros (LBO points at it);
+// TMEM lanes 64..127 then hold zeros that the epilogue ignores.  N = 64 = the whole patch, K = 64 pixels
 // per step, split over the grid; partials [split][64][64] are reduced by edge_wgrad_unpack.
-// ------------------------------------------------------------------------------------------------
-struct EdgeWgradParams { int total_steps, steps_per_split; };
-constexpr int kEdgeWStages = 4;
-constexpr int kEdgeWStage = 2 * kWgradKPix * 128;          // 8 KB small + 8 KB patches
-constexpr int kEdgeWZeroOff = kEdgeWStages * kEdgeWStage;  // 8 KB of zeros: the upper 64-row atom of the M = 128 MMA
-constexpr int kEdgeWBarOff = kEdgeWZeroOff + kWgradKPix * 128;
-constexpr int kEdgeWSmem = kEdgeWBarOff + 256 + 1024;
-
-__global__ void __launch_bounds__(kConvThreads)
-wgrad_edge_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapP,
-                     float* __restrict__ part, const EdgeWgradParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kEdgeWBarOff);
-    uint64_t* empty = full + kEdgeWStages;
-    uint64_t* tmem_full = empty + kEdgeWStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x;
-    const int step_beg = split * p.steps_per_split;
-    const int nsteps = max(0, min(p.total_steps, step_beg + p.steps_per_split) - step_beg);
-    for (int i = threadIdx.x; i < kWgradKPix * 128 / 16; i += kConvThreads)
-        reinterpret_cast<uint4*>(smem + kEdgeWZeroOff)[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> visible to the MMA
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&mapS);
-        prefetch_tmap(&mapP);
-        for (int s = 0; s < kEdgeWStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 64);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int it = 0; it < nsteps; ++it) {
-                const int s = it % kEdgeWStages;
-                mbar_wait(&empty[s], ((it / kEdgeWStages) & 1) ^ 1);
-                uint8_t* sa = smem + s * kEdgeWStage;
-                mbar_arrive_expect_tx(&full[s], kEdgeWStage);
-                const int row0 = (step_beg + it) * kWgradKPix;
-                tma_load_2d(sa, &mapS, &full[s], 0, row0);
-                tma_load_2d(sa + kWgradKPix * 128, &mapP, &full[s], 0, row0);
-            }
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(64, 1, 1);
-        for (int it = 0; it < nsteps; ++it) {
-            const int s = it % kEdgeWStages;
-            mbar_wait(&full[s], (it / kEdgeWStages) & 1);
-            fence_after_sync();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + s * kEdgeWStage);
-                const uint32_t b_addr = a_addr + kWgradKPix * 128;
-                const uint32_t lbo = smem_u32(smem + kEdgeWZeroOff) - a_addr;   // second M atom = the zero block
-#pragma unroll
-                for (int k = 0; k < kWgradKPix / 16; ++k)
-                    umma_bf16(tmem_base, make_sdesc(a_addr + k * 2048, lbo, 1024), make_sdesc(b_addr + k * 2048, 0, 1024),
-                              idesc, (it > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&empty[s]);
-                if (it == nsteps - 1) umma_commit(tmem_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        const int wq = warp & 3;
-        if (wq < 2) {                                  // lanes 0..63 carry the 64 real rows
-            const int a = wq * 32 + lane;
-            if (nsteps > 0) { mbar_wait(tmem_full, 0); fence_after_sync(); }
-            float* dst = part + ((size_t)split * 64 + a) * 64;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float v[32];
-                if (nsteps > 0) {
-                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                }
-                float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            }
-        }
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 1) {
-        fence_after_sync();
-        tmem_dealloc(tmem_base, 64);
-    }
-}
-
-// Same weight gradient with the patch operand built in shared memory from the padded image itself (see
+// The patch operand is built in shared memory from the padded image itself (see
 // edge_down_direct_kernel): per 64-pixel K step the producer bulk-copies the 2*rps + 2 image rows next to the TMA
 // box of `small`, warps 2..5 re-pack them into the swizzled [64 pixels][64] tile (half a pixel row per thread),
 // and the MMA warp consumes the stage once both the TMA bytes and the re-pack have landed.
@@ -1708,23 +1359,6 @@ extern "C" int jck_conv_wgrad(const void* small, const void* large, float* dw4, 
 // ------------------------------------------------------------------------------------------------
 // image-edge entry points (bf16, JCK_IMG_P4 image layout)
 // ------------------------------------------------------------------------------------------------
-extern "C" int jck_edge_down(const void* patches, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
-                             int Ca, int imgs_per_group, void* stream) {
-    JCK_REQUIRE(patches && w_down_e && out_small && B > 0 && Hs > 0 && Ws > 0, "edge_down: bad argument");
-    if (imgs_per_group <= 0) imgs_per_group = B;
-    PatchGeom g;
-    if (Ca != 64 || !patch_geom(Hs, Ws, kTileM, &g) || (imgs_per_group < B && imgs_per_group % g.nb != 0))
-        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_down: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
-    ConvTcParams p{B, Hs, Ws, Ca, 4, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, imgs_per_group};
-    const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
-    CUtensorMap mA, mB;
-    int rc;
-    if ((rc = map_rows64(&mA, patches, (long long)B * Hs * Ws, kTileM))) return rc;
-    if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
-    if (use_persistent()) return launch_conv_tc_persist<64, 6, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
-    return launch_conv_tc_mode<64, 2, kEdgeDown>(mA, mB, out_small, stats, p, m_tiles, 1, as_stream(stream));
-}
-
 extern "C" int jck_edge_down_img(const void* img_p4, const void* w_down_e, void* out_small, float* stats, int B, int Hs, int Ws,
                                  int Ca, int imgs_per_group, void* stream) {
     JCK_REQUIRE(img_p4 && w_down_e && out_small && B > 0 && Hs > 0 && Ws > 0, "edge_down_img: bad argument");
@@ -1753,24 +1387,6 @@ extern "C" int jck_edge_down_img(const void* img_p4, const void* w_down_e, void*
     return JCK_OK;
 }
 
-extern "C" int jck_edge_down_bnbwd(const void* patches, const void* w_down_e, const void* y_saved, const float* scale_shift,
-                                   const float* mean_rstd, float slope, void* out_g, float* sums, int B, int Hs, int Ws,
-                                   int Ca, int imgs_per_group, void* stream) {
-    JCK_REQUIRE(patches && w_down_e && y_saved && scale_shift && mean_rstd && out_g && sums && B > 0, "edge_down_bnbwd: bad argument");
-    if (imgs_per_group <= 0) imgs_per_group = B;
-    PatchGeom g;
-    if (Ca != 64 || !patch_geom(Hs, Ws, kTileM, &g) || (imgs_per_group < B && imgs_per_group % g.nb != 0))
-        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_down_bnbwd: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
-    ConvTcParams p{B, Hs, Ws, Ca, 4, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, imgs_per_group};
-    const int m_tiles = p.tiles_x * p.tiles_y * ((B + g.nb - 1) / g.nb);
-    CUtensorMap mA, mB;
-    int rc;
-    if ((rc = map_rows64(&mA, patches, (long long)B * Hs * Ws, kTileM))) return rc;
-    if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
-    const BnBwdEpi bb{(const __nv_bfloat16*)y_saved, scale_shift, mean_rstd, slope};
-    return launch_conv_tc_persist<64, 6, kEdgeDown>(mA, mB, out_g, sums, p, m_tiles, 1, as_stream(stream), &bb);
-}
-
 extern "C" int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4, int B, int Hs, int Ws, int Ca, void* stream) {
     JCK_REQUIRE(in_small && w_up9 && img_p4 && B > 0 && Hs > 0 && Ws > 0, "edge_up: bad argument");
     PatchGeom g;
@@ -1782,38 +1398,12 @@ extern "C" int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4
     int rc;
     if ((rc = map_small(&mA, in_small, Ca, Ws, Hs, B, g.bw, g.bh, g.nb))) return rc;
     if ((rc = map_matrix(&mB, w_up9, 16, 9 * Ca, 16))) return rc;
-    if (use_persistent()) return launch_conv_tc_persist<16, 8, kEdgeUp>(mA, mB, img_p4, nullptr, p, m_tiles, 1, as_stream(stream));
-    return launch_conv_tc_mode<16, 4, kEdgeUp>(mA, mB, img_p4, nullptr, p, m_tiles, 1, as_stream(stream));
+    return launch_conv_tc_persist<16, 4, kEdgeUp>(mA, mB, img_p4, nullptr, p, m_tiles, 1, as_stream(stream));
 }
 
 extern "C" size_t jck_edge_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca) {
     EdgePlan pl = edge_wgrad_plan(B, Hs, Ws);
     return pl.ok ? (size_t)pl.splits * 64 * 64 * sizeof(float) : 0;
-}
-
-extern "C" int jck_edge_wgrad(const void* small, const void* patches, float* dw4, void* workspace, size_t workspace_bytes,
-                              int B, int Hs, int Ws, int Ca, int nc, int accumulate, void* stream) {
-    JCK_REQUIRE(small && patches && dw4 && workspace && B > 0 && nc > 0 && nc <= 4, "edge_wgrad: bad argument");
-    EdgePlan pl = edge_wgrad_plan(B, Hs, Ws);
-    if (Ca != 64 || !pl.ok) return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_wgrad: Ca=%d Hs=%d Ws=%d", Ca, Hs, Ws);
-    JCK_REQUIRE(workspace_bytes >= (size_t)pl.splits * 64 * 64 * sizeof(float), "edge_wgrad: workspace too small");
-    cudaStream_t st = as_stream(stream);
-    CUtensorMap mS, mP;
-    int rc;
-    if ((rc = map_rows64(&mS, small, (long long)B * Hs * Ws, kWgradKPix))) return rc;
-    if ((rc = map_rows64(&mP, patches, (long long)B * Hs * Ws, kWgradKPix))) return rc;
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeWSmem);
-        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_wgrad smem attr: %s", cudaGetErrorString(e));
-        cfg = true;
-    }
-    EdgeWgradParams p{pl.total_steps, pl.steps_per_split};
-    wgrad_edge_tc_kernel<<<pl.splits, kConvThreads, kEdgeWSmem, st>>>(mS, mP, (float*)workspace, p);
-    JCK_LAUNCH_CHECK("edge_wgrad_tc");
-    edge_wgrad_unpack_kernel<<<(64 * nc * 16 + 255) / 256, 256, 0, st>>>((const float*)workspace, dw4, nc, pl.splits, accumulate);
-    JCK_LAUNCH_CHECK("edge_wgrad_unpack");
-    return JCK_OK;
 }
 
 extern "C" int jck_edge_wgrad_img(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes,

@@ -176,22 +176,6 @@ __global__ void pack_weights_edge_kernel(const float* __restrict__ w4, __nv_bflo
     }
 }
 
-// patches[pix][ky*16 + kx*4 + c] = P4 image row 2*oy+ky, columns 2*ox .. 2*ox+3 (4 channels each): one thread
-// moves one 32-byte run (two 128-bit loads / stores, both sides coalesced).
-__global__ void p4_to_patches_kernel(const uint4* __restrict__ img, uint4* __restrict__ patches, int B, int Hs, int Ws) {
-    const unsigned total = (unsigned)B * Hs * Ws * 4;          // host guarantees < 2^31
-    const unsigned Wp = 2 * Ws + 2, Hp = 2 * Hs + 2;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned ky = i & 3, pix = i >> 2;
-        const unsigned ox = pix % Ws, t = pix / Ws;
-        const unsigned oy = t % Hs, n = t / Hs;
-        const size_t src = (((size_t)n * Hp + 2 * oy + ky) * Wp + 2 * ox) / 2;   // uint4 units (8 B per pixel)
-        const uint4 v0 = img[src], v1 = img[src + 1];
-        patches[(size_t)i * 2] = v0;
-        patches[(size_t)i * 2 + 1] = v1;
-    }
-}
-
 template <typename T>
 __global__ void pack_fc_kernel(const float* __restrict__ w4, T* __restrict__ w_fc, int K, int C) {
     const long long total = (long long)K * C * 16;
@@ -683,15 +667,6 @@ extern "C" int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up
     pack_weights_edge_kernel<<<grid_for((long long)Ca * 64 + 144LL * Ca, 256), 256, 0, as_stream(stream)>>>(
         w4, (__nv_bfloat16*)w_down_e, (__nv_bfloat16*)w_up9, Ca, nc);
     JCK_LAUNCH_CHECK("pack_weights_edge");
-    return JCK_OK;
-}
-
-extern "C" int jck_p4_to_patches(const void* img_p4, void* patches, int B, int Hs, int Ws, void* stream) {
-    JCK_REQUIRE(img_p4 && patches && B > 0 && Hs > 0 && Ws > 0 && (long long)B * Hs * Ws * 4 < (1LL << 31),
-                "p4_to_patches: bad argument");
-    p4_to_patches_kernel<<<grid_for((long long)B * Hs * Ws * 4, 256), 256, 0, as_stream(stream)>>>(
-        (const uint4*)img_p4, (uint4*)patches, B, Hs, Ws);
-    JCK_LAUNCH_CHECK("p4_to_patches");
     return JCK_OK;
 }
 

@@ -60,18 +60,6 @@ def pack_weights_edge(w4, w_down_e, w_up9):
     check(L().jck_pack_weights_edge(_p(w4), _p(w_down_e), _p(w_up9), w4.shape[0], w4.shape[1], _s()), "pack_weights_edge")
 
 
-def p4_to_patches(img_p4, patches=None):
-    """[B][2Hs+2][2Ws+2][4] image -> patch matrix [B*Hs*Ws][64] (row = output pixel of a 4x4 stride-2 conv)."""
-    B, Hs, Ws = img_p4.shape[0], (img_p4.shape[1] - 2) // 2, (img_p4.shape[2] - 2) // 2
-    if patches is None:
-        patches = torch.empty(B * Hs * Ws, 64, dtype=img_p4.dtype, device=img_p4.device)
-    check(L().jck_p4_to_patches(_p(img_p4), _p(patches), B, Hs, Ws, _s()), "p4_to_patches")
-    return patches
-
-
-def edge_down(patches, w_down_e, out_small, stats, Ca, ipg=0):
-    B, Hs, Ws = out_small.shape[0], out_small.shape[1], out_small.shape[2]
-    check(L().jck_edge_down(_p(patches), _p(w_down_e), _p(out_small), _p(stats), B, Hs, Ws, Ca, ipg, _s()), "edge_down")
 
 
 def edge_wgrad_img(small, img_p4, dw4, workspace, Ca, nc, accumulate):
@@ -95,11 +83,6 @@ def edge_up(x_small, w_up9, img_p4, Ca):
 def edge_wgrad_workspace_bytes(B, Hs, Ws, Ca):
     return int(L().jck_edge_wgrad_workspace_bytes(B, Hs, Ws, Ca))
 
-
-def edge_wgrad(small, patches, dw4, workspace, Ca, nc, accumulate):
-    B, Hs, Ws = small.shape[0], small.shape[1], small.shape[2]
-    check(L().jck_edge_wgrad(_p(small), _p(patches), _p(dw4), _p(workspace), workspace.numel() * workspace.element_size(),
-                             B, Hs, Ws, Ca, nc, int(accumulate), _s()), "edge_wgrad")
 
 
 def pack_fc(w4, w_fc):
@@ -145,11 +128,6 @@ def conv_down_bnbwd(x_large, w_down, y_saved, scale_shift, mean_rstd, slope, out
     check(L().jck_conv_down_bnbwd(_p(x_large), _p(w_down), _p(y_saved), _p(scale_shift), _p(mean_rstd), float(slope),
                                   _p(out_g), _p(sums), B, Hs, Ws, Ca, Cb, ipg, dt(x_large), _s()), "conv_down_bnbwd")
 
-
-def edge_down_bnbwd(patches, w_down_e, y_saved, scale_shift, mean_rstd, slope, out_g, sums, Ca, ipg=0):
-    B, Hs, Ws = out_g.shape[0], out_g.shape[1], out_g.shape[2]
-    check(L().jck_edge_down_bnbwd(_p(patches), _p(w_down_e), _p(y_saved), _p(scale_shift), _p(mean_rstd), float(slope),
-                                  _p(out_g), _p(sums), B, Hs, Ws, Ca, ipg, _s()), "edge_down_bnbwd")
 
 
 def wgrad_workspace_bytes(B, Hs, Ws, Ca, Cb, dtype, algo=ALGO_AUTO):

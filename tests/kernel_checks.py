@@ -94,7 +94,7 @@ def _bnbwd_want(da, y, C, groups, slope):
 
 
 def check_bnbwd(kind, shape, B=8, groups=1, slope=0.2):
-    """jck_conv_up_bnbwd / jck_conv_down_bnbwd / jck_edge_down_bnbwd vs conv + torch BatchNorm-backward reduction."""
+    """jck_conv_up_bnbwd / jck_conv_down_bnbwd vs conv + torch BatchNorm-backward reduction."""
     from jck_generation_b200 import ops
     dtype = torch.bfloat16
     if kind == "up":
@@ -109,31 +109,20 @@ def check_bnbwd(kind, shape, B=8, groups=1, slope=0.2):
         w4 = _mk((Ca, Cb, 4, 4), dtype, 2, 0.05)
         da = F.conv2d(x, w4, stride=2, padding=1)
         C, Ho = Ca, Hs
-    else:   # image edge: 3-channel 64x64 gradient image -> 64 channels at 32x32
-        Ca, Cb, Hs = 64, 3, 32
-        x = _mk((B, Cb, 64, 64), dtype, 1)
-        w4 = _mk((Ca, Cb, 4, 4), dtype, 2, 0.05)
-        da = F.conv2d(x, w4, stride=2, padding=1)
-        C, Ho = Ca, Hs
+    else:
+        raise ValueError(kind)
     y = _mk((B, C, Ho, Ho), dtype, 7)
     g_want, s_want, ss, mr = _bnbwd_want(da, y, C, groups, slope)
     out = torch.full((B, Ho, Ho, C), float("nan"), dtype=dtype, device="cuda")
     sums = torch.zeros(groups, 2 * C, device="cuda")
     y_dev = y.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
     ss, mr = ss.cuda().contiguous(), mr.cuda().contiguous()
-    if kind == "edge":
-        wde = torch.empty(Ca * 64, dtype=dtype, device="cuda")
-        wu9 = torch.empty(16 * 9 * Ca, dtype=dtype, device="cuda")
-        ops.pack_weights_edge(w4.cuda().contiguous(), wde, wu9)
-        patches = ops.p4_to_patches(_to_p4(x))
-        ops.edge_down_bnbwd(patches, wde, y_dev, ss, mr, slope, out, sums, Ca, ipg=B // groups)
+    wd, wu = _packed(w4, dtype)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    if kind == "up":
+        ops.conv_up_bnbwd(xin, wu, y_dev, ss, mr, slope, out, sums, Ca, Cb, ipg=B // groups)
     else:
-        wd, wu = _packed(w4, dtype)
-        xin = x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
-        if kind == "up":
-            ops.conv_up_bnbwd(xin, wu, y_dev, ss, mr, slope, out, sums, Ca, Cb, ipg=B // groups)
-        else:
-            ops.conv_down_bnbwd(xin, wd, y_dev, ss, mr, slope, out, sums, Ca, Cb, ipg=B // groups)
+        ops.conv_down_bnbwd(xin, wd, y_dev, ss, mr, slope, out, sums, Ca, Cb, ipg=B // groups)
     torch.cuda.synchronize()
     return {"out": _rel(out.float().permute(0, 3, 1, 2), g_want), "stats": _rel(sums, s_want)}
 
@@ -171,16 +160,13 @@ def check_edge(which, B=8, nc=3):
     w4 = _mk((Ca, nc, 4, 4), dt, 31, 0.05)
     wde = torch.empty(Ca * 64, dtype=dt, device="cuda"); wu9 = torch.empty(16 * 9 * Ca, dtype=dt, device="cuda")
     ops.pack_weights_edge(w4.cuda().contiguous(), wde, wu9)
-    if which in ("down", "downimg"):
+    if which == "down":
         x = _mk((B, nc, 64, 64), dt, 32)
         want = F.conv2d(x, w4, stride=2, padding=1)
         out = torch.full((B, Hs, Hs, Ca), float("nan"), dtype=dt, device="cuda")
-        groups = 2 if (which == "downimg" and B % 2 == 0) else 1
+        groups = 2 if B % 2 == 0 else 1         # two BatchNorm groups when the batch splits evenly
         stats = torch.zeros(groups, 2 * Ca, device="cuda")
-        if which == "down":
-            ops.edge_down(ops.p4_to_patches(_to_p4(x)), wde, out, stats, Ca)
-        else:                                   # straight from the padded image, two BatchNorm groups
-            ops.edge_down_img(_to_p4(x), wde, out, stats, Ca, ipg=B // groups)
+        ops.edge_down_img(_to_p4(x), wde, out, stats, Ca, ipg=B // groups)
         torch.cuda.synchronize()
         per = B // groups
         ws = torch.stack([torch.cat([want[g * per:(g + 1) * per].sum((0, 2, 3)), (want[g * per:(g + 1) * per] ** 2).sum((0, 2, 3))])
@@ -201,14 +187,9 @@ def check_edge(which, B=8, nc=3):
     ws = torch.empty(ops.edge_wgrad_workspace_bytes(B, Hs, Hs, Ca) // 4, device="cuda")
     dw = torch.full((Ca, nc, 4, 4), float("nan"), device="cuda")
     s = small.permute(0, 2, 3, 1).contiguous().to(dt).cuda()
-    if which == "wgradimg":                      # straight from the padded image
-        img = _to_p4(large)
-        ops.edge_wgrad_img(s, img, dw, ws, Ca, nc, False)
-        ops.edge_wgrad_img(s, img, dw, ws, Ca, nc, True)
-    else:
-        patches = ops.p4_to_patches(_to_p4(large))
-        ops.edge_wgrad(s, patches, dw, ws, Ca, nc, False)
-        ops.edge_wgrad(s, patches, dw, ws, Ca, nc, True)
+    img = _to_p4(large)
+    ops.edge_wgrad_img(s, img, dw, ws, Ca, nc, False)
+    ops.edge_wgrad_img(s, img, dw, ws, Ca, nc, True)
     torch.cuda.synchronize()
     return {"dw": _rel(dw, 2 * want)}
 
@@ -367,14 +348,12 @@ def all_cases():
                 cases.append((op, shape, "bf16", "tc", 3))      # ragged: batch not a multiple of the tile
     cases += [("down_groups", "c3", "bf16", "tc", 8), ("up_groups", "c4", "bf16", "tc", 16),
               ("down_groups", "c4", "f32", "simt", 6)]
-    cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_up", "-", "bf16", "tc", 8),
-              ("edge_up", "-", "bf16", "tc", 5), ("edge_wgrad", "-", "bf16", "tc", 8), ("edge_wgrad", "-", "bf16", "tc", 3),
-              ("edge_downimg", "-", "bf16", "tc", 8), ("edge_downimg", "-", "bf16", "tc", 3), ("edge_downimg", "-", "bf16", "tc", 150),
-              ("edge_downimg1", "-", "bf16", "tc", 4), ("edge_wgradimg", "-", "bf16", "tc", 8), ("edge_wgradimg", "-", "bf16", "tc", 3),
-              ("edge_wgradimg", "-", "bf16", "tc", 150), ("edge_wgradimg1", "-", "bf16", "tc", 4), ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
+    cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_down", "-", "bf16", "tc", 150),
+              ("edge_up", "-", "bf16", "tc", 8), ("edge_up", "-", "bf16", "tc", 5), ("edge_wgrad", "-", "bf16", "tc", 8),
+              ("edge_wgrad", "-", "bf16", "tc", 3), ("edge_wgrad", "-", "bf16", "tc", 150),
+              ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
     cases += [("bnbwd_up", "c2", "bf16", "tc", 8), ("bnbwd_up", "c3", "bf16", "tc", 8), ("bnbwd_up", "c4", "bf16", "tc", 3),
-              ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16),
-              ("bnbwd_edge", "-", "bf16", "tc", 8), ("bnbwd_edge", "-", "bf16", "tc", 3)]
+              ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16)]
     cases += [("bn", "-", "f32", "-", 8), ("bn", "-", "bf16", "-", 8), ("head", "-", "f32", "-", 8),
               ("head", "-", "bf16", "-", 8), ("fc", "-", "f32", "-", 8), ("fc", "-", "bf16", "-", 8),
               ("misc", "-", "f32", "-", 4)]
