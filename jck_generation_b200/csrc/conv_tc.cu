@@ -1092,27 +1092,28 @@ __global__ void edge_wgrad_unpack_kernel(const float* __restrict__ part, float* 
 // HBM traffic per output pixel: 8 B of image (L2-shared between neighbouring tiles) + 128 B written, instead of
 // 128 B (patches written) + 128 B (patches read) + 128 B.
 // ------------------------------------------------------------------------------------------------
-constexpr int kEdgeRawStages = 3;
+constexpr int kEdgeRawStages = 2;
 struct EdgeDirectParams {
     int B, Hs, Ws, bh, tiles_y, ipg, raw_bytes, raw_stride;
 };
 
 __global__ void __launch_bounds__(192, 3)
-edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfloat16* __restrict__ img,
-                        __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const EdgeDirectParams p,
+edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                        const __nv_bfloat16* __restrict__ img, float* __restrict__ stats, const EdgeDirectParams p,
                         const int total_tiles) {
     constexpr int BN_ = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;                                   // [128][64] bf16, 128B swizzle
-    uint8_t* sB = smem + kTileM * 128;                    // [64][64] bf16, 128B swizzle
-    uint8_t* sRaw = sB + BN_ * 128;                       // kEdgeRawStages x raw_stride
+    uint8_t* sA = smem;                                   // 2 x [128][64] bf16, 128B swizzle (double-buffered)
+    uint8_t* sB = smem + 2 * kTileM * 128;                // [64][64] bf16, 128B swizzle
+    uint8_t* sOut = sB + BN_ * 128;                       // [128][64] bf16 output tile, 128B swizzle, stored by TMA
+    uint8_t* sRaw = sOut + kTileM * 128;                  // kEdgeRawStages x raw_stride
     uint64_t* raw_full = reinterpret_cast<uint64_t*>(sRaw + kEdgeRawStages * p.raw_stride);
     uint64_t* raw_empty = raw_full + kEdgeRawStages;
     uint64_t* b_full = raw_empty + kEdgeRawStages;
-    uint64_t* a_ready = b_full + 1;
-    uint64_t* tfull = a_ready + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    uint64_t* a_ready = b_full + 1;                       // [2]
+    uint64_t* tfull = a_ready + 2;                        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
     float* red = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][2][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1120,13 +1121,13 @@ edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfl
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapB);
+        prefetch_tmap(&mapOut);
         for (int s = 0; s < kEdgeRawStages; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
         mbar_init(b_full, 1);
-        mbar_init(a_ready, 128);
-        mbar_init(tfull, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&a_ready[a], 128); mbar_init(&tfull[a], 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN_);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN_);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -1151,15 +1152,16 @@ edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfl
         mbar_wait(b_full, 0);
         int lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-            mbar_wait(a_ready, lt & 1);
+            const int buf = lt & 1;
+            mbar_wait(&a_ready[buf], (lt >> 1) & 1);
             fence_after_sync();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+                const uint32_t a_addr = smem_u32(sA + buf * kTileM * 128), b_addr = smem_u32(sB);
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k)
-                    umma_bf16(tmem_base, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024), idesc,
-                              k > 0 ? 1u : 0u);
-                umma_commit(tfull);
+                    umma_bf16(tmem_base + buf * BN_, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024),
+                              idesc, k > 0 ? 1u : 0u);
+                umma_commit(&tfull[buf]);
             }
             __syncwarp();
         }
@@ -1167,11 +1169,12 @@ edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfl
         const int wq = warp & 3;
         const int r = wq * 32 + lane;                      // tile row = output pixel = TMEM lane
         const int ox = r % p.Ws, oyl = r / p.Ws;
-        int lt = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int e = threadIdx.x - 64;                    // 0..127: the (sum | sum of squares, channel) column this thread flushes
+        float acc_stat = 0.f;
+        int acc_group = -1;
+        // re-pack tile `lt` (the lt-th tile of this CTA) into A buffer lt & 1 and hand it to the MMA warp
+        auto repack = [&](int lt) {
             const int s = lt % kEdgeRawStages;
-            const int n = t / p.tiles_y, oy0 = (t - n * p.tiles_y) * p.bh;
-            // ---- re-pack this pixel's 4x4x4 patch: raw rows -> swizzled K-major row r of A ----
             mbar_wait(&raw_full[s], (lt / kEdgeRawStages) & 1);
             const uint8_t* raw = sRaw + s * p.raw_stride;
             uint4 q[8];
@@ -1181,25 +1184,35 @@ edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfl
                 q[2 * ky] = src[0];
                 q[2 * ky + 1] = src[1];
             }
-            mbar_arrive(&raw_empty[s]);                    // raw slot read into registers
+            mbar_arrive(&raw_empty[s]);                    // raw slot is in registers
+            uint8_t* dst = sA + (lt & 1) * kTileM * 128 + r * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(sA + r * 128 + ((c ^ (r & 7)) << 4)) = q[c];
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + ((c ^ (r & 7)) << 4)) = q[c];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-            fence_before_sync();                           // orders this thread's earlier tcgen05.ld before the next MMA
-            mbar_arrive(a_ready);
-            // ---- epilogue ----
-            mbar_wait(tfull, lt & 1);
+            fence_before_sync();                           // this thread's earlier tcgen05.ld of that TMEM buffer is done
+            mbar_arrive(&a_ready[lt & 1]);
+        };
+        int lt = 0;
+        if (blockIdx.x < total_tiles) repack(0);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            // tile lt+1 is re-packed (and its MMA runs) while tile lt's accumulator is drained below; its A / TMEM
+            // buffer (lt+1)&1 was last used by tile lt-1, whose epilogue this thread finished in the previous iteration
+            if (t + (int)gridDim.x < total_tiles) repack(lt + 1);
+            const int n = t / p.tiles_y, oy0 = (t - n * p.tiles_y) * p.bh;
+            const int buf = lt & 1;
+            mbar_wait(&tfull[buf], (lt >> 1) & 1);
             fence_after_sync();
-            const size_t pix = ((size_t)n * p.Hs + oy0 + oyl) * p.Ws + ox;
-            __nv_bfloat16* orow = out + pix * BN_;
-            const uint32_t tmem_d = tmem_base + ((uint32_t)(wq * 32) << 16);
+            const uint32_t tmem_d = tmem_base + buf * BN_ + ((uint32_t)(wq * 32) << 16);
+            // the output tile = 128 consecutive pixels x 64 channels = 16 KB contiguous in HBM: stage it (swizzled,
+            // conflict-free 16-byte shared stores) and let ONE TMA store write full lines, instead of 128 threads
+            // each dribbling 16-byte pieces of their own row
+            if (e == 0) tma_store_wait_read0();                // previous tile's store has finished reading sOut
+            asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
             for (int c = 0; c < BN_ / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_d + c * 32, v);
                 tmem_ld_wait();
-                uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     uint4 u;
@@ -1207,7 +1220,7 @@ edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfl
                     u.y = pack_bf16x2(v[qq * 8 + 2], v[qq * 8 + 3]);
                     u.z = pack_bf16x2(v[qq * 8 + 4], v[qq * 8 + 5]);
                     u.w = pack_bf16x2(v[qq * 8 + 6], v[qq * 8 + 7]);
-                    dst[qq] = u;
+                    *reinterpret_cast<uint4*>(sOut + r * 128 + (((c * 4 + qq) ^ (r & 7)) << 4)) = u;
                 }
                 if (stats != nullptr) {
                     float sq[32];
@@ -1219,23 +1232,36 @@ edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __nv_bfl
                     red[(wq * 2 + 1) * BN_ + c * 32 + lane] = s2;
                 }
             }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e == 0) {
+                tma_store_2d(&mapOut, sOut, 0, (n * p.Hs + oy0) * p.Ws);
+                tma_store_commit();
+            }
             if (stats != nullptr) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int e = threadIdx.x - 64;            // 128 threads = 2 * BN_ columns
-                const int which = e / BN_, cc = e % BN_;
-                const float sv = red[(0 * 2 + which) * BN_ + cc] + red[(1 * 2 + which) * BN_ + cc] +
-                                 red[(2 * 2 + which) * BN_ + cc] + red[(3 * 2 + which) * BN_ + cc];
-                atomicAdd(stats + (size_t)(n / p.ipg) * 2 * BN_ + which * BN_ + cc, sv);
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // red[] is rewritten by the next tile
+                // per-CTA running sums, flushed with ONE atomic per column when the BatchNorm group changes / at the
+                // end (a CTA walks its tiles in image order), instead of 128 same-address atomics per tile;
+                // red[] is safe until the next tile's first bar.sync
+                const int which = e / BN_, cc = e % BN_, g = n / p.ipg;
+                if (g != acc_group) {
+                    if (acc_group >= 0) atomicAdd(stats + (size_t)acc_group * 2 * BN_ + which * BN_ + cc, acc_stat);
+                    acc_group = g;
+                    acc_stat = 0.f;
+                }
+                acc_stat += red[(0 * 2 + which) * BN_ + cc] + red[(1 * 2 + which) * BN_ + cc] +
+                            red[(2 * 2 + which) * BN_ + cc] + red[(3 * 2 + which) * BN_ + cc];
             }
         }
+        if (e == 0) tma_store_wait_all();
+        if (stats != nullptr && acc_group >= 0)
+            atomicAdd(stats + (size_t)acc_group * 2 * BN_ + (e / BN_) * BN_ + (e % BN_), acc_stat);
     }
 
     fence_before_sync();
     __syncthreads();
     if (warp == 1) {
         fence_after_sync();
-        tmem_dealloc(tmem_base, BN_);
+        tmem_dealloc(tmem_base, 2 * BN_);
     }
 }
 
@@ -1368,11 +1394,12 @@ extern "C" int jck_edge_down_img(const void* img_p4, const void* w_down_e, void*
         return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_down_img: Ca=%d Hs=%d Ws=%d (needs Ca = 64, Ws <= 128, Hs*Ws >= 128)", Ca, Hs, Ws);
     EdgeDirectParams p{B, Hs, Ws, g.bh, Hs / g.bh, imgs_per_group, (2 * g.bh + 2) * (2 * Ws + 2) * 8, 0};
     p.raw_stride = (p.raw_bytes + 127) & ~127;
-    const int smem = kTileM * 128 + 64 * 128 + kEdgeRawStages * p.raw_stride + 256 + 4 * 2 * 64 * 4 + 1024;
+    const int smem = 3 * kTileM * 128 + 64 * 128 + kEdgeRawStages * p.raw_stride + 256 + 4 * 2 * 64 * 4 + 1024;
     JCK_REQUIRE(smem <= 72 * 1024, "edge_down_img: tile too large for the raw ring (%d bytes)", smem);
-    CUtensorMap mB;
+    CUtensorMap mB, mOut;
     int rc;
     if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
+    if ((rc = map_rows64(&mOut, out_small, (long long)B * Hs * Ws, kTileM))) return rc;
     static bool cfg = false;
     if (!cfg) {
         cudaError_t e = cudaFuncSetAttribute(edge_down_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
@@ -1381,8 +1408,7 @@ extern "C" int jck_edge_down_img(const void* img_p4, const void* w_down_e, void*
     }
     const int total = B * p.tiles_y;
     const int grid = total < 3 * kNumSMs ? total : 3 * kNumSMs;
-    edge_down_direct_kernel<<<grid, 192, smem, as_stream(stream)>>>(mB, (const __nv_bfloat16*)img_p4, (__nv_bfloat16*)out_small,
-                                                                  stats, p, total);
+    edge_down_direct_kernel<<<grid, 192, smem, as_stream(stream)>>>(mB, mOut, (const __nv_bfloat16*)img_p4, stats, p, total);
     JCK_LAUNCH_CHECK("edge_down_img");
     return JCK_OK;
 }
