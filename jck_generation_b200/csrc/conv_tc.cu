@@ -533,6 +533,24 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const int wq = warp & 3;
         const int r = wq * 32 + lane;
         const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+        // BatchNorm partial sums stay in registers across this CTA's tiles (thread e owns columns e, e + 128 of the
+        // [sum | sum of squares] x BN_ block) and are flushed with one atomic per column when the (group, n-tile)
+        // they belong to changes -- a cluster keeps its n-tile when the cluster count divides by n_tiles -- instead
+        // of 2*BN_ same-address atomics per tile
+        float acc_stat[(2 * BN_ + 127) / 128];
+#pragma unroll
+        for (int j = 0; j < (2 * BN_ + 127) / 128; ++j) acc_stat[j] = 0.f;
+        long long acc_key = -1;
+        auto flush_stats = [&]() {
+            if (acc_key < 0) return;
+            float* sp = stats + (size_t)acc_key;
+#pragma unroll
+            for (int j = 0; j < (2 * BN_ + 127) / 128; ++j) {
+                const int col = (threadIdx.x - 64) + j * 128;
+                if (col < 2 * BN_) atomicAdd(sp + (col / BN_) * Cout + (col % BN_), acc_stat[j]);
+                acc_stat[j] = 0.f;
+            }
+        };
         int lt = 0;
         for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
             int nt, phase, x0, y0, n0;
@@ -619,17 +637,24 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             if (stats != nullptr) {
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
                 if (tile_live) {
-                    const int e = threadIdx.x - 64;
-                    float* sp = stats + (size_t)(n0 / p.ipg) * 2 * Cout + nt * BN_;
-                    for (int col = e; col < 2 * BN_; col += 32 * EPI) {
-                        const int which = col / BN_, cc = col % BN_;
-                        const float sv = rbuf[(0 * 2 + which) * BN_ + cc] + rbuf[(1 * 2 + which) * BN_ + cc] +
-                                         rbuf[(2 * 2 + which) * BN_ + cc] + rbuf[(3 * 2 + which) * BN_ + cc];
-                        atomicAdd(sp + which * Cout + cc, sv);
+                    const long long key = (long long)(n0 / p.ipg) * 2 * Cout + nt * BN_;   // offset of this tile's block
+                    if (key != acc_key) {
+                        flush_stats();
+                        acc_key = key;
+                    }
+#pragma unroll
+                    for (int j = 0; j < (2 * BN_ + 127) / 128; ++j) {
+                        const int col = (threadIdx.x - 64) + j * 128;
+                        if (col < 2 * BN_) {
+                            const int which = col / BN_, cc = col % BN_;
+                            acc_stat[j] += rbuf[(0 * 2 + which) * BN_ + cc] + rbuf[(1 * 2 + which) * BN_ + cc] +
+                                           rbuf[(2 * 2 + which) * BN_ + cc] + rbuf[(3 * 2 + which) * BN_ + cc];
+                        }
                     }
                 }
             }
         }
+        if (stats != nullptr) flush_stats();
     }
 
     fence_before_sync();
