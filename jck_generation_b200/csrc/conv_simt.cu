@@ -310,18 +310,63 @@ int launch(const P& p, int M, int N, int zdim, int k_per_split, cudaStream_t st,
     return JCK_OK;
 }
 
-// reduce split-K partials [splits][Ca][16][Cb] and transpose into w4[Ca][Cb][16] (+= or =)
-__global__ void wgrad_unpack_kernel(const float* __restrict__ part, float* __restrict__ dw4, int Ca, int Cb,
-                                    int splits, int accumulate) {
+// reduce split-K partials [splits][Ca][16][Cb] and transpose into w4[Ca][Cb][16] (+= or =).
+// One block per (a, 64-wide b tile): the 16 x 64 slab is read as 16 coalesced 256-byte rows per split, summed,
+// transposed through shared memory and written as ONE contiguous 4 KB run of w4 (the old element-wise version
+// scattered 4-byte read-modify-writes 64 bytes apart).
+constexpr int kUnpackBT = 64;
+// any Cb (the 3-channel image edge in fp32 parity mode): element-wise
+__global__ void wgrad_unpack_small_kernel(const float* __restrict__ part, float* __restrict__ dw4, int Ca, int Cb,
+                                          int splits, int accumulate) {
     const size_t total = (size_t)Ca * 16 * Cb;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        // idx enumerates packed order (a, tap, b): coalesced reads
         const int b = idx % Cb; const size_t t = idx / Cb; const int tap = t % 16; const int a = t / 16;
         float s = 0.f;
         for (int z = 0; z < splits; ++z) s += part[(size_t)z * total + idx];
         float* dst = dw4 + ((size_t)a * Cb + b) * 16 + tap;
         *dst = accumulate ? *dst + s : s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_unpack_kernel(const float* __restrict__ part, float* __restrict__ dw4, int Ca, int Cb, int splits, int accumulate) {
+    __shared__ float tile[16][kUnpackBT + 1];
+    const int btiles = Cb / kUnpackBT;
+    const size_t total = (size_t)Ca * 16 * Cb;
+    for (int blk = blockIdx.x; blk < Ca * btiles; blk += gridDim.x) {
+        const int a = blk / btiles, b0 = (blk % btiles) * kUnpackBT;
+        // thread t sums element (tap = t / 64 + 4 j, b = t % 64), j = 0..3
+        const int bl = threadIdx.x % kUnpackBT, t0 = threadIdx.x / kUnpackBT;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* src = part + ((size_t)a * 16 + t0) * Cb + b0 + bl;
+        int z = 0;
+        for (; z + 4 <= splits; z += 4) {                         // 16 independent loads in flight per thread
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[u][j] = __ldg(src + (size_t)(z + u) * total + (size_t)(4 * j) * Cb);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[j] += v[u][j];
+        }
+        for (; z < splits; ++z) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] += __ldg(src + (size_t)z * total + (size_t)(4 * j) * Cb);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile[t0 + 4 * j][bl] = s[j];
+        __syncthreads();
+        float* dst = dw4 + ((size_t)a * Cb + b0) * 16;            // 64 * 16 contiguous floats
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = threadIdx.x + 256 * j;                     // o = b_local * 16 + tap
+            const float v = tile[o & 15][o >> 4];
+            dst[o] = accumulate ? dst[o] + v : v;
+        }
+        __syncthreads();
     }
 }
 
@@ -339,9 +384,16 @@ int simt_wgrad_splits(int B, int Hs, int Ws, int Ca, int Cb) {
 }
 
 int launch_wgrad_unpack(const float* part, float* dw4, int Ca, int Cb, int splits, int accumulate, cudaStream_t st) {
-    const size_t total = (size_t)Ca * 16 * Cb;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    if (Cb % kUnpackBT != 0) {
+        const size_t total = (size_t)Ca * 16 * Cb;
+        int nb = (int)((total + 255) / 256);
+        if (nb > 4 * kNumSMs) nb = 4 * kNumSMs;
+        wgrad_unpack_small_kernel<<<nb, 256, 0, st>>>(part, dw4, Ca, Cb, splits, accumulate);
+        JCK_LAUNCH_CHECK("wgrad_unpack");
+        return JCK_OK;
+    }
+    int blocks = Ca * (Cb / kUnpackBT);
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
     wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(part, dw4, Ca, Cb, splits, accumulate);
     JCK_LAUNCH_CHECK("wgrad_unpack");
     return JCK_OK;

@@ -144,6 +144,42 @@ __global__ void pack_weights_kernel(const float* __restrict__ w4, T* __restrict_
     }
 }
 
+// The same packing for the trunk layers (Ca % 16 == 0, Cb % 32 == 0) through a shared-memory tile of 16 a x 32 b x
+// 16 taps: w4 is read as contiguous 2 KB runs, w_down written as 64-byte runs over b, w_up as 32-byte runs over a
+// (the element-wise version above scatters 2-byte stores Cb / Ca elements apart).
+constexpr int kPackAT = 16, kPackBT = 32;
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weights_tiled_kernel(const float* __restrict__ w4, T* __restrict__ w_down, T* __restrict__ w_up, int Ca, int Cb) {
+    __shared__ float tile[kPackAT][16 * (kPackBT + 1) + 1];   // [a][tap * 33 + b] (+1: odd row stride), 33 KB
+    const int btiles = Cb / kPackBT;
+    for (int blk = blockIdx.x; blk < (Ca / kPackAT) * btiles; blk += gridDim.x) {
+        const int a0 = (blk / btiles) * kPackAT, b0 = (blk % btiles) * kPackBT;
+        for (int i = threadIdx.x; i < kPackAT * 512; i += 256) {   // per a: 32 b x 16 taps = 512 contiguous floats
+            const int al = i >> 9, r = i & 511;
+            tile[al][(r & 15) * (kPackBT + 1) + (r >> 4)] = w4[((size_t)(a0 + al) * Cb + b0) * 16 + r];
+        }
+        __syncthreads();
+        if (w_down) {
+            for (int i = threadIdx.x; i < kPackAT * 16 * kPackBT; i += 256) {
+                const int bl = i & 31, tap = (i >> 5) & 15, al = i >> 9;
+                st_act(w_down + ((size_t)(a0 + al) * 16 + tap) * Cb + b0 + bl, tile[al][tap * (kPackBT + 1) + bl]);
+            }
+        }
+        if (w_up) {
+            for (int i = threadIdx.x; i < kPackAT * 16 * kPackBT; i += 256) {
+                const int al = i & 15, tap = (i >> 4) & 15, bl = i >> 8;
+                const int ky = tap >> 2, kx = tap & 3;
+                const int py = (ky == 1 || ky == 3) ? 0 : 1, ty = (ky == 1 || ky == 2) ? 0 : 1;
+                const int px = (kx == 1 || kx == 3) ? 0 : 1, tx = (kx == 1 || kx == 2) ? 0 : 1;
+                st_act(w_up + (((size_t)(py * 2 + px) * Cb + b0 + bl) * 4 + (ty * 2 + tx)) * Ca + a0 + al,
+                       tile[al][tap * (kPackBT + 1) + bl]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Image-edge layers (Cb = nc <= 4 image channels) for the tcgen05 path:
 //   w_down_e[a][ky*16 + kx*4 + c]                 one 64-wide K step = the whole 4x4x(4) patch
 //   w_up9[(py*2+px)*4 + c][s*Ca + a], s = 3x3 input shift (di+1)*3+(dj+1); zero where output parity
@@ -656,6 +692,14 @@ extern "C" int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B,
 extern "C" int jck_pack_weights(const float* w4, void* w_down, void* w_up, int Ca, int Cb, int dtype, void* stream) {
     JCK_REQUIRE(w4 && (w_down || w_up) && Ca > 0 && Cb > 0, "pack_weights: bad argument");
     const long long total = (long long)Ca * Cb * 16;
+    if (Ca % kPackAT == 0 && Cb % kPackBT == 0) {
+        int blocks = (Ca / kPackAT) * (Cb / kPackBT);
+        if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+        DISPATCH_DTYPE(dtype, "pack_weights",
+            pack_weights_tiled_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(w4, (T*)w_down, (T*)w_up, Ca, Cb);)
+        JCK_LAUNCH_CHECK("pack_weights");
+        return JCK_OK;
+    }
     DISPATCH_DTYPE(dtype, "pack_weights",
         pack_weights_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w_down, (T*)w_up, Ca, Cb);)
     JCK_LAUNCH_CHECK("pack_weights");

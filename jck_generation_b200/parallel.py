@@ -59,13 +59,30 @@ class TorchComm:
         from . import ops
         if self.peer is not None or self.world_size == 1 or self.world_size > 8 or not torch.cuda.is_available():
             return self
-        comm, handle = ops.comm_create(self.rank, self.world_size)
         dev = torch.device("cuda", torch.cuda.current_device())
-        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+        comm, err = None, ""
+        try:
+            comm, handle = ops.comm_create(self.rank, self.world_size)
+            mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+        except Exception as e:          # noqa: BLE001 -- e.g. CUDA IPC not permitted in this container
+            err, mine = str(e), torch.zeros(ops.COMM_HANDLE_BYTES, dtype=torch.uint8, device=dev)
         gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
         dist.all_gather(gathered, mine, group=self.group)
-        ops.comm_connect(comm, b"".join(bytes(g.cpu().tolist()) for g in gathered))
-        dist.barrier(group=self.group)            # every mailbox is zeroed and mapped before the first store
+        if comm is not None:
+            try:
+                ops.comm_connect(comm, b"".join(bytes(g.cpu().tolist()) for g in gathered))
+            except Exception as e:      # noqa: BLE001 -- no peer access between two of the GPUs
+                err = str(e)
+        # every rank must take the same transport: the mailboxes are used only if ALL ranks mapped ALL peers
+        ok = torch.tensor([0 if err else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # also: every mailbox is zeroed and mapped from here on
+        if int(ok) == 0:
+            if self.rank == 0:
+                import warnings
+                warnings.warn("peer-memory communicator unavailable (%s); SyncBN statistics travel over NCCL" % (err or "a peer failed"))
+            if comm is not None:
+                ops.comm_destroy(comm)
+            return self
         self.peer = comm
         return self
 
