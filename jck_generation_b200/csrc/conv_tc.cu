@@ -50,11 +50,11 @@ EncodeTiledFn get_encode() {
 }
 
 int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box) {
+           const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return set_error(JCK_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+    CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims,
                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(JCK_E_DRIVER, "cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
@@ -83,6 +83,14 @@ int map_matrix(CUtensorMap* m, const void* p, int rows, int cols, int box_rows) 
     cuuint64_t str[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     return encode(m, p, 2, dims, str, box);
+}
+
+// row-major fp32 matrix [rows][cols], box (32 floats = one 128-byte swizzle row | box_rows): TMA stores of partials
+int map_matrix_f32(CUtensorMap* m, const void* p, long long rows, int cols, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    return encode(m, p, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 // Patch matrix [B*Hs*Ws][64] bf16 made by jck_p4_to_patches: row = output pixel, 64 = (ky, kx, c4).
@@ -788,7 +796,7 @@ constexpr int kWgradSmem = kWgradStages * kWgradStage + 256 + 1024;
 template <int BNW>  // 64 (G = 8 taps) or 128 (G = 4 taps)
 __global__ void __launch_bounds__(kConvThreads)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapL,
-                float* __restrict__ part, const WgradTcParams p) {
+                const __grid_constant__ CUtensorMap mapP, const WgradTcParams p) {
     constexpr int G = 512 / BNW;
     constexpr int ATOMS_B = BNW / 64;
     extern __shared__ uint8_t smem_raw[];
@@ -809,6 +817,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapS);
         prefetch_tmap(&mapL);
+        prefetch_tmap(&mapP);
         for (int s = 0; s < kWgradStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
@@ -872,31 +881,54 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant_
             __syncwarp();
         }
     } else {
+        // The 128 x 512 fp32 partial tile (256 KB) leaves through shared memory: the pipeline stages are idle once the
+        // last MMA has retired, so each 32-column chunk is staged as a 128B-swizzled [128 rows][32 floats] block
+        // (conflict-free 16-byte stores) and written by ONE TMA store as full 128-byte lines -- eight chunks per
+        // round.  (Thread-per-row float4 stores wrote 16-byte pieces of 32 different lines per instruction.)
         const int wq = warp & 3;
-        const int a = a_tile * 128 + wq * 32 + lane;
-        float* prow = part + ((size_t)split * p.Ca + a) * 16 * p.Cb;
+        const int r = wq * 32 + lane;                               // row of the tile = TMEM lane
+        const int e = threadIdx.x - 64;
         if (nsteps > 0) {
             mbar_wait(tmem_full, 0);
             fence_after_sync();
         }
+        constexpr int kChunks = 16;                                 // 512 columns / 32
+        constexpr int kRound = 8;                                   // 8 x 16 KB staging blocks = 128 KB of the 160 KB ring
 #pragma unroll 1
-        for (int g = 0; g < G; ++g) {
-            float* dst = prow + (size_t)(tap0 + g) * p.Cb + b_tile * BNW;
+        for (int c0 = 0; c0 < kChunks; c0 += kRound) {
+            if (c0 > 0) {
+                if (e == 0) tma_store_wait_read0();                 // previous round's stores have read their blocks
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
 #pragma unroll 1
-            for (int c = 0; c < BNW / 32; ++c) {
+            for (int j = 0; j < kRound; ++j) {
+                const int c = c0 + j;                               // column chunk: g = c / (BNW/32), cc = c % (BNW/32)
                 float v[32];
                 if (nsteps > 0) {
-                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + g * BNW + c * 32, v);
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
-                float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+                uint8_t* blk = smem + j * (128 * 128) + r * 128;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(blk + ((q ^ (r & 7)) << 4)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e == 0) {
+#pragma unroll 1
+                for (int j = 0; j < kRound; ++j) {
+                    const int c = c0 + j, g = c / (BNW / 32), cc = c % (BNW / 32);
+                    tma_store_2d(&mapP, smem + j * (128 * 128), (tap0 + g) * p.Cb + b_tile * BNW + cc * 32,
+                                 split * p.Ca + a_tile * 128);
+                }
+                tma_store_commit();
             }
         }
+        if (e == 0) tma_store_wait_all();
     }
 
     fence_before_sync();
@@ -929,10 +961,11 @@ WgradPlan wgrad_plan(int B, int Hs, int Ws, int Ca, int Cb) {
 
 int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan& pl, int B, int Hs, int Ws, int Ca,
              int Cb, cudaStream_t st) {
-    CUtensorMap mS, mL;
+    CUtensorMap mS, mL, mP;
     int rc;
     if ((rc = map_small(&mS, small, Ca, Ws, Hs, B, pl.g.bw, pl.g.bh, pl.g.nb))) return rc;
     if ((rc = map_large(&mL, large, Cb, 2 * Ws, 2 * Hs, B, pl.g.bw, pl.g.bh, pl.g.nb))) return rc;
+    if ((rc = map_matrix_f32(&mP, part, (long long)pl.splits * Ca, 16 * Cb, 128))) return rc;
     WgradTcParams p{B, Hs, Ws, Ca, Cb, pl.g.bw, pl.g.bh, pl.g.nb, Ws / pl.g.bw, Hs / pl.g.bh,
                     pl.total_steps, pl.steps_per_split, Cb / pl.bnw};
     dim3 grid(pl.splits, (Ca / 128) * (Cb / pl.bnw), 16 / pl.G);
@@ -943,14 +976,14 @@ int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan&
             if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
             cfg64 = true;
         }
-        wgrad_tc_kernel<64><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, part, p);
+        wgrad_tc_kernel<64><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, mP, p);
     } else {
         if (!cfg128) {
             cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
             if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
             cfg128 = true;
         }
-        wgrad_tc_kernel<128><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, part, p);
+        wgrad_tc_kernel<128><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, mP, p);
     }
     JCK_LAUNCH_CHECK("wgrad_tc");
     return JCK_OK;
