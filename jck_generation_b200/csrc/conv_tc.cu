@@ -620,16 +620,16 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                 }
                 if (valid) {
-                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+                    uint4 u[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                        u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                        u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                        u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                        dst[q] = u;
+                        u[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                        u[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                        u[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                        u[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
                     }
+                    st_global_256(orow + c * 32, u[0], u[1]);          // two full 32-byte sectors per 32 channels
+                    st_global_256(orow + c * 32 + 16, u[2], u[3]);
                 }
                 if (stats != nullptr) {
                     if constexpr (EPIM == 0) {
