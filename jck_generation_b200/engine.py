@@ -15,6 +15,8 @@ BatchNorm "groups": D is run on several independent batches at once (real / fake
 with its own batch statistics, exactly as the reference's separate D(...) calls -- the conv kernels
 take the whole concatenation, the statistics are kept per group.
 """
+import contextlib
+
 import torch
 
 from . import ops
@@ -154,8 +156,26 @@ class _Workspace:
 
 class _GradTarget:
     """Where parameter gradients are written: the parameters' own .grad buffers (trainer hot path) or,
-    when `sink` is a dict, fresh tensors collected for torch.autograd (module API)."""
+    when `sink` is a dict, fresh tensors collected for torch.autograd (module API).
+
+    `wgrad_stream`: when the step sets it, the weight-gradient kernels (tensor bound, not on the critical path
+    of the sweep) are launched on that side stream, forked after the tensor they read is complete, so they overlap
+    the HBM-bound BatchNorm-backward streams of the next layer.  Whoever sets it must call join_wgrad() before the
+    gradients are used; every operand is kept alive by the Ctx until then."""
     sink = None
+    wgrad_stream = None
+
+    def _wgrad_scope(self):
+        if self.wgrad_stream is None:
+            return contextlib.nullcontext()
+        self.wgrad_stream.wait_stream(torch.cuda.current_stream())
+        self._wgrad_pending = True
+        return torch.cuda.stream(self.wgrad_stream)
+
+    def join_wgrad(self):
+        if self.wgrad_stream is not None and getattr(self, "_wgrad_pending", False):
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+            self._wgrad_pending = False
 
     def _gb(self, p):
         if self.sink is not None:
@@ -296,13 +316,14 @@ class DiscriminatorEngine(_GradTarget):
                 ops.axpy(inject[k], dy[lo:hi], 1.0)
             inp = ctx.a[k - 1] if k > 1 else ctx.x
             if wgrad:
-                if cv.edge:
-                    nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
-                    ops.edge_wgrad_img(dy, ctx.x, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
-                else:
-                    nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
-                    ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
-                                   algo=self.algo)
+                with self._wgrad_scope():
+                    if cv.edge:
+                        nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
+                        ops.edge_wgrad_img(dy, ctx.x, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                    else:
+                        nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
+                        ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
+                                       algo=self.algo)
             reduced = False
             if k > 1 or input_grad:
                 if cv.edge:
@@ -411,13 +432,16 @@ class GeneratorEngine(_GradTarget):
             da = torch.empty_like(ctx.a[k - 1])
             if cv.edge:
                 nbytes = ops.edge_wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca)
-                ops.edge_wgrad_img(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc, accumulate)
+                with self._wgrad_scope():
+                    ops.edge_wgrad_img(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc,
+                                       accumulate)
                 ops.edge_down_img(d_large, cv.w_down_e, da, None, cv.Ca)
                 reduced = False
             else:
                 nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
-                ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,
-                               accumulate, algo=self.algo)
+                with self._wgrad_scope():
+                    ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,
+                                   accumulate, algo=self.algo)
                 reduced = fuse and cv.Ca >= FUSE_MIN_C
                 if reduced:
                     ops.conv_down_bnbwd(d_large, cv.w_down, yk, ssk, mrk, 0.0, da, sums, cv.Ca, cv.Cb)

@@ -41,6 +41,9 @@ class DCGANStep:
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._graph = None
         self._static = None
+        # weight-gradient kernels run beside the sweep that produces their operands (engine._GradTarget)
+        if self.dtype == torch.bfloat16:
+            self.eg.wgrad_stream = self.ed.wgrad_stream = torch.cuda.Stream(device=self.dev)
 
     # ---- random tensors ----------------------------------------------------------------------------
     def draw(self, B):
@@ -89,6 +92,8 @@ class DCGANStep:
         cab = ctx.slice(0, 2)                                                                              # :164,175
         da4 = ed.head_backward(cab, mode=0, targets=[LABEL_REAL, LABEL_FAKE], wgrad=True, accumulate=False)
         ed.trunk_backward(cab, da4, wgrad=True, input_grad=False, accumulate=False)
+        if self.comm.world_size > 1:
+            ed.join_wgrad()
         pending = self.comm.allreduce_mean_begin(self.flat_d.grad)      # D's gradients are final: exchange them ...
 
         cc = ctx.slice(2, 3)                                                                               # :116-126
@@ -96,6 +101,7 @@ class DCGANStep:
         dx = ed.trunk_backward(cc, da4, wgrad=False, input_grad=True)   # ... while the penalty's input-gradient sweep runs
         ops.gp_penalty(dx, scal[S_GP])
 
+        ed.join_wgrad()
         self.comm.allreduce_mean_end(pending, self.flat_d.grad)
         self.opt_d.step()                                                                                  # :180
         if after_d_update is not None:
@@ -109,6 +115,7 @@ class DCGANStep:
         dy5 = torch.zeros_like(dmix) if lay == ops.IMG_P4 else torch.empty_like(dmix)
         ops.g_out_bwd(dmix, fake_raw, 0.9, dy5, layout=lay)
         eg.backward(gctx, dy5, accumulate=False)
+        eg.join_wgrad()
         self.comm.allreduce_mean_(self.flat_g.grad)
         self.opt_g.step()                                                                                  # :189
         eg.refresh(force=True)
