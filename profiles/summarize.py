@@ -49,7 +49,34 @@ def table(rep):
     return "\n".join(lines)
 
 
+def launches(path):
+    """share table of an `ncu --metrics gpu__time_duration.sum --csv` launch list"""
+    import re
+    agg = {}
+    with open(path, newline="") as f:
+        lines = [l for l in f if l.startswith('"')]
+    for r in csv.DictReader(lines):
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("jck::<unnamed>::", "")
+        name = re.sub(r"at::native::|at::<unnamed>::|<unnamed>::", "", name)[:90]
+        v = float(r["Metric Value"].replace(",", ""))
+        us = v / 1e3 if r["Metric Unit"] in ("ns", "nsecond") else v
+        t = agg.setdefault(name, [0.0, 0])
+        t[0] += us
+        t[1] += 1
+    total = sum(t[0] for t in agg.values())
+    out = [f"{sum(t[1] for t in agg.values())} launches, {total / 1e3:.2f} ms serialised", "",
+           "| share | total us | launches | avg us | kernel |", "|---:|---:|---:|---:|---|"]
+    for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        out.append(f"| {100 * us / total:.1f}% | {us:.0f} | {n} | {us / n:.1f} | `{name}` |")
+    return "\n".join(out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "--launches":
+        print(launches(sys.argv[2]))
+        sys.exit(0)
     for rep in sys.argv[1:]:
         print(table(rep))
         print()
