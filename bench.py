@@ -337,6 +337,15 @@ def run_b200(args):
                 "avg_launch_ms": tv["ms"] / tv["calls"], "share_of_step": tv["ms"] / tot,
                 "step_tensor_frac": FLOP_PER_IMAGE * value / (comm.world_size * pk["tf_sustained"] * 1e12),
                 "families": {k: {"share": f["ms"] / tot, "tflops": f["flop"] / (f["ms"] * 1e-3) / 1e12} for k, f in fam.items()}}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f).get(tk)
+        if tr:
+            roofline["traffic"] = tr["avg_bytes_per_launch"]
+            roofline["traffic_source"] = "profiles/r01_ncu_conv_pair.md: DRAM read+write bytes per launch (ncu --set full), " \
+                                         f"algorithmic {tr['algorithmic_avg_bytes_per_launch']:.3g} B"
+    except OSError:
+        pass
     if args.kernel_table and rank == 0:
         # per-kernel device time from CUPTI (torch.profiler), warm caches, eager launches
         from torch.profiler import ProfilerActivity, profile

@@ -77,6 +77,12 @@ int jck_prep_image(const float* x1, const float* m1, float a1, float b1, const f
                    const float* alpha, void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W,
                    int layout, int dtype, void* stream);
 
+/* The same with the Gaussian m1 drawn in registers: m1[i] = what jck_randn(seed, stream_id, counter_base) writes at
+ * flat NCHW index i, never stored (needs W % 4 == 0, C <= 4).  torch.randn_like train/dcgan_trainer.py:160. */
+int jck_prep_image_rng(const float* x1, unsigned long long seed, unsigned long long stream_id,
+                       const unsigned long long* counter_base, float a1, float b1, void* out_nhwc,
+                       float* out_nchw_f32, int B, int C, int H, int W, int layout, int dtype, void* stream);
+
 /* NHWC activation-dtype tensor -> NCHW fp32 (e.g. the GP input-gradient handed back to the caller). */
 int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int layout,
                          int dtype, void* stream);
@@ -192,6 +198,11 @@ int jck_unpack_head_grad(const float* dw5, float* dw4, int C4, int accumulate, v
 int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, float* fake_raw_nchw,
                   float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout, int dtype,
                   void* stream);
+/* jck_g_out_fwd with the noise drawn in registers (see jck_prep_image_rng).  train/dcgan_trainer.py:171. */
+int jck_g_out_fwd_rng(const void* y5_nhwc, unsigned long long seed, unsigned long long stream_id,
+                      const unsigned long long* counter_base, float a, float b, float* fake_raw_nchw,
+                      float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout,
+                      int dtype, void* stream);
 /* dy5 = a * dmix * (1 - fake_raw^2)  (dmix NHWC dtype, fake_raw NCHW fp32, dy5 NHWC dtype) */
 int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, float a, void* dy5_nhwc, int B, int C,
                   int H, int W, int layout, int dtype, void* stream);

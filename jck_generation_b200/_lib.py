@@ -62,6 +62,8 @@ _SIGNATURES = {
     "jck_head_bwd": [c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_head": [c_p, c_p, c_i, c_i, c_p],
     "jck_unpack_head_grad": [c_p, c_p, c_i, c_i, c_p],
+    "jck_prep_image_rng": [c_p, c_ull, c_ull, c_p, c_f, c_f, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_g_out_fwd_rng": [c_p, c_ull, c_ull, c_p, c_f, c_f, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_g_out_fwd": [c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_g_out_bwd": [c_p, c_p, c_f, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_gp_penalty": [c_p, c_p, c_i, c_ll, c_i, c_p],

@@ -74,6 +74,49 @@ template <> struct Vec8<__nv_bfloat16> {
     }
 };
 
+// ---- Philox4x32-10 ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.f / 16777216.f); }  // (0,1)
+
+// Four N(0,1) / U[0,1) values of counter c of stream `stream_id` -- the ONE definition of the random streams: the
+// stand-alone generator kernels and the kernels that draw their noise in registers both call these.
+__device__ __forceinline__ void philox_normal4(unsigned long long seed, unsigned long long stream_id, unsigned long long c,
+                                               float o[4]) {
+    const uint4 r = philox(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)),
+                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float r0 = sqrtf(-2.f * logf(u01(r.x))), r1 = sqrtf(-2.f * logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u01(r.y), &s0, &c0);
+    sincospif(2.f * u01(r.w), &s1, &c1);
+    o[0] = r0 * c0; o[1] = r0 * s0; o[2] = r1 * c1; o[3] = r1 * s1;
+}
+__device__ __forceinline__ void philox_uniform4(unsigned long long seed, unsigned long long stream_id, unsigned long long c,
+                                                float o[4]) {
+    const uint4 r = philox(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)),
+                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    o[0] = (float)(r.x >> 8) * (1.f / 16777216.f); o[1] = (float)(r.y >> 8) * (1.f / 16777216.f);
+    o[2] = (float)(r.z >> 8) * (1.f / 16777216.f); o[3] = (float)(r.w >> 8) * (1.f / 16777216.f);
+}
+
+// Where a kernel's Gaussian noise comes from: a tensor in memory (parity mode: host-made draws are injected), or
+// drawn in registers from stream (seed, stream_id) at *counter + flat_index / 4 (what jck_randn would have written).
+struct NoiseSrc {
+    const float* mem;
+    unsigned long long seed, stream_id;
+    const unsigned long long* counter;
+    int rng;
+};
+
 // ---- image edge ------------------------------------------------------------------------------
 // Activation-side image layouts.  JCK_IMG_NHWC: dense [B][H][W][C].  JCK_IMG_P4: [B][H+2][W+2][4] with a
 // zero border and zero pad channels -- the layout whose 4x4 patches are TMA-addressable (conv_tc.cu).
@@ -118,6 +161,165 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict_
         const int n = (int)(pix / HW), hw = (int)(pix % HW);
         const size_t o = lay.off(n, hw);
         for (int c = 0; c < C; ++c) out[((size_t)n * C + c) * HW + hw] = ld_act(in + o + c);
+    }
+}
+
+
+// Image-edge kernels, quad form (W % 4 == 0, C <= 4): a thread owns 4 consecutive pixels of a row -- one 128-bit
+// access per channel on the NCHW fp32 side, 8-byte pixel records (all 4 channels, pad = 0) on the P4 side, and one
+// Philox call per channel when the noise is drawn in registers.
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <typename T>
+__device__ __forceinline__ void store_quad(T* out, const ImgLayout& lay, int n, int hw0, int C, const float v[4][4]) {
+    const size_t o = lay.off(n, hw0);
+    if constexpr (sizeof(T) == 2) {
+        if (lay.pad) {      // P4: 4 pixels x (c0 c1 c2 c3) bf16
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint2 u;
+                u.x = pack_bf16x2_rn(v[0][j], v[1][j]);
+                u.y = pack_bf16x2_rn(v[2][j], v[3][j]);
+                *reinterpret_cast<uint2*>(out + o + 4 * j) = u;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < C; ++c) st_act(out + o + (size_t)j * lay.cs + c, v[c][j]);
+}
+template <typename T>
+__device__ __forceinline__ void load_quad(const T* in, const ImgLayout& lay, int n, int hw0, int C, float v[4][4]) {
+    const size_t o = lay.off(n, hw0);
+    if constexpr (sizeof(T) == 2) {
+        if (lay.pad) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint2 u = *reinterpret_cast<const uint2*>(in + o + 4 * j);
+                const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+                const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+                v[0][j] = __low2float(lo); v[1][j] = __high2float(lo);
+                v[2][j] = __low2float(hi); v[3][j] = __high2float(hi);
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < C; ++c) v[c][j] = ld_act(in + o + (size_t)j * lay.cs + c);
+}
+__device__ __forceinline__ void noise_quad(const NoiseSrc& ns, unsigned long long base, size_t src, float m[4]) {
+    if (ns.rng) {
+        philox_normal4(ns.seed, ns.stream_id, base + (unsigned long long)(src >> 2), m);
+    } else {
+        const float4 t = *reinterpret_cast<const float4*>(ns.mem + src);
+        m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_image_quad_kernel(const float* __restrict__ x1, const NoiseSrc ns, float a1, float b1, const float* __restrict__ x2,
+                       const float* __restrict__ alpha, T* __restrict__ out_nhwc, float* __restrict__ out_nchw, int B, int C,
+                       int HW, const ImgLayout lay) {
+    const int qpi = HW / 4;
+    const long long total = (long long)B * qpi;
+    const bool noisy = ns.rng || ns.mem;
+    const unsigned long long base = (ns.rng && ns.counter) ? *ns.counter : 0ull;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(q / qpi), hw0 = (int)(q % qpi) * 4;
+        const float al = alpha ? alpha[n] : 1.f;
+        float v[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < C) {
+                const size_t src = ((size_t)n * C + c) * HW + hw0;
+                const float4 x = *reinterpret_cast<const float4*>(x1 + src);
+                const float xs[4] = {x.x, x.y, x.z, x.w};
+                float m[4] = {0.f, 0.f, 0.f, 0.f}, y[4] = {0.f, 0.f, 0.f, 0.f};
+                if (noisy) noise_quad(ns, base, src, m);
+                if (alpha) {
+                    const float4 t = *reinterpret_cast<const float4*>(x2 + src);
+                    y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float r = a1 * xs[j];
+                    if (noisy) r += b1 * m[j];
+                    if (alpha) r = al * r + (1.f - al) * y[j];
+                    v[c][j] = r;
+                }
+                if (out_nchw) *reinterpret_cast<float4*>(out_nchw + src) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[c][j] = 0.f;
+            }
+        }
+        if (out_nhwc) store_quad(out_nhwc, lay, n, hw0, C, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+g_out_fwd_quad_kernel(const T* __restrict__ y5, const NoiseSrc ns, float a, float b, float* __restrict__ fake_raw,
+                      float* __restrict__ fake_mix, T* __restrict__ mix_nhwc, int B, int C, int HW, const ImgLayout lay) {
+    const int qpi = HW / 4;
+    const long long total = (long long)B * qpi;
+    const bool noisy = ns.rng || ns.mem;
+    const unsigned long long base = (ns.rng && ns.counter) ? *ns.counter : 0ull;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(q / qpi), hw0 = (int)(q % qpi) * 4;
+        float v[4][4], mx[4][4];
+        load_quad(y5, lay, n, hw0, C, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < C) {
+                const size_t dst = ((size_t)n * C + c) * HW + hw0;
+                float m[4] = {0.f, 0.f, 0.f, 0.f};
+                if (noisy) noise_quad(ns, base, dst, m);
+                float t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    t[j] = tanhf(v[c][j]);
+                    mx[c][j] = noisy ? a * t[j] + b * m[j] : a * t[j];
+                }
+                if (fake_raw) *reinterpret_cast<float4*>(fake_raw + dst) = make_float4(t[0], t[1], t[2], t[3]);
+                if (fake_mix) *reinterpret_cast<float4*>(fake_mix + dst) = make_float4(mx[c][0], mx[c][1], mx[c][2], mx[c][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mx[c][j] = 0.f;
+            }
+        }
+        if (mix_nhwc) store_quad(mix_nhwc, lay, n, hw0, C, mx);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+g_out_bwd_quad_kernel(const T* __restrict__ dmix, const float* __restrict__ fake_raw, float a, T* __restrict__ dy5, int B,
+                      int C, int HW, const ImgLayout lay) {
+    const int qpi = HW / 4;
+    const long long total = (long long)B * qpi;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(q / qpi), hw0 = (int)(q % qpi) * 4;
+        float v[4][4];
+        load_quad(dmix, lay, n, hw0, C, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < C) {
+                const float4 t4 = *reinterpret_cast<const float4*>(fake_raw + ((size_t)n * C + c) * HW + hw0);
+                const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[c][j] = a * v[c][j] * (1.f - t[j] * t[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[c][j] = 0.f;
+            }
+        }
+        store_quad(dy5, lay, n, hw0, C, v);
     }
 }
 
@@ -607,40 +809,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 __global__ void adam_advance_kernel(int* step_count) { *step_count += 1; }
 
-// ---- Philox4x32-10 ---------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += W0; key.y += W1;
-    }
-    return ctr;
-}
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.f / 16777216.f); }  // (0,1)
-
 template <bool kNormal>
 __global__ void rng_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long stream_id,
                            const unsigned long long* __restrict__ counter_base) {
     const unsigned long long base = counter_base ? *counter_base : 0ull;
     const long long nquads = (n + 3) / 4;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquads; q += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long c = base + (unsigned long long)q;
-        const uint4 r = philox(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32)),
-                               make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
         float o[4];
-        if (kNormal) {
-            const float r0 = sqrtf(-2.f * logf(u01(r.x))), r1 = sqrtf(-2.f * logf(u01(r.z)));
-            float s0, c0, s1, c1;
-            sincospif(2.f * u01(r.y), &s0, &c0);
-            sincospif(2.f * u01(r.w), &s1, &c1);
-            o[0] = r0 * c0; o[1] = r0 * s0; o[2] = r1 * c1; o[3] = r1 * s1;
-        } else {
-            o[0] = (float)(r.x >> 8) * (1.f / 16777216.f); o[1] = (float)(r.y >> 8) * (1.f / 16777216.f);
-            o[2] = (float)(r.z >> 8) * (1.f / 16777216.f); o[3] = (float)(r.w >> 8) * (1.f / 16777216.f);
-        }
+        if (kNormal) philox_normal4(seed, stream_id, base + (unsigned long long)q, o);
+        else philox_uniform4(seed, stream_id, base + (unsigned long long)q, o);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (q * 4 + j < n) out[q * 4 + j] = o[j];
@@ -662,19 +839,40 @@ extern "C" int jck_version(void) { return 100; }
 extern "C" const char* jck_last_error_string(void) { return g_err; }
 extern "C" unsigned long long jck_launch_count(void) { return g_launches.load(); }
 
-extern "C" int jck_prep_image(const float* x1, const float* m1, float a1, float b1, const float* x2, const float* alpha,
-                              void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W, int layout, int dtype,
-                              void* stream) {
+static int prep_image_launch(const float* x1, const NoiseSrc& ns, float a1, float b1, const float* x2, const float* alpha,
+                             void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W, int layout, int dtype,
+                             void* stream) {
     JCK_REQUIRE(x1 && (out_nhwc || out_nchw_f32) && B > 0 && C > 0 && H > 0 && W > 0, "prep_image: bad argument");
     JCK_REQUIRE(!alpha || x2, "prep_image: alpha needs x2");
     JCK_REQUIRE(layout == JCK_IMG_NHWC || (layout == JCK_IMG_P4 && C <= 4), "prep_image: bad layout");
     const long long total = (long long)B * H * W;
     const ImgLayout lay(H, W, C, layout);
-    DISPATCH_DTYPE(dtype, "prep_image",
-        prep_image_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x1, m1, a1, b1, x2, alpha, (T*)out_nhwc,
-                                                                                  out_nchw_f32, B, C, H * W, lay);)
+    if (W % 4 == 0 && C <= 4) {
+        DISPATCH_DTYPE(dtype, "prep_image",
+            prep_image_quad_kernel<T><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(
+                x1, ns, a1, b1, x2, alpha, (T*)out_nhwc, out_nchw_f32, B, C, H * W, lay);)
+    } else {
+        JCK_REQUIRE(!ns.rng, "prep_image: in-register noise needs W % 4 == 0 and C <= 4");
+        DISPATCH_DTYPE(dtype, "prep_image",
+            prep_image_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x1, ns.mem, a1, b1, x2, alpha, (T*)out_nhwc,
+                                                                                      out_nchw_f32, B, C, H * W, lay);)
+    }
     JCK_LAUNCH_CHECK("prep_image");
     return JCK_OK;
+}
+
+extern "C" int jck_prep_image(const float* x1, const float* m1, float a1, float b1, const float* x2, const float* alpha,
+                              void* out_nhwc, float* out_nchw_f32, int B, int C, int H, int W, int layout, int dtype,
+                              void* stream) {
+    const NoiseSrc ns{m1, 0ull, 0ull, nullptr, 0};
+    return prep_image_launch(x1, ns, a1, b1, x2, alpha, out_nhwc, out_nchw_f32, B, C, H, W, layout, dtype, stream);
+}
+
+extern "C" int jck_prep_image_rng(const float* x1, unsigned long long seed, unsigned long long stream_id,
+                                  const unsigned long long* counter_base, float a1, float b1, void* out_nhwc,
+                                  float* out_nchw_f32, int B, int C, int H, int W, int layout, int dtype, void* stream) {
+    const NoiseSrc ns{nullptr, seed, stream_id, counter_base, 1};
+    return prep_image_launch(x1, ns, a1, b1, nullptr, nullptr, out_nhwc, out_nchw_f32, B, C, H, W, layout, dtype, stream);
 }
 
 extern "C" int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B, int C, int H, int W, int layout, int dtype,
@@ -848,28 +1046,57 @@ extern "C" int jck_head_bwd(const float* prob, const float* dprob, float target,
     return JCK_OK;
 }
 
-extern "C" int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, float* fake_raw_nchw,
-                             float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout, int dtype,
-                             void* stream) {
+static int g_out_fwd_launch(const void* y5_nhwc, const NoiseSrc& ns, float a, float b, float* fake_raw_nchw,
+                            float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout, int dtype,
+                            void* stream) {
     JCK_REQUIRE(y5_nhwc && B > 0 && C > 0 && H > 0 && W > 0, "g_out_fwd: bad argument");
     JCK_REQUIRE(layout == JCK_IMG_NHWC || (layout == JCK_IMG_P4 && C <= 4), "g_out_fwd: bad layout");
     const long long total = (long long)B * H * W;
     const ImgLayout lay(H, W, C, layout);
-    DISPATCH_DTYPE(dtype, "g_out_fwd",
-        g_out_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)y5_nhwc, noise, a, b, fake_raw_nchw,
-                                                                               fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W, lay);)
+    if (W % 4 == 0 && C <= 4) {
+        DISPATCH_DTYPE(dtype, "g_out_fwd",
+            g_out_fwd_quad_kernel<T><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(
+                (const T*)y5_nhwc, ns, a, b, fake_raw_nchw, fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W, lay);)
+    } else {
+        JCK_REQUIRE(!ns.rng, "g_out_fwd: in-register noise needs W % 4 == 0 and C <= 4");
+        DISPATCH_DTYPE(dtype, "g_out_fwd",
+            g_out_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)y5_nhwc, ns.mem, a, b, fake_raw_nchw,
+                                                                                   fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W, lay);)
+    }
     JCK_LAUNCH_CHECK("g_out_fwd");
     return JCK_OK;
 }
+
+extern "C" int jck_g_out_fwd(const void* y5_nhwc, const float* noise, float a, float b, float* fake_raw_nchw,
+                             float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout, int dtype,
+                             void* stream) {
+    const NoiseSrc ns{noise, 0ull, 0ull, nullptr, 0};
+    return g_out_fwd_launch(y5_nhwc, ns, a, b, fake_raw_nchw, fake_mix_nchw, fake_mix_nhwc, B, C, H, W, layout, dtype, stream);
+}
+
+extern "C" int jck_g_out_fwd_rng(const void* y5_nhwc, unsigned long long seed, unsigned long long stream_id,
+                                 const unsigned long long* counter_base, float a, float b, float* fake_raw_nchw,
+                                 float* fake_mix_nchw, void* fake_mix_nhwc, int B, int C, int H, int W, int layout, int dtype,
+                                 void* stream) {
+    const NoiseSrc ns{nullptr, seed, stream_id, counter_base, 1};
+    return g_out_fwd_launch(y5_nhwc, ns, a, b, fake_raw_nchw, fake_mix_nchw, fake_mix_nhwc, B, C, H, W, layout, dtype, stream);
+}
+
 extern "C" int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, float a, void* dy5_nhwc, int B, int C, int H,
                              int W, int layout, int dtype, void* stream) {
     JCK_REQUIRE(dmix_nhwc && fake_raw_nchw && dy5_nhwc && B > 0 && C > 0, "g_out_bwd: bad argument");
     JCK_REQUIRE(layout == JCK_IMG_NHWC || (layout == JCK_IMG_P4 && C <= 4), "g_out_bwd: bad layout");
     const long long total = (long long)B * H * W;
     const ImgLayout lay(H, W, C, layout);
-    DISPATCH_DTYPE(dtype, "g_out_bwd",
-        g_out_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)dmix_nhwc, fake_raw_nchw, a,
-                                                                               (T*)dy5_nhwc, B, C, H * W, lay);)
+    if (W % 4 == 0 && C <= 4) {
+        DISPATCH_DTYPE(dtype, "g_out_bwd",
+            g_out_bwd_quad_kernel<T><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(
+                (const T*)dmix_nhwc, fake_raw_nchw, a, (T*)dy5_nhwc, B, C, H * W, lay);)
+    } else {
+        DISPATCH_DTYPE(dtype, "g_out_bwd",
+            g_out_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)dmix_nhwc, fake_raw_nchw, a,
+                                                                                   (T*)dy5_nhwc, B, C, H * W, lay);)
+    }
     JCK_LAUNCH_CHECK("g_out_bwd");
     return JCK_OK;
 }

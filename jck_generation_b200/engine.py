@@ -282,7 +282,7 @@ class DiscriminatorEngine(_GradTarget):
         return da4.view(B, 4, 4, self.convs[4].Ca)
 
     def trunk_backward(self, ctx, da4, wgrad=True, input_grad=False, accumulate=False, inject=None, inject_rows=None,
-                       fuse=True):
+                       fuse=True, dx_out=None):
         """Backward through conv4..conv1 given d/d(a4).  Returns d/d(input) (NHWC) when asked.
         `inject[k]` (rows `inject_rows` of the batch) is added to the gradient of the raw conv-k output
         before it is used: the second-order terms of the CGAN gradient penalty enter here.  The sweep
@@ -290,7 +290,9 @@ class DiscriminatorEngine(_GradTarget):
         `fuse` (bf16 / tcgen05): the input-gradient convolution of layer k also performs the BatchNorm-backward
         reduction of layer k-1 in its epilogue and hands down g = da * act'(pre) instead of da; with
         fuse=False every layer runs the separate reduce pass and ctx.da[k] keeps d/d(activation) (the CGAN
-        penalty sweep needs it)."""
+        penalty sweep needs it).
+        `dx_out`: a caller-owned JCK_IMG_P4 buffer (zero border / pad channel, e.g. one kept across steps) that
+        receives the image-side input gradient instead of a freshly zeroed one."""
         B, groups = ctx.B, ctx.groups
         world = self.comm.world_size
         fuse = fuse and self.fused_bn_bwd
@@ -327,7 +329,8 @@ class DiscriminatorEngine(_GradTarget):
             reduced = False
             if k > 1 or input_grad:
                 if cv.edge:
-                    da = torch.zeros_like(inp)          # border / pad channel of the P4 image stay zero
+                    # border / pad channel of the P4 image stay zero (the kernel writes interior pixels only)
+                    da = dx_out if dx_out is not None else torch.zeros_like(inp)
                     ops.edge_up(dy, cv.w_up9, da, cv.Ca)
                 elif fuse and k > 1 and cv.Cb >= FUSE_MIN_C:
                     da = torch.empty_like(inp)
@@ -387,9 +390,10 @@ class GeneratorEngine(_GradTarget):
         ctx.y[k], ctx.a[k], ctx.ss[k], ctx.mr[k] = y, a, ss, mr
         return a
 
-    def forward(self, z2d, update_running=True):
+    def forward(self, z2d, update_running=True, y5_out=None):
         """z2d: [B, K1] fp32 (z, or cat(z, one-hot) for CGAN).  Returns ctx; ctx.y[5] is the raw conv5
-        output [B,64,64,nc] (tanh is applied by ops.g_out_fwd at the image edge)."""
+        output [B,64,64,nc] (tanh is applied by ops.g_out_fwd at the image edge).  `y5_out`: caller-owned
+        JCK_IMG_P4 buffer for it (zero border / pad channel), else a freshly zeroed one."""
         self.refresh()
         B = z2d.shape[0]
         ctx = Ctx()
@@ -402,7 +406,8 @@ class GeneratorEngine(_GradTarget):
         for k in range(2, 6):
             cv = self.convs[k]
             if cv.edge:
-                y = ops.img_alloc(B, self.nc, 2 * cv.Hs, 2 * cv.Ws, self.dtype, self.dev, ops.IMG_P4)
+                y = y5_out if y5_out is not None else ops.img_alloc(B, self.nc, 2 * cv.Hs, 2 * cv.Ws, self.dtype, self.dev,
+                                                                    ops.IMG_P4)
                 ops.edge_up(cur, cv.w_up9, y, cv.Ca)
                 ctx.y[5] = y
                 continue

@@ -44,6 +44,14 @@ def prep_image(x1, out_nhwc=None, m1=None, a1=1.0, b1=0.0, x2=None, alpha=None, 
                              B, C, H, W, layout, d, _s()), "prep_image")
 
 
+def prep_image_rng(x1, seed, stream_id, counter, a1, b1, out_nhwc=None, out_nchw=None, layout=IMG_NHWC):
+    """prep_image with m1 ~ N(0,1) drawn in registers from our Philox stream (never stored)."""
+    B, C, H, W = x1.shape
+    d = dt(out_nhwc) if out_nhwc is not None else JCK_F32
+    check(L().jck_prep_image_rng(_p(x1), seed, stream_id, _p(counter), a1, b1, _p(out_nhwc), _p(out_nchw),
+                                 B, C, H, W, layout, d, _s()), "prep_image_rng")
+
+
 def nhwc_to_nchw(x_nhwc, out_nchw, layout=IMG_NHWC):
     B, C, H, W = out_nchw.shape
     check(L().jck_nhwc_to_nchw_f32(_p(x_nhwc), _p(out_nchw), B, C, H, W, layout, dt(x_nhwc), _s()), "nhwc_to_nchw")
@@ -240,6 +248,12 @@ def g_out_fwd(y5, noise, a, b, fake_raw, fake_mix, mix_nhwc, shape, layout=IMG_N
     B, C, H, W = shape
     check(L().jck_g_out_fwd(_p(y5), _p(noise), a, b, _p(fake_raw), _p(fake_mix), _p(mix_nhwc), B, C, H, W, layout,
                             dt(y5), _s()), "g_out_fwd")
+
+
+def g_out_fwd_rng(y5, seed, stream_id, counter, a, b, fake_raw, fake_mix, mix_nhwc, shape, layout=IMG_NHWC):
+    B, C, H, W = shape
+    check(L().jck_g_out_fwd_rng(_p(y5), seed, stream_id, _p(counter), a, b, _p(fake_raw), _p(fake_mix), _p(mix_nhwc),
+                                B, C, H, W, layout, dt(y5), _s()), "g_out_fwd_rng")
 
 
 def g_out_bwd(dmix, fake_raw, a, dy5, layout=IMG_NHWC):

@@ -47,14 +47,25 @@ class CGANStep(DCGANStep):
         else:
             lab = labels.contiguous()
 
-        X = ops.img_alloc(3 * B, self.nc, 64, 64, dt, dev, lay)
+        p4 = lay == ops.IMG_P4
+        X = self._p4("X", 3 * B) if p4 else ops.img_alloc(3 * B, self.nc, 64, 64, dt, dev, lay)
         real_n = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
-        ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n, layout=lay)   # :182
+        drawn = not torch.is_tensor(r["noise_real"])        # instance noise drawn in registers (DCGANStep.draw)
+        if drawn:
+            ops.prep_image_rng(real, self.seed, r["noise_real"], self.rng_counter, 0.9, 0.1, out_nhwc=X[0:B],
+                               out_nchw=real_n, layout=lay)                                                       # :182
+        else:
+            ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n, layout=lay)
         z2d = self.g.concat_inputs(r["z"], lab)
-        gctx = eg.forward(z2d)                                                                                    # :190
+        gctx = eg.forward(z2d, y5_out=self._p4("y5", B) if eg.img_layout == ops.IMG_P4 else None)                 # :190
         fake_raw = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
         fake_n = torch.empty_like(fake_raw)
-        ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B], (B, self.nc, 64, 64), layout=lay)
+        if drawn:
+            ops.g_out_fwd_rng(gctx.y[5], self.seed, r["noise_fake"], self.rng_counter, 0.9, 0.1, fake_raw, fake_n,
+                              X[B:2 * B], (B, self.nc, 64, 64), layout=lay)
+            ops.rng_advance(self.rng_counter, (B * self.nc * 64 * 64 + 3) // 4)
+        else:
+            ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B], (B, self.nc, 64, 64), layout=lay)
         ops.prep_image(real_n, out_nhwc=X[2 * B:3 * B], a1=1.0, x2=fake_n, alpha=r["alpha"].reshape(B), layout=lay)  # :115
 
         scal = torch.zeros(4, 2, dtype=torch.float32, device=dev)
@@ -69,8 +80,9 @@ class CGANStep(DCGANStep):
         cc = ctx.slice(2, 3)
         cc.head = {k: (v[2 * B:3 * B] if (torch.is_tensor(v) and v.shape[0] == 3 * B) else v) for k, v in ctx.head.items()}
         g_a4 = ed.head_gp_seed(cc)
-        v = ed.trunk_backward(cc, g_a4, wgrad=False, input_grad=True, fuse=False)                                          # :120-127
-        u = torch.zeros_like(v) if lay == ops.IMG_P4 else torch.empty_like(v)
+        v = ed.trunk_backward(cc, g_a4, wgrad=False, input_grad=True, fuse=False,                                 # :120-127
+                              dx_out=self._p4("dx", B) if p4 else None)
+        u = self._p4("u", B) if p4 else torch.empty_like(v)
         world_b = B * self.comm.world_size
         ops.gp_seed(v, u, scal[S_GP], self.lambda_gp * 2.0 / B)                                                # :130, 201
         sbar, ybar = ed.adjoint_sweep(cc, u)
@@ -81,6 +93,7 @@ class CGANStep(DCGANStep):
         da4 = ed.head_backward(ctx, dls, wgrad=True)
         ed.flush_linear1_grad(accumulate=True)
         ed.trunk_backward(ctx, da4, wgrad=True, input_grad=False, accumulate=True, inject=ybar, inject_rows=(2 * B, 3 * B))  # :203
+        ed.join_wgrad()
         self.comm.allreduce_mean_(self.flat_d.grad)
         self.opt_d.step()                                                                                         # :204
         if after_d_update is not None:
@@ -93,10 +106,11 @@ class CGANStep(DCGANStep):
         dls2 = torch.empty(B, dtype=torch.float32, device=dev)
         ops.logit_grad(ctx2.prob, dls2, mode=0, target=LABEL_REAL, scale=1.0 / B)
         da4 = ed.head_backward(ctx2, dls2, wgrad=False)
-        dmix = ed.trunk_backward(ctx2, da4, wgrad=False, input_grad=True)                                         # :211
-        dy5 = torch.zeros_like(dmix) if lay == ops.IMG_P4 else torch.empty_like(dmix)
+        dmix = ed.trunk_backward(ctx2, da4, wgrad=False, input_grad=True, dx_out=self._p4("dmix", B) if p4 else None)  # :211
+        dy5 = self._p4("dy5", B) if p4 else torch.empty_like(dmix)
         ops.g_out_bwd(dmix, fake_raw, 0.9, dy5, layout=lay)
         eg.backward(gctx, dy5, accumulate=False)
+        eg.join_wgrad()
         self.comm.allreduce_mean_(self.flat_g.grad)
         self.opt_g.step()                                                                                         # :213
         eg.refresh(force=True)

@@ -41,24 +41,35 @@ class DCGANStep:
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._graph = None
         self._static = None
+        self._p4_bufs = {}
         # weight-gradient kernels run beside the sweep that produces their operands (engine._GradTarget)
         if self.dtype == torch.bfloat16:
             self.eg.wgrad_stream = self.ed.wgrad_stream = torch.cuda.Stream(device=self.dev)
 
     # ---- random tensors ----------------------------------------------------------------------------
     def draw(self, B):
+        """Device-side draws.  z and alpha are materialised; the two instance-noise tensors (the bulk: 2 x B*nc*64*64
+        Gaussians) are NOT -- they are named by their Philox stream id and drawn in registers by the kernels that
+        consume them (ops.prep_image_rng / ops.g_out_fwd_rng produce exactly what ops.randn would have stored).
+        run() advances the counter once every consumer of this step's streams has been queued."""
         sid = 16 * self.comm.rank
         dev = self.dev
-        r = {"noise_real": torch.empty(B, self.nc, 64, 64, device=dev),
+        r = {"noise_real": sid + 1,
              "z": torch.empty(B, self.nz, 1, 1, device=dev),
-             "noise_fake": torch.empty(B, self.nc, 64, 64, device=dev),
+             "noise_fake": sid + 3,
              "alpha": torch.empty(B, 1, 1, 1, device=dev)}
-        ops.randn(r["noise_real"], self.seed, sid + 1, self.rng_counter)
         ops.randn(r["z"], self.seed, sid + 2, self.rng_counter)
-        ops.randn(r["noise_fake"], self.seed, sid + 3, self.rng_counter)
         ops.rand(r["alpha"], self.seed, sid + 4, self.rng_counter)
-        ops.rng_advance(self.rng_counter, (B * self.nc * 64 * 64 + 3) // 4)
         return r
+
+    def _p4(self, tag, B):
+        """Image-side buffers in the zero-bordered JCK_IMG_P4 layout, kept across steps: every kernel writes interior
+        pixels only (pad channel = 0), so the border is zeroed once instead of once per step."""
+        key = (tag, B)
+        buf = self._p4_bufs.get(key)
+        if buf is None:
+            buf = self._p4_bufs[key] = ops.img_alloc(B, self.nc, 64, 64, self.dtype, self.dev, ops.IMG_P4)
+        return buf
 
     # ---- the step ------------------------------------------------------------------------------------
     def run(self, real, rng=None, after_d_update=None):
@@ -73,15 +84,26 @@ class DCGANStep:
         self.flat_g.rebind()
 
         lay = ed.img_layout
-        X = ops.img_alloc(3 * B, self.nc, 64, 64, dt, dev, lay)                 # [real_n | fake_n | x_hat]
+        p4 = lay == ops.IMG_P4
+        X = self._p4("X", 3 * B) if p4 else ops.img_alloc(3 * B, self.nc, 64, 64, dt, dev, lay)   # [real_n | fake_n | x_hat]
         real_n = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
-        ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n, layout=lay)  # :160
+        drawn = not torch.is_tensor(r["noise_real"])
+        if drawn:
+            ops.prep_image_rng(real, self.seed, r["noise_real"], self.rng_counter, 0.9, 0.1, out_nhwc=X[0:B],
+                               out_nchw=real_n, layout=lay)                                                # :160
+        else:
+            ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n, layout=lay)
 
-        gctx = eg.forward(r["z"].reshape(B, self.nz))                                                      # :169
+        gctx = eg.forward(r["z"].reshape(B, self.nz), y5_out=self._p4("y5", B) if eg.img_layout == ops.IMG_P4 else None)  # :169
         fake_raw = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
         fake_n = torch.empty_like(fake_raw)
-        ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B],
-                      (B, self.nc, 64, 64), layout=lay)                                                    # :171
+        if drawn:
+            ops.g_out_fwd_rng(gctx.y[5], self.seed, r["noise_fake"], self.rng_counter, 0.9, 0.1, fake_raw, fake_n,
+                              X[B:2 * B], (B, self.nc, 64, 64), layout=lay)                                # :171
+            ops.rng_advance(self.rng_counter, (B * self.nc * 64 * 64 + 3) // 4)
+        else:
+            ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B],
+                          (B, self.nc, 64, 64), layout=lay)
         ops.prep_image(real_n, out_nhwc=X[2 * B:3 * B], a1=1.0, x2=fake_n, alpha=r["alpha"].reshape(B),
                        layout=lay)                                                                         # :112
 
@@ -98,7 +120,8 @@ class DCGANStep:
 
         cc = ctx.slice(2, 3)                                                                               # :116-126
         da4 = ed.head_backward(cc, mode=1, wgrad=False)
-        dx = ed.trunk_backward(cc, da4, wgrad=False, input_grad=True)   # ... while the penalty's input-gradient sweep runs
+        dx = ed.trunk_backward(cc, da4, wgrad=False, input_grad=True,   # ... while the penalty's input-gradient sweep runs
+                               dx_out=self._p4("dx", B) if p4 else None)
         ops.gp_penalty(dx, scal[S_GP])
 
         ed.join_wgrad()
@@ -111,8 +134,8 @@ class DCGANStep:
         ctx2 = ed.trunk_forward(X[B:2 * B], groups=1)                                                      # :185
         ed.head_forward(ctx2, targets=[LABEL_REAL], scalars=scal[S_G:S_G + 1])
         da4 = ed.head_backward(ctx2, mode=0, targets=[LABEL_REAL], wgrad=False)                            # :187
-        dmix = ed.trunk_backward(ctx2, da4, wgrad=False, input_grad=True)
-        dy5 = torch.zeros_like(dmix) if lay == ops.IMG_P4 else torch.empty_like(dmix)
+        dmix = ed.trunk_backward(ctx2, da4, wgrad=False, input_grad=True, dx_out=self._p4("dmix", B) if p4 else None)
+        dy5 = self._p4("dy5", B) if p4 else torch.empty_like(dmix)
         ops.g_out_bwd(dmix, fake_raw, 0.9, dy5, layout=lay)
         eg.backward(gctx, dy5, accumulate=False)
         eg.join_wgrad()

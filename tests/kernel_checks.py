@@ -308,6 +308,43 @@ def check_misc():
     ops.gp_penalty(dm, sc)
     wantgp = ((dm.cpu().reshape(B, -1).norm(2, dim=1) - 1) ** 2).mean()
     res["gp"] = abs(float(sc[0]) - float(wantgp)) / float(wantgp)
+    # JCK_IMG_P4 (bf16) quad path, and the noise drawn in registers == randn + the memory path, bit for bit
+    bf = torch.bfloat16
+    xb, ctr = x.cuda(), torch.full((1,), 77, dtype=torch.int64, device="cuda")
+    noise = torch.empty(B, C, 64, 64, device="cuda")
+    ops.randn(noise, 99, 5, ctr)
+    pa, pb = torch.zeros(B, 66, 66, 4, dtype=bf, device="cuda"), torch.zeros(B, 66, 66, 4, dtype=bf, device="cuda")
+    na, nb = torch.empty(B, C, 64, 64, device="cuda"), torch.empty(B, C, 64, 64, device="cuda")
+    ops.prep_image(xb, out_nhwc=pa, m1=noise, a1=0.9, b1=0.1, out_nchw=na, layout=ops.IMG_P4)
+    ops.prep_image_rng(xb, 99, 5, ctr, 0.9, 0.1, out_nhwc=pb, out_nchw=nb, layout=ops.IMG_P4)
+    res["exact_prep_rng"] = float(bool((pa != pb).any()) or bool((na != nb).any()))
+    wantp = 0.9 * x + 0.1 * noise.cpu()
+    res["prep_p4_bf16"] = _rel(pa[:, 1:65, 1:65, :3].permute(0, 3, 1, 2).float(), wantp)
+    inner = torch.zeros(B, 66, 66, 4, dtype=torch.bool, device="cuda")
+    inner[:, 1:65, 1:65, :3] = True
+    res["border"] = float(bool((pa[~inner] != 0).any()))
+    y5p = torch.zeros(B, 66, 66, 4, dtype=bf, device="cuda")
+    y5p[:, 1:65, 1:65, :3] = y5.to(bf)
+    outs = []
+    for drawn in (False, True):
+        fr2, fm2 = torch.empty(B, C, 64, 64, device="cuda"), torch.empty(B, C, 64, 64, device="cuda")
+        mp = torch.zeros(B, 66, 66, 4, dtype=bf, device="cuda")
+        if drawn:
+            ops.g_out_fwd_rng(y5p, 99, 5, ctr, 0.9, 0.1, fr2, fm2, mp, (B, C, 64, 64), layout=ops.IMG_P4)
+        else:
+            ops.g_out_fwd(y5p, noise, 0.9, 0.1, fr2, fm2, mp, (B, C, 64, 64), layout=ops.IMG_P4)
+        outs.append((fr2, fm2, mp))
+    res["exact_g_out_rng"] = float(any(bool((a != b).any()) for a, b in zip(*outs)))
+    tp = torch.tanh(y5.to(bf).float().cpu().permute(0, 3, 1, 2))
+    res["g_out_p4_raw"] = _rel(outs[0][0], tp)
+    res["g_out_p4_mix_bf16"] = _rel(outs[0][2][:, 1:65, 1:65, :3].permute(0, 3, 1, 2).float(), 0.9 * tp + 0.1 * noise.cpu())
+    dmp = torch.zeros(B, 66, 66, 4, dtype=bf, device="cuda")
+    dmp[:, 1:65, 1:65, :3] = dm.to(bf)
+    dyp = torch.zeros_like(dmp)
+    ops.g_out_bwd(dmp, outs[0][0], 0.9, dyp, layout=ops.IMG_P4)
+    res["g_out_bwd_p4_bf16"] = _rel(dyp[:, 1:65, 1:65, :3].permute(0, 3, 1, 2).float(),
+                                    0.9 * dm.to(bf).float().cpu().permute(0, 3, 1, 2) * (1 - tp * tp))
+    res["border2"] = float(bool((dyp[~inner] != 0).any()) or bool((outs[1][2][~inner] != 0).any()))
     # Adam, 3 steps against torch.optim.Adam
     p0, g0 = _mk((1000,), torch.float32, 22), [_mk((1000,), torch.float32, 23 + i) for i in range(3)]
     pt = p0.clone().requires_grad_(True)
@@ -389,8 +426,10 @@ def run_case(op, shape, dtype, algo, B):
 
 
 def tolerance(op, dtype, key):
-    if key in ("nbt", "rand_range", "border"):
+    if key in ("nbt", "rand_range", "border", "border2") or key.startswith("exact_"):
         return 0.5
+    if key.endswith("_bf16"):
+        return 4e-3
     if key.startswith("randn") or key.startswith("rand_"):
         return 5e-3
     if dtype == "f32":
