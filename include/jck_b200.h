@@ -221,6 +221,16 @@ int jck_sigmoid_bce(const float* logit, float* prob, float target, float* scalar
 /* d/d(logit): mode 0 BCE-mean, 1 ones on prob, 2 up*p(1-p), 3 second order up*p(1-p)(1-2p); all times `scale` */
 int jck_logit_grad(const float* prob, const float* up, float target, float* out, int B, int mode, float scale, void* stream);
 int jck_i64_to_f32(const long long* in, float* out, long long n, void* stream);
+int jck_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
+/* The head's large products (Linear(16*C4 + E -> 256), CGAN.py:105,120: forward x.W^T, input gradient g.W, weight
+ * gradient g^T.x and their second-order twins) on tcgen05:  C[m][n] (+)= sum_k A(m,k) * B(n,k), bf16 operands, fp32
+ * accumulation.  Operand X is K-major (x_mn_major = 0: X[row*ldx + k]) or MN-major (1: X[k*ldx + row]); ldx % 8 == 0.
+ * C: row-major, JCK_F32 (accumulate allowed) or JCK_BF16.  Split-K partials live in `workspace`
+ * (jck_gemm_tc_workspace_bytes; 0 when the plan has one split). */
+size_t jck_gemm_tc_workspace_bytes(int M, int N, int K);
+int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, void* C,
+                int c_dtype, long long ldc, int M, int N, int K, int accumulate, void* workspace,
+                size_t workspace_bytes, void* stream);
 int jck_axpy(const void* x, void* y, float a, long long n, int dtype, void* stream);   /* y += a*x */
 /* per sample b: norm = ||v_b||; scalars[0] += (norm-1)^2/B; u_b = scale*(1 - 1/norm)*v_b (u nullable) */
 int jck_gp_seed(const void* v, void* u, float* scalars, int B, long long per_sample, float scale, int dtype, void* stream);

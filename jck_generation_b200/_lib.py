@@ -42,6 +42,9 @@ _SIGNATURES = {
     "jck_sigmoid_bce": [c_p, c_p, c_f, c_p, c_i, c_p],
     "jck_logit_grad": [c_p, c_p, c_f, c_p, c_i, c_i, c_f, c_p],
     "jck_i64_to_f32": [c_p, c_p, c_ll, c_p],
+    "jck_f32_to_bf16": [c_p, c_p, c_ll, c_p],
+    "jck_gemm_tc_workspace_bytes": [c_i, c_i, c_i],
+    "jck_gemm_tc": [c_p, c_i, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_sz, c_p],
     "jck_axpy": [c_p, c_p, c_f, c_ll, c_i, c_p],
     "jck_gp_seed": [c_p, c_p, c_p, c_i, c_ll, c_f, c_i, c_p],
     "jck_pack_linear": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -80,7 +83,8 @@ _SIGNATURES = {
     "jck_bn_bwd_sums_sync": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"jck_last_error_string": ctypes.c_char_p, "jck_launch_count": c_ull,
-             "jck_conv_wgrad_workspace_bytes": c_sz, "jck_edge_wgrad_workspace_bytes": c_sz}
+             "jck_conv_wgrad_workspace_bytes": c_sz, "jck_edge_wgrad_workspace_bytes": c_sz,
+             "jck_gemm_tc_workspace_bytes": c_sz}
 
 
 class JckError(RuntimeError):

@@ -67,6 +67,10 @@ __global__ void logit_grad_kernel(const float* __restrict__ prob, const float* _
     }
 }
 
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(in[i]);
+}
 __global__ void i64_to_f32_kernel(const long long* __restrict__ in, float* __restrict__ out, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = (float)in[i];
@@ -225,6 +229,12 @@ extern "C" int jck_logit_grad(const float* prob, const float* up, float target, 
     return JCK_OK;
 }
 
+extern "C" int jck_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
+    JCK_REQUIRE(in && out && n > 0, "f32_to_bf16: bad argument");
+    f32_to_bf16_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(in, (__nv_bfloat16*)out, n);
+    JCK_LAUNCH_CHECK("f32_to_bf16");
+    return JCK_OK;
+}
 extern "C" int jck_i64_to_f32(const long long* in, float* out, long long n, void* stream) {
     JCK_REQUIRE(in && out && n > 0, "i64_to_f32: bad argument");
     i64_to_f32_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(in, out, n);

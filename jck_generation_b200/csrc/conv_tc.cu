@@ -1337,6 +1337,220 @@ EdgePlan edge_wgrad_plan(int B, int Hs, int Ws) {
 
 bool want_tc(int dtype, int algo) { return dtype == JCK_BF16 && algo != JCK_ALGO_SIMT; }
 
+// ------------------------------------------------------------------------------------------------
+// Dense GEMM on tcgen05 (the CGAN discriminator head, model/CGAN.py:118-120 Linear(16*C4 + E -> 256), forward,
+// input gradient, weight gradient and their second-order twins):   C[m][n] (+)= sum_k A(m,k) * B(n,k),  bf16 -> fp32.
+// Either operand may be K-major (A[m*lda + k]: one TMA box of 128 rows x 64 k, the conv kernels' operand form) or
+// MN-major (A[k*lda + m]: two boxes of 64 k-rows x 64 m, the weight-gradient form), so x.W^T, g.W and g^T.x all run
+// without a transposed copy.  One CTA = one 128 x 128 tile over a contiguous range of 64-wide K steps (split-K over
+// blockIdx.x, so the 8192-long contraction of the forward product fills the chip); 4-stage TMA ring, accumulator
+// in TMEM, thread-per-row epilogue straight to C (fp32, fp32 +=, or bf16) or to a per-split fp32 partial that
+// gemm_reduce_kernel sums.  Ragged M / N / K are zero-filled by TMA on the way in and masked on the way out.
+// ------------------------------------------------------------------------------------------------
+struct GemmParams {
+    int M, N, K;
+    long long ldc;             // row pitch of C (elements)
+    int ksteps, steps_per_split;
+    int n_tiles;
+    int mode;                  // 0: C fp32 =, 1: C fp32 +=, 2: C bf16 =, 3: fp32 partial [split][M][N]
+};
+constexpr int kGemmStages = 4;
+constexpr int kGemmStage = 2 * kTileM * kBK * 2;   // A 16 KB + B 16 KB
+constexpr int kGemmSmem = kGemmStages * kGemmStage + 256 + 1024;
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(kConvThreads)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void* __restrict__ Cout,
+               const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStage);
+    uint64_t* empty = full + kGemmStages;
+    uint64_t* tmem_full = empty + kGemmStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
+    const int m0 = (blockIdx.y / p.n_tiles) * kTileM, n0 = (blockIdx.y % p.n_tiles) * 128;
+    const int step_beg = split * p.steps_per_split;
+    const int nsteps = max(0, min(p.ksteps, step_beg + p.steps_per_split) - step_beg);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % kGemmStages;
+                mbar_wait(&empty[s], ((it / kGemmStages) & 1) ^ 1);
+                uint8_t* sa = smem + s * kGemmStage;
+                uint8_t* sb = sa + kTileM * kBK * 2;
+                mbar_arrive_expect_tx(&full[s], kGemmStage);
+                const int k0 = (step_beg + it) * kBK;
+                if (A_MN) {
+                    tma_load_2d(sa, &mapA, &full[s], m0, k0);
+                    tma_load_2d(sa + kBK * 128, &mapA, &full[s], m0 + 64, k0);
+                } else {
+                    tma_load_2d(sa, &mapA, &full[s], k0, m0);
+                }
+                if (B_MN) {
+                    tma_load_2d(sb, &mapB, &full[s], n0, k0);
+                    tma_load_2d(sb + kBK * 128, &mapB, &full[s], n0 + 64, k0);
+                } else {
+                    tma_load_2d(sb, &mapB, &full[s], k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(128, A_MN, B_MN);
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % kGemmStages;
+            mbar_wait(&full[s], (it / kGemmStages) & 1);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + s * kGemmStage);
+                const uint32_t b_addr = a_addr + kTileM * kBK * 2;
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t da = A_MN ? make_sdesc(a_addr + k * 2048, kBK * 128, 1024) : make_sdesc(a_addr + k * 32, 0, 1024);
+                    const uint64_t db = B_MN ? make_sdesc(b_addr + k * 2048, kBK * 128, 1024) : make_sdesc(b_addr + k * 32, 0, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);
+                if (it == nsteps - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int wq = warp & 3;
+        const int m = m0 + wq * 32 + lane;
+        if (nsteps > 0) {
+            mbar_wait(tmem_full, 0);
+            fence_after_sync();
+        }
+        float* cf = reinterpret_cast<float*>(Cout);
+        __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(Cout);
+        long long row;
+        if (p.mode == 3) row = ((long long)split * p.M + m) * p.N;
+        else row = (long long)m * p.ldc;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float v[32];
+            if (nsteps > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            const int nb = n0 + c * 32;
+            if (m >= p.M || nb >= p.N) continue;
+            const bool whole = nb + 32 <= p.N;
+            if (p.mode == 2) {
+                if (whole && (((row + nb) & 7) == 0)) {
+                    uint4* dst = reinterpret_cast<uint4*>(cb + row + nb);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                        u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                        u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                        u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                        dst[q] = u;
+                    }
+                } else {
+                    for (int i = 0; i < 32 && nb + i < p.N; ++i) cb[row + nb + i] = __float2bfloat16_rn(v[i]);
+                }
+            } else if (whole && (((row + nb) & 3) == 0)) {
+                float4* dst = reinterpret_cast<float4*>(cf + row + nb);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    if (p.mode == 1) {
+                        const float4 old = dst[q];
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    dst[q] = o;
+                }
+            } else {
+                for (int i = 0; i < 32 && nb + i < p.N; ++i) {
+                    if (p.mode == 1) cf[row + nb + i] += v[i];
+                    else cf[row + nb + i] = v[i];
+                }
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// C[m][n] (=, +=) sum over splits of part[s][m][n]; mode as GemmParams (0 fp32 =, 1 fp32 +=, 2 bf16 =)
+__global__ void gemm_reduce_kernel(const float* __restrict__ part, void* __restrict__ Cout, int M, int N, long long ldc,
+                                   int splits, int mode) {
+    const long long total = (long long)M * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += part[(long long)s * total + i];
+        const long long o = (i / N) * ldc + (i % N);
+        if (mode == 2) reinterpret_cast<__nv_bfloat16*>(Cout)[o] = __float2bfloat16_rn(acc);
+        else if (mode == 1) reinterpret_cast<float*>(Cout)[o] += acc;
+        else reinterpret_cast<float*>(Cout)[o] = acc;
+    }
+}
+
+// operand maps: K-major [rows][ld] -> dims (K | rows), box (64 | 128);  MN-major [K][ld] -> dims (rows | K), box (64 | 64)
+int map_gemm_operand(CUtensorMap* m, const void* p, int mn_major, int rows, int K, long long ld) {
+    cuuint64_t dims[2];
+    cuuint32_t box[2];
+    if (mn_major) { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = 64; }
+    else { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; box[0] = 64; box[1] = 128; }
+    cuuint64_t str[1] = {(cuuint64_t)ld * 2};
+    return encode(m, p, 2, dims, str, box);
+}
+
+struct GemmPlan { int m_tiles, n_tiles, ksteps, splits, steps_per_split; };
+GemmPlan gemm_plan(int M, int N, int K) {
+    GemmPlan pl;
+    pl.m_tiles = (M + kTileM - 1) / kTileM;
+    pl.n_tiles = (N + 127) / 128;
+    pl.ksteps = (K + kBK - 1) / kBK;
+    const int tiles = pl.m_tiles * pl.n_tiles;
+    int splits = tiles >= kNumSMs ? 1 : kNumSMs / tiles;
+    const int max_splits = pl.ksteps / 4 > 0 ? pl.ksteps / 4 : 1;     // at least 4 K steps per CTA
+    if (splits > max_splits) splits = max_splits;
+    pl.steps_per_split = (pl.ksteps + splits - 1) / splits;
+    pl.splits = (pl.ksteps + pl.steps_per_split - 1) / pl.steps_per_split;
+    return pl;
+}
+
+template <int A_MN, int B_MN>
+int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, void* C, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "gemm_tc smem attr: %s", cudaGetErrorString(e));
+        cfg = true;
+    }
+    gemm_tc_kernel<A_MN, B_MN><<<grid, kConvThreads, kGemmSmem, st>>>(mA, mB, C, p);
+    JCK_LAUNCH_CHECK("gemm_tc");
+    return JCK_OK;
+}
+
 }  // namespace
 }  // namespace jck
 
@@ -1516,5 +1730,45 @@ extern "C" int jck_edge_wgrad_img(const void* small, const void* img_p4, float* 
     JCK_LAUNCH_CHECK("edge_wgrad_img");
     edge_wgrad_unpack_kernel<<<(64 * nc * 16 + 255) / 256, 256, 0, st>>>((const float*)workspace, dw4, nc, pl.splits, accumulate);
     JCK_LAUNCH_CHECK("edge_wgrad_unpack");
+    return JCK_OK;
+}
+
+extern "C" size_t jck_gemm_tc_workspace_bytes(int M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const GemmPlan pl = gemm_plan(M, N, K);
+    return pl.splits > 1 ? (size_t)pl.splits * M * N * sizeof(float) : 0;
+}
+
+extern "C" int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, void* C,
+                           int c_dtype, long long ldc, int M, int N, int K, int accumulate, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    JCK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "gemm_tc: bad argument");
+    JCK_REQUIRE(c_dtype == JCK_F32 || (c_dtype == JCK_BF16 && !accumulate), "gemm_tc: C must be fp32, or bf16 without accumulate");
+    if (lda % 8 != 0 || ldb % 8 != 0 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "gemm_tc: operand pitch / base not 16-byte aligned (lda=%lld ldb=%lld)", lda, ldb);
+    cudaStream_t st = as_stream(stream);
+    const GemmPlan pl = gemm_plan(M, N, K);
+    const int final_mode = c_dtype == JCK_BF16 ? 2 : (accumulate ? 1 : 0);
+    JCK_REQUIRE(pl.splits == 1 || (workspace && workspace_bytes >= (size_t)pl.splits * M * N * sizeof(float)),
+                "gemm_tc: workspace too small");
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = map_gemm_operand(&mA, A, a_mn_major, M, K, lda))) return rc;
+    if ((rc = map_gemm_operand(&mB, B, b_mn_major, N, K, ldb))) return rc;
+    GemmParams p{M, N, K, ldc, pl.ksteps, pl.steps_per_split, pl.n_tiles, pl.splits > 1 ? 3 : final_mode};
+    void* dst = pl.splits > 1 ? workspace : C;
+    dim3 grid(pl.splits, pl.m_tiles * pl.n_tiles);
+    if (!a_mn_major && !b_mn_major) rc = launch_gemm<0, 0>(mA, mB, dst, p, grid, st);
+    else if (!a_mn_major && b_mn_major) rc = launch_gemm<0, 1>(mA, mB, dst, p, grid, st);
+    else if (a_mn_major && !b_mn_major) rc = launch_gemm<1, 0>(mA, mB, dst, p, grid, st);
+    else rc = launch_gemm<1, 1>(mA, mB, dst, p, grid, st);
+    if (rc) return rc;
+    if (pl.splits > 1) {
+        const long long total = (long long)M * N;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+        gemm_reduce_kernel<<<(int)blocks, 256, 0, st>>>((const float*)workspace, C, M, N, ldc, pl.splits, final_mode);
+        JCK_LAUNCH_CHECK("gemm_reduce");
+    }
     return JCK_OK;
 }

@@ -15,12 +15,14 @@ engine); tests/notes/cgan_second_order_check.py proves the algorithm against tor
   3. ONE ordinary backward over all three D passes with per-row logit gradients [BCE real | BCE fake | sbar]
      and ybar_k injected at the raw conv outputs of the penalty rows.
 
-Dense products with the 8192-wide feature vector use the CUDA-core jck_dense kernel in this round (the head
-is 2 % of the step's FLOPs); everything else is small fp32 row ops."""
+The three large products of the head -- with the 16*C4 = 8192-wide feature vector: linear1 forward (x.W^T), its
+input gradient (g.W) and weight gradient (g^T.x), and their twins in the second-order sweep -- run on tcgen05
+(jck_gemm_tc: K-major and MN-major operands, so no transposed copies; split-K where the contraction is long) in bf16
+mode and on the exact CUDA-core jck_dense kernel in fp32 parity mode; everything else is small fp32 row ops."""
 import torch
 
 from . import ops
-from .engine import DiscriminatorEngine, LRELU
+from .engine import DiscriminatorEngine, LRELU, _Workspace
 
 P_DROP = 0.25
 KEEP_SCALE = 1.0 / (1.0 - P_DROP)
@@ -41,6 +43,8 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
         self.dw1b = torch.zeros(self.H, self.E, dtype=torch.float32, device=dev)
         self.ones = torch.ones(1 << 16, dtype=torch.float32, device=dev)
         self._w1_seen = None
+        self.tc_head = dtype == torch.bfloat16 and algo != ops.ALGO_SIMT
+        self.gws = _Workspace(dev)          # split-K partials of the head GEMMs (self.ws belongs to the conv wgrads)
 
     # parameters (detached views)
     def _p(self, name):
@@ -54,6 +58,38 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
         if force or key != self._w1_seen:
             ops.pack_linear(w.detach(), self.w1a, self.w1b, self.C4, 16)
             self._w1_seen = key
+
+    # ---- the head's large products ----------------------------------------------------------------------------
+    def _bf(self, x):
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=self.dev)
+        ops.f32_to_bf16(x, out)
+        return out
+
+    def _gemm(self, A, a_mn, lda, Bm, b_mn, ldb, C, M, N, K, accumulate=False):
+        nbytes = ops.gemm_tc_workspace_bytes(M, N, K)
+        ops.gemm_tc(A, a_mn, lda, Bm, b_mn, ldb, C, M, N, K, accumulate=accumulate,
+                    workspace=self.gws.get(nbytes) if nbytes else None)
+
+    def _feat_fwd(self, x, out, B):
+        """out[B,H] = x[B,F] . w1a^T"""
+        if self.tc_head:
+            self._gemm(x, 0, self.F, self.w1a, 0, self.F, out, B, self.H, self.F)
+        else:
+            ops.dense(x, self.F, 1, self.w1a, self.F, 1, out, B, self.H, self.F)
+
+    def _feat_dgrad(self, g_h, out, B):
+        """out[B,F] = g_h[B,H] . w1a   (g_h fp32; rounded to bf16 for the tensor cores like every other gradient)"""
+        if self.tc_head:
+            self._gemm(self._bf(g_h), 0, self.H, self.w1a, 1, self.F, out, B, self.F, self.H)
+        else:
+            ops.dense(g_h, self.H, 1, self.w1a, 1, self.F, out, B, self.F, self.H)
+
+    def _feat_wgrad(self, g_h, x, B):
+        """dw1a[H,F] += g_h^T[H,B] . x[B,F]"""
+        if self.tc_head:
+            self._gemm(self._bf(g_h), 1, self.H, x, 1, self.F, self.dw1a, self.H, self.F, B, accumulate=True)
+        else:
+            ops.dense(g_h, 1, self.H, x, 1, self.F, self.dw1a, self.H, self.F, B, accumulate=True)
 
     # ---- small helpers -------------------------------------------------------------------------------------
     def _colsum_into(self, x, out, rows, cols):
@@ -87,7 +123,7 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
         ops.rowop(ops.ROW_BIAS_ACT, he, self._p("linear1.bias"), he, Bg, self.H, s=1.0)
         a4 = ctx.a[4].view(B, self.F)
         h = self._f32(B, self.H)
-        ops.dense(a4, self.F, 1, self.w1a, self.F, 1, h, B, self.H, self.F)
+        self._feat_fwd(a4, h, B)
         ops.rowop(ops.ROW_ADD_BCAST, h, he, h, B, self.H, rows_y=Bg)
         hdrop = self._f32(B, self.H)
         ops.rowop(ops.ROW_MUL, h, masks, hdrop, B, self.H, s=KEEP_SCALE)
@@ -118,11 +154,11 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
         g_h = self._f32(B, self.H)
         ops.rowop(ops.ROW_MUL, g_hd, hd["masks"], g_h, B, self.H, s=KEEP_SCALE)
         da4 = torch.empty(B, self.F, dtype=self.dtype, device=self.dev)
-        ops.dense(g_h, self.H, 1, self.w1a, 1, self.F, da4, B, self.F, self.H)
+        self._feat_dgrad(g_h, da4, B)
         if wgrad:
             ops.dense(dls, 0, 1, hd["hdrop"], 1, self.H, self._gb(self.m.linear2.weight), 1, self.H, B, accumulate=True)
             self._colsum_into(dls.view(B, 1), self._gb(self.m.linear2.bias), B, 1)
-            ops.dense(g_h, 1, self.H, ctx.a[4].view(B, self.F), 1, self.F, self.dw1a, self.H, self.F, B, accumulate=True)
+            self._feat_wgrad(g_h, ctx.a[4].view(B, self.F), B)
             g_he = self._f32(Bg, self.H)
             ops.rowop(ops.ROW_SUM_GROUPS, g_h, g_h, g_he, B, self.H, rows_y=Bg)
             ops.dense(g_he, 1, self.H, hd["e"], 1, self.E, self.dw1b, self.H, self.E, Bg, accumulate=True)
@@ -153,7 +189,7 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
         g_h = self._f32(B, self.H)
         ops.rowop(ops.ROW_MUL, g_hd, hd["masks"], g_h, B, self.H, s=KEEP_SCALE)
         g_a4 = torch.empty(B, self.F, dtype=self.dtype, device=self.dev)
-        ops.dense(g_h, self.H, 1, self.w1a, 1, self.F, g_a4, B, self.F, self.H)
+        self._feat_dgrad(g_h, g_a4, B)
         hd.update(g_s=g_s, g_h=g_h)
         return g_a4.view(B, 4, 4, self.C4)
 
@@ -189,8 +225,8 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
         hd = ctx.head
         ga4 = abar.view(B, self.F)
         gbar_h = self._f32(B, self.H)
-        ops.dense(ga4, self.F, 1, self.w1a, self.F, 1, gbar_h, B, self.H, self.F)
-        ops.dense(hd["g_h"], 1, self.H, ga4, 1, self.F, self.dw1a, self.H, self.F, B, accumulate=True)
+        self._feat_fwd(ga4, gbar_h, B)
+        self._feat_wgrad(hd["g_h"], ga4, B)
         gbar_hd = self._f32(B, self.H)
         ops.rowop(ops.ROW_MUL, gbar_h, hd["masks"], gbar_hd, B, self.H, s=KEEP_SCALE)
         w2 = self._p("linear2.weight")

@@ -295,6 +295,24 @@ def dense(A, sam, sak, B, sbn, sbk, C, M, N, K, accumulate=False):
           "dense")
 
 
+def f32_to_bf16(x, out):
+    check(L().jck_f32_to_bf16(_p(x), _p(out), x.numel(), _s()), "f32_to_bf16")
+
+
+def gemm_tc_workspace_bytes(M, N, K):
+    return int(L().jck_gemm_tc_workspace_bytes(M, N, K))
+
+
+def gemm_tc(A, a_mn, lda, B, b_mn, ldb, C, M, N, K, accumulate=False, workspace=None):
+    """C[m][n] (+)= sum_k A(m,k) * B(n,k) on tcgen05: bf16 operands, K-major (x_mn = 0: X[row*ldx + k]) or MN-major
+    (x_mn = 1: X[k*ldx + row]); C row-major fp32 (accumulate allowed) or bf16, leading dimension C.shape[-1]."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    ldc = C.shape[-1] if C.dim() > 1 else N
+    wsb = workspace.numel() * workspace.element_size() if workspace is not None else 0
+    check(L().jck_gemm_tc(_p(A), int(a_mn), lda, _p(B), int(b_mn), ldb, _p(C), dt(C), ldc, M, N, K, int(accumulate),
+                          _p(workspace), wsb, _s()), "gemm_tc")
+
+
 ROW_BIAS_ACT, ROW_MUL, ROW_ACT_BWD, ROW_ADD_BCAST, ROW_SUM_GROUPS, ROW_OUTER, ROW_SCALE_ROWS, ROW_THRESH = range(8)
 
 

@@ -365,6 +365,42 @@ def check_misc():
     return res
 
 
+def check_gemm():
+    """jck_gemm_tc: all operand major-ness combinations, ragged M / N / K, split-K, accumulate, bf16 output."""
+    from jck_generation_b200 import ops
+    bf = torch.bfloat16
+    res = {}
+
+    def operand(rows, K, mn, seed):
+        x = _mk((rows, K), torch.float32, seed).to(bf)            # logical [rows][K]
+        pad = lambda v: (v + 7) // 8 * 8
+        if mn:
+            st = torch.zeros(K, pad(rows), dtype=bf)
+            st[:, :rows] = x.t()
+        else:
+            st = torch.zeros(rows, pad(K), dtype=bf)
+            st[:, :K] = x
+        return x.float(), st.cuda(), st.shape[1]
+
+    for name, (M, N, K, amn, bmn, cdt, acc) in {
+            "fwd_splitk": (300, 256, 8192, 0, 0, torch.float32, False),
+            "fwd_acc": (300, 256, 1000, 0, 0, torch.float32, True),
+            "dgrad_bf16": (300, 1000, 256, 0, 1, bf, False),
+            "wgrad_acc": (256, 1000, 300, 1, 1, torch.float32, True),
+            "mn_k": (130, 70, 200, 1, 0, torch.float32, False)}.items():
+        a, A, lda = operand(M, K, amn, 40)
+        b, Bm, ldb = operand(N, K, bmn, 41)
+        c0 = _mk((M, N), torch.float32, 42)
+        C = (c0.clone() if acc else torch.full((M, N), 7.0)).to(cdt).cuda()
+        nbytes = ops.gemm_tc_workspace_bytes(M, N, K)
+        ws = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device="cuda")
+        ops.gemm_tc(A, amn, lda, Bm, bmn, ldb, C, M, N, K, accumulate=acc, workspace=ws)
+        want = a @ b.t() + (c0 if acc else 0)
+        res["gemm_" + name] = _rel(C.float(), want)
+    torch.cuda.synchronize()
+    return res
+
+
 def _alg(name):
     from jck_generation_b200 import ops
     return {"simt": ops.ALGO_SIMT, "tc": ops.ALGO_TC, "auto": ops.ALGO_AUTO}[name]
@@ -393,7 +429,7 @@ def all_cases():
               ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16)]
     cases += [("bn", "-", "f32", "-", 8), ("bn", "-", "bf16", "-", 8), ("head", "-", "f32", "-", 8),
               ("head", "-", "bf16", "-", 8), ("fc", "-", "f32", "-", 8), ("fc", "-", "bf16", "-", 8),
-              ("misc", "-", "f32", "-", 4)]
+              ("misc", "-", "f32", "-", 4), ("gemm", "-", "bf16", "tc", 0)]
     return cases
 
 
@@ -422,6 +458,8 @@ def run_case(op, shape, dtype, algo, B):
         return check_fc(_dt(dtype))
     if op == "misc":
         return check_misc()
+    if op == "gemm":
+        return check_gemm()
     raise ValueError(op)
 
 
