@@ -17,6 +17,7 @@ inline int grid1d(long long n, int threads = 256) {
 
 __global__ void rowop_kernel(int op, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
                              int M, int N, int rows_y, float s) {
+    pdl_entry();
     const long long total = (op == 4) ? (long long)rows_y * N : (long long)M * N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i % N), m = (int)(i / N);
@@ -37,6 +38,7 @@ __global__ void rowop_kernel(int op, const float* __restrict__ x, const float* _
 
 __global__ void sigmoid_bce_kernel(const float* __restrict__ logit, float* __restrict__ prob, float target,
                                    float* __restrict__ scalars, int B) {
+    pdl_entry();
     float l = 0.f, ps = 0.f;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         const float p = 1.f / (1.f + expf(-logit[b]));
@@ -56,6 +58,7 @@ __global__ void sigmoid_bce_kernel(const float* __restrict__ logit, float* __res
 // 2: caller-supplied d/d(prob); 3: second order, up = adjoint of g_s = sigma'(s): d/ds sigma'(s) = pq(1-2p).
 __global__ void logit_grad_kernel(const float* __restrict__ prob, const float* __restrict__ up, float target,
                                   float* __restrict__ out, int B, int mode, float scale) {
+    pdl_entry();
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         const float p = prob[b], pq = p * (1.f - p);
         float v;
@@ -68,16 +71,19 @@ __global__ void logit_grad_kernel(const float* __restrict__ prob, const float* _
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+    pdl_entry();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = __float2bfloat16_rn(in[i]);
 }
 __global__ void i64_to_f32_kernel(const long long* __restrict__ in, float* __restrict__ out, long long n) {
+    pdl_entry();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = (float)in[i];
 }
 
 template <typename T>
 __global__ void axpy_kernel(const T* __restrict__ x, T* __restrict__ y, float a, long long n) {
+    pdl_entry();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         st_act(y + i, ld_act(y + i) + a * ld_act(x + i));
 }
@@ -88,6 +94,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gp_seed_kernel(const T* __restrict__ v, T* __restrict__ u, float* __restrict__ scalars, int B, long long per_sample,
                float scale) {
+    pdl_entry();
     __shared__ float wsum[8];
     __shared__ float coef;
     const size_t base = (size_t)blockIdx.x * per_sample;
@@ -113,6 +120,7 @@ gp_seed_kernel(const T* __restrict__ v, T* __restrict__ u, float* __restrict__ s
 template <typename T>
 __global__ void pack_linear_kernel(const float* __restrict__ w, T* __restrict__ wa, float* __restrict__ wb, int O, int C,
                                    int HW, int E) {
+    pdl_entry();
     const int F = C * HW, ld = F + E;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)O * ld; i += (long long)gridDim.x * blockDim.x) {
         const int col = (int)(i % ld), o = (int)(i / ld);
@@ -122,6 +130,7 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 __global__ void unpack_linear_grad_kernel(const float* __restrict__ dwa, const float* __restrict__ dwb, float* __restrict__ dw,
                                           int O, int C, int HW, int E, int accumulate) {
+    pdl_entry();
     const int F = C * HW, ld = F + E;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)O * ld; i += (long long)gridDim.x * blockDim.x) {
         const int col = (int)(i % ld), o = (int)(i / ld);
@@ -148,6 +157,7 @@ __global__ void __launch_bounds__(256)
 bn_adj_reduce_kernel(const T* __restrict__ dbar, const T* __restrict__ da, const T* __restrict__ y,
                      const float* __restrict__ ss, const float* __restrict__ mr, const float* __restrict__ sums1,
                      float* __restrict__ asums, int C, long long npix, float inv_count, float slope) {
+    pdl_entry();
     // one thread per (pixel-slab, channel): simple and exact; this pass only runs on the GP group
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -171,6 +181,7 @@ __global__ void bn_adj_apply_kernel(const T* __restrict__ dbar, const T* __restr
                                     const float* __restrict__ gamma, const float* __restrict__ sums1,
                                     const float* __restrict__ asums, T* __restrict__ gbar_a, T* __restrict__ ybar,
                                     int C, long long npix, float inv_count, float slope) {
+    pdl_entry();
     const long long total = npix * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -191,6 +202,7 @@ __global__ void bn_adj_apply_kernel(const T* __restrict__ dbar, const T* __restr
 
 __global__ void bn_adj_param_kernel(const float* __restrict__ asums, const float* __restrict__ mr, float* __restrict__ dgamma,
                                     int C, float scale) {
+    pdl_entry();
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x)
         dgamma[c] += scale * asums[2 * C + c] * mr[C + c];
 }
@@ -209,14 +221,14 @@ extern "C" int jck_rowop(int op, const float* x, const float* y, float* out, int
     JCK_REQUIRE(x && out && M > 0 && N > 0 && op >= 0 && op <= 7 && (y || op == 0 || op == 7), "rowop: bad argument");
     JCK_REQUIRE((op != 3 && op != 4) || (rows_y > 0 && M % rows_y == 0), "rowop: rows_y must divide M");
     const long long total = op == 4 ? (long long)rows_y * N : (long long)M * N;
-    rowop_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(op, x, y, out, M, N, rows_y, s);
+    launch_pdl(rowop_kernel, dim3(grid1d(total)), dim3(256), 0, as_stream(stream), op, x, y, out, M, N, rows_y, s);
     JCK_LAUNCH_CHECK("rowop");
     return JCK_OK;
 }
 
 extern "C" int jck_sigmoid_bce(const float* logit, float* prob, float target, float* scalars, int B, void* stream) {
     JCK_REQUIRE(logit && prob && B > 0, "sigmoid_bce: bad argument");
-    sigmoid_bce_kernel<<<grid1d(B), 256, 0, as_stream(stream)>>>(logit, prob, target, scalars, B);
+    launch_pdl(sigmoid_bce_kernel, dim3(grid1d(B)), dim3(256), 0, as_stream(stream), logit, prob, target, scalars, B);
     JCK_LAUNCH_CHECK("sigmoid_bce");
     return JCK_OK;
 }
@@ -224,27 +236,27 @@ extern "C" int jck_sigmoid_bce(const float* logit, float* prob, float target, fl
 extern "C" int jck_logit_grad(const float* prob, const float* up, float target, float* out, int B, int mode, float scale,
                               void* stream) {
     JCK_REQUIRE(prob && out && B > 0 && mode >= 0 && mode <= 3 && (mode < 2 || up), "logit_grad: bad argument");
-    logit_grad_kernel<<<grid1d(B), 256, 0, as_stream(stream)>>>(prob, up, target, out, B, mode, scale);
+    launch_pdl(logit_grad_kernel, dim3(grid1d(B)), dim3(256), 0, as_stream(stream), prob, up, target, out, B, mode, scale);
     JCK_LAUNCH_CHECK("logit_grad");
     return JCK_OK;
 }
 
 extern "C" int jck_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
     JCK_REQUIRE(in && out && n > 0, "f32_to_bf16: bad argument");
-    f32_to_bf16_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(in, (__nv_bfloat16*)out, n);
+    launch_pdl(f32_to_bf16_kernel, dim3(grid1d(n)), dim3(256), 0, as_stream(stream), in, (__nv_bfloat16*)out, n);
     JCK_LAUNCH_CHECK("f32_to_bf16");
     return JCK_OK;
 }
 extern "C" int jck_i64_to_f32(const long long* in, float* out, long long n, void* stream) {
     JCK_REQUIRE(in && out && n > 0, "i64_to_f32: bad argument");
-    i64_to_f32_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(in, out, n);
+    launch_pdl(i64_to_f32_kernel, dim3(grid1d(n)), dim3(256), 0, as_stream(stream), in, out, n);
     JCK_LAUNCH_CHECK("i64_to_f32");
     return JCK_OK;
 }
 
 extern "C" int jck_axpy(const void* x, void* y, float a, long long n, int dtype, void* stream) {
     JCK_REQUIRE(x && y && n > 0, "axpy: bad argument");
-    DISPATCH_DTYPE(dtype, "axpy", axpy_kernel<T><<<grid1d(n), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, a, n);)
+    DISPATCH_DTYPE(dtype, "axpy", launch_pdl(axpy_kernel<T>, dim3(grid1d(n)), dim3(256), 0, as_stream(stream), (const T*)x, (T*)y, a, n);)
     JCK_LAUNCH_CHECK("axpy");
     return JCK_OK;
 }
@@ -253,7 +265,7 @@ extern "C" int jck_gp_seed(const void* v, void* u, float* scalars, int B, long l
                            void* stream) {
     JCK_REQUIRE(v && B > 0 && per_sample > 0, "gp_seed: bad argument");
     DISPATCH_DTYPE(dtype, "gp_seed",
-        gp_seed_kernel<T><<<B, 256, 0, as_stream(stream)>>>((const T*)v, (T*)u, scalars, B, per_sample, scale);)
+        launch_pdl(gp_seed_kernel<T>, dim3(B), dim3(256), 0, as_stream(stream), (const T*)v, (T*)u, scalars, B, per_sample, scale);)
     JCK_LAUNCH_CHECK("gp_seed");
     return JCK_OK;
 }
@@ -261,14 +273,14 @@ extern "C" int jck_gp_seed(const void* v, void* u, float* scalars, int B, long l
 extern "C" int jck_pack_linear(const float* w, void* w_a, float* w_b, int O, int C, int HW, int E, int dtype, void* stream) {
     JCK_REQUIRE(w && w_a && w_b && O > 0 && C > 0 && HW > 0 && E >= 0, "pack_linear: bad argument");
     DISPATCH_DTYPE(dtype, "pack_linear",
-        pack_linear_kernel<T><<<grid1d((long long)O * (C * HW + E)), 256, 0, as_stream(stream)>>>(w, (T*)w_a, w_b, O, C, HW, E);)
+        launch_pdl(pack_linear_kernel<T>, dim3(grid1d((long long)O * (C * HW + E))), dim3(256), 0, as_stream(stream), w, (T*)w_a, w_b, O, C, HW, E);)
     JCK_LAUNCH_CHECK("pack_linear");
     return JCK_OK;
 }
 extern "C" int jck_unpack_linear_grad(const float* dwa, const float* dwb, float* dw, int O, int C, int HW, int E, int accumulate,
                                       void* stream) {
     JCK_REQUIRE(dwa && dwb && dw && O > 0, "unpack_linear_grad: bad argument");
-    unpack_linear_grad_kernel<<<grid1d((long long)O * (C * HW + E)), 256, 0, as_stream(stream)>>>(dwa, dwb, dw, O, C, HW, E, accumulate);
+    launch_pdl(unpack_linear_grad_kernel, dim3(grid1d((long long)O * (C * HW + E))), dim3(256), 0, as_stream(stream), dwa, dwb, dw, O, C, HW, E, accumulate);
     JCK_LAUNCH_CHECK("unpack_linear_grad");
     return JCK_OK;
 }
@@ -284,7 +296,7 @@ extern "C" int jck_bn_adj_reduce(const void* dbar, const void* da, const void* y
     if (slabs < 1) slabs = 1;
     dim3 grid((unsigned)slabs, (unsigned)((C + tx - 1) / tx));
     DISPATCH_DTYPE(dtype, "bn_adj_reduce",
-        bn_adj_reduce_kernel<T><<<grid, tx, 0, as_stream(stream)>>>((const T*)dbar, (const T*)da, (const T*)y, scale_shift,
+        launch_pdl(bn_adj_reduce_kernel<T>, dim3(grid), dim3(tx), 0, as_stream(stream), (const T*)dbar, (const T*)da, (const T*)y, scale_shift,
                                                                    mean_rstd, sums1, asums, C, npix, 1.f / count, slope);)
     JCK_LAUNCH_CHECK("bn_adj_reduce");
     return JCK_OK;
@@ -296,7 +308,7 @@ extern "C" int jck_bn_adj_apply(const void* dbar, const void* da, const void* y,
     JCK_REQUIRE(dbar && da && y && scale_shift && mean_rstd && gamma && sums1 && asums && gbar_a && ybar && npix > 0 && count > 0,
                 "bn_adj_apply: bad argument");
     DISPATCH_DTYPE(dtype, "bn_adj_apply",
-        bn_adj_apply_kernel<T><<<grid1d(npix * C), 256, 0, as_stream(stream)>>>((const T*)dbar, (const T*)da, (const T*)y,
+        launch_pdl(bn_adj_apply_kernel<T>, dim3(grid1d(npix * C)), dim3(256), 0, as_stream(stream), (const T*)dbar, (const T*)da, (const T*)y,
                                                                               scale_shift, mean_rstd, gamma, sums1, asums,
                                                                               (T*)gbar_a, (T*)ybar, C, npix, 1.f / count, slope);)
     JCK_LAUNCH_CHECK("bn_adj_apply");
@@ -305,7 +317,7 @@ extern "C" int jck_bn_adj_apply(const void* dbar, const void* da, const void* y,
 
 extern "C" int jck_bn_adj_param(const float* asums, const float* mean_rstd, float* dgamma, int C, float scale, void* stream) {
     JCK_REQUIRE(asums && mean_rstd && dgamma && C > 0, "bn_adj_param: bad argument");
-    bn_adj_param_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(asums, mean_rstd, dgamma, C, scale);
+    launch_pdl(bn_adj_param_kernel, dim3((C + 127) / 128), dim3(128), 0, as_stream(stream), asums, mean_rstd, dgamma, C, scale);
     JCK_LAUNCH_CHECK("bn_adj_param");
     return JCK_OK;
 }

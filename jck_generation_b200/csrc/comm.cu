@@ -78,6 +78,7 @@ __device__ void allreduce_block(const CommDev& c, float* __restrict__ data, int 
 }
 
 __global__ void __launch_bounds__(1024) comm_allreduce_kernel(const CommDev c, float* __restrict__ data, int n) {
+    pdl_entry();
     allreduce_block(c, data, n);
 }
 
@@ -87,6 +88,7 @@ bn_finalize_sync_kernel(const CommDev c, float* __restrict__ stats, const float*
                         const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                         long long* __restrict__ nbt, float* __restrict__ scale_shift, float* __restrict__ mean_rstd, int C,
                         int groups, float count, float eps, float momentum) {
+    pdl_entry();
     allreduce_block(c, stats, groups * 2 * C);
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
         float rm = running_mean ? running_mean[ch] : 0.f, rv = running_var ? running_var[ch] : 0.f;
@@ -115,6 +117,7 @@ bn_finalize_sync_kernel(const CommDev c, float* __restrict__ stats, const float*
 __global__ void __launch_bounds__(1024)
 bn_bwd_sums_sync_kernel(const CommDev c, float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                         int C, int groups, int accumulate) {
+    pdl_entry();
     if (dgamma != nullptr) {
         for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
             float sb = 0.f, sg = 0.f;
@@ -186,7 +189,7 @@ extern "C" int jck_comm_destroy(void* comm) {
 extern "C" int jck_comm_allreduce_small(void* comm, float* data, int n, void* stream) {
     JCK_REQUIRE(comm && data && n > 0 && n <= kMaxN, "comm_allreduce_small: n=%d (max %d)", n, kMaxN);
     Comm* cm = static_cast<Comm*>(comm);
-    comm_allreduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(cm->dev, data, n);
+    launch_pdl(comm_allreduce_kernel, dim3(1), dim3(1024), 0, as_stream(stream), cm->dev, data, n);
     JCK_LAUNCH_CHECK("comm_allreduce_small");
     return JCK_OK;
 }
@@ -197,7 +200,7 @@ extern "C" int jck_bn_finalize_sync(void* comm, float* stats, const float* gamma
     JCK_REQUIRE(comm && stats && gamma && beta && scale_shift && mean_rstd && C > 0 && groups > 0 && count > 0 &&
                 groups * 2 * C <= kMaxN, "bn_finalize_sync: bad argument");
     Comm* cm = static_cast<Comm*>(comm);
-    bn_finalize_sync_kernel<<<1, 1024, 0, as_stream(stream)>>>(cm->dev, stats, gamma, beta, running_mean, running_var,
+    launch_pdl(bn_finalize_sync_kernel, dim3(1), dim3(1024), 0, as_stream(stream), cm->dev, stats, gamma, beta, running_mean, running_var,
                                                              num_batches_tracked, scale_shift, mean_rstd, C, groups, count,
                                                              eps, momentum);
     JCK_LAUNCH_CHECK("bn_finalize_sync");
@@ -209,7 +212,7 @@ extern "C" int jck_bn_bwd_sums_sync(void* comm, float* sums, float* dgamma, floa
     JCK_REQUIRE(comm && sums && C > 0 && groups > 0 && groups * 2 * C <= kMaxN && ((dgamma == nullptr) == (dbeta == nullptr)),
                 "bn_bwd_sums_sync: bad argument");
     Comm* cm = static_cast<Comm*>(comm);
-    bn_bwd_sums_sync_kernel<<<1, 1024, 0, as_stream(stream)>>>(cm->dev, sums, dgamma, dbeta, C, groups, accumulate);
+    launch_pdl(bn_bwd_sums_sync_kernel, dim3(1), dim3(1024), 0, as_stream(stream), cm->dev, sums, dgamma, dbeta, C, groups, accumulate);
     JCK_LAUNCH_CHECK("bn_bwd_sums_sync");
     return JCK_OK;
 }

@@ -59,4 +59,33 @@ __host__ __device__ __forceinline__ int up_d(int parity, int t) { return t == 0 
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------
+// The train step is ~150 dependent launches in one CUDA graph; a full kernel -> kernel dependency costs a drain +
+// launch gap of a few microseconds each.  Every kernel here is launched with programmatic stream serialization:
+// it signals `launch_dependents` on entry (its successor may be scheduled as soon as all of this grid's CTAs are
+// resident) and executes `griddepcontrol.wait` before its first global-memory access -- which blocks until the
+// predecessor grid has COMPLETED and flushed, so data dependencies are exactly those of a normal launch; only the
+// launch latency, CTA scheduling and the on-chip prologue (barrier init, TMEM allocation, descriptor prefetch)
+// overlap the predecessor's tail.  Both instructions are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
+
+bool pdl_enabled();   // JCK_PDL=0 in the environment turns the attribute off (A/B timing)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace jck

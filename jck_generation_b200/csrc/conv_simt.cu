@@ -205,6 +205,7 @@ struct DenseProblem {
 // ---------------------------------------------------------------------------------------------
 template <typename P>
 __global__ void __launch_bounds__(NT) simt_gemm_kernel(const P p, int k_per_split) {
+    pdl_entry();
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Bs[BK][BN + PAD];
     __shared__ float red[2][16][BN];
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(NT) simt_gemm_kernel(const P p, int k_per_spli
 template <typename P>
 int launch(const P& p, int M, int N, int zdim, int k_per_split, cudaStream_t st, const char* name) {
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, zdim);
-    simt_gemm_kernel<P><<<grid, NT, 0, st>>>(p, k_per_split);
+    launch_pdl(simt_gemm_kernel<P>, dim3(grid), dim3(NT), 0, st, p, k_per_split);
     JCK_LAUNCH_CHECK(name);
     return JCK_OK;
 }
@@ -318,6 +319,7 @@ constexpr int kUnpackBT = 64;
 // any Cb (the 3-channel image edge in fp32 parity mode): element-wise
 __global__ void wgrad_unpack_small_kernel(const float* __restrict__ part, float* __restrict__ dw4, int Ca, int Cb,
                                           int splits, int accumulate) {
+    pdl_entry();
     const size_t total = (size_t)Ca * 16 * Cb;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
@@ -331,6 +333,7 @@ __global__ void wgrad_unpack_small_kernel(const float* __restrict__ part, float*
 
 __global__ void __launch_bounds__(256)
 wgrad_unpack_kernel(const float* __restrict__ part, float* __restrict__ dw4, int Ca, int Cb, int splits, int accumulate) {
+    pdl_entry();
     __shared__ float tile[16][kUnpackBT + 1];
     const int btiles = Cb / kUnpackBT;
     const size_t total = (size_t)Ca * 16 * Cb;
@@ -388,13 +391,13 @@ int launch_wgrad_unpack(const float* part, float* dw4, int Ca, int Cb, int split
         const size_t total = (size_t)Ca * 16 * Cb;
         int nb = (int)((total + 255) / 256);
         if (nb > 4 * kNumSMs) nb = 4 * kNumSMs;
-        wgrad_unpack_small_kernel<<<nb, 256, 0, st>>>(part, dw4, Ca, Cb, splits, accumulate);
+        launch_pdl(wgrad_unpack_small_kernel, dim3(nb), dim3(256), 0, st, part, dw4, Ca, Cb, splits, accumulate);
         JCK_LAUNCH_CHECK("wgrad_unpack");
         return JCK_OK;
     }
     int blocks = Ca * (Cb / kUnpackBT);
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-    wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(part, dw4, Ca, Cb, splits, accumulate);
+    launch_pdl(wgrad_unpack_kernel, dim3(blocks), dim3(256), 0, st, part, dw4, Ca, Cb, splits, accumulate);
     JCK_LAUNCH_CHECK("wgrad_unpack");
     return JCK_OK;
 }

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI, EPI == 4 ? 2 : 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                        __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p,
                        const int n_tiles, const int total_tiles, const BnBwdEpi bb) {
+    pdl_trigger();
     constexpr bool kUp = (MODE == kUpM);
     constexpr int kAccCols = BN_ < 32 ? 32 : BN_;
     using L = PersistSmem<BN_, STAGES>;
@@ -201,6 +202,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above is on-chip set-up; global memory is first touched below
 
     if (warp == 0) {
         if (lane == 0) {
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(192, 2)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p,
                     const int n_tiles, const int total_pairs, const BnBwdEpi bb) {
+    pdl_trigger();
     static_assert(MODE == kDown || MODE == kUpM, "pair kernel: trunk layers only");
     constexpr bool kUp = (MODE == kUpM);
     constexpr int kAccCols = BN_;
@@ -467,6 +470,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     cluster_sync_all();                    // barriers of BOTH CTAs are initialised before anyone signals across
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above is on-chip set-up; global memory is first touched below
 
     auto decode = [&](int tp, int& nt, int& phase, int& x0, int& y0, int& n0) {
         nt = tp % n_tiles;
@@ -691,13 +695,15 @@ int launch_pair_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, flo
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = L::kTotal;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA, mB, (__nv_bfloat16*)out, stats, p, n_tiles, total_pairs, bb);
     if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_pair launch: %s", cudaGetErrorString(e));
     JCK_LAUNCH_CHECK(MODE == kUpM ? "conv_up_tc_pair" : "conv_down_tc_pair");
@@ -718,7 +724,7 @@ int launch_persist_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, 
     const int total = m_tiles * n_tiles * (MODE == kUpM ? 4 : 1);
     const int cap = kNumSMs * CTAS_PER_SM;
     const int grid = total < cap ? total : cap;
-    conv_tc_persist_kernel<BN_, STAGES, MODE, EPI, EPIM><<<grid, 64 + 32 * EPI, L::kTotal, st>>>(
+    launch_pdl(conv_tc_persist_kernel<BN_, STAGES, MODE, EPI, EPIM>, dim3(grid), dim3(64 + 32 * EPI), L::kTotal, st, 
         mA, mB, (__nv_bfloat16*)out, stats, p, n_tiles, total, bb);
     return JCK_OK;
 }
@@ -797,6 +803,7 @@ template <int BNW>  // 64 (G = 8 taps) or 128 (G = 4 taps)
 __global__ void __launch_bounds__(kConvThreads)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapL,
                 const __grid_constant__ CUtensorMap mapP, const WgradTcParams p) {
+    pdl_trigger();
     constexpr int G = 512 / BNW;
     constexpr int ATOMS_B = BNW / 64;
     extern __shared__ uint8_t smem_raw[];
@@ -827,6 +834,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant_
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above is on-chip set-up; global memory is first touched below
 
     if (warp == 0) {
         if (lane == 0) {
@@ -976,14 +984,14 @@ int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan&
             if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
             cfg64 = true;
         }
-        wgrad_tc_kernel<64><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, mP, p);
+        launch_pdl(wgrad_tc_kernel<64>, dim3(grid), dim3(kConvThreads), kWgradSmem, st, mS, mL, mP, p);
     } else {
         if (!cfg128) {
             cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
             if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
             cfg128 = true;
         }
-        wgrad_tc_kernel<128><<<grid, kConvThreads, kWgradSmem, st>>>(mS, mL, mP, p);
+        launch_pdl(wgrad_tc_kernel<128>, dim3(grid), dim3(kConvThreads), kWgradSmem, st, mS, mL, mP, p);
     }
     JCK_LAUNCH_CHECK("wgrad_tc");
     return JCK_OK;
@@ -1004,6 +1012,7 @@ constexpr int kEdgeWDStages = 4;
 __global__ void __launch_bounds__(kConvThreads)
 wgrad_edge_direct_kernel(const __grid_constant__ CUtensorMap mapS, const __nv_bfloat16* __restrict__ img,
                          float* __restrict__ part, const EdgeWgradDirectParams p) {
+    pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kTile = kWgradKPix * 128;                        // 8 KB
@@ -1127,6 +1136,7 @@ wgrad_edge_direct_kernel(const __grid_constant__ CUtensorMap mapS, const __nv_bf
 // dw4[a][c][ky][kx] (+)= sum_split part[split][a][ky*16 + kx*4 + c], c < nc
 __global__ void edge_wgrad_unpack_kernel(const float* __restrict__ part, float* __restrict__ dw4, int nc, int splits,
                                          int accumulate) {
+    pdl_entry();
     const int total = 64 * nc * 16;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int kx = idx & 3, ky = (idx >> 2) & 3, c = (idx >> 4) % nc, a = (idx >> 4) / nc;
@@ -1159,6 +1169,7 @@ __global__ void __launch_bounds__(192, 3)
 edge_down_direct_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                         const __nv_bfloat16* __restrict__ img, float* __restrict__ stats, const EdgeDirectParams p,
                         const int total_tiles) {
+    pdl_entry();
     constexpr int BN_ = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1362,6 +1373,7 @@ template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(kConvThreads)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void* __restrict__ Cout,
                const GemmParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStage);
@@ -1387,6 +1399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above is on-chip set-up; global memory is first touched below
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1502,6 +1515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // C[m][n] (=, +=) sum over splits of part[s][m][n]; mode as GemmParams (0 fp32 =, 1 fp32 +=, 2 bf16 =)
 __global__ void gemm_reduce_kernel(const float* __restrict__ part, void* __restrict__ Cout, int M, int N, long long ldc,
                                    int splits, int mode) {
+    pdl_entry();
     const long long total = (long long)M * N;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         float acc = 0.f;
@@ -1546,7 +1560,7 @@ int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, void* C, const Gem
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "gemm_tc smem attr: %s", cudaGetErrorString(e));
         cfg = true;
     }
-    gemm_tc_kernel<A_MN, B_MN><<<grid, kConvThreads, kGemmSmem, st>>>(mA, mB, C, p);
+    launch_pdl(gemm_tc_kernel<A_MN, B_MN>, dim3(grid), dim3(kConvThreads), kGemmSmem, st, mA, mB, C, p);
     JCK_LAUNCH_CHECK("gemm_tc");
     return JCK_OK;
 }
@@ -1680,7 +1694,7 @@ extern "C" int jck_edge_down_img(const void* img_p4, const void* w_down_e, void*
     }
     const int total = B * p.tiles_y;
     const int grid = total < 3 * kNumSMs ? total : 3 * kNumSMs;
-    edge_down_direct_kernel<<<grid, 192, smem, as_stream(stream)>>>(mB, mOut, (const __nv_bfloat16*)img_p4, stats, p, total);
+    launch_pdl(edge_down_direct_kernel, dim3(grid), dim3(192), smem, as_stream(stream), mB, mOut, (const __nv_bfloat16*)img_p4, stats, p, total);
     JCK_LAUNCH_CHECK("edge_down_img");
     return JCK_OK;
 }
@@ -1726,9 +1740,9 @@ extern "C" int jck_edge_wgrad_img(const void* small, const void* img_p4, float* 
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_wgrad_img smem attr: %s", cudaGetErrorString(e));
         cfg = true;
     }
-    wgrad_edge_direct_kernel<<<pl.splits, kConvThreads, smem, st>>>(mS, (const __nv_bfloat16*)img_p4, (float*)workspace, p);
+    launch_pdl(wgrad_edge_direct_kernel, dim3(pl.splits), dim3(kConvThreads), smem, st, mS, (const __nv_bfloat16*)img_p4, (float*)workspace, p);
     JCK_LAUNCH_CHECK("edge_wgrad_img");
-    edge_wgrad_unpack_kernel<<<(64 * nc * 16 + 255) / 256, 256, 0, st>>>((const float*)workspace, dw4, nc, pl.splits, accumulate);
+    launch_pdl(edge_wgrad_unpack_kernel, dim3((64 * nc * 16 + 255) / 256), dim3(256), 0, st, (const float*)workspace, dw4, nc, pl.splits, accumulate);
     JCK_LAUNCH_CHECK("edge_wgrad_unpack");
     return JCK_OK;
 }
@@ -1767,7 +1781,7 @@ extern "C" int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const v
         const long long total = (long long)M * N;
         long long blocks = (total + 255) / 256;
         if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-        gemm_reduce_kernel<<<(int)blocks, 256, 0, st>>>((const float*)workspace, C, M, N, ldc, pl.splits, final_mode);
+        launch_pdl(gemm_reduce_kernel, dim3((int)blocks), dim3(256), 0, st, (const float*)workspace, C, M, N, ldc, pl.splits, final_mode);
         JCK_LAUNCH_CHECK("gemm_reduce");
     }
     return JCK_OK;

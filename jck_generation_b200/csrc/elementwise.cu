@@ -4,12 +4,18 @@
 // accesses on the NHWC tensors, fp32 math, grid sized in multiples of the SM count.
 #include <stdarg.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace jck {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("JCK_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -135,6 +141,7 @@ __global__ void prep_image_kernel(const float* __restrict__ x1, const float* __r
                                   const float* __restrict__ x2, const float* __restrict__ alpha,
                                   T* __restrict__ out_nhwc, float* __restrict__ out_nchw, int B, int C, int HW,
                                   const ImgLayout lay) {
+    pdl_entry();
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
@@ -155,6 +162,7 @@ __global__ void prep_image_kernel(const float* __restrict__ x1, const float* __r
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int C, int HW,
                                     const ImgLayout lay) {
+    pdl_entry();
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
@@ -225,6 +233,7 @@ __global__ void __launch_bounds__(256)
 prep_image_quad_kernel(const float* __restrict__ x1, const NoiseSrc ns, float a1, float b1, const float* __restrict__ x2,
                        const float* __restrict__ alpha, T* __restrict__ out_nhwc, float* __restrict__ out_nchw, int B, int C,
                        int HW, const ImgLayout lay) {
+    pdl_entry();
     const int qpi = HW / 4;
     const long long total = (long long)B * qpi;
     const bool noisy = ns.rng || ns.mem;
@@ -266,6 +275,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 g_out_fwd_quad_kernel(const T* __restrict__ y5, const NoiseSrc ns, float a, float b, float* __restrict__ fake_raw,
                       float* __restrict__ fake_mix, T* __restrict__ mix_nhwc, int B, int C, int HW, const ImgLayout lay) {
+    pdl_entry();
     const int qpi = HW / 4;
     const long long total = (long long)B * qpi;
     const bool noisy = ns.rng || ns.mem;
@@ -301,6 +311,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 g_out_bwd_quad_kernel(const T* __restrict__ dmix, const float* __restrict__ fake_raw, float a, T* __restrict__ dy5, int B,
                       int C, int HW, const ImgLayout lay) {
+    pdl_entry();
     const int qpi = HW / 4;
     const long long total = (long long)B * qpi;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
@@ -327,6 +338,7 @@ g_out_bwd_quad_kernel(const T* __restrict__ dmix, const float* __restrict__ fake
 template <typename T>
 __global__ void pack_weights_kernel(const float* __restrict__ w4, T* __restrict__ w_down, T* __restrict__ w_up, int Ca,
                                     int Cb) {
+    pdl_entry();
     const long long total = (long long)Ca * Cb * 16;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -353,6 +365,7 @@ constexpr int kPackAT = 16, kPackBT = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_weights_tiled_kernel(const float* __restrict__ w4, T* __restrict__ w_down, T* __restrict__ w_up, int Ca, int Cb) {
+    pdl_entry();
     __shared__ float tile[kPackAT][16 * (kPackBT + 1) + 1];   // [a][tap * 33 + b] (+1: odd row stride), 33 KB
     const int btiles = Cb / kPackBT;
     for (int blk = blockIdx.x; blk < (Ca / kPackAT) * btiles; blk += gridDim.x) {
@@ -392,6 +405,7 @@ __device__ __forceinline__ int edge_k_of(int parity, int d) {   // kernel index 
 }
 __global__ void pack_weights_edge_kernel(const float* __restrict__ w4, __nv_bfloat16* __restrict__ w_down_e,
                                          __nv_bfloat16* __restrict__ w_up9, int Ca, int nc) {
+    pdl_entry();
     const int n_down = Ca * 64, n_up = 16 * 9 * Ca;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_down + n_up; idx += gridDim.x * blockDim.x) {
         if (idx < n_down) {
@@ -416,6 +430,7 @@ __global__ void pack_weights_edge_kernel(const float* __restrict__ w4, __nv_bflo
 
 template <typename T>
 __global__ void pack_fc_kernel(const float* __restrict__ w4, T* __restrict__ w_fc, int K, int C) {
+    pdl_entry();
     const long long total = (long long)K * C * 16;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -426,6 +441,7 @@ __global__ void pack_fc_kernel(const float* __restrict__ w4, T* __restrict__ w_f
     }
 }
 __global__ void unpack_fc_grad_kernel(const float* __restrict__ dw_fc, float* __restrict__ dw4, int K, int C, int accumulate) {
+    pdl_entry();
     const long long total = (long long)K * C * 16;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -438,6 +454,7 @@ __global__ void unpack_fc_grad_kernel(const float* __restrict__ dw_fc, float* __
 }
 template <typename T>
 __global__ void pack_head_kernel(const float* __restrict__ w4, T* __restrict__ w5, int C4) {
+    pdl_entry();
     const int total = C4 * 16;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int tap = idx % 16, c = idx / 16;
@@ -445,6 +462,7 @@ __global__ void pack_head_kernel(const float* __restrict__ w4, T* __restrict__ w
     }
 }
 __global__ void unpack_head_grad_kernel(const float* __restrict__ dw5, float* __restrict__ dw4, int C4, int accumulate) {
+    pdl_entry();
     const int total = C4 * 16;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int tap = idx % 16, c = idx / 16;
@@ -459,6 +477,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
                                    float* __restrict__ running_var, long long* __restrict__ nbt,
                                    float* __restrict__ scale_shift, float* __restrict__ mean_rstd, int C, int groups,
                                    float count, float eps, float momentum) {
+    pdl_entry();
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
         for (int g = 0; g < groups; ++g) {   // in order: the reference updates running stats pass by pass
@@ -496,6 +515,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift, T* __restrict__ a, int C,
                   unsigned pix_per_group, unsigned slab, float slope) {
+    pdl_entry();
     typedef typename Vec8<T>::Raw Raw;
     const unsigned cv = C / 8, rows = 256 / cv;
     const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
@@ -534,6 +554,7 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
                          const float* __restrict__ mean_rstd, float* __restrict__ sums, int C, unsigned pix_per_group,
                          unsigned slab, float slope) {
+    pdl_entry();
     typedef typename Vec8<T>::Raw Raw;
     __shared__ float red[256][17];
     const unsigned cv = C / 8, rows = 256 / cv;
@@ -598,6 +619,7 @@ bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y, const
                         const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                         const float* __restrict__ sums, T* __restrict__ dy, int C, unsigned pix_per_group,
                         unsigned slab, float inv_count, float slope) {
+    pdl_entry();
     typedef typename Vec8<T>::Raw Raw;
     const unsigned cv = C / 8, rows = 256 / cv;
     const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv;
@@ -655,6 +677,7 @@ bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y, const
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      int C, int groups, int accumulate) {
+    pdl_entry();
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         float sb = 0.f, sg = 0.f;
         for (int g = 0; g < groups; ++g) { sb += sums[(size_t)g * 2 * C + c]; sg += sums[(size_t)g * 2 * C + C + c]; }
@@ -668,6 +691,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const T* __restrict__ a4, const T* __restrict__ w5, float* __restrict__ prob, float target,
                 float* __restrict__ scalars, int B, int K) {
+    pdl_entry();
     __shared__ float wsum[8];
     const int b = blockIdx.x;
     float acc = 0.f;
@@ -708,6 +732,7 @@ __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob, float target, const T* __restrict__ w5,
                 const T* __restrict__ a4,
                 T* __restrict__ da4, float* __restrict__ dw5, int B, int K, int mode, int chunk) {
+    pdl_entry();
     const int k = (blockIdx.x * 256 + threadIdx.x) * 8;
     if (k >= K) return;
     float w[8], acc[8];
@@ -740,6 +765,7 @@ template <typename T>
 __global__ void g_out_fwd_kernel(const T* __restrict__ y5, const float* __restrict__ noise, float a, float b,
                                  float* __restrict__ fake_raw, float* __restrict__ fake_mix, T* __restrict__ mix_nhwc,
                                  int B, int C, int HW, const ImgLayout lay) {
+    pdl_entry();
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
@@ -758,6 +784,7 @@ __global__ void g_out_fwd_kernel(const T* __restrict__ y5, const float* __restri
 template <typename T>
 __global__ void g_out_bwd_kernel(const T* __restrict__ dmix, const float* __restrict__ fake_raw, float a,
                                  T* __restrict__ dy5, int B, int C, int HW, const ImgLayout lay) {
+    pdl_entry();
     const long long total = (long long)B * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
@@ -774,6 +801,7 @@ __global__ void g_out_bwd_kernel(const T* __restrict__ dmix, const float* __rest
 template <typename T>
 __global__ void __launch_bounds__(256)
 gp_penalty_kernel(const T* __restrict__ dx, float* __restrict__ scalars, int B, long long per_sample) {
+    pdl_entry();
     __shared__ float wsum[8];
     const int n = blockIdx.x;
     float acc = 0.f;
@@ -795,6 +823,7 @@ gp_penalty_kernel(const T* __restrict__ dx, float* __restrict__ scalars, int B, 
 // ---- Adam ------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, const int* __restrict__ step_count) {
+    pdl_entry();
     const float t = (float)(*step_count + 1);
     const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
@@ -807,11 +836,13 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         p[i] -= step_size * (mi / denom);
     }
 }
-__global__ void adam_advance_kernel(int* step_count) { *step_count += 1; }
+__global__ void adam_advance_kernel(int* step_count) {
+    pdl_entry(); *step_count += 1; }
 
 template <bool kNormal>
 __global__ void rng_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long stream_id,
                            const unsigned long long* __restrict__ counter_base) {
+    pdl_entry();
     const unsigned long long base = counter_base ? *counter_base : 0ull;
     const long long nquads = (n + 3) / 4;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquads; q += (long long)gridDim.x * blockDim.x) {
@@ -823,7 +854,8 @@ __global__ void rng_kernel(float* __restrict__ out, long long n, unsigned long l
             if (q * 4 + j < n) out[q * 4 + j] = o[j];
     }
 }
-__global__ void rng_advance_kernel(unsigned long long* c, unsigned long long by) { *c += by; }
+__global__ void rng_advance_kernel(unsigned long long* c, unsigned long long by) {
+    pdl_entry(); *c += by; }
 
 }  // namespace
 }  // namespace jck
@@ -849,12 +881,12 @@ static int prep_image_launch(const float* x1, const NoiseSrc& ns, float a1, floa
     const ImgLayout lay(H, W, C, layout);
     if (W % 4 == 0 && C <= 4) {
         DISPATCH_DTYPE(dtype, "prep_image",
-            prep_image_quad_kernel<T><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(
+            launch_pdl(prep_image_quad_kernel<T>, dim3(grid_for(total / 4, 256)), dim3(256), 0, as_stream(stream), 
                 x1, ns, a1, b1, x2, alpha, (T*)out_nhwc, out_nchw_f32, B, C, H * W, lay);)
     } else {
         JCK_REQUIRE(!ns.rng, "prep_image: in-register noise needs W % 4 == 0 and C <= 4");
         DISPATCH_DTYPE(dtype, "prep_image",
-            prep_image_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x1, ns.mem, a1, b1, x2, alpha, (T*)out_nhwc,
+            launch_pdl(prep_image_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), x1, ns.mem, a1, b1, x2, alpha, (T*)out_nhwc,
                                                                                       out_nchw_f32, B, C, H * W, lay);)
     }
     JCK_LAUNCH_CHECK("prep_image");
@@ -882,7 +914,7 @@ extern "C" int jck_nhwc_to_nchw_f32(const void* in_nhwc, float* out_nchw, int B,
     const long long total = (long long)B * H * W;
     const ImgLayout lay(H, W, C, layout);
     DISPATCH_DTYPE(dtype, "nhwc_to_nchw",
-        nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)in_nhwc, out_nchw, B, C, H * W, lay);)
+        launch_pdl(nhwc_to_nchw_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), (const T*)in_nhwc, out_nchw, B, C, H * W, lay);)
     JCK_LAUNCH_CHECK("nhwc_to_nchw");
     return JCK_OK;
 }
@@ -894,19 +926,19 @@ extern "C" int jck_pack_weights(const float* w4, void* w_down, void* w_up, int C
         int blocks = (Ca / kPackAT) * (Cb / kPackBT);
         if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
         DISPATCH_DTYPE(dtype, "pack_weights",
-            pack_weights_tiled_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(w4, (T*)w_down, (T*)w_up, Ca, Cb);)
+            launch_pdl(pack_weights_tiled_kernel<T>, dim3(blocks), dim3(256), 0, as_stream(stream), w4, (T*)w_down, (T*)w_up, Ca, Cb);)
         JCK_LAUNCH_CHECK("pack_weights");
         return JCK_OK;
     }
     DISPATCH_DTYPE(dtype, "pack_weights",
-        pack_weights_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w_down, (T*)w_up, Ca, Cb);)
+        launch_pdl(pack_weights_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), w4, (T*)w_down, (T*)w_up, Ca, Cb);)
     JCK_LAUNCH_CHECK("pack_weights");
     return JCK_OK;
 }
 
 extern "C" int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up9, int Ca, int nc, void* stream) {
     JCK_REQUIRE(w4 && (w_down_e || w_up9) && Ca > 0 && nc > 0 && nc <= 4, "pack_weights_edge: bad argument");
-    pack_weights_edge_kernel<<<grid_for((long long)Ca * 64 + 144LL * Ca, 256), 256, 0, as_stream(stream)>>>(
+    launch_pdl(pack_weights_edge_kernel, dim3(grid_for((long long)Ca * 64 + 144LL * Ca, 256)), dim3(256), 0, as_stream(stream), 
         w4, (__nv_bfloat16*)w_down_e, (__nv_bfloat16*)w_up9, Ca, nc);
     JCK_LAUNCH_CHECK("pack_weights_edge");
     return JCK_OK;
@@ -915,26 +947,26 @@ extern "C" int jck_pack_weights_edge(const float* w4, void* w_down_e, void* w_up
 extern "C" int jck_pack_fc(const float* w4, void* w_fc, int K, int C, int dtype, void* stream) {
     JCK_REQUIRE(w4 && w_fc && K > 0 && C > 0, "pack_fc: bad argument");
     DISPATCH_DTYPE(dtype, "pack_fc",
-        pack_fc_kernel<T><<<grid_for((long long)K * C * 16, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w_fc, K, C);)
+        launch_pdl(pack_fc_kernel<T>, dim3(grid_for((long long)K * C * 16, 256)), dim3(256), 0, as_stream(stream), w4, (T*)w_fc, K, C);)
     JCK_LAUNCH_CHECK("pack_fc");
     return JCK_OK;
 }
 extern "C" int jck_unpack_fc_grad(const float* dw_fc, float* dw4, int K, int C, int accumulate, void* stream) {
     JCK_REQUIRE(dw_fc && dw4 && K > 0 && C > 0, "unpack_fc_grad: bad argument");
-    unpack_fc_grad_kernel<<<grid_for((long long)K * C * 16, 256), 256, 0, as_stream(stream)>>>(dw_fc, dw4, K, C, accumulate);
+    launch_pdl(unpack_fc_grad_kernel, dim3(grid_for((long long)K * C * 16, 256)), dim3(256), 0, as_stream(stream), dw_fc, dw4, K, C, accumulate);
     JCK_LAUNCH_CHECK("unpack_fc_grad");
     return JCK_OK;
 }
 extern "C" int jck_pack_head(const float* w4, void* w5, int C4, int dtype, void* stream) {
     JCK_REQUIRE(w4 && w5 && C4 > 0, "pack_head: bad argument");
     DISPATCH_DTYPE(dtype, "pack_head",
-        pack_head_kernel<T><<<grid_for(C4 * 16, 256), 256, 0, as_stream(stream)>>>(w4, (T*)w5, C4);)
+        launch_pdl(pack_head_kernel<T>, dim3(grid_for(C4 * 16, 256)), dim3(256), 0, as_stream(stream), w4, (T*)w5, C4);)
     JCK_LAUNCH_CHECK("pack_head");
     return JCK_OK;
 }
 extern "C" int jck_unpack_head_grad(const float* dw5, float* dw4, int C4, int accumulate, void* stream) {
     JCK_REQUIRE(dw5 && dw4 && C4 > 0, "unpack_head_grad: bad argument");
-    unpack_head_grad_kernel<<<grid_for(C4 * 16, 256), 256, 0, as_stream(stream)>>>(dw5, dw4, C4, accumulate);
+    launch_pdl(unpack_head_grad_kernel, dim3(grid_for(C4 * 16, 256)), dim3(256), 0, as_stream(stream), dw5, dw4, C4, accumulate);
     JCK_LAUNCH_CHECK("unpack_head_grad");
     return JCK_OK;
 }
@@ -943,7 +975,7 @@ extern "C" int jck_bn_finalize(const float* stats, const float* gamma, const flo
                                float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_rstd,
                                int C, int groups, float count, float eps, float momentum, void* stream) {
     JCK_REQUIRE(stats && gamma && beta && scale_shift && mean_rstd && C > 0 && groups > 0 && count > 0, "bn_finalize: bad argument");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(stats, gamma, beta, running_mean, running_var,
+    launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, as_stream(stream), stats, gamma, beta, running_mean, running_var,
                                                                        num_batches_tracked, scale_shift, mean_rstd, C,
                                                                        groups, count, eps, momentum);
     JCK_LAUNCH_CHECK("bn_finalize");
@@ -976,7 +1008,7 @@ extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, 
     unsigned slab;
     const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 6, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_fwd",
-        bn_act_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)y, scale_shift, (T*)a, C, (unsigned)pix_per_group,
+        launch_pdl(bn_act_fwd_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)y, scale_shift, (T*)a, C, (unsigned)pix_per_group,
                                                                 slab, slope);)
     JCK_LAUNCH_CHECK("bn_act_fwd");
     return JCK_OK;
@@ -990,7 +1022,7 @@ extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float*
     unsigned slab;
     const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 3, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
-        bn_act_bwd_reduce_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)da, (const T*)y, scale_shift, mean_rstd,
+        launch_pdl(bn_act_bwd_reduce_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y, scale_shift, mean_rstd,
                                                                        sums, C, (unsigned)pix_per_group, slab, slope);)
     JCK_LAUNCH_CHECK("bn_act_bwd_reduce");
     return JCK_OK;
@@ -1004,7 +1036,7 @@ extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* 
     unsigned slab;
     const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 6, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
-        bn_act_bwd_apply_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)da, (const T*)y, scale_shift, mean_rstd,
+        launch_pdl(bn_act_bwd_apply_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y, scale_shift, mean_rstd,
                                                                       gamma, sums, (T*)dy, C, (unsigned)pix_per_group, slab,
                                                                       1.f / count, slope);)
     JCK_LAUNCH_CHECK("bn_act_bwd_apply");
@@ -1013,7 +1045,7 @@ extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* 
 
 extern "C" int jck_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int groups, int accumulate, void* stream) {
     JCK_REQUIRE(sums && dgamma && dbeta && C > 0 && groups > 0, "bn_param_grad: bad argument");
-    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(sums, dgamma, dbeta, C, groups, accumulate);
+    launch_pdl(bn_param_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, as_stream(stream), sums, dgamma, dbeta, C, groups, accumulate);
     JCK_LAUNCH_CHECK("bn_param_grad");
     return JCK_OK;
 }
@@ -1022,7 +1054,7 @@ extern "C" int jck_head_fwd(const void* a4, const void* w5, float* prob, float t
                             int dtype, void* stream) {
     JCK_REQUIRE(a4 && w5 && prob && B > 0 && K > 0 && K % 8 == 0, "head_fwd: bad argument");
     DISPATCH_DTYPE(dtype, "head_fwd",
-        head_fwd_kernel<T><<<B, 256, 0, as_stream(stream)>>>((const T*)a4, (const T*)w5, prob, target, scalars, B, K);)
+        launch_pdl(head_fwd_kernel<T>, dim3(B), dim3(256), 0, as_stream(stream), (const T*)a4, (const T*)w5, prob, target, scalars, B, K);)
     JCK_LAUNCH_CHECK("head_fwd");
     return JCK_OK;
 }
@@ -1041,7 +1073,7 @@ extern "C" int jck_head_bwd(const float* prob, const float* dprob, float target,
     chunks = (B + chunk - 1) / chunk;
     dim3 grid((K / 8 + 255) / 256, chunks);
     DISPATCH_DTYPE(dtype, "head_bwd",
-        head_bwd_kernel<T><<<grid, 256, 0, st>>>(prob, dprob, target, (const T*)w5, (const T*)a4, (T*)da4, dw5, B, K, mode, chunk);)
+        launch_pdl(head_bwd_kernel<T>, dim3(grid), dim3(256), 0, st, prob, dprob, target, (const T*)w5, (const T*)a4, (T*)da4, dw5, B, K, mode, chunk);)
     JCK_LAUNCH_CHECK("head_bwd");
     return JCK_OK;
 }
@@ -1055,12 +1087,12 @@ static int g_out_fwd_launch(const void* y5_nhwc, const NoiseSrc& ns, float a, fl
     const ImgLayout lay(H, W, C, layout);
     if (W % 4 == 0 && C <= 4) {
         DISPATCH_DTYPE(dtype, "g_out_fwd",
-            g_out_fwd_quad_kernel<T><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(
+            launch_pdl(g_out_fwd_quad_kernel<T>, dim3(grid_for(total / 4, 256)), dim3(256), 0, as_stream(stream), 
                 (const T*)y5_nhwc, ns, a, b, fake_raw_nchw, fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W, lay);)
     } else {
         JCK_REQUIRE(!ns.rng, "g_out_fwd: in-register noise needs W % 4 == 0 and C <= 4");
         DISPATCH_DTYPE(dtype, "g_out_fwd",
-            g_out_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)y5_nhwc, ns.mem, a, b, fake_raw_nchw,
+            launch_pdl(g_out_fwd_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), (const T*)y5_nhwc, ns.mem, a, b, fake_raw_nchw,
                                                                                    fake_mix_nchw, (T*)fake_mix_nhwc, B, C, H * W, lay);)
     }
     JCK_LAUNCH_CHECK("g_out_fwd");
@@ -1090,11 +1122,11 @@ extern "C" int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, 
     const ImgLayout lay(H, W, C, layout);
     if (W % 4 == 0 && C <= 4) {
         DISPATCH_DTYPE(dtype, "g_out_bwd",
-            g_out_bwd_quad_kernel<T><<<grid_for(total / 4, 256), 256, 0, as_stream(stream)>>>(
+            launch_pdl(g_out_bwd_quad_kernel<T>, dim3(grid_for(total / 4, 256)), dim3(256), 0, as_stream(stream), 
                 (const T*)dmix_nhwc, fake_raw_nchw, a, (T*)dy5_nhwc, B, C, H * W, lay);)
     } else {
         DISPATCH_DTYPE(dtype, "g_out_bwd",
-            g_out_bwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)dmix_nhwc, fake_raw_nchw, a,
+            launch_pdl(g_out_bwd_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), (const T*)dmix_nhwc, fake_raw_nchw, a,
                                                                                    (T*)dy5_nhwc, B, C, H * W, lay);)
     }
     JCK_LAUNCH_CHECK("g_out_bwd");
@@ -1104,7 +1136,7 @@ extern "C" int jck_g_out_bwd(const void* dmix_nhwc, const float* fake_raw_nchw, 
 extern "C" int jck_gp_penalty(const void* dx, float* scalars, int B, long long per_sample, int dtype, void* stream) {
     JCK_REQUIRE(dx && scalars && B > 0 && per_sample > 0, "gp_penalty: bad argument");
     DISPATCH_DTYPE(dtype, "gp_penalty",
-        gp_penalty_kernel<T><<<B, 256, 0, as_stream(stream)>>>((const T*)dx, scalars, B, per_sample);)
+        launch_pdl(gp_penalty_kernel<T>, dim3(B), dim3(256), 0, as_stream(stream), (const T*)dx, scalars, B, per_sample);)
     JCK_LAUNCH_CHECK("gp_penalty");
     return JCK_OK;
 }
@@ -1112,14 +1144,14 @@ extern "C" int jck_gp_penalty(const void* dx, float* scalars, int B, long long p
 extern "C" int jck_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                         float beta1, float beta2, float eps, const int* step_count, void* stream) {
     JCK_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step_count, "adam: bad argument");
-    adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+    launch_pdl(adam_kernel, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                  step_count);
     JCK_LAUNCH_CHECK("adam");
     return JCK_OK;
 }
 extern "C" int jck_adam_advance(int* step_count, void* stream) {
     JCK_REQUIRE(step_count, "adam_advance: bad argument");
-    adam_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(step_count);
+    launch_pdl(adam_advance_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_count);
     JCK_LAUNCH_CHECK("adam_advance");
     return JCK_OK;
 }
@@ -1127,20 +1159,20 @@ extern "C" int jck_adam_advance(int* step_count, void* stream) {
 extern "C" int jck_randn(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
                          const unsigned long long* counter_base, void* stream) {
     JCK_REQUIRE(out && n > 0, "randn: bad argument");
-    rng_kernel<true><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(out, n, seed, stream_id, counter_base);
+    launch_pdl(rng_kernel<true>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), out, n, seed, stream_id, counter_base);
     JCK_LAUNCH_CHECK("randn");
     return JCK_OK;
 }
 extern "C" int jck_rand(float* out, long long n, unsigned long long seed, unsigned long long stream_id,
                         const unsigned long long* counter_base, void* stream) {
     JCK_REQUIRE(out && n > 0, "rand: bad argument");
-    rng_kernel<false><<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(out, n, seed, stream_id, counter_base);
+    launch_pdl(rng_kernel<false>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, as_stream(stream), out, n, seed, stream_id, counter_base);
     JCK_LAUNCH_CHECK("rand");
     return JCK_OK;
 }
 extern "C" int jck_rng_advance(unsigned long long* counter_base, unsigned long long by, void* stream) {
     JCK_REQUIRE(counter_base, "rng_advance: bad argument");
-    rng_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(counter_base, by);
+    launch_pdl(rng_advance_kernel, dim3(1), dim3(1), 0, as_stream(stream), counter_base, by);
     JCK_LAUNCH_CHECK("rng_advance");
     return JCK_OK;
 }
