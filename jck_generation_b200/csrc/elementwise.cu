@@ -550,7 +550,7 @@ bn_act_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift
 
 // sums[g][0:C] += sum g,  sums[g][C:2C] += sum g*xhat, g = da * act'(pre)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
                          const float* __restrict__ mean_rstd, float* __restrict__ sums, int C, unsigned pix_per_group,
                          unsigned slab, float slope) {
@@ -1020,7 +1020,8 @@ extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float*
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && sums, "bn_act_bwd_reduce: bad argument");
     BN_COMMON_CHECKS("bn_act_bwd_reduce")
     unsigned slab;
-    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 3, &slab);
+    static const int rw = [] { const char* e = getenv("JCK_BN_RW"); return e ? atoi(e) : 4; }();
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, rw, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
         launch_pdl(bn_act_bwd_reduce_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y, scale_shift, mean_rstd,
                                                                        sums, C, (unsigned)pix_per_group, slab, slope);)
