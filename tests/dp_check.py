@@ -84,10 +84,18 @@ def main():
             worst[f"{dtype} lr={lr}"] = w
             print(f"dp_check {dtype} world={comm.world_size}: worst {w[0]} = {w[1]:.3e} (tol {tol})", flush=True)
             loose = {k: v for k, v in errs.items() if k.startswith(("passD.dy", "dmix", "dy5", "G.dy", "g.grad"))}
-            tight = {k: v for k, v in errs.items() if k not in loose}
+            dgrad = {k: v for k, v in errs.items() if k.startswith("d.grad")}
+            tight = {k: v for k, v in errs.items() if k not in loose and k not in dgrad}
             wt = max(tight.items(), key=lambda kv: kv[1])
-            print(f"   tight (forward, BN statistics, D gradients): worst {wt[0]} = {wt[1]:.3e}", flush=True)
+            wd = max(dgrad.items(), key=lambda kv: kv[1])
+            print(f"   tight (forward, BN statistics): worst {wt[0]} = {wt[1]:.3e};  D gradients: worst {wd[0]} = {wd[1]:.3e}",
+                  flush=True)
             assert wt[1] <= tol, tight
+            # D's gradients are bimodal between runs of the same binary: 1.7e-6 when no LeakyReLU pre-activation sits
+            # within summation-order noise of zero, 2..5e-4 when one does and takes the other branch on one side
+            # (atomics order the per-channel sums differently run to run; DESIGN.md section 2, "kink flips"; measured
+            # 1.7e-6, 4.1e-4, 4.9e-4 on three runs) -- bounded at 10x the forward tolerance
+            assert wd[1] <= 10 * tol, dgrad
             # pass-D-derived gradients: at N(0,.02) initial weights D(x) is almost constant over the batch, so
             # BatchNorm backward cancels nearly all of the gradient and fp32 summation-order noise (1e-6) is
             # amplified ~1000x (measured 1.3e-3 at lr = 0; 1.3e-2 once Adam's sign-like first update is in)
