@@ -150,6 +150,12 @@ int jck_fc_wgrad(const void* dy, const float* x, float* dw, int M, int N, int K,
 /* G.conv1 weight w4[K][C][16] fp32 <-> fc layout w[n = tap*C + c][k] */
 int jck_pack_fc(const float* w4, void* w_fc, int K, int C, int dtype, void* stream);
 int jck_unpack_fc_grad(const float* dw_fc, float* dw4, int K, int C, int accumulate, void* stream);
+/* G.conv1 on tcgen05 (jck_gemm_tc): weight as the MN-major operand w_t[k][n = tap*C + c] (bf16), its gradient back from
+ * dw_t[k][n] (fp32), and fp32 rows x[M][K] -> bf16 rows of pitch ldo >= K (zero padded; TMA needs ldo % 8 == 0).
+ * nn.ConvTranspose2d(100,512,4,1,0) model/DCGAN.py:42,62; CGAN.py:132 (200 inputs). */
+int jck_pack_fc_t(const float* w4, void* w_t_bf16, int K, int C, void* stream);
+int jck_unpack_fc_grad_t(const float* dw_t, float* dw4, int K, int C, int accumulate, void* stream);
+int jck_cast_rows_bf16(const float* x, void* out_bf16, int M, int K, int ldo, void* stream);
 
 /* ---- BatchNorm2d (train mode) + activation ---------------------------------------------------
  * Replaces nn.BatchNorm2d + nn.LeakyReLU(0.2)/nn.ReLU model/DCGAN.py:11-12,43-44 (forward) and
@@ -226,11 +232,12 @@ int jck_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
  * gradient g^T.x and their second-order twins) on tcgen05:  C[m][n] (+)= sum_k A(m,k) * B(n,k), bf16 operands, fp32
  * accumulation.  Operand X is K-major (x_mn_major = 0: X[row*ldx + k]) or MN-major (1: X[k*ldx + row]); ldx % 8 == 0.
  * C: row-major, JCK_F32 (accumulate allowed) or JCK_BF16.  Split-K partials live in `workspace`
- * (jck_gemm_tc_workspace_bytes; 0 when the plan has one split). */
+ * (jck_gemm_tc_workspace_bytes; 0 when the plan has one split).  `stats` (nullable, single-split plans): BatchNorm
+ * sums of the product, stats[n % stats_channels] += sum_m C[m][n], stats[stats_channels + ...] += sum_m C[m][n]^2. */
 size_t jck_gemm_tc_workspace_bytes(int M, int N, int K);
 int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, void* C,
-                int c_dtype, long long ldc, int M, int N, int K, int accumulate, void* workspace,
-                size_t workspace_bytes, void* stream);
+                int c_dtype, long long ldc, int M, int N, int K, int accumulate, float* stats, int stats_channels,
+                void* workspace, size_t workspace_bytes, void* stream);
 int jck_axpy(const void* x, void* y, float a, long long n, int dtype, void* stream);   /* y += a*x */
 /* per sample b: norm = ||v_b||; scalars[0] += (norm-1)^2/B; u_b = scale*(1 - 1/norm)*v_b (u nullable) */
 int jck_gp_seed(const void* v, void* u, float* scalars, int B, long long per_sample, float scale, int dtype, void* stream);

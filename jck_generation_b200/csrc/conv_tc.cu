@@ -1364,6 +1364,8 @@ struct GemmParams {
     int ksteps, steps_per_split;
     int n_tiles;
     int mode;                  // 0: C fp32 =, 1: C fp32 +=, 2: C bf16 =, 3: fp32 partial [split][M][N]
+    float* stats;              // optional (single split only): stats[n % sC] += sum_m C, stats[sC + n % sC] += sum_m C^2
+    int stats_C;
 };
 constexpr int kGemmStages = 4;
 constexpr int kGemmStage = 2 * kTileM * kBK * 2;   // A 16 KB + B 16 KB
@@ -1467,6 +1469,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
             const int nb = n0 + c * 32;
+            if (p.stats != nullptr) {
+                // BatchNorm statistics of the product (G.conv1: channel = n % C) from the fp32 accumulators; rows past M
+                // are zero (TMA zero-fill), so they add nothing
+                float s1v[32], s2v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { s1v[i] = v[i]; s2v[i] = v[i] * v[i]; }
+                const float s1 = warp_transpose_sum(s1v, lane);
+                const float s2 = warp_transpose_sum(s2v, lane);
+                if (nb + lane < p.N) {
+                    const int ch = (nb + lane) % p.stats_C;
+                    atomicAdd(p.stats + ch, s1);
+                    atomicAdd(p.stats + p.stats_C + ch, s2);
+                }
+            }
             if (m >= p.M || nb >= p.N) continue;
             const bool whole = nb + 32 <= p.N;
             if (p.mode == 2) {
@@ -1754,8 +1770,8 @@ extern "C" size_t jck_gemm_tc_workspace_bytes(int M, int N, int K) {
 }
 
 extern "C" int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb, void* C,
-                           int c_dtype, long long ldc, int M, int N, int K, int accumulate, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+                           int c_dtype, long long ldc, int M, int N, int K, int accumulate, float* stats, int stats_channels,
+                           void* workspace, size_t workspace_bytes, void* stream) {
     JCK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "gemm_tc: bad argument");
     JCK_REQUIRE(c_dtype == JCK_F32 || (c_dtype == JCK_BF16 && !accumulate), "gemm_tc: C must be fp32, or bf16 without accumulate");
     if (lda % 8 != 0 || ldb % 8 != 0 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
@@ -1769,7 +1785,8 @@ extern "C" int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const v
     int rc;
     if ((rc = map_gemm_operand(&mA, A, a_mn_major, M, K, lda))) return rc;
     if ((rc = map_gemm_operand(&mB, B, b_mn_major, N, K, ldb))) return rc;
-    GemmParams p{M, N, K, ldc, pl.ksteps, pl.steps_per_split, pl.n_tiles, pl.splits > 1 ? 3 : final_mode};
+    JCK_REQUIRE(!stats || (pl.splits == 1 && stats_channels > 0), "gemm_tc: statistics need a single-split plan");
+    GemmParams p{M, N, K, ldc, pl.ksteps, pl.steps_per_split, pl.n_tiles, pl.splits > 1 ? 3 : final_mode, stats, stats_channels};
     void* dst = pl.splits > 1 ? workspace : C;
     dim3 grid(pl.splits, pl.m_tiles * pl.n_tiles);
     if (!a_mn_major && !b_mn_major) rc = launch_gemm<0, 0>(mA, mB, dst, p, grid, st);

@@ -452,6 +452,38 @@ __global__ void unpack_fc_grad_kernel(const float* __restrict__ dw_fc, float* __
         dw4[idx] = accumulate ? dw4[idx] + v : v;
     }
 }
+// G.conv1 as a tcgen05 GEMM: the weight as an MN-major operand w_t[k][n = tap*C + c] (bf16), its gradient back from
+// dw_t[k][n] (fp32), and the fp32 input rows cast to bf16 with the row pitch padded to a multiple of 8 elements (TMA).
+__global__ void pack_fc_t_kernel(const float* __restrict__ w4, __nv_bfloat16* __restrict__ w_t, int K, int C) {
+    pdl_entry();
+    const long long total = (long long)K * C * 16;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(o % C);
+        const long long kt = o / C;
+        const int tap = (int)(kt % 16), k = (int)(kt / 16);
+        w_t[o] = __float2bfloat16_rn(w4[((size_t)k * C + c) * 16 + tap]);       // coalesced writes, 64-byte-strided reads (L2 hits)
+    }
+}
+__global__ void unpack_fc_grad_t_kernel(const float* __restrict__ dw_t, float* __restrict__ dw4, int K, int C, int accumulate) {
+    pdl_entry();
+    const long long total = (long long)K * C * 16;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % 16);
+        const long long kc = idx / 16;
+        const int c = (int)(kc % C), k = (int)(kc / C);
+        const float v = dw_t[((size_t)k * 16 + tap) * C + c];
+        dw4[idx] = accumulate ? dw4[idx] + v : v;
+    }
+}
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int M, int K, int ldo) {
+    pdl_entry();
+    const long long total = (long long)M * ldo;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(o % ldo);
+        const long long m = o / ldo;
+        out[o] = __float2bfloat16_rn(k < K ? x[m * K + k] : 0.f);
+    }
+}
 template <typename T>
 __global__ void pack_head_kernel(const float* __restrict__ w4, T* __restrict__ w5, int C4) {
     pdl_entry();
@@ -955,6 +987,27 @@ extern "C" int jck_unpack_fc_grad(const float* dw_fc, float* dw4, int K, int C, 
     JCK_REQUIRE(dw_fc && dw4 && K > 0 && C > 0, "unpack_fc_grad: bad argument");
     launch_pdl(unpack_fc_grad_kernel, dim3(grid_for((long long)K * C * 16, 256)), dim3(256), 0, as_stream(stream), dw_fc, dw4, K, C, accumulate);
     JCK_LAUNCH_CHECK("unpack_fc_grad");
+    return JCK_OK;
+}
+extern "C" int jck_pack_fc_t(const float* w4, void* w_t_bf16, int K, int C, void* stream) {
+    JCK_REQUIRE(w4 && w_t_bf16 && K > 0 && C > 0, "pack_fc_t: bad argument");
+    launch_pdl(pack_fc_t_kernel, dim3(grid_for((long long)K * C * 16, 256)), dim3(256), 0, as_stream(stream), w4,
+               (__nv_bfloat16*)w_t_bf16, K, C);
+    JCK_LAUNCH_CHECK("pack_fc_t");
+    return JCK_OK;
+}
+extern "C" int jck_unpack_fc_grad_t(const float* dw_t, float* dw4, int K, int C, int accumulate, void* stream) {
+    JCK_REQUIRE(dw_t && dw4 && K > 0 && C > 0, "unpack_fc_grad_t: bad argument");
+    launch_pdl(unpack_fc_grad_t_kernel, dim3(grid_for((long long)K * C * 16, 256)), dim3(256), 0, as_stream(stream), dw_t, dw4, K, C,
+               accumulate);
+    JCK_LAUNCH_CHECK("unpack_fc_grad_t");
+    return JCK_OK;
+}
+extern "C" int jck_cast_rows_bf16(const float* x, void* out_bf16, int M, int K, int ldo, void* stream) {
+    JCK_REQUIRE(x && out_bf16 && M > 0 && K > 0 && ldo >= K, "cast_rows_bf16: bad argument");
+    launch_pdl(cast_rows_bf16_kernel, dim3(grid_for((long long)M * ldo, 256)), dim3(256), 0, as_stream(stream), x,
+               (__nv_bfloat16*)out_bf16, M, K, ldo);
+    JCK_LAUNCH_CHECK("cast_rows_bf16");
     return JCK_OK;
 }
 extern "C" int jck_pack_head(const float* w4, void* w5, int C4, int dtype, void* stream) {

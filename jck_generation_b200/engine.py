@@ -357,8 +357,16 @@ class GeneratorEngine(_GradTarget):
         self.dev = dev
         w1 = module.conv1.weight
         self.K1, self.C1 = int(w1.shape[0]), int(w1.shape[1])
-        self.w_fc = torch.empty(16 * self.C1, self.K1, dtype=dtype, device=dev)
-        self.dw_fc = torch.empty(16 * self.C1, self.K1, dtype=torch.float32, device=dev)
+        # conv1 (1x1 -> 4x4) is a matrix product: on tcgen05 (jck_gemm_tc) in bf16 mode -- weight kept as the MN-major
+        # operand [K1][16*C1], z cast to bf16 rows of pitch K1p -- and on the exact CUDA-core kernel in fp32 mode
+        self.tc_fc = dtype == torch.bfloat16 and algo != ops.ALGO_SIMT
+        self.K1p = (self.K1 + 7) // 8 * 8
+        if self.tc_fc:
+            self.w_fc = torch.empty(self.K1, 16 * self.C1, dtype=dtype, device=dev)
+            self.dw_fc = torch.empty(self.K1, 16 * self.C1, dtype=torch.float32, device=dev)
+        else:
+            self.w_fc = torch.empty(16 * self.C1, self.K1, dtype=dtype, device=dev)
+            self.dw_fc = torch.empty(16 * self.C1, self.K1, dtype=torch.float32, device=dev)
         self._w1_seen = None
         w5 = module.conv5.weight
         self.nc = int(w5.shape[1])
@@ -368,12 +376,16 @@ class GeneratorEngine(_GradTarget):
                       for k in range(2, 6)}
         self.norms = {k: _Norm(getattr(module, f"norm{k}")) for k in range(1, 5)}
         self.ws = _Workspace(dev)
+        self.gws = _Workspace(dev)
 
     def refresh(self, force=False):
         w = self.m.conv1.weight
         key = (w._version, w.data_ptr())
         if force or key != self._w1_seen:
-            ops.pack_fc(w.detach(), self.w_fc)
+            if self.tc_fc:
+                ops.pack_fc_t(w.detach(), self.w_fc)
+            else:
+                ops.pack_fc(w.detach(), self.w_fc)
             self._w1_seen = key
         for c in self.convs.values():
             c.refresh(force)
@@ -401,7 +413,13 @@ class GeneratorEngine(_GradTarget):
         y1 = torch.empty(B, 4, 4, self.C1, dtype=self.dtype, device=self.dev)
         zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev)
         stats = zeros[0]
-        ops.fc_fwd(z2d, self.w_fc, y1, stats, self.C1)
+        N1 = 16 * self.C1
+        if self.tc_fc:
+            ctx.zb = torch.empty(B, self.K1p, dtype=torch.bfloat16, device=self.dev)
+            ops.cast_rows_bf16(z2d.contiguous(), ctx.zb)
+            ops.gemm_tc(ctx.zb, 0, self.K1p, self.w_fc, 1, N1, y1.view(B, N1), B, N1, self.K1, stats=stats, stats_channels=self.C1)
+        else:
+            ops.fc_fwd(z2d, self.w_fc, y1, stats, self.C1)
         cur = self._bn_relu(ctx, 1, y1, stats, 1, update_running)
         for k in range(2, 6):
             cv = self.convs[k]
@@ -461,5 +479,13 @@ class GeneratorEngine(_GradTarget):
             ops.bn_act_bwd_apply(da, yk, ssk, mrk, nm.gamma, sums, dy, C, 1, count, 1.0 if reduced else 0.0)
             ctx.dy[k - 1] = dy
             d_large = dy
-        ops.fc_wgrad(d_large.view(B, 16 * self.C1), ctx.x, self.dw_fc, accumulate=False)
-        ops.unpack_fc_grad(self.dw_fc, self._gb(self.m.conv1.weight), accumulate)
+        N1 = 16 * self.C1
+        if self.tc_fc:
+            # dw_t[k][n] = sum_b z[b][k] * dy[b][n]: both operands MN-major, split over the batch
+            nbytes = ops.gemm_tc_workspace_bytes(self.K1, N1, B)
+            ops.gemm_tc(ctx.zb, 1, self.K1p, d_large.view(B, N1), 1, N1, self.dw_fc, self.K1, N1, B,
+                        workspace=self.gws.get(nbytes) if nbytes else None)   # self.ws belongs to the side-stream wgrads
+            ops.unpack_fc_grad_t(self.dw_fc, self._gb(self.m.conv1.weight), accumulate)
+        else:
+            ops.fc_wgrad(d_large.view(B, N1), ctx.x, self.dw_fc, accumulate=False)
+            ops.unpack_fc_grad(self.dw_fc, self._gb(self.m.conv1.weight), accumulate)

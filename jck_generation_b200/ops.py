@@ -303,14 +303,27 @@ def gemm_tc_workspace_bytes(M, N, K):
     return int(L().jck_gemm_tc_workspace_bytes(M, N, K))
 
 
-def gemm_tc(A, a_mn, lda, B, b_mn, ldb, C, M, N, K, accumulate=False, workspace=None):
+def pack_fc_t(w4, w_t):
+    check(L().jck_pack_fc_t(_p(w4), _p(w_t), w4.shape[0], w4.shape[1], _s()), "pack_fc_t")
+
+
+def unpack_fc_grad_t(dw_t, dw4, accumulate):
+    check(L().jck_unpack_fc_grad_t(_p(dw_t), _p(dw4), dw4.shape[0], dw4.shape[1], int(accumulate), _s()), "unpack_fc_grad_t")
+
+
+def cast_rows_bf16(x, out):
+    M, K = x.shape
+    check(L().jck_cast_rows_bf16(_p(x), _p(out), M, K, out.shape[1], _s()), "cast_rows_bf16")
+
+
+def gemm_tc(A, a_mn, lda, B, b_mn, ldb, C, M, N, K, accumulate=False, workspace=None, stats=None, stats_channels=0):
     """C[m][n] (+)= sum_k A(m,k) * B(n,k) on tcgen05: bf16 operands, K-major (x_mn = 0: X[row*ldx + k]) or MN-major
     (x_mn = 1: X[k*ldx + row]); C row-major fp32 (accumulate allowed) or bf16, leading dimension C.shape[-1]."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     ldc = C.shape[-1] if C.dim() > 1 else N
     wsb = workspace.numel() * workspace.element_size() if workspace is not None else 0
     check(L().jck_gemm_tc(_p(A), int(a_mn), lda, _p(B), int(b_mn), ldb, _p(C), dt(C), ldc, M, N, K, int(accumulate),
-                          _p(workspace), wsb, _s()), "gemm_tc")
+                          _p(stats), stats_channels, _p(workspace), wsb, _s()), "gemm_tc")
 
 
 ROW_BIAS_ACT, ROW_MUL, ROW_ACT_BWD, ROW_ADD_BCAST, ROW_SUM_GROUPS, ROW_OUTER, ROW_SCALE_ROWS, ROW_THRESH = range(8)
