@@ -134,6 +134,11 @@ int jck_edge_down_img(const void* img_p4, const void* w_down_e, void* out_small,
                       int imgs_per_group, void* stream);
 /* G.conv5 forward (nn.ConvTranspose2d(64,nc,4,2,1) model/DCGAN.py:58,66) / D.conv1 input-gradient (GP sweep, pass D) */
 int jck_edge_up(const void* in_small, const void* w_up9, void* img_p4, int B, int Hs, int Ws, int Ca, void* stream);
+/* The same product in scatter form (the step's path for 32-pixel rows): every 4-row activation tile is read once and
+ * multiplied by the whole filter bank (w_down_e of jck_pack_weights_edge read as an MN-major operand), the 16 tap images
+ * are folded in the epilogue; tiles overlap by one input row so every output pixel is written exactly once. */
+int jck_edge_up_scatter(const void* in_small, const void* w_down_e, void* img_p4, int B, int Hs, int Ws, int Ca,
+                        void* stream);
 /* weight gradient of either (small = the 64-channel side, img_p4 = the image side) */
 size_t jck_edge_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca);
 int jck_edge_wgrad_img(const void* small, const void* img_p4, float* dw4, void* workspace, size_t workspace_bytes, int B,

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "jck_edge_wgrad_img": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_down_img": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_up": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "jck_edge_up_scatter": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "jck_edge_wgrad_workspace_bytes": [c_i, c_i, c_i, c_i],
     "jck_pack_weights": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_conv_down": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

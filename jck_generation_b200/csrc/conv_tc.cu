@@ -1346,6 +1346,172 @@ EdgePlan edge_wgrad_plan(int B, int Hs, int Ws) {
     return pl;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Image-edge up conv, scatter form (G.conv5 forward, D.conv1 input gradient; Ca = 64 -> nc <= 4 image channels):
+//     img[2i - 1 + ky][2j - 1 + kx][c] += x[i][j][:] . w[:][c][ky][kx]
+// The 9-shift gather form above re-reads every activation tile nine times (its bound is the L2 -> shared-memory
+// stream, 3.4x the HBM time).  Here each tile of 4 input rows x 32 pixels is loaded ONCE and multiplied by the whole
+// filter bank in one K = 64, N = 64 = (ky, kx, c4) MMA -- B is the edge-down weight matrix w_down_e[ca][(ky,kx,c4)] read
+// as an MN-major operand, so no second packing exists -- and the 16 tap images are folded in the epilogue: columns
+// across neighbouring lanes by shuffle (a warp owns one input row), rows across warps through 8 KB of shared memory.
+// A tile of input rows 3t-1 .. 3t+2 (rows outside the image arrive as TMA zero fill) completes output rows
+// 6t-1 .. 6t+4, so tiles are independent (11 per 32-row image: 1.375x the activation bytes instead of 9x) and every
+// output pixel is written exactly once, as 8-byte (c0 c1 c2 0) records of the JCK_IMG_P4 layout.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEUStages = 4;
+constexpr int kEUABytes = kTileM * kBK * 2;                  // 16 KB: 4 rows x 32 pixels x 64 channels
+constexpr int kEUBOff = kEUStages * kEUABytes;               // weights, 8 KB
+constexpr int kEUXOff = kEUBOff + 64 * 128;                  // 2 x [128 threads][4 float4] row-exchange buffers
+constexpr int kEUBarOff = kEUXOff + 2 * 128 * 64;
+constexpr int kEUSmem = kEUBarOff + 256 + 1024;
+
+__global__ void __launch_bounds__(192, 2)
+edge_up_scatter_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                       __nv_bfloat16* __restrict__ img, const int B, const int Hs, const int tiles_img, const int total_tiles) {
+    pdl_trigger();
+    constexpr int Ws = 32;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kEUBarOff);
+    uint64_t* empty = full + kEUStages;
+    uint64_t* tfull = empty + kEUStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wfull = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < kEUStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wfull, 64 * 128);
+            tma_load_2d(smem + kEUBOff, &mapB, wfull, 0, 0);
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int s = it % kEUStages;
+                mbar_wait(&empty[s], ((it / kEUStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full[s], kEUABytes);
+                const int n = t / tiles_img, y0 = 3 * (t % tiles_img) - 1;
+                tma_load_4d(smem + s * kEUABytes, &mapA, &full[s], 0, 0, y0, n);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(64, 0, 1);
+        mbar_wait(wfull, 0);
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int s = it % kEUStages, acc = it & 1;
+            mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+            mbar_wait(&full[s], (it / kEUStages) & 1);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + s * kEUABytes), b_addr = smem_u32(smem + kEUBOff);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                    umma_bf16(tmem_base + acc * 64, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 2048, kBK * 128, 1024),
+                              idesc, k > 0 ? 1u : 0u);
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[acc]);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int r = warp & 3;                    // local input row = TMEM lane quarter; lane = input column j
+        const int e = r * 32 + lane;
+        const int Hp = 2 * Hs + 2, Wp = 2 * Ws + 2;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int n = t / tiles_img, y0 = 3 * (t % tiles_img) - 1;
+            mbar_wait(&tfull[acc], (it >> 1) & 1);
+            fence_after_sync();
+            float v[64];                           // v[(ky*4 + kx)*4 + c]
+            {
+                float lo[32], hi[32];
+                const uint32_t ta = tmem_base + acc * 64 + ((uint32_t)(r * 32) << 16);
+                tmem_ld32(ta, lo);
+                tmem_ld32(ta + 32, hi);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { v[i] = lo[i]; v[32 + i] = hi[i]; }
+            }
+            fence_before_sync();
+            mbar_arrive(&tempty[acc]);
+            // columns: X = 2j (b = 0) takes kx = 1 of column j and kx = 3 of column j-1; X = 2j+1 takes kx = 2 of j, kx = 0 of j+1
+            float R[4][2][4];
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float left = __shfl_up_sync(0xffffffffu, v[(ky * 4 + 3) * 4 + c], 1);
+                    float right = __shfl_down_sync(0xffffffffu, v[(ky * 4 + 0) * 4 + c], 1);
+                    if (lane == 0) left = 0.f;
+                    if (lane == 31) right = 0.f;
+                    R[ky][0][c] = v[(ky * 4 + 1) * 4 + c] + left;
+                    R[ky][1][c] = v[(ky * 4 + 2) * 4 + c] + right;
+                }
+            }
+            // rows: Y = 2i (a = 0) takes ky = 1 of row i and ky = 3 of row i-1; Y = 2i+1 takes ky = 2 of i and ky = 0 of i+1
+            float4* xb = reinterpret_cast<float4*>(smem + kEUXOff + (it & 1) * (128 * 64));
+            xb[e * 4 + 0] = make_float4(R[3][0][0], R[3][0][1], R[3][0][2], R[3][0][3]);
+            xb[e * 4 + 1] = make_float4(R[3][1][0], R[3][1][1], R[3][1][2], R[3][1][3]);
+            xb[e * 4 + 2] = make_float4(R[0][0][0], R[0][0][1], R[0][0][2], R[0][0][3]);
+            xb[e * 4 + 3] = make_float4(R[0][1][0], R[0][1][1], R[0][1][2], R[0][1][3]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int i = y0 + r;
+            if (r >= 1) {                          // a = 0: output row 2i
+                const int Y = 2 * i;
+                if (Y >= 0 && Y < 2 * Hs) {
+                    const float4 u0 = xb[(e - 32) * 4 + 0], u1 = xb[(e - 32) * 4 + 1];
+                    uint2 p0, p1;
+                    p0.x = pack_bf16x2(R[1][0][0] + u0.x, R[1][0][1] + u0.y);
+                    p0.y = pack_bf16x2(R[1][0][2] + u0.z, R[1][0][3] + u0.w);
+                    p1.x = pack_bf16x2(R[1][1][0] + u1.x, R[1][1][1] + u1.y);
+                    p1.y = pack_bf16x2(R[1][1][2] + u1.z, R[1][1][3] + u1.w);
+                    __nv_bfloat16* o = img + (((size_t)n * Hp + Y + 1) * Wp + 2 * lane + 1) * 4;
+                    *reinterpret_cast<uint2*>(o) = p0;
+                    *reinterpret_cast<uint2*>(o + 4) = p1;
+                }
+            }
+            if (r <= 2) {                          // a = 1: output row 2i + 1
+                const int Y = 2 * i + 1;
+                if (Y >= 0 && Y < 2 * Hs) {
+                    const float4 u0 = xb[(e + 32) * 4 + 2], u1 = xb[(e + 32) * 4 + 3];
+                    uint2 p0, p1;
+                    p0.x = pack_bf16x2(R[2][0][0] + u0.x, R[2][0][1] + u0.y);
+                    p0.y = pack_bf16x2(R[2][0][2] + u0.z, R[2][0][3] + u0.w);
+                    p1.x = pack_bf16x2(R[2][1][0] + u1.x, R[2][1][1] + u1.y);
+                    p1.y = pack_bf16x2(R[2][1][2] + u1.z, R[2][1][3] + u1.w);
+                    __nv_bfloat16* o = img + (((size_t)n * Hp + Y + 1) * Wp + 2 * lane + 1) * 4;
+                    *reinterpret_cast<uint2*>(o) = p0;
+                    *reinterpret_cast<uint2*>(o + 4) = p1;
+                }
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
 bool want_tc(int dtype, int algo) { return dtype == JCK_BF16 && algo != JCK_ALGO_SIMT; }
 
 // ------------------------------------------------------------------------------------------------
@@ -1801,5 +1967,29 @@ extern "C" int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const v
         launch_pdl(gemm_reduce_kernel, dim3((int)blocks), dim3(256), 0, st, (const float*)workspace, C, M, N, ldc, pl.splits, final_mode);
         JCK_LAUNCH_CHECK("gemm_reduce");
     }
+    return JCK_OK;
+}
+
+extern "C" int jck_edge_up_scatter(const void* in_small, const void* w_down_e, void* img_p4, int B, int Hs, int Ws, int Ca,
+                                   void* stream) {
+    JCK_REQUIRE(in_small && w_down_e && img_p4 && B > 0 && Hs > 0, "edge_up_scatter: bad argument");
+    if (Ca != 64 || Ws != 32)
+        return set_error(JCK_E_UNSUPPORTED_SHAPE, "edge_up_scatter: Ca=%d Ws=%d (needs 64 channels, 32-pixel rows)", Ca, Ws);
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = map_small(&mA, in_small, Ca, Ws, Hs, B, Ws, 4, 1))) return rc;
+    if ((rc = map_gemm_operand(&mB, w_down_e, 1, 64, 64, 64))) return rc;
+    const int tiles_img = (2 * Hs + 6) / 6;                // tile t completes output rows 6t-1 .. 6t+4
+    const int total = B * tiles_img;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(edge_up_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEUSmem);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_up_scatter smem attr: %s", cudaGetErrorString(e));
+        cfg = true;
+    }
+    const int grid = total < 2 * kNumSMs ? total : 2 * kNumSMs;
+    launch_pdl(edge_up_scatter_kernel, dim3(grid), dim3(192), kEUSmem, as_stream(stream), mA, mB, (__nv_bfloat16*)img_p4, B, Hs,
+               tiles_img, total);
+    JCK_LAUNCH_CHECK("edge_up_scatter");
     return JCK_OK;
 }

@@ -64,6 +64,14 @@ def use_edge_kernels(dtype, algo, Ca, nc):
     return dtype == torch.bfloat16 and algo != ops.ALGO_SIMT and Ca == 64 and nc <= 4
 
 
+def _edge_up(cv, x_small, img_p4):
+    """image-edge up conv: scatter form where the rows are 32 pixels (the 64x64 image), else the 9-shift gather form"""
+    if cv.Ws == 32:
+        ops.edge_up_scatter(x_small, cv.w_down_e, img_p4, cv.Ca)
+    else:
+        ops.edge_up(x_small, cv.w_up9, img_p4, cv.Ca)
+
+
 class _Norm:
     def __init__(self, bn):
         self.bn = bn
@@ -331,7 +339,7 @@ class DiscriminatorEngine(_GradTarget):
                 if cv.edge:
                     # border / pad channel of the P4 image stay zero (the kernel writes interior pixels only)
                     da = dx_out if dx_out is not None else torch.zeros_like(inp)
-                    ops.edge_up(dy, cv.w_up9, da, cv.Ca)
+                    _edge_up(cv, dy, da)
                 elif fuse and k > 1 and cv.Cb >= FUSE_MIN_C:
                     da = torch.empty_like(inp)
                     ops.conv_up_bnbwd(dy, cv.w_up, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], LRELU, da, zeros[k - 2],
@@ -426,7 +434,7 @@ class GeneratorEngine(_GradTarget):
             if cv.edge:
                 y = y5_out if y5_out is not None else ops.img_alloc(B, self.nc, 2 * cv.Hs, 2 * cv.Ws, self.dtype, self.dev,
                                                                     ops.IMG_P4)
-                ops.edge_up(cur, cv.w_up9, y, cv.Ca)
+                _edge_up(cv, cur, y)
                 ctx.y[5] = y
                 continue
             y = torch.empty(B, 2 * cv.Hs, 2 * cv.Ws, cv.Cb, dtype=self.dtype, device=self.dev)

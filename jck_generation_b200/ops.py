@@ -83,6 +83,12 @@ def edge_down_img(img_p4, w_down_e, out_small, stats, Ca, ipg=0):
     check(L().jck_edge_down_img(_p(img_p4), _p(w_down_e), _p(out_small), _p(stats), B, Hs, Ws, Ca, ipg, _s()), "edge_down_img")
 
 
+def edge_up_scatter(x_small, w_down_e, img_p4, Ca):
+    """edge_up in scatter form (one read of the activations; needs 32-pixel rows)."""
+    B, Hs, Ws = x_small.shape[0], x_small.shape[1], x_small.shape[2]
+    check(L().jck_edge_up_scatter(_p(x_small), _p(w_down_e), _p(img_p4), B, Hs, Ws, Ca, _s()), "edge_up_scatter")
+
+
 def edge_up(x_small, w_up9, img_p4, Ca):
     B, Hs, Ws = x_small.shape[0], x_small.shape[1], x_small.shape[2]
     check(L().jck_edge_up(_p(x_small), _p(w_up9), _p(img_p4), B, Hs, Ws, Ca, _s()), "edge_up")

@@ -172,11 +172,14 @@ def check_edge(which, B=8, nc=3):
         ws = torch.stack([torch.cat([want[g * per:(g + 1) * per].sum((0, 2, 3)), (want[g * per:(g + 1) * per] ** 2).sum((0, 2, 3))])
                           for g in range(groups)])
         return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats, ws)}
-    if which == "up":
+    if which in ("up", "upscatter"):
         x = _mk((B, Ca, Hs, Hs), dt, 33)
         want = F.conv_transpose2d(x, w4, stride=2, padding=1)
         img = torch.zeros(B, 66, 66, 4, dtype=dt, device="cuda")
-        ops.edge_up(x.permute(0, 2, 3, 1).contiguous().to(dt).cuda(), wu9, img, Ca)
+        if which == "up":
+            ops.edge_up(x.permute(0, 2, 3, 1).contiguous().to(dt).cuda(), wu9, img, Ca)
+        else:
+            ops.edge_up_scatter(x.permute(0, 2, 3, 1).contiguous().to(dt).cuda(), wde, img, Ca)
         torch.cuda.synchronize()
         border = float(img[:, 0].abs().sum() + img[:, -1].abs().sum() + img[:, :, 0].abs().sum() + img[:, :, -1].abs().sum()
                        + img[..., nc:].abs().sum())
@@ -424,6 +427,8 @@ def all_cases():
     cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_down", "-", "bf16", "tc", 150),
               ("edge_up", "-", "bf16", "tc", 8), ("edge_up", "-", "bf16", "tc", 5), ("edge_wgrad", "-", "bf16", "tc", 8),
               ("edge_wgrad", "-", "bf16", "tc", 3), ("edge_wgrad", "-", "bf16", "tc", 150),
+              ("edge_upscatter", "-", "bf16", "tc", 8), ("edge_upscatter", "-", "bf16", "tc", 5), ("edge_upscatter", "-", "bf16", "tc", 150),
+              ("edge_upscatter1", "-", "bf16", "tc", 4),
               ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
     cases += [("bnbwd_up", "c2", "bf16", "tc", 8), ("bnbwd_up", "c3", "bf16", "tc", 8), ("bnbwd_up", "c4", "bf16", "tc", 3),
               ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16)]
