@@ -342,7 +342,7 @@ def run_b200(args):
             tr = json.load(f).get(tk)
         if tr:
             roofline["traffic"] = tr["avg_bytes_per_launch"]
-            roofline["traffic_source"] = "profiles/r01_ncu_conv_pair.md: DRAM read+write bytes per launch (ncu --set full), " \
+            roofline["traffic_source"] = "profiles/r01_ncu_kernels.md: DRAM read+write bytes per launch (ncu --set full), " \
                                          f"algorithmic {tr['algorithmic_avg_bytes_per_launch']:.3g} B"
     except OSError:
         pass
