@@ -1532,10 +1532,11 @@ struct GemmParams {
     int mode;                  // 0: C fp32 =, 1: C fp32 +=, 2: C bf16 =, 3: fp32 partial [split][M][N]
     float* stats;              // optional (single split only): stats[n % sC] += sum_m C, stats[sC + n % sC] += sum_m C^2
     int stats_C;
+    int stages;                // depth of the TMA ring: 4 for long contractions, 2 for short ones (3 CTAs per SM instead of 1)
 };
-constexpr int kGemmStages = 4;
+constexpr int kGemmMaxStages = 4;
 constexpr int kGemmStage = 2 * kTileM * kBK * 2;   // A 16 KB + B 16 KB
-constexpr int kGemmSmem = kGemmStages * kGemmStage + 256 + 1024;
+constexpr int gemm_smem(int stages) { return 1024 + stages * kGemmStage + 1024; }   // barriers | ring | alignment slack
 
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(kConvThreads)
@@ -1544,10 +1545,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStage);
-    uint64_t* empty = full + kGemmStages;
-    uint64_t* tmem_full = empty + kGemmStages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kGemmMaxStages;
+    uint64_t* tmem_full = empty + kGemmMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint8_t* ring = smem + 1024;
+    const int stages = p.stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x;
@@ -1558,7 +1561,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
-        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
@@ -1572,9 +1575,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < nsteps; ++it) {
-                const int s = it % kGemmStages;
-                mbar_wait(&empty[s], ((it / kGemmStages) & 1) ^ 1);
-                uint8_t* sa = smem + s * kGemmStage;
+                const int s = it % stages;
+                mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+                uint8_t* sa = ring + s * kGemmStage;
                 uint8_t* sb = sa + kTileM * kBK * 2;
                 mbar_arrive_expect_tx(&full[s], kGemmStage);
                 const int k0 = (step_beg + it) * kBK;
@@ -1595,11 +1598,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc(128, A_MN, B_MN);
         for (int it = 0; it < nsteps; ++it) {
-            const int s = it % kGemmStages;
-            mbar_wait(&full[s], (it / kGemmStages) & 1);
+            const int s = it % stages;
+            mbar_wait(&full[s], (it / stages) & 1);
             fence_after_sync();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + s * kGemmStage);
+                const uint32_t a_addr = smem_u32(ring + s * kGemmStage);
                 const uint32_t b_addr = a_addr + kTileM * kBK * 2;
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
@@ -1738,11 +1741,12 @@ template <int A_MN, int B_MN>
 int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, void* C, const GemmParams& p, dim3 grid, cudaStream_t st) {
     static bool cfg = false;
     if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             gemm_smem(kGemmMaxStages));
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "gemm_tc smem attr: %s", cudaGetErrorString(e));
         cfg = true;
     }
-    launch_pdl(gemm_tc_kernel<A_MN, B_MN>, dim3(grid), dim3(kConvThreads), kGemmSmem, st, mA, mB, C, p);
+    launch_pdl(gemm_tc_kernel<A_MN, B_MN>, dim3(grid), dim3(kConvThreads), gemm_smem(p.stages), st, mA, mB, C, p);
     JCK_LAUNCH_CHECK("gemm_tc");
     return JCK_OK;
 }
@@ -1952,7 +1956,8 @@ extern "C" int jck_gemm_tc(const void* A, int a_mn_major, long long lda, const v
     if ((rc = map_gemm_operand(&mA, A, a_mn_major, M, K, lda))) return rc;
     if ((rc = map_gemm_operand(&mB, B, b_mn_major, N, K, ldb))) return rc;
     JCK_REQUIRE(!stats || (pl.splits == 1 && stats_channels > 0), "gemm_tc: statistics need a single-split plan");
-    GemmParams p{M, N, K, ldc, pl.ksteps, pl.steps_per_split, pl.n_tiles, pl.splits > 1 ? 3 : final_mode, stats, stats_channels};
+    GemmParams p{M, N, K, ldc, pl.ksteps, pl.steps_per_split, pl.n_tiles, pl.splits > 1 ? 3 : final_mode, stats, stats_channels,
+                 pl.steps_per_split >= kGemmMaxStages ? kGemmMaxStages : 2};
     void* dst = pl.splits > 1 ? workspace : C;
     dim3 grid(pl.splits, pl.m_tiles * pl.n_tiles);
     if (!a_mn_major && !b_mn_major) rc = launch_gemm<0, 0>(mA, mB, dst, p, grid, st);

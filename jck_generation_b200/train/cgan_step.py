@@ -117,5 +117,19 @@ class CGANStep(DCGANStep):
         self.last = {"fake_raw": fake_raw, "gp_grad_nhwc": v, "ctx": ctx, "ctx_g": gctx, "ctx_d": ctx2, "world_b": world_b}
         return scal
 
-    def capture(self, batch, n_classes=100):
-        raise NotImplementedError("CUDA-graph capture of the CGAN step is not wired up in this round")
+    # ---- CUDA graph: DCGANStep.capture() with (real, labels) as the static inputs --------------------------------
+    def _make_static(self, batch):
+        super()._make_static(batch)
+        self._static_labels = torch.zeros(batch, self.g.n_classes, dtype=self._label_dtype, device=self.dev)
+        self._static_labels[:, 0] = 1                       # a valid one-hot for the warm-up steps
+
+    def _run_static(self):
+        return self.run(self._static, self._static_labels)
+
+    def capture(self, batch, label_dtype=torch.int64):
+        self._label_dtype = label_dtype
+        return super().capture(batch)
+
+    def replay(self, real, labels):
+        self._static_labels.copy_(labels, non_blocking=True)
+        return super().replay(real)

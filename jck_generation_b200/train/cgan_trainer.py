@@ -66,6 +66,8 @@ class CGANTrainer(Trainer):
         self.criterion = nn.BCELoss()
         self.step = CGANStep(self.model_g, self.model_d, self.optimizer_g, self.optimizer_d, self.flat_g, self.flat_d,
                              self.comm, self.lambda_gp, seed=int(getattr(args, "seed", 12345)))
+        self.use_graph = bool(getattr(args, "cuda_graph", 0)) and (
+            self.comm.world_size == 1 or bool(int(os.environ.get("JCK_DP_GRAPH", "1"))))
         self.max_iters = int(getattr(args, "max_iters", 0))
         self.model_save_path = args.save_path
         if self.comm.rank == 0:
@@ -125,6 +127,13 @@ class CGANTrainer(Trainer):
         return out[0]
 
     def train_step(self, real_data, labels_data, rng=None):
+        """One G+D step on this rank's rows; returns the [4,2] device scalar block.  With args.cuda_graph the step is
+        captured once per (batch size, label dtype) and replayed."""
+        if self.use_graph and rng is None:
+            st = self.step
+            if (st._graph is None or st._static.shape[0] != real_data.shape[0] or st._static_labels.dtype != labels_data.dtype):
+                st.capture(real_data.shape[0], label_dtype=labels_data.dtype)
+            return st.replay(real_data, labels_data)
         return self.step.run(real_data, labels_data, rng)
 
     def train(self):
@@ -160,7 +169,8 @@ class CGANTrainer(Trainer):
             for i, data in enumerate(DevicePrefetcher(real_images_loader, self.device)):
                 real_data, labels_data = data
                 real_data = real_data.contiguous().float()
-                pending.append((epoch, i, self.train_step(real_data, labels_data)))
+                scal = self.train_step(real_data, labels_data)
+                pending.append((epoch, i, scal if not self.use_graph else scal.clone()))
                 if len(pending) >= 100:
                     flush()
                 last = (epoch == self.epoch - 1) and (i == len(real_images_loader) - 1)

@@ -151,7 +151,7 @@ class DCGANStep:
         """Capture one step (device-drawn random tensors) into a CUDA graph; replay() then costs one
         launch.  Under data parallelism the NCCL all-reduces (SyncBN statistics, gradient buckets) are
         captured with it: every rank replays the same sequence, so the collectives still pair up."""
-        self._static = torch.zeros(batch, self.nc, 64, 64, dtype=torch.float32, device=self.dev)
+        self._make_static(batch)
         # warm-up steps really train; put the training state back afterwards
         bufs = [b for m in (self.g, self.d) for b in m.buffers()]
         keep = [t.clone() for t in (self.flat_g.flat, self.flat_g.exp_avg, self.flat_g.exp_avg_sq,
@@ -162,12 +162,12 @@ class DCGANStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):                      # warm-up: allocator pools, smem attributes, packs
-                self.run(self._static)
+                self._run_static()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._graph_out = self.run(self._static)
+            self._graph_out = self._run_static()
         for dst, src in zip((self.flat_g.flat, self.flat_g.exp_avg, self.flat_g.exp_avg_sq,
                              self.flat_d.flat, self.flat_d.exp_avg, self.flat_d.exp_avg_sq,
                              self.opt_g.step_dev, self.opt_d.step_dev, self.rng_counter, *bufs), keep):
@@ -177,6 +177,13 @@ class DCGANStep:
         self.ed.refresh(force=True)
         torch.cuda.synchronize()
         return self
+
+    # static inputs of the captured step (subclasses with more inputs override these two)
+    def _make_static(self, batch):
+        self._static = torch.zeros(batch, self.nc, 64, 64, dtype=torch.float32, device=self.dev)
+
+    def _run_static(self):
+        return self.run(self._static)
 
     def replay(self, real):
         self._static.copy_(real, non_blocking=True)

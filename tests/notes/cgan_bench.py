@@ -17,7 +17,7 @@ class _Data:
 
 
 args = argparse.Namespace(epoch=1, max_learning_rate=2e-4, model_path="cganbench", log_file=0, batch_size=B, num_worker=0,
-                          dtype="bf16", cuda_graph=int(os.environ.get("GRAPH", "0")), metrics=0, save_path="/tmp/cgan_bench_save")
+                          dtype="bf16", cuda_graph=int(os.environ.get("GRAPH", "1")), metrics=0, save_path="/tmp/cgan_bench_save")
 torch.manual_seed(12345)
 tr = CGANTrainer(args, CGAN.Generator(), CGAN.Discriminator(), _Data())
 real = (torch.rand(B, 3, 64, 64) * 2 - 1).cuda()
