@@ -318,11 +318,15 @@ def run_b200(args):
                   "(H2D of the next batch overlaps the running step); losses read back every step"}
 
     # dominant kernel roofline: eager pass with CUDA events around every op
+    # (weight gradients back on the main stream for this pass: per-kernel times must not include a concurrent kernel)
     pk = peaks()
+    side = (step.eg.wgrad_stream, step.ed.wgrad_stream)
+    step.eg.wgrad_stream = step.ed.wgrad_stream = None
     with OpTimer(ops, torch) as ot:
         for _ in range(2):
             step.run(real)
         tab = ot.table()
+    step.eg.wgrad_stream, step.ed.wgrad_stream = side
     tot = sum(t["ms"] for t in tab.values()) or 1.0
     conv = {k: t for k, t in tab.items() if t["flop"] > 0}
     top = max(conv.items(), key=lambda kv: kv[1]["ms"])
