@@ -646,7 +646,7 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, cons
 // dy = gamma*rstd*(g - sum_g/N - xhat*sum_gx/N) = k1*g - k3*y + k4,  k1 = gamma*rstd, k3 = k1*rstd*sum_gx/N,
 // k4 = k3*mean - k1*sum_g/N
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
                         const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                         const float* __restrict__ sums, T* __restrict__ dy, int C, unsigned pix_per_group,
@@ -1039,7 +1039,8 @@ static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (256 % (C / 8)) == 0
 
 // grid (blocks per group, groups): `waves` x 148 blocks of 256 threads in total, each thread row gets >= 4 pixels.
 // `waves` is chosen per kernel as a multiple of the blocks of that kernel that fit on one SM (registers:
-// fwd 40 -> 6, reduce 66 -> 3, apply 70 -> 3), so the grid is a whole number of resident waves (no ragged tail)
+// fwd 40 -> 6; reduce and apply are capped at 64 by __launch_bounds__(256, 4) -> 4), so the grid is a whole number of
+// resident waves (no ragged tail)
 static dim3 bn_grid(long long pix_per_group, int groups, int C, int waves, unsigned* slab) {
     const int rows = 256 / (C / 8);
     long long bpg = ((long long)waves * kNumSMs + groups - 1) / groups;
@@ -1073,8 +1074,7 @@ extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float*
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && sums, "bn_act_bwd_reduce: bad argument");
     BN_COMMON_CHECKS("bn_act_bwd_reduce")
     unsigned slab;
-    static const int rw = [] { const char* e = getenv("JCK_BN_RW"); return e ? atoi(e) : 4; }();
-    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, rw, &slab);
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 4, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
         launch_pdl(bn_act_bwd_reduce_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y, scale_shift, mean_rstd,
                                                                        sums, C, (unsigned)pix_per_group, slab, slope);)
@@ -1088,7 +1088,7 @@ extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* 
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && gamma && sums && dy && count > 0, "bn_act_bwd_apply: bad argument");
     BN_COMMON_CHECKS("bn_act_bwd_apply")
     unsigned slab;
-    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 6, &slab);
+    const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 4, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
         launch_pdl(bn_act_bwd_apply_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y, scale_shift, mean_rstd,
                                                                       gamma, sums, (T*)dy, C, (unsigned)pix_per_group, slab,
