@@ -173,6 +173,7 @@ struct DenseProblem {
     int a_dt, b_dt, c_dt;
     long long sam, sak, sbn, sbk, ldc;
     int Mm, Nn, Kk, accumulate;
+    int atomic;                // split-K launch: every split adds its partial with atomicAdd (C zeroed or accumulated into)
     __device__ int M() const { return Mm; }
     __device__ int N() const { return Nn; }
     __device__ int K() const { return Kk; }
@@ -192,7 +193,8 @@ struct DenseProblem {
             *p = __float2bfloat16_rn(accumulate ? __bfloat162float(*p) + v : v);
         } else {
             float* p = reinterpret_cast<float*>(C) + i;
-            *p = accumulate ? *p + v : v;
+            if (atomic) atomicAdd(p, v);
+            else *p = accumulate ? *p + v : v;
         }
     }
     __device__ float* stats_ptr(int, int) const { return nullptr; }
@@ -465,10 +467,26 @@ extern "C" int jck_dense(const void* A, int a_dt, long long sam, long long sak, 
                          long long sbk, void* C, int c_dt, long long ldc, int M, int N, int K, int accumulate, void* stream) {
     JCK_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "dense: bad argument");
     JCK_REQUIRE((a_dt | 1) == 1 && (b_dt | 1) == 1 && (c_dt | 1) == 1, "dense: bad dtype");
-    if (sak == 1) {
-        DenseProblem<true> p{A, B, C, a_dt, b_dt, c_dt, sam, sak, sbn, sbk, ldc, M, N, K, accumulate};
-        return launch(p, M, N, 1, 0, as_stream(stream), "dense");
+    // The CGAN head's small products (bias sums, 256 x 200 weight gradients ...) have a handful of output tiles and a
+    // contraction over the batch: one CTA per tile walks it serially (~0.5 us per 16-wide step).  Split the contraction
+    // over the grid instead; the splits add their partials atomically into C (zeroed first unless accumulating).
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int splits = 1, k_per_split = 0;
+    if (c_dt == JCK_F32 && tiles * 2 <= kNumSMs && K >= 8 * BK) {
+        splits = kNumSMs / tiles;
+        if (splits > K / (2 * BK)) splits = K / (2 * BK);
+        k_per_split = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+        splits = (K + k_per_split - 1) / k_per_split;
     }
-    DenseProblem<false> p{A, B, C, a_dt, b_dt, c_dt, sam, sak, sbn, sbk, ldc, M, N, K, accumulate};
-    return launch(p, M, N, 1, 0, as_stream(stream), "dense");
+    const int atomic = splits > 1;
+    if (atomic && !accumulate) {
+        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, as_stream(stream));
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "dense memset: %s", cudaGetErrorString(e));
+    }
+    if (sak == 1) {
+        DenseProblem<true> p{A, B, C, a_dt, b_dt, c_dt, sam, sak, sbn, sbk, ldc, M, N, K, accumulate, atomic};
+        return launch(p, M, N, splits, k_per_split, as_stream(stream), "dense");
+    }
+    DenseProblem<false> p{A, B, C, a_dt, b_dt, c_dt, sam, sak, sbn, sbk, ldc, M, N, K, accumulate, atomic};
+    return launch(p, M, N, splits, k_per_split, as_stream(stream), "dense");
 }

@@ -513,30 +513,32 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (rank == 0) {
-            // ---------------- MMA issuer (leader CTA only) ----------------
+        if (rank == 0 && lane == 0) {
+            // ---------------- MMA issuer: ONE thread of the leader CTA ----------------
+            // (no per-stage warp reconvergence; the operand descriptors of a stage differ from those of stage 0 only in the
+            // start-address field, so they are formed by one 64-bit add)
             constexpr uint32_t idesc = make_idesc(BN_, 0, 0, 256);
-            int it = 0, lt = 0;
+            const uint64_t a_desc0 = make_sdesc(smem_u32(smem), 0, 1024);
+            const uint64_t b_desc0 = make_sdesc(smem_u32(smem) + L::kABytes, 0, 1024);
+            int s = 0;
+            uint32_t full_par = 0;
+            int lt = 0;
             for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
                 const int acc = lt & 1;
                 mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);
                 fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * kAccCols;
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full[s], (it / STAGES) & 1);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full[s], full_par);
                     fence_after_sync();
-                    if (lane == 0) {
-                        const uint32_t a_addr = smem_u32(smem + s * L::kStage);
-                        const uint32_t b_addr = a_addr + L::kABytes;
+                    const uint64_t so = (uint64_t)((s * L::kStage) >> 4);
 #pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k)
-                            umma_bf16_2cta(tmem_d, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024),
-                                           idesc, (ks > 0 || k > 0) ? 1u : 0u);
-                        umma_commit_2cta(&empty[s], 3);
-                        if (ks == ksteps - 1) umma_commit_2cta(&tfull[acc], 3);
-                    }
-                    __syncwarp();
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16_2cta(tmem_d, a_desc0 + so + (uint64_t)(k * 2), b_desc0 + so + (uint64_t)(k * 2), idesc,
+                                       (ks > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2cta(&empty[s], 3);
+                    if (ks == ksteps - 1) umma_commit_2cta(&tfull[acc], 3);
+                    if (++s == STAGES) { s = 0; full_par ^= 1; }
                 }
             }
         }
