@@ -784,7 +784,8 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
 // wgrad: D[a][tap, b] = sum over pixels small[pix][a] * large[shift_tap(pix)][b]   (split over pixels)
 // Both operands are MN-major (channels contiguous, contraction over rows).  One CTA owns 128 `a`
 // channels x (G taps x BNW `b` channels) = 512 TMEM columns and a contiguous range of 64-pixel K steps;
-// partial tiles go to a workspace that wgrad_unpack reduces into the reference's [Ca][Cb][4][4] layout.
+// partial tiles are summed into a [Ca][16*Cb] workspace by TMA reducing stores; wgrad_unpack transposes it into the
+// reference's [Ca][Cb][4][4] layout.
 // ------------------------------------------------------------------------------------------------
 struct WgradTcParams {
     int B, Hs, Ws, Ca, Cb;
@@ -937,8 +938,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant_
 #pragma unroll 1
                 for (int j = 0; j < kRound; ++j) {
                     const int c = c0 + j, g = c / (BNW / 32), cc = c % (BNW / 32);
-                    tma_store_2d(&mapP, smem + j * (128 * 128), (tap0 + g) * p.Cb + b_tile * BNW + cc * 32,
-                                 split * p.Ca + a_tile * 128);
+                    tma_reduce_add_2d(&mapP, smem + j * (128 * 128), (tap0 + g) * p.Cb + b_tile * BNW + cc * 32, a_tile * 128);
                 }
                 tma_store_commit();
             }
@@ -980,7 +980,13 @@ int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan&
     int rc;
     if ((rc = map_small(&mS, small, Ca, Ws, Hs, B, pl.g.bw, pl.g.bh, pl.g.nb))) return rc;
     if ((rc = map_large(&mL, large, Cb, 2 * Ws, 2 * Hs, B, pl.g.bw, pl.g.bh, pl.g.nb))) return rc;
-    if ((rc = map_matrix_f32(&mP, part, (long long)pl.splits * Ca, 16 * Cb, 128))) return rc;
+    // all splits reduce into ONE [Ca][16*Cb] fp32 matrix with TMA reducing stores (the adds resolve in L2): the 148 partial
+    // tiles of 256 KB (38 MB written and read back per layer) never reach HBM
+    if ((rc = map_matrix_f32(&mP, part, (long long)Ca, 16 * Cb, 128))) return rc;
+    {
+        cudaError_t e = cudaMemsetAsync(part, 0, (size_t)Ca * 16 * Cb * sizeof(float), st);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc memset: %s", cudaGetErrorString(e));
+    }
     WgradTcParams p{B, Hs, Ws, Ca, Cb, pl.g.bw, pl.g.bh, pl.g.nb, Ws / pl.g.bw, Hs / pl.g.bh,
                     pl.total_steps, pl.steps_per_split, Cb / pl.bnw};
     dim3 grid(pl.splits, (Ca / 128) * (Cb / pl.bnw), 16 / pl.G);
@@ -1835,7 +1841,7 @@ static bool wgrad_uses_tc(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int 
 
 extern "C" size_t jck_conv_wgrad_workspace_bytes(int B, int Hs, int Ws, int Ca, int Cb, int dtype, int algo) {
     WgradPlan pl;
-    int splits = wgrad_uses_tc(B, Hs, Ws, Ca, Cb, dtype, algo, &pl) ? pl.splits : simt_wgrad_splits(B, Hs, Ws, Ca, Cb);
+    int splits = wgrad_uses_tc(B, Hs, Ws, Ca, Cb, dtype, algo, &pl) ? 1 : simt_wgrad_splits(B, Hs, Ws, Ca, Cb);
     return (size_t)splits * Ca * 16 * Cb * sizeof(float);
 }
 
@@ -1848,7 +1854,7 @@ extern "C" int jck_conv_wgrad(const void* small, const void* large, float* dw4, 
     WgradPlan pl;
     int rc, splits;
     if (wgrad_uses_tc(B, Hs, Ws, Ca, Cb, dtype, algo, &pl)) {
-        splits = pl.splits;
+        splits = 1;             // the tcgen05 kernel's splits have already been summed (TMA reducing stores)
         rc = wgrad_tc(small, large, (float*)workspace, pl, B, Hs, Ws, Ca, Cb, st);
     } else {
         if (algo == JCK_ALGO_TC) return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_wgrad: no tcgen05 path for this shape/dtype");
