@@ -233,6 +233,11 @@ int jck_sigmoid_bce(const float* logit, float* prob, float target, float* scalar
 int jck_logit_grad(const float* prob, const float* up, float target, float* out, int B, int mode, float scale, void* stream);
 int jck_i64_to_f32(const long long* in, float* out, long long n, void* stream);
 int jck_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
+/* FID feature moments on the tensor cores (metrics.py:118-124 np.mean / np.cov): hi + lo = x - mean as two bf16 matrices
+ * of row pitch ldo (zero padded); the covariance is (hi^T hi + hi^T lo + lo^T hi) / (rows - 1) through jck_gemm_tc with
+ * both operands MN-major. */
+int jck_center_split_bf16(const float* x, const float* mean, void* hi_bf16, void* lo_bf16, long long rows, int d, int ldo,
+                          void* stream);
 /* The head's large products (Linear(16*C4 + E -> 256), CGAN.py:105,120: forward x.W^T, input gradient g.W, weight
  * gradient g^T.x and their second-order twins) on tcgen05:  C[m][n] (+)= sum_k A(m,k) * B(n,k), bf16 operands, fp32
  * accumulation.  Operand X is K-major (x_mn_major = 0: X[row*ldx + k]) or MN-major (1: X[k*ldx + row]); ldx % 8 == 0.

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "jck_logit_grad": [c_p, c_p, c_f, c_p, c_i, c_i, c_f, c_p],
     "jck_i64_to_f32": [c_p, c_p, c_ll, c_p],
     "jck_f32_to_bf16": [c_p, c_p, c_ll, c_p],
+    "jck_center_split_bf16": [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_p],
     "jck_gemm_tc_workspace_bytes": [c_i, c_i, c_i],
     "jck_gemm_tc": [c_p, c_i, c_ll, c_p, c_i, c_ll, c_p, c_i, c_ll, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_sz, c_p],
     "jck_pack_fc_t": [c_p, c_p, c_i, c_i, c_p],

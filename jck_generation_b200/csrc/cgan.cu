@@ -75,6 +75,23 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = __float2bfloat16_rn(in[i]);
 }
+// FID feature moments (metrics.py:118-124): centred features split into two bf16 terms, f - mean = hi + lo with
+// |lo| <= 2^-9 |hi|, so that the Gram matrix hi^T hi + hi^T lo + lo^T hi on the bf16 tensor cores carries ~2^-17 relative
+// error per product instead of 2^-9.  Output rows have pitch ldo >= d (zero padded: TMA wants 16-byte row pitches).
+__global__ void center_split_kernel(const float* __restrict__ x, const float* __restrict__ mean, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, long long rows, int d, int ldo) {
+    pdl_entry();
+    const long long total = rows * ldo;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(o % ldo);
+        const long long r = o / ldo;
+        float v = 0.f;
+        if (c < d) v = x[r * d + c] - mean[c];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[o] = h;
+        lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
 __global__ void i64_to_f32_kernel(const long long* __restrict__ in, float* __restrict__ out, long long n) {
     pdl_entry();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -245,6 +262,14 @@ extern "C" int jck_f32_to_bf16(const float* in, void* out, long long n, void* st
     JCK_REQUIRE(in && out && n > 0, "f32_to_bf16: bad argument");
     launch_pdl(f32_to_bf16_kernel, dim3(grid1d(n)), dim3(256), 0, as_stream(stream), in, (__nv_bfloat16*)out, n);
     JCK_LAUNCH_CHECK("f32_to_bf16");
+    return JCK_OK;
+}
+extern "C" int jck_center_split_bf16(const float* x, const float* mean, void* hi, void* lo, long long rows, int d, int ldo,
+                                     void* stream) {
+    JCK_REQUIRE(x && mean && hi && lo && rows > 0 && d > 0 && ldo >= d, "center_split_bf16: bad argument");
+    launch_pdl(center_split_kernel, dim3(grid1d(rows * ldo)), dim3(256), 0, as_stream(stream), x, mean, (__nv_bfloat16*)hi,
+               (__nv_bfloat16*)lo, rows, d, ldo);
+    JCK_LAUNCH_CHECK("center_split_bf16");
     return JCK_OK;
 }
 extern "C" int jck_i64_to_f32(const long long* in, float* out, long long n, void* stream) {

@@ -6,9 +6,11 @@ Same public surface -- `Metrics(real_images)`, `.inception_score(loader, splits=
 (:46-52, :87); IS = exp(mean KL(p(y|x) || p(y))) per split; FID = |mu1-mu2|^2 + tr(S1+S2-2 sqrtm(S1 S2));
 intra-FID sums the 20 CIFAR-100 superclass FIDs and divides by 100 (sic, :141 -- kept for parity).
 
-Status in this round: NOT on our kernels.  The Inception forward is torchvision's (library code) and
-the moments / sqrtm are numpy + scipy as in the reference; only the device round trips were removed
-(features stay on the GPU until the moments are taken).  Differences forced by the environment:
+Status in this round: PARTLY on our kernels.  The feature moments of the generated set (np.mean / np.cov of the
+reference, metrics.py:118-124) are taken on the device by ops.feature_moments -- column sums, a centred hi/lo bf16
+split and the Gram matrix as three tcgen05 GEMMs with fp32 accumulation (jck_gemm_tc, both operands MN-major),
+all-reducible across ranks -- and only the d x d result goes to the host for scipy's sqrtm.  The Inception forward
+is still torchvision's (library code) and the IS reduction numpy.  Differences forced by the environment:
   * ./save/iception_v3/loss_bset.pt (:51; spelling is the on-disk contract) is loaded when present,
     otherwise the network is seeded random-init -- there is no network to fetch weights;
   * `real_images` may be a dataset with `.targets` (the CGAN preprocessor, as the reference expects), a
@@ -74,14 +76,24 @@ class Metrics:
             self.real_features = self._extract(loader, real=True)
 
     @torch.no_grad()
-    def _extract(self, images, real=False, softmax=False):
+    def _extract(self, images, real=False, softmax=False, on_device=False):
         feats = []
         for image in images:
             if real or isinstance(image, (list, tuple)):
                 image = image[0]
             out = self.inception_model(image.to(self.device, non_blocking=True).float())
             feats.append(nn.functional.softmax(out, dim=1) if softmax else out)
-        return torch.cat(feats).double().cpu().numpy()
+        feats = torch.cat(feats)
+        return feats.float().contiguous() if on_device else feats.double().cpu().numpy()
+
+    def _moments(self, feats):
+        """(mean, covariance) as float64 numpy: on our kernels for device-resident features, numpy otherwise."""
+        if torch.is_tensor(feats) and feats.is_cuda and feats.shape[0] > 1:
+            from . import ops
+            mean, cov = ops.feature_moments(feats)
+            return mean.double().cpu().numpy(), cov.double().cpu().numpy()
+        feats = feats.double().cpu().numpy() if torch.is_tensor(feats) else feats
+        return np.mean(feats, axis=0), np.cov(feats, rowvar=False)
 
     def inception_score(self, images, splits=10):
         n = len(images.dataset)
@@ -97,14 +109,14 @@ class Metrics:
 
     def fid(self, generated_images, intra_fid=False, label=0):
         from scipy.linalg import sqrtm
-        generated_features = self._extract(generated_images)
+        generated_features = self._extract(generated_images, on_device=torch.cuda.is_available())
         real = self.real_features
         if real is None:
             raise RuntimeError("Metrics.fid: no real-image features (construct Metrics with a dataset or loader)")
         if intra_fid:
             real = real[self.real_superclass_idx[label]]
-        mu1, sigma1 = np.mean(real, axis=0), np.cov(real, rowvar=False)
-        mu2, sigma2 = np.mean(generated_features, axis=0), np.cov(generated_features, rowvar=False)
+        mu1, sigma1 = self._moments(real)
+        mu2, sigma2 = self._moments(generated_features)
         diff = np.sum((mu1 - mu2) ** 2.0)
         covmean = sqrtm(sigma1.dot(sigma2))
         if np.iscomplexobj(covmean):

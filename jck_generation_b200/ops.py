@@ -305,6 +305,48 @@ def f32_to_bf16(x, out):
     check(L().jck_f32_to_bf16(_p(x), _p(out), x.numel(), _s()), "f32_to_bf16")
 
 
+def center_split_bf16(x, mean, hi, lo):
+    rows, d = x.shape
+    check(L().jck_center_split_bf16(_p(x), _p(mean), _p(hi), _p(lo), rows, d, hi.shape[1], _s()), "center_split_bf16")
+
+
+def feature_moments(feats, comm=None):
+    """Mean [d] and covariance [d, d] (np.cov(rowvar=False): divisor N - 1) of device-resident fp32 features [N, d] on our
+    kernels: column sums by jck_dense, centred hi/lo bf16 split, Gram matrix = three jck_gemm_tc products with both
+    operands MN-major and fp32 accumulation.  With `comm` every rank passes its shard of the rows: the sums and the
+    Gram matrix are all-reduced (N = total rows), every rank gets the same result.  Returns fp32 device tensors."""
+    assert feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 2
+    feats = feats.contiguous()
+    n_loc, d = feats.shape
+    dev = feats.device
+    n = n_loc
+    if comm is not None and comm.world_size > 1:
+        cnt = torch.full((1,), float(n_loc), dtype=torch.float32, device=dev)
+        comm.allreduce_sum_(cnt)
+        n = int(round(float(cnt.item())))
+    ones = torch.ones(n_loc, dtype=torch.float32, device=dev)
+    sums = torch.zeros(d, dtype=torch.float32, device=dev)
+    dense(ones, 0, 1, feats, 1, d, sums, 1, d, n_loc)                     # column sums
+    if comm is not None:
+        comm.allreduce_sum_(sums)
+    mean = torch.empty(d, dtype=torch.float32, device=dev)
+    rowop(ROW_SCALE_ROWS, sums.view(d, 1), torch.full((d,), 1.0 / n, dtype=torch.float32, device=dev), mean.view(d, 1), d, 1)
+    ld = (d + 7) // 8 * 8
+    hi = torch.empty(n_loc, ld, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty(n_loc, ld, dtype=torch.bfloat16, device=dev)
+    center_split_bf16(feats, mean, hi, lo)
+    gram = torch.zeros(d, d, dtype=torch.float32, device=dev)
+    nbytes = gemm_tc_workspace_bytes(d, d, n_loc)
+    ws = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=dev)
+    for a, b in ((hi, hi), (hi, lo), (lo, hi)):
+        gemm_tc(a, 1, ld, b, 1, ld, gram, d, d, n_loc, accumulate=True, workspace=ws)
+    if comm is not None:
+        comm.allreduce_sum_(gram)
+    cov = torch.empty_like(gram)
+    rowop(ROW_SCALE_ROWS, gram, torch.full((d,), 1.0 / max(n - 1, 1), dtype=torch.float32, device=dev), cov, d, d)
+    return mean, cov
+
+
 def gemm_tc_workspace_bytes(M, N, K):
     return int(L().jck_gemm_tc_workspace_bytes(M, N, K))
 

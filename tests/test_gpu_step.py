@@ -187,3 +187,33 @@ def test_trainer_runs_and_checkpoints(tmp_path, monkeypatch):
     assert float(ck["optimizer_d"]["state"][0]["step"]) == 6.0
     gp = tr.compute_gradient_penalty(torch.rand(8, 3, 64, 64, device="cuda"), torch.rand(8, 3, 64, 64, device="cuda"))
     assert gp.item() >= 0
+
+
+def test_metrics_fid_moments_on_device(tmp_path, monkeypatch):
+    """Metrics (interface of the reference's metrics.py): the generated set's feature moments taken on our kernels equal
+    numpy's on the same Inception features, and fid() runs end to end on them.  (The FID value itself is not compared: with
+    fewer samples than feature dimensions the covariances are singular and scipy's sqrtm amplifies rounding.)"""
+    monkeypatch.chdir(tmp_path)
+    import numpy as np
+    from jck_generation_b200.metrics import Metrics
+    g = torch.Generator().manual_seed(11)
+    real = torch.utils.data.TensorDataset(torch.rand(48, 3, 299, 299, generator=g), torch.zeros(48, dtype=torch.long))
+    m = Metrics(None)
+    # a seeded random-init Inception maps every image to the same logits to 1e-10 (no checkpoint offline): swap in a small
+    # random feature extractor with the same 100-d interface so that the moments are well conditioned
+    torch.manual_seed(5)
+    m.inception_model = torch.nn.Sequential(torch.nn.AdaptiveAvgPool2d(8), torch.nn.Flatten(), torch.nn.Linear(192, 100)).cuda()
+    with torch.no_grad():
+        m.inception_model[2].weight.mul_(30.0)
+    m.real_features = m._extract(torch.utils.data.DataLoader(real, 16), real=True)
+    assert m.real_features.shape == (48, 100)
+    fake = torch.rand(40, 3, 299, 299, generator=g)
+    loader = torch.utils.data.DataLoader(fake, 20)
+    feats_dev = m._extract(loader, on_device=True)
+    assert feats_dev.is_cuda and feats_dev.shape == (40, 100)
+    mu, cov = m._moments(feats_dev)
+    f64 = feats_dev.double().cpu().numpy()
+    want_mu, want_cov = np.mean(f64, axis=0), np.cov(f64, rowvar=False)
+    assert np.linalg.norm(mu - want_mu) <= 1e-5 * max(np.linalg.norm(want_mu), 1e-3)
+    assert np.linalg.norm(cov - want_cov) <= 1e-4 * np.linalg.norm(want_cov)
+    assert np.isfinite(m.fid(loader))
