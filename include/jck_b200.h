@@ -284,6 +284,46 @@ int jck_rand(float* out, long long n, unsigned long long seed, unsigned long lon
              const unsigned long long* counter_base, void* stream);
 int jck_rng_advance(unsigned long long* counter_base, unsigned long long by, void* stream);
 
+/* ---- FID / IS evaluation: the Inception-v3 feature extractor of metrics.py on our kernels ----------------------
+ * Replaces `self.inception_model(image)` metrics.py:87 (torchvision models.inception_v3, fc = Linear(2048, 100),
+ * metrics.py:46-52), the pre-processing of the eval branch (train/dcgan_trainer.py:203-207, cgan_trainer.py:227-231)
+ * and the score reduction metrics.py:96-110.  Activations: NHWC bf16 buffers described by
+ *     geom = {Hb, Wb, by, bx, c_off}  + channel pitch ld:   pixel (b, y, x), channel c  at
+ *     ((b*Hb + y + by)*Wb + x + bx)*ld + c_off + c        (a zero border of by / bx pixels, a slice of a wider concat).
+ *
+ * jck_conv_gemm: out = act(scale[n] * sum_{tap,c} A[m + shift[tap]][c] * W[n][tap*Cp + c] + bias[n]) on tcgen05.
+ *   A: bf16 rows [rows_a][C], pitch lda (% 8 == 0); rows outside [0, rows_a) read as zero.  W: bf16 [N][ntaps*Cp],
+ *   Cp = C rounded up to 64 (zero filled).  scale / bias: fp32 [N], nullable (1 / 0).  Row m of the M = B*Hq*Wq computed
+ *   rows is grid position (b, Y, X); it is stored iff oy = Y - oy0 in [0, Ho) and ox = X - ox0 in [0, Wo), at
+ *   out[((b*Hob + oy + opy)*Wob + ox + opx)*ldc + c_off + n], dtype JCK_BF16 or JCK_F32.
+ *   geom = {M, N, C, ntaps, Hq, Wq, oy0, ox0, Ho, Wo, Hob, Wob, opy, opx, c_off, relu, out_dtype, rows_a, shift[ntaps]}
+ *   (host array).  A stride-1 kh x kw convolution with padding (py, px) over a buffer whose border is >= the padding:
+ *   tap (ky, kx) has shift (ky - py)*Wb + (kx - px), oy0 = by, ox0 = bx; a 1x1 convolution, a Linear layer or a patch
+ *   matrix from jck_im2col is the one-tap case. */
+int jck_conv_gemm(const void* act, long long lda, const void* w, const float* scale, const float* bias, void* out,
+                  long long ldc, const int* geom, int ngeom, void* stream);
+/* patches[(b, oy, ox)][(ky*kw + kx)*C + c] (bf16, row pitch Kp % 8 == 0, zero beyond kh*kw*C and outside the image):
+ * the stride-2 convolutions and the 3-channel stem.  in_geom as above (host array of 5 ints). */
+int jck_im2col(const void* x, const int* in_geom, long long ldx, void* patches, int B, int H, int W, int C, int kh, int kw,
+               int sy, int sx, int py, int px, int Ho, int Wo, int Kp, void* stream);
+/* 3x3 pooling: mode 0 = max (F.max_pool2d(x, 3, stride), no padding), 1 = average over the zero-padded window / 9
+ * (F.avg_pool2d(x, 3, 1, 1), count_include_pad).  Channels and pitches multiples of 8. */
+int jck_pool3(const void* x, const int* in_geom, long long ldx, void* out, const int* out_geom, long long ldo, int B, int H,
+              int W, int C, int stride, int pad, int Ho, int Wo, int mode, void* stream);
+/* adaptive_avg_pool2d(x, 1) of a dense [B][HW][C] bf16 tensor -> fp32 and / or bf16 [B][C] */
+int jck_global_avgpool(const void* x, float* out_f32, void* out_bf16, int B, int HW, int C, void* stream);
+/* out[b][y][x][c] (NHWC bf16, channel pitch ldo, pad channels zero) = (a*bilinear(in_nchw)[b][c][y][x] + b - mean[c]) / std[c];
+ * bilinear = F.resize / F.interpolate(align_corners=False) for an enlargement.  mean3 / std3: HOST pointers, 3 floats. */
+int jck_resize_norm(const float* in_nchw, void* out_nhwc, int B, int C, int Hi, int Wi, int Ho, int Wo, int ldo, float a,
+                    float b, const float* mean3, const float* std3, void* stream);
+/* jck_resize_norm + jck_im2col of the 3x3 stride-2 stem (Conv2d_1a_3x3) in one pass: patches[(b, oy, ox)][(ky*3 + kx)*3 + c]
+ * (bf16, row pitch 32, columns 27..31 zero) of the Hr x Wr resized, normalised 3-channel image, never materialised. */
+int jck_stem_patches(const float* in_nchw, void* patches, int B, int Hi, int Wi, int Hr, int Wr, float a, float b,
+                     const float* mean3, const float* std3, void* stream);
+/* metrics.py:96-110: scores[k] = exp(mean_i KL(softmax(logits_i) || mean_i softmax(logits_i))) over rows
+ * [k*(n/splits), (k+1)*(n/splits)) of fp32 logits [n][d] */
+int jck_inception_score(const float* logits, int n, int d, int splits, float* scores, void* stream);
+
 /* ---- data-parallel exchange over NVLink peer memory -------------------------------------------
  * The reference is single-GPU: these entry points have no reference counterpart.  They make
  * an N-GPU run equal the reference at the global batch: nn.BatchNorm2d's batch statistics (model/DCGAN.py:

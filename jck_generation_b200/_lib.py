@@ -80,6 +80,13 @@ _SIGNATURES = {
     "jck_randn": [c_p, c_ll, c_ull, c_ull, c_p, c_p],
     "jck_rand": [c_p, c_ll, c_ull, c_ull, c_p, c_p],
     "jck_rng_advance": [c_p, c_ull, c_p],
+    "jck_conv_gemm": [c_p, c_ll, c_p, c_p, c_p, c_p, c_ll, c_p, c_i, c_p],
+    "jck_im2col": [c_p, c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_pool3": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_global_avgpool": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "jck_resize_norm": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
+    "jck_stem_patches": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
+    "jck_inception_score": [c_p, c_i, c_i, c_i, c_p, c_p],
     "jck_comm_create": [c_i, c_i, ctypes.POINTER(c_p), c_p],
     "jck_comm_connect": [c_p, c_p],
     "jck_comm_destroy": [c_p],

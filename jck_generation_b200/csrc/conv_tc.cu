@@ -1765,6 +1765,15 @@ int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, void* C, const Gem
 }
 
 }  // namespace
+
+// 2-D bf16 tensor map (dims / box innermost first, 128-byte swizzle) for the other translation units (incep.cu)
+int encode_bf16_2d(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long rows,
+                   unsigned long long pitch_bytes, unsigned box_inner, unsigned box_rows) {
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t str[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    return encode(m, base, 2, dims, str, box);
+}
 }  // namespace jck
 
 using namespace jck;

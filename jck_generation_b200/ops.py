@@ -432,3 +432,51 @@ def bn_adj_apply(dbar, da, y, ss, mr, gamma, sums1, asums, gbar_a, ybar, C, coun
 
 def bn_adj_param(asums, mr, dgamma, C, scale=1.0):
     check(L().jck_bn_adj_param(_p(asums), _p(mr), _p(dgamma), C, float(scale), _s()), "bn_adj_param")
+
+
+# ---- Inception-v3 feature extractor (metrics.py) -----------------------------------------------------------------
+import ctypes as _ct
+
+
+def _ints(vals):
+    return (_ct.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def conv_gemm(act, lda, w, scale, bias, out, ldc, geom):
+    """jck_conv_gemm (include/jck_b200.h): implicit-GEMM convolution / linear layer on tcgen05; geom is the host int list."""
+    g = _ints(geom)
+    check(L().jck_conv_gemm(_p(act), lda, _p(w), _p(scale), _p(bias), _p(out), ldc, _ct.cast(g, _ct.c_void_p), len(geom), _s()),
+          "conv_gemm")
+
+
+def im2col(x, in_geom, ldx, patches, B, H, W, C, kh, kw, sy, sx, py, px, Ho, Wo, Kp):
+    g = _ints(in_geom)
+    check(L().jck_im2col(_p(x), _ct.cast(g, _ct.c_void_p), ldx, _p(patches), B, H, W, C, kh, kw, sy, sx, py, px, Ho, Wo, Kp, _s()),
+          "im2col")
+
+
+def pool3(x, in_geom, ldx, out, out_geom, ldo, B, H, W, C, stride, pad, Ho, Wo, mode):
+    gi, go = _ints(in_geom), _ints(out_geom)
+    check(L().jck_pool3(_p(x), _ct.cast(gi, _ct.c_void_p), ldx, _p(out), _ct.cast(go, _ct.c_void_p), ldo, B, H, W, C, stride, pad,
+                        Ho, Wo, mode, _s()), "pool3")
+
+
+def global_avgpool(x, out_f32, out_bf16, B, HW, C):
+    check(L().jck_global_avgpool(_p(x), _p(out_f32), _p(out_bf16), B, HW, C, _s()), "global_avgpool")
+
+
+def resize_norm(x_nchw, out_nhwc, B, C, Hi, Wi, Ho, Wo, ldo, a, b, mean3, std3):
+    m, s = (_ct.c_float * 3)(*mean3), (_ct.c_float * 3)(*std3)
+    check(L().jck_resize_norm(_p(x_nchw), _p(out_nhwc), B, C, Hi, Wi, Ho, Wo, ldo, a, b, _ct.cast(m, _ct.c_void_p),
+                              _ct.cast(s, _ct.c_void_p), _s()), "resize_norm")
+
+
+def stem_patches(x_nchw, patches, B, Hi, Wi, Hr, Wr, a, b, mean3, std3):
+    m, s = (_ct.c_float * 3)(*mean3), (_ct.c_float * 3)(*std3)
+    check(L().jck_stem_patches(_p(x_nchw), _p(patches), B, Hi, Wi, Hr, Wr, a, b, _ct.cast(m, _ct.c_void_p),
+                               _ct.cast(s, _ct.c_void_p), _s()), "stem_patches")
+
+
+def inception_score(logits, splits, scores):
+    n, d = logits.shape
+    check(L().jck_inception_score(_p(logits), n, d, splits, _p(scores), _s()), "inception_score")

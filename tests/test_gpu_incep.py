@@ -1,0 +1,214 @@
+"""Inception-v3 feature extractor (metrics.py) on the GPU, through the C ABI.
+
+Oracles: tests/incep_emul.py (a torch restatement of every primitive with the same bf16 storage -- tight tolerances) and
+torchvision's inception_v3 in fp32 on the CPU (the reference's own arithmetic, metrics.py:46-52,87 -- loose tolerance for
+the bf16 mode, because a random-weight network amplifies a perturbation ~1000x from stem to logits: the fp32 emulation of
+our graph itself differs from torchvision by 2e-5 at the logits although every layer agrees to 1e-7)."""
+import pytest
+import torch
+
+from tests import incep_emul as emu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as entry
+    entry.build()
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def _conv_case(B, H, W, C, N, kh, kw, pad, border, out_border, c_off, ldc_extra, seed):
+    """stride-1 convolution through the implicit-tap path: GPU kernel vs emulator vs F.conv2d"""
+    from jck_generation_b200 import ops
+    from jck_generation_b200.inception import Buf
+    g = torch.Generator().manual_seed(seed)
+    src = Buf(B, H, W, C, border[0], border[1], device="cpu")
+    src.interior().copy_(torch.randn(B, H, W, C, generator=g).to(torch.bfloat16))
+    Ho, Wo = H + 2 * pad[0] - kh + 1, W + 2 * pad[1] - kw + 1
+    dst = Buf(B, Ho, Wo, c_off + N + ldc_extra, out_border[0], out_border[1], device="cpu")
+    dst.t.fill_(5.0)                                     # sentinel: whatever the kernel must not touch
+    Cp = (C + 63) // 64 * 64
+    w4 = torch.randn(N, C, kh, kw, generator=g) / (C * kh * kw) ** 0.5
+    wm = torch.zeros(N, kh * kw, Cp)
+    wm[:, :, :C] = w4.permute(0, 2, 3, 1).reshape(N, kh * kw, C)
+    wm = wm.reshape(N, -1).to(torch.bfloat16)
+    scale, bias = 0.5 + torch.rand(N, generator=g), torch.randn(N, generator=g) * 0.1
+    shifts = [(ky - pad[0]) * src.Wb + (kx - pad[1]) for ky in range(kh) for kx in range(kw)]
+    rows = B * src.Hb * src.Wb
+    geom = [rows, N, C, len(shifts), src.Hb, src.Wb, src.py, src.px, Ho, Wo, dst.Hb, dst.Wb, dst.py, dst.px, c_off, 1, 1, rows] + shifts
+    want = dst.t.clone()
+    emu.conv_gemm(src.t, src.ld, wm, scale, bias, want, dst.ld, geom)
+    got = dst.t.clone().cuda()
+    ops.conv_gemm(src.t.cuda(), src.ld, wm.cuda(), scale.cuda(), bias.cuda(), got, dst.ld, geom)
+    torch.cuda.synchronize()
+    # the emulator against torch's own convolution on the same bf16 operands
+    x = src.interior().float().permute(0, 3, 1, 2)
+    ref = torch.relu(torch.nn.functional.conv2d(x, w4.to(torch.bfloat16).float(), padding=pad) * scale.view(1, N, 1, 1) + bias.view(1, N, 1, 1))
+    wv = want.view(B, dst.Hb, dst.Wb, dst.ld)[:, dst.py:dst.py + Ho, dst.px:dst.px + Wo, c_off:c_off + N].float().permute(0, 3, 1, 2)
+    assert _rel(wv, ref) < 5e-3, ("emulator vs conv2d", _rel(wv, ref))
+    return got.cpu(), want
+
+
+@pytest.mark.parametrize("case", [
+    (2, 35, 35, 192, 64, 1, 1, (0, 0), (0, 0), (0, 0), 0, 0),          # 1x1
+    (2, 35, 35, 192, 48, 1, 1, (0, 0), (0, 0), (2, 2), 0, 0),          # 1x1 into a bordered buffer
+    (2, 35, 35, 48, 64, 5, 5, (2, 2), (2, 2), (0, 0), 64, 128),        # 5x5 into a concat slice
+    (2, 35, 35, 96, 96, 3, 3, (1, 1), (1, 1), (0, 0), 128, 32),        # 3x3, C = 96 (ragged 64-chunk)
+    (1, 149, 149, 32, 32, 3, 3, (0, 0), (0, 0), (1, 1), 0, 0),         # valid 3x3, C = 32
+    (3, 17, 17, 160, 160, 1, 7, (0, 3), (0, 3), (3, 0), 0, 0),         # 1x7
+    (3, 17, 17, 160, 192, 7, 1, (3, 0), (3, 0), (0, 0), 192, 384),     # 7x1 into a slice
+    (4, 8, 8, 448, 384, 3, 3, (1, 1), (1, 1), (1, 1), 0, 0),           # N = 384 (two 192-column tiles)
+    (4, 8, 8, 384, 384, 1, 3, (0, 1), (1, 1), (0, 0), 320, 1344),      # 1x3 on a (1,1) border
+    (4, 8, 8, 1280, 320, 1, 1, (0, 0), (0, 0), (0, 0), 0, 1728),       # N = 320 (two 160-column tiles), long K
+    (2, 73, 73, 64, 80, 1, 1, (0, 0), (0, 0), (0, 0), 0, 0),           # N = 80
+], ids=lambda c: "x".join(map(str, c[1:7])))
+def test_conv_gemm(case):
+    got, want = _conv_case(*case, seed=11)
+    g, w = got.float(), want.float()
+    assert float((g - w).abs().max()) <= 2e-2 * float(w.abs().max()), float((g - w).abs().max())
+    assert _rel(g, w) < 2e-3, _rel(g, w)
+    # nothing outside the valid window / channel slice was written
+    assert bool((got[want == 5.0] == 5.0).all())
+
+
+def test_fc_gemm_f32_ragged():
+    from jck_generation_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, K, N = 37, 2048, 100
+    a = torch.randn(B, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    geom = [B, N, K, 1, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 0, B, 0]
+    out = torch.full((B, N), 7.0, device="cuda")
+    ops.conv_gemm(a.cuda(), K, w.cuda(), None, bias.cuda(), out, N, geom)
+    torch.cuda.synchronize()
+    want = a.float() @ w.float().t() + bias
+    assert float((out.cpu() - want).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("C,ld,stride,k,pad", [(3, 4, 2, 3, 0), (96, 96, 2, 3, 0), (192, 192, 2, 3, 0), (64, 64, 1, 3, 1)])
+def test_im2col_bit_exact(C, ld, stride, k, pad):
+    from jck_generation_b200 import ops
+    from jck_generation_b200.inception import Buf
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 35, 35
+    src = Buf(B, H, W, C, 1, 2, ld=ld, device="cpu")
+    src.interior().copy_(torch.randn(B, H, W, C, generator=g).to(torch.bfloat16))
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    Kp = (k * k * C + 7) // 8 * 8
+    want = torch.zeros(B * Ho * Wo * Kp, dtype=torch.bfloat16)
+    emu.im2col(src.t, src.geom(), src.ld, want, B, H, W, C, k, k, stride, stride, pad, pad, Ho, Wo, Kp)
+    got = torch.full_like(want, 3.0).cuda()
+    ops.im2col(src.t.cuda(), src.geom(), src.ld, got, B, H, W, C, k, k, stride, stride, pad, pad, Ho, Wo, Kp)
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("mode,stride,pad", [(0, 2, 0), (1, 1, 1)])
+def test_pool3(mode, stride, pad):
+    from jck_generation_b200 import ops
+    from jck_generation_b200.inception import Buf
+    g = torch.Generator().manual_seed(6)
+    B, H, W, C = 3, 17, 17, 768
+    src = Buf(B, H, W, C, device="cpu")
+    src.interior().copy_(torch.randn(B, H, W, C, generator=g).to(torch.bfloat16))
+    Ho, Wo = (H + 2 * pad - 3) // stride + 1, (W + 2 * pad - 3) // stride + 1
+    dst = Buf(B, Ho, Wo, 512 + C, device="cpu")
+    want = dst.t.clone()
+    emu.pool3(src.t, src.geom(), src.ld, want, dst.geom(512), dst.ld, B, H, W, C, stride, pad, Ho, Wo, mode)
+    got = dst.t.clone().cuda()
+    ops.pool3(src.t.cuda(), src.geom(), src.ld, got, dst.geom(512), dst.ld, B, H, W, C, stride, pad, Ho, Wo, mode)
+    torch.cuda.synchronize()
+    if mode == 0:
+        assert torch.equal(got.cpu(), want)
+    else:
+        assert float((got.cpu().float() - want.float()).abs().max()) <= 2 ** -7 * float(want.float().abs().max())
+
+
+def test_resize_norm_and_avgpool():
+    from jck_generation_b200 import ops
+    from jck_generation_b200.inception import IMAGENET_MEAN, IMAGENET_STD
+    g = torch.Generator().manual_seed(8)
+    fake = torch.tanh(torch.randn(3, 3, 64, 64, generator=g))
+    want = torch.zeros(3 * 299 * 299 * 4, dtype=torch.bfloat16)
+    emu.resize_norm(fake, want, 3, 3, 64, 64, 299, 299, 4, 0.5, 0.5, IMAGENET_MEAN, IMAGENET_STD)
+    got = torch.ones_like(want).cuda()
+    ops.resize_norm(fake.cuda(), got, 3, 3, 64, 64, 299, 299, 4, 0.5, 0.5, IMAGENET_MEAN, IMAGENET_STD)
+    torch.cuda.synchronize()
+    assert float((got.cpu().float() - want.float()).abs().max()) <= 2 ** -6          # one bf16 ulp at |x| <= 2.7
+    wantp = torch.zeros(3 * 149 * 149 * 32, dtype=torch.bfloat16)
+    emu.stem_patches(fake, wantp, 3, 64, 64, 299, 299, 0.5, 0.5, IMAGENET_MEAN, IMAGENET_STD)
+    gotp = torch.ones_like(wantp).cuda()
+    ops.stem_patches(fake.cuda(), gotp, 3, 64, 64, 299, 299, 0.5, 0.5, IMAGENET_MEAN, IMAGENET_STD)
+    torch.cuda.synchronize()
+    assert float((gotp.cpu().float() - wantp.float()).abs().max()) <= 2 ** -6
+    assert bool((gotp.view(-1, 32)[:, 27:] == 0).all())
+    x = torch.randn(5, 64, 2048, generator=g).to(torch.bfloat16)
+    o32 = torch.empty(5, 2048, device="cuda")
+    ob = torch.empty(5, 2048, dtype=torch.bfloat16, device="cuda")
+    ops.global_avgpool(x.cuda(), o32, ob, 5, 64, 2048)
+    torch.cuda.synchronize()
+    assert float((o32.cpu() - x.float().mean(1)).abs().max()) < 1e-5
+
+
+def test_inception_score_kernel():
+    """metrics.py:96-110 against scipy.stats.entropy, as the reference computes it"""
+    import numpy as np
+    from scipy.stats import entropy
+    from jck_generation_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    n, d, splits = 1003, 100, 10
+    logits = torch.randn(n, d, generator=g) * 3
+    scores = torch.zeros(splits, device="cuda")
+    ops.inception_score(logits.cuda(), splits, scores)
+    torch.cuda.synchronize()
+    preds = torch.softmax(logits, 1).numpy()
+    want = []
+    for k in range(splits):
+        part = preds[k * (n // splits):(k + 1) * (n // splits), :]
+        py = np.mean(part, axis=0)
+        want.append(np.exp(np.mean([entropy(part[i, :], py) for i in range(part.shape[0])])))
+    assert np.allclose(scores.cpu().numpy(), np.array(want), rtol=2e-5), (scores.cpu().numpy(), want)
+
+
+def test_inception_forward():
+    """the whole feature extractor: GPU kernels vs the emulated graph (same bf16 arithmetic) and vs torchvision fp32"""
+    from tests.incep_fixture import calibrated_inception
+    from jck_generation_b200.inception import InceptionV3
+    model = calibrated_inception(seed=1)
+    x = torch.randn(2, 3, 299, 299, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = model(x)
+    sd = model.state_dict()
+    cpu = InceptionV3(sd, device="cpu", K=emu)
+    want = cpu.forward(x)
+    gpu = InceptionV3(sd, device="cuda")
+    got = gpu.forward(x.cuda())
+    torch.cuda.synchronize()
+    worst = 0.0
+    for key, b in cpu._bufs.items():
+        if isinstance(b, torch.Tensor) or key not in gpu._bufs:
+            continue
+        e = _rel(gpu._bufs[key].interior(), b.interior())
+        worst = max(worst, e)
+        assert e < 0.15, (key, e)      # one-ulp flips of bf16 stores, amplified by the random network
+    print("worst block vs emulator", worst, "logits vs emulator", _rel(got, want), "vs torchvision fp32", _rel(got, ref))
+    assert _rel(got, want) < 3e-2
+    assert _rel(got, ref) < 0.3          # bf16 storage through a 1000x-amplifying random network (see module docstring)
+    # pool3 features and the fused generated-image entry
+    p3 = InceptionV3(sd, feature="pool3", device="cuda")
+    f = p3.forward(x.cuda())
+    assert f.shape == (2, 2048) and bool(torch.isfinite(f).all())
+    fake = torch.tanh(torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(2)))
+    pre = torch.nn.functional.interpolate(0.5 * fake + 0.5, size=(299, 299), mode="bilinear", align_corners=False)
+    pre = (pre - torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    a = gpu.forward_generated(fake.cuda()).clone()
+    b = gpu.forward(pre.cuda())
+    torch.cuda.synchronize()
+    assert _rel(a, b) < 3e-2
