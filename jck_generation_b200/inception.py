@@ -253,26 +253,36 @@ class InceptionV3:
         299 x 299, ImageNet normalise) into the stem's patch kernel."""
         return self._run(fake, 0.5, 0.5, IMAGENET_MEAN, IMAGENET_STD)
 
+    def _stages(self):
+        """the trunk after the stem as (output buffer key, function of the previous stage's buffer)"""
+        return [
+            ("c2a", lambda x: self._conv("Conv2d_2a_3x3", x, self._buf("c2a", x.B, 147, 147, 32, 1, 1))),
+            ("c2b", lambda x: self._conv("Conv2d_2b_3x3", x, self._buf("c2b", x.B, 147, 147, 64))),
+            ("p1", lambda x: self._pool(x, self._buf("p1", x.B, 73, 73, 64), 0, 2, 0, 0)),
+            ("c3b", lambda x: self._conv("Conv2d_3b_1x1", x, self._buf("c3b", x.B, 73, 73, 80))),
+            ("c4a", lambda x: self._conv("Conv2d_4a_3x3", x, self._buf("c4a", x.B, 71, 71, 192))),
+            ("p2", lambda x: self._pool(x, self._buf("p2", x.B, 35, 35, 192), 0, 2, 0, 0)),
+            ("Mixed_5b.out", lambda x: self._block_a("Mixed_5b", x, 32)),
+            ("Mixed_5c.out", lambda x: self._block_a("Mixed_5c", x, 64)),
+            ("Mixed_5d.out", lambda x: self._block_a("Mixed_5d", x, 64)),
+            ("Mixed_6a.out", lambda x: self._block_b("Mixed_6a", x)),
+            ("Mixed_6b.out", lambda x: self._block_c("Mixed_6b", x, 128)),
+            ("Mixed_6c.out", lambda x: self._block_c("Mixed_6c", x, 160)),
+            ("Mixed_6d.out", lambda x: self._block_c("Mixed_6d", x, 160)),
+            ("Mixed_6e.out", lambda x: self._block_c("Mixed_6e", x, 192)),
+            ("Mixed_7a.out", lambda x: self._block_d("Mixed_7a", x)),
+            ("Mixed_7b.out", lambda x: self._block_e("Mixed_7b", x)),
+            ("Mixed_7c.out", lambda x: self._block_e("Mixed_7c", x)),
+        ]
+
     def _trunk(self, x):
         B = x.B
-        x = self._conv("Conv2d_2a_3x3", x, self._buf("c2a", B, 147, 147, 32, 1, 1))
-        x = self._conv("Conv2d_2b_3x3", x, self._buf("c2b", B, 147, 147, 64))
-        x = self._pool(x, self._buf("p1", B, 73, 73, 64), 0, 2, 0, 0)
-        x = self._conv("Conv2d_3b_1x1", x, self._buf("c3b", B, 73, 73, 80))
-        x = self._conv("Conv2d_4a_3x3", x, self._buf("c4a", B, 71, 71, 192))
-        x = self._pool(x, self._buf("p2", B, 35, 35, 192), 0, 2, 0, 0)
-        x = self._block_a("Mixed_5b", x, 32)
-        x = self._block_a("Mixed_5c", x, 64)
-        x = self._block_a("Mixed_5d", x, 64)
-        x = self._block_b("Mixed_6a", x)
-        x = self._block_c("Mixed_6b", x, 128)
-        x = self._block_c("Mixed_6c", x, 160)
-        x = self._block_c("Mixed_6d", x, 160)
-        x = self._block_c("Mixed_6e", x, 192)
-        x = self._block_d("Mixed_7a", x)
-        x = self._block_e("Mixed_7b", x)
-        x = self._block_e("Mixed_7c", x)
-        self.last = x
+        for _, stage in self._stages():
+            x = stage(x)
+        return self._head(x)
+
+    def _head(self, x):
+        B = x.B
         pooled = torch.empty(B, 2048, dtype=torch.float32, device=self.device)
         pooled_bf = self._scratch("pooled_bf", B * 2048, self.dtype)
         self.K.global_avgpool(x.t, pooled, pooled_bf, B, x.H * x.W, 2048)

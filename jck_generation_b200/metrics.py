@@ -1,4 +1,4 @@
-"""Interface-compatible stand-in for the reference's metrics.py (secondary path).
+"""The reference's metrics.py (secondary path) on the jck kernels.
 
 Same public surface -- `Metrics(real_images)`, `.inception_score(loader, splits=10)`,
 `.fid(loader, intra_fid=False, label=0)`, `.intra_fid(tensor)` -- and the same definitions
@@ -6,11 +6,15 @@ Same public surface -- `Metrics(real_images)`, `.inception_score(loader, splits=
 (:46-52, :87); IS = exp(mean KL(p(y|x) || p(y))) per split; FID = |mu1-mu2|^2 + tr(S1+S2-2 sqrtm(S1 S2));
 intra-FID sums the 20 CIFAR-100 superclass FIDs and divides by 100 (sic, :141 -- kept for parity).
 
-Status in this round: PARTLY on our kernels.  The feature moments of the generated set (np.mean / np.cov of the
-reference, metrics.py:118-124) are taken on the device by ops.feature_moments -- column sums, a centred hi/lo bf16
-split and the Gram matrix as three tcgen05 GEMMs with fp32 accumulation (jck_gemm_tc, both operands MN-major),
-all-reducible across ranks -- and only the d x d result goes to the host for scipy's sqrtm.  The Inception forward
-is still torchvision's (library code) and the IS reduction numpy.  Differences forced by the environment:
+What runs where:
+  * the Inception-v3 forward (`self.inception_model(image)`, :87): `inception.InceptionV3` -- 94 tcgen05 implicit-GEMM
+    launches + pooling kernels in one CUDA graph; the torchvision module built here is only the parameter container the
+    reference's checkpoint loads into (same state_dict keys), its forward is never called;
+  * the eval branch's pre-processing (dcgan_trainer.py:203-207): fused into the stem kernel (`evaluate_generated`);
+  * softmax + split marginals + KL (:96-110): `jck_inception_score`;
+  * np.mean / np.cov (:118-124): `ops.feature_moments` (tcgen05 Gram matrix, all-reducible across ranks);
+  * the d x d matrix square root stays scipy's `sqrtm` on the host, as in the reference (:128).
+There is no CPU path: without a CUDA device the constructor raises.  Differences forced by the environment:
   * ./save/iception_v3/loss_bset.pt (:51; spelling is the on-disk contract) is loaded when present,
     otherwise the network is seeded random-init -- there is no network to fetch weights;
   * `real_images` may be a dataset with `.targets` (the CGAN preprocessor, as the reference expects), a
@@ -33,30 +37,25 @@ SUPERCLASS = [
     [27, 29, 44, 78, 93], [36, 50, 65, 74, 80], [47, 52, 56, 59, 96], [8, 13, 48, 58, 90], [41, 69, 81, 85, 89]]
 
 
-def _entropy(pk, qk):
-    """scipy.stats.entropy(pk, qk): KL divergence after normalising both."""
-    pk = pk / pk.sum()
-    qk = qk / qk.sum()
-    mask = pk > 0
-    return float(np.sum(pk[mask] * np.log(pk[mask] / qk[mask])))
-
-
 class Metrics:
     def __init__(self, real_images=None, feature="logits", checkpoint=os.path.join('./save/iception_v3', 'loss_bset.pt'),
-                 cache=os.path.join('./data', 'metric_data.pikl')):
+                 cache=os.path.join('./data', 'metric_data.pikl'), batch=128):
         from torchvision import models
+        from .inception import InceptionV3
+        if not torch.cuda.is_available():
+            raise RuntimeError("Metrics: the Inception-v3 forward runs on the jck sm_100a kernels; there is no CPU path")
         self.device = get_default_device()
-        self.feature = feature
+        self.feature, self.batch = feature, batch
         self.class_to_superclass = {c: s for s, cs in enumerate(SUPERCLASS) for c in cs}
         torch.manual_seed(12345)
+        # parameter container only (the reference's checkpoint format); the forward below is ours
         self.inception_model = models.inception_v3(weights=None, aux_logits=True, init_weights=False)
         self.inception_model.aux_logits = False
         self.inception_model.fc = nn.Sequential(nn.Linear(self.inception_model.fc.in_features, 100))
         if os.path.exists(checkpoint):
             self.inception_model.load_state_dict(torch.load(checkpoint, map_location="cpu"))
-        if feature == "pool3":
-            self.inception_model.fc = nn.Identity()
-        self.inception_model.to(self.device).eval()
+        self.inception_model.eval()
+        self.extractor = InceptionV3(self.inception_model.state_dict(), feature=feature, device=self.device)
 
         real_targets = getattr(real_images, "targets", None)
         fake_targets = [i for i in range(100) for _ in range(10)]
@@ -72,44 +71,44 @@ class Metrics:
                 self.real_features = pickle.load(f)
         elif real_images is not None:
             loader = real_images if isinstance(real_images, torch.utils.data.DataLoader) else \
-                torch.utils.data.DataLoader(real_images, 128, shuffle=False, num_workers=0, pin_memory=True)
-            self.real_features = self._extract(loader, real=True)
+                torch.utils.data.DataLoader(real_images, batch, shuffle=False, num_workers=0, pin_memory=True)
+            self.real_features = self._extract(loader, real=True).cpu().numpy()
 
     @torch.no_grad()
-    def _extract(self, images, real=False, softmax=False, on_device=False):
+    def _extract(self, images, real=False, generated=False):
+        """features [n, d] fp32 on the device (metrics.py:80-93 without the per-batch .cpu().numpy())"""
         feats = []
         for image in images:
             if real or isinstance(image, (list, tuple)):
                 image = image[0]
-            out = self.inception_model(image.to(self.device, non_blocking=True).float())
-            feats.append(nn.functional.softmax(out, dim=1) if softmax else out)
-        feats = torch.cat(feats)
-        return feats.float().contiguous() if on_device else feats.double().cpu().numpy()
+            image = image.to(self.device, non_blocking=True).float()
+            feats.append(self.extractor.forward_generated(image) if generated else self.extractor.forward(image))
+        return torch.cat(feats).float().contiguous()
 
     def _moments(self, feats):
-        """(mean, covariance) as float64 numpy: on our kernels for device-resident features, numpy otherwise."""
-        if torch.is_tensor(feats) and feats.is_cuda and feats.shape[0] > 1:
-            from . import ops
-            mean, cov = ops.feature_moments(feats)
-            return mean.double().cpu().numpy(), cov.double().cpu().numpy()
-        feats = feats.double().cpu().numpy() if torch.is_tensor(feats) else feats
-        return np.mean(feats, axis=0), np.cov(feats, rowvar=False)
+        """(mean, covariance) as float64 numpy, taken on the device (ops.feature_moments)"""
+        from . import ops
+        if not torch.is_tensor(feats):
+            feats = torch.as_tensor(np.ascontiguousarray(feats), dtype=torch.float32)
+        feats = feats.to(self.device).float().contiguous()
+        mean, cov = ops.feature_moments(feats)
+        return mean.double().cpu().numpy(), cov.double().cpu().numpy()
+
+    def _score(self, logits, n, splits):
+        from . import ops
+        per = n // splits
+        if per == 0:
+            return float("nan")
+        scores = torch.zeros(splits, dtype=torch.float32, device=self.device)
+        ops.inception_score(logits[:per * splits].contiguous(), splits, scores)
+        return float(scores.mean().item())
 
     def inception_score(self, images, splits=10):
         n = len(images.dataset)
-        preds = self._extract(images, softmax=True)
-        split_scores = []
-        for k in range(splits):
-            part = preds[k * (n // splits): (k + 1) * (n // splits), :]
-            if part.shape[0] == 0:
-                continue
-            py = np.mean(part, axis=0)
-            split_scores.append(np.exp(np.mean([_entropy(part[i, :], py) for i in range(part.shape[0])])))
-        return float(np.mean(split_scores))
+        return self._score(self._extract(images), n, splits)
 
-    def fid(self, generated_images, intra_fid=False, label=0):
+    def _fid_from(self, generated_features, intra_fid=False, label=0):
         from scipy.linalg import sqrtm
-        generated_features = self._extract(generated_images, on_device=torch.cuda.is_available())
         real = self.real_features
         if real is None:
             raise RuntimeError("Metrics.fid: no real-image features (construct Metrics with a dataset or loader)")
@@ -123,6 +122,9 @@ class Metrics:
             covmean = covmean.real
         return float(diff + np.trace(sigma1 + sigma2 - 2.0 * covmean))
 
+    def fid(self, generated_images, intra_fid=False, label=0):
+        return self._fid_from(self._extract(generated_images), intra_fid, label)
+
     def intra_fid(self, generated_images):
         total = 0.0
         for sidx in range(20):
@@ -132,14 +134,11 @@ class Metrics:
         return total / 100
 
     def evaluate_generated(self, fake):
-        """The reference's eval branch (dcgan_trainer.py:203-211) without the GPU->CPU->GPU round trip:
-        de-normalise, resize to 299, ImageNet-normalise on the device, then IS and FID."""
-        x = 0.5 * fake.float() + 0.5
-        x = nn.functional.interpolate(x, size=(299, 299), mode="bilinear", align_corners=False, antialias=False)
-        mean = torch.tensor([0.485, 0.456, 0.406], device=x.device).view(1, 3, 1, 1)
-        std = torch.tensor([0.229, 0.224, 0.225], device=x.device).view(1, 3, 1, 1)
-        x = (x - mean) / std
-        loader = torch.utils.data.DataLoader(x, batch_size=64)
-        score = self.inception_score(loader)
-        fid = self.fid(loader) if self.real_features is not None else float("nan")
+        """The reference's eval branch (dcgan_trainer.py:198-211) on the device: `fake` is the generator's output in
+        [-1, 1]; de-normalise / resize to 299 / ImageNet-normalise are fused into the Inception stem kernel, the features
+        are extracted ONCE and feed both the score and the FID (the reference runs the network twice)."""
+        fake = fake.to(self.device).float()
+        feats = self._extract(fake.split(self.batch), generated=True)
+        score = self._score(feats, feats.shape[0], 10) if self.feature == "logits" else float("nan")
+        fid = self._fid_from(feats) if self.real_features is not None else float("nan")
         return score, fid

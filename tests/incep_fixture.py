@@ -11,8 +11,7 @@ def calibrated_inception(seed=1, n_out=100, calib_batch=2):
     from torchvision import models
     torch.manual_seed(seed)
     m = models.inception_v3(weights=None, aux_logits=True, init_weights=False)
-    m.aux_logits = False
-    m.AuxLogits = None
+    m.aux_logits = False                             # metrics.py:48; AuxLogits stays in the state_dict, as in the reference's checkpoint
     m.fc = nn.Sequential(nn.Linear(m.fc.in_features, n_out))
     g = torch.Generator().manual_seed(seed + 1)
     for mod in m.modules():

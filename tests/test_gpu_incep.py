@@ -178,37 +178,55 @@ def test_inception_score_kernel():
 
 
 def test_inception_forward():
-    """the whole feature extractor: GPU kernels vs the emulated graph (same bf16 arithmetic) and vs torchvision fp32"""
+    """the whole feature extractor on the GPU.  (a) stage by stage, each Inception block fed the emulator's input for that
+    block (same bf16 arithmetic; only the fp32 summation order differs) -- tight; (b) free running, against the emulated
+    graph and against torchvision fp32 -- loose: a random-weight BatchNorm network is chaotic in depth (one-ulp bf16 flips
+    grow ~1.5x per block here), a trained one is not, but the reference's checkpoint is not available offline."""
     from tests.incep_fixture import calibrated_inception
-    from jck_generation_b200.inception import InceptionV3
+    from jck_generation_b200.inception import InceptionV3, IMAGENET_MEAN, IMAGENET_STD
     model = calibrated_inception(seed=1)
     x = torch.randn(2, 3, 299, 299, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
         ref = model(x)
     sd = model.state_dict()
     cpu = InceptionV3(sd, device="cpu", K=emu)
-    want = cpu.forward(x)
-    gpu = InceptionV3(sd, device="cuda")
-    got = gpu.forward(x.cuda())
+    gpu = InceptionV3(sd, device="cuda", use_graph=False)
+    got = gpu.forward(x.cuda())                      # free running; also allocates every buffer
     torch.cuda.synchronize()
+    ident = (1.0, 0.0, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0))
+    xc = cpu._stem(x, *ident)
+    xg = gpu._stem(x.cuda(), *ident)
+    assert _rel(xg.interior(), xc.interior()) < 5e-3
     worst = 0.0
-    for key, b in cpu._bufs.items():
-        if isinstance(b, torch.Tensor) or key not in gpu._bufs:
-            continue
-        e = _rel(gpu._bufs[key].interior(), b.interior())
+    for (key, fc), (_, fg) in zip(cpu._stages(), gpu._stages()):
+        xg.t.copy_(xc.t)                             # teacher forcing: the emulator's input for this stage
+        yc, yg = fc(xc), fg(xg)
+        torch.cuda.synchronize()
+        e = _rel(yg.interior(), yc.interior())
         worst = max(worst, e)
-        assert e < 0.15, (key, e)      # one-ulp flips of bf16 stores, amplified by the random network
-    print("worst block vs emulator", worst, "logits vs emulator", _rel(got, want), "vs torchvision fp32", _rel(got, ref))
-    assert _rel(got, want) < 3e-2
-    assert _rel(got, ref) < 0.3          # bf16 storage through a 1000x-amplifying random network (see module docstring)
-    # pool3 features and the fused generated-image entry
+        assert e < 2e-2, (key, e)
+        xc, xg = yc, yg
+    xg.t.copy_(xc.t)
+    want = cpu._head(xc)
+    head = gpu._head(xg)
+    torch.cuda.synchronize()
+    assert _rel(head, want) < 5e-3, _rel(head, want)
+    print("worst stage vs emulator (teacher forced)", worst, "| free running: logits vs emulator", _rel(got, want),
+          "vs torchvision fp32", _rel(got, ref))
+    assert _rel(got, want) < 0.3 and _rel(got, ref) < 0.3
+    # CUDA-graph replay, pool3 features, and the fused generated-image entry against the unfused pre-processing
+    graphed = InceptionV3(sd, device="cuda")
+    for _ in range(2):
+        again = graphed.forward(x.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(again, got)
     p3 = InceptionV3(sd, feature="pool3", device="cuda")
     f = p3.forward(x.cuda())
     assert f.shape == (2, 2048) and bool(torch.isfinite(f).all())
     fake = torch.tanh(torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(2)))
     pre = torch.nn.functional.interpolate(0.5 * fake + 0.5, size=(299, 299), mode="bilinear", align_corners=False)
-    pre = (pre - torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
-    a = gpu.forward_generated(fake.cuda()).clone()
-    b = gpu.forward(pre.cuda())
+    pre = (pre - torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)) / torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    a = graphed.forward_generated(fake.cuda())
+    b = graphed.forward(pre.cuda())
     torch.cuda.synchronize()
-    assert _rel(a, b) < 3e-2
+    assert _rel(a, b) < 0.3

@@ -189,31 +189,45 @@ def test_trainer_runs_and_checkpoints(tmp_path, monkeypatch):
     assert gp.item() >= 0
 
 
-def test_metrics_fid_moments_on_device(tmp_path, monkeypatch):
-    """Metrics (interface of the reference's metrics.py): the generated set's feature moments taken on our kernels equal
-    numpy's on the same Inception features, and fid() runs end to end on them.  (The FID value itself is not compared: with
-    fewer samples than feature dimensions the covariances are singular and scipy's sqrtm amplifies rounding.)"""
-    monkeypatch.chdir(tmp_path)
+def test_metrics_end_to_end(tmp_path, monkeypatch):
+    """Metrics (interface of the reference's metrics.py) end to end on the device: checkpoint in the reference's on-disk
+    format -> Inception features on our kernels -> IS and FID, against the reference's own formulas (metrics.py:96-131:
+    scipy entropy, np.mean / np.cov, scipy sqrtm) evaluated on the same features."""
+    import os
     import numpy as np
+    from scipy.linalg import sqrtm
+    from scipy.stats import entropy
+    from tests.incep_fixture import calibrated_inception
     from jck_generation_b200.metrics import Metrics
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("save/iception_v3")
+    torch.save(calibrated_inception(seed=1).state_dict(), "save/iception_v3/loss_bset.pt")
     g = torch.Generator().manual_seed(11)
-    real = torch.utils.data.TensorDataset(torch.rand(48, 3, 299, 299, generator=g), torch.zeros(48, dtype=torch.long))
-    m = Metrics(None)
-    # a seeded random-init Inception maps every image to the same logits to 1e-10 (no checkpoint offline): swap in a small
-    # random feature extractor with the same 100-d interface so that the moments are well conditioned
-    torch.manual_seed(5)
-    m.inception_model = torch.nn.Sequential(torch.nn.AdaptiveAvgPool2d(8), torch.nn.Flatten(), torch.nn.Linear(192, 100)).cuda()
-    with torch.no_grad():
-        m.inception_model[2].weight.mul_(30.0)
-    m.real_features = m._extract(torch.utils.data.DataLoader(real, 16), real=True)
-    assert m.real_features.shape == (48, 100)
-    fake = torch.rand(40, 3, 299, 299, generator=g)
-    loader = torch.utils.data.DataLoader(fake, 20)
-    feats_dev = m._extract(loader, on_device=True)
-    assert feats_dev.is_cuda and feats_dev.shape == (40, 100)
-    mu, cov = m._moments(feats_dev)
-    f64 = feats_dev.double().cpu().numpy()
-    want_mu, want_cov = np.mean(f64, axis=0), np.cov(f64, rowvar=False)
-    assert np.linalg.norm(mu - want_mu) <= 1e-5 * max(np.linalg.norm(want_mu), 1e-3)
-    assert np.linalg.norm(cov - want_cov) <= 1e-4 * np.linalg.norm(want_cov)
-    assert np.isfinite(m.fid(loader))
+    real = torch.utils.data.TensorDataset(torch.randn(256, 3, 64, 64, generator=g), torch.zeros(256, dtype=torch.long))
+    m = Metrics(real)
+    assert m.real_features.shape == (256, 100) and np.isfinite(m.real_features).all()
+    fake = torch.tanh(torch.randn(320, 3, 64, 64, generator=g))
+    score, fid = m.evaluate_generated(fake)
+    feats = m._extract(fake.split(128), generated=True)
+    f64 = feats.double().cpu().numpy()
+    # IS as the reference computes it
+    preds = torch.softmax(feats, 1).cpu().numpy()
+    want = []
+    for k in range(10):
+        part = preds[k * 32:(k + 1) * 32, :]
+        py = np.mean(part, axis=0)
+        want.append(np.exp(np.mean([entropy(part[i, :], py) for i in range(part.shape[0])])))
+    assert abs(score - np.mean(want)) <= 1e-4 * np.mean(want), (score, np.mean(want))
+    # FID as the reference computes it
+    mu1, s1 = np.mean(m.real_features.astype(np.float64), axis=0), np.cov(m.real_features.astype(np.float64), rowvar=False)
+    mu2, s2 = np.mean(f64, axis=0), np.cov(f64, rowvar=False)
+    cm = sqrtm(s1.dot(s2))
+    cm = cm.real if np.iscomplexobj(cm) else cm
+    want_fid = np.sum((mu1 - mu2) ** 2.0) + np.trace(s1 + s2 - 2.0 * cm)
+    assert abs(fid - want_fid) <= 2e-3 * (np.trace(s1) + np.trace(s2)), (fid, want_fid)
+    # loader-based entry points of the reference interface
+    loader = torch.utils.data.DataLoader(torch.randn(64, 3, 299, 299, generator=g), batch_size=64)
+    assert np.isfinite(m.inception_score(loader)) and np.isfinite(m.fid(loader))
+    mu, cov = m._moments(feats)
+    assert np.linalg.norm(mu - mu2) <= 1e-5 * np.linalg.norm(mu2)
+    assert np.linalg.norm(cov - s2) <= 1e-4 * np.linalg.norm(s2)
