@@ -324,6 +324,18 @@ int jck_stem_patches(const float* in_nchw, void* patches, int B, int Hi, int Wi,
  * [k*(n/splits), (k+1)*(n/splits)) of fp32 logits [n][d] */
 int jck_inception_score(const float* logits, int n, int d, int splits, float* scores, void* stream);
 
+/* ---- input pipeline on the device (preprocess/dcgan_data_preprocessor.py:38-49, cgan_data_preprocessor.py:11-16,51-62) ----
+ * The uint8 dataset [N][Hi][Wi][C] lives in HBM.  out[b] = Normalize(ToTensor(Resize(data[index[b]]))) as NCHW fp32, bit-exact
+ * with Pillow's bilinear resample (horizontal pass, then vertical pass on the uint8-rounded result; 22-bit fixed-point
+ * coefficients: *_bounds [out][2] = (first source index, count), *_coef [out][ksize], device int32 tables built by the host as
+ * Pillow's precompute_coeffs / normalize_coeffs_8bpc do) and with torchvision's fp32 (u8 / 255 - mean) / std.  index: device
+ * int64 [B] (nullable = identity); mean / std: HOST pointers to C floats; a pass whose size does not change is skipped. */
+int jck_u8_resize_norm(const void* data_u8, const long long* index, float* out_nchw, int B, int Hi, int Wi, int C, int Ho,
+                       int Wo, const int* h_bounds, const int* h_coef, int h_ksize, const int* v_bounds, const int* v_coef,
+                       int v_ksize, const float* mean, const float* std, void* stream);
+/* out[b][j] = (labels[index[b]] == j), int64 (OneHotEncoder + default collate) */
+int jck_one_hot_i64(const long long* labels, const long long* index, long long* out, int B, int n_classes, void* stream);
+
 /* ---- data-parallel exchange over NVLink peer memory -------------------------------------------
  * The reference is single-GPU: these entry points have no reference counterpart.  They make
  * an N-GPU run equal the reference at the global batch: nn.BatchNorm2d's batch statistics (model/DCGAN.py:

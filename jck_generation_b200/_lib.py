@@ -87,6 +87,8 @@ _SIGNATURES = {
     "jck_resize_norm": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
     "jck_stem_patches": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
     "jck_inception_score": [c_p, c_i, c_i, c_i, c_p, c_p],
+    "jck_u8_resize_norm": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p],
+    "jck_one_hot_i64": [c_p, c_p, c_p, c_i, c_i, c_p],
     "jck_comm_create": [c_i, c_i, ctypes.POINTER(c_p), c_p],
     "jck_comm_connect": [c_p, c_p],
     "jck_comm_destroy": [c_p],

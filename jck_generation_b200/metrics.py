@@ -70,7 +70,9 @@ class Metrics:
             with open(cache, 'rb') as f:
                 self.real_features = pickle.load(f)
         elif real_images is not None:
-            loader = real_images if isinstance(real_images, torch.utils.data.DataLoader) else \
+            is_loader = isinstance(real_images, torch.utils.data.DataLoader) or not isinstance(real_images, torch.utils.data.Dataset) \
+                and hasattr(real_images, "__iter__") and hasattr(real_images, "batch_size")    # e.g. preprocess.DeviceImageLoader
+            loader = real_images if is_loader else \
                 torch.utils.data.DataLoader(real_images, batch, shuffle=False, num_workers=0, pin_memory=True)
             self.real_features = self._extract(loader, real=True).cpu().numpy()
 

@@ -4,7 +4,7 @@ as in the reference :90, returns the inception *dataset*, not a loader)."""
 import torch
 
 from ..logger.main_logger import MainLogger
-from .dcgan_data_preprocessor import _cifar_available
+from .dcgan_data_preprocessor import _cifar_available, u8_source, IMAGENET_MEAN, IMAGENET_STD
 from .synthetic import SyntheticLoader
 
 
@@ -33,10 +33,12 @@ class CGANDataPreprocessor:
             self._trainset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
             self._inceptionset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
             self.idx_to_labels = {v: k for k, v in self._trainset.class_to_idx.items()}
-        self._logger.debug('data preprocessor init' + (' (synthetic source)' if self.synthetic else ''))
+        self._u8 = u8_source(self, args, self.n_classes)
+        self._logger.debug('data preprocessor init' + (' (synthetic source)' if self.synthetic else '') +
+                           (' (device pipeline)' if self._u8 is not None else ''))
 
     def transform_data(self):
-        if self.synthetic:
+        if self.synthetic or self._u8 is not None:
             return
         import torchvision.transforms as tt
         self._trainset.transform = tt.Compose([
@@ -49,7 +51,15 @@ class CGANDataPreprocessor:
         self._logger.debug('data transform')
 
     def get_data_loader(self):
-        if self.synthetic:
+        if self._u8 is not None:
+            # Resize(64) / ToTensor / Normalize + OneHotEncoder (:49-62) and the loaders (:82-92) on the device
+            from .device_pipeline import DeviceImageLoader
+            data, targets = self._u8
+            n_cls = self.n_classes if self.synthetic else len(self._trainset.classes)
+            self.trainloader = DeviceImageLoader(data, targets, self.batch_size, 64, [0.5] * 3, [0.5] * 3, shuffle=True,
+                                                 n_classes=n_cls)
+            self.inceptionloader = DeviceImageLoader(data, targets, 128, (299, 299), IMAGENET_MEAN, IMAGENET_STD, shuffle=False)
+        elif self.synthetic:
             self.trainloader = SyntheticLoader(self.batch_size, self.synthetic_batches, n_classes=self.n_classes)
             self.inceptionloader = None
         else:

@@ -13,6 +13,27 @@ import torch
 from ..logger.main_logger import MainLogger
 from .synthetic import SyntheticLoader
 
+IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+
+
+def synthetic_u8(n, n_classes=100, hw=32, seed=12345):
+    """CIFAR-shaped stand-in: uint8 [n, hw, hw, 3] + class indices (no network here to download the real set)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (n, hw, hw, 3), dtype=np.uint8), rng.integers(0, n_classes, n).tolist()
+
+
+def u8_source(pre, args, n_classes=100):
+    """(uint8 [N,H,W,3], targets) for the device pipeline, or None: CIFAR-100 when it is on disk, a synthetic uint8 set with
+    args.synthetic_u8=1; None (-> the host loaders) without a CUDA device or with args.device_pipeline=0."""
+    if not torch.cuda.is_available() or not int(getattr(args, "device_pipeline", 1)):
+        return None
+    if int(getattr(args, "synthetic_u8", 0)):
+        return synthetic_u8(pre.synthetic_batches * pre.batch_size, n_classes)
+    if not pre.synthetic:
+        return pre._trainset.data, pre._trainset.targets
+    return None
+
 
 def _cifar_available(root="./data"):
     return os.path.isdir(os.path.join(root, "cifar-100-python"))
@@ -30,10 +51,12 @@ class DCGANDataPreprocessor:
             import torchvision
             self._trainset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
             self._inceptionset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
-        self._logger.debug('data preprocessor init' + (' (synthetic source)' if self.synthetic else ''))
+        self._u8 = u8_source(self, args)
+        self._logger.debug('data preprocessor init' + (' (synthetic source)' if self.synthetic else '') +
+                           (' (device pipeline)' if self._u8 is not None else ''))
 
     def transform_data(self):
-        if self.synthetic:
+        if self.synthetic or self._u8 is not None:
             return
         import torchvision.transforms as tt
         self._trainset.transform = tt.Compose([
@@ -45,7 +68,14 @@ class DCGANDataPreprocessor:
         self._logger.debug('data transform')
 
     def get_data_loader(self):
-        if self.synthetic:
+        if self._u8 is not None:
+            # the reference's two transforms (:37-49) and loaders (:69-75) on the device, bit-identical results
+            from .device_pipeline import DeviceImageLoader
+            data, targets = self._u8
+            self.trainloader = DeviceImageLoader(data, targets, self.batch_size, 64, [0.5] * 3, [0.5] * 3, shuffle=True)
+            self.inceptionloader = DeviceImageLoader(data, targets, self.batch_size * 2, (299, 299), IMAGENET_MEAN, IMAGENET_STD,
+                                                     shuffle=False)
+        elif self.synthetic:
             self.trainloader = SyntheticLoader(self.batch_size, self.synthetic_batches)
             self.inceptionloader = None
         else:
