@@ -60,11 +60,11 @@ def test_device_pipeline_bit_exact(h, w, size, norm):
     data = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
     data[0], data[1] = 0, 255                                    # saturated images
     targets = rng.integers(0, 100, n).tolist()
-    torch.manual_seed(77)
     loader = DeviceImageLoader(data, targets, 16, size, norm[0], norm[1], shuffle=True, n_classes=100)
     torch.manual_seed(77)
     ref_idx = [b for b in torch.utils.data.DataLoader(torch.arange(n), 16, shuffle=True)]   # the reference loader's batches
     assert len(loader) == 3 and len(loader.dataset) == n
+    torch.manual_seed(77)                                        # same global RNG state -> same permutation as the reference
     for (x, y), idx in zip(loader, ref_idx):
         idx = idx.tolist()
         want = np.stack([pr.transform(data[i], loader.Ho, loader.Wo, *norm) for i in idx])
