@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the FID-eval / input-pipeline side measurements")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device time table")
     ap.add_argument("--kernel-table", action="store_true", help="print per-kernel device time (CUPTI via torch.profiler)")
     return ap.parse_args()
@@ -225,6 +226,62 @@ class OpTimer:
         return agg
 
 
+def secondary_paths(torch, trainer, dev):
+    """SURVEY.md 8f rows measured beside the headline (device time, CUDA events, after a warm-up pass):
+    * fid_eval: BASELINE configs[4] on one GPU, scaled to 4096 samples: generator -> fused resize/normalise -> Inception-v3
+      pool3 features on our tcgen05 conv kernels -> 2048 x 2048 covariance (ops.feature_moments);
+    * input_pipeline: the reference's Resize(64)/ToTensor/Normalize loader on a CIFAR-shaped uint8 set resident in HBM."""
+    import numpy as np
+    from jck_generation_b200 import ops
+    from jck_generation_b200.inception import InceptionV3
+    from jck_generation_b200.preprocess.device_pipeline import DeviceImageLoader
+    from torchvision import models
+    out = {}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    torch.manual_seed(12345)
+    net = models.inception_v3(weights=None, aux_logits=True, init_weights=False)
+    ext = InceptionV3(net.state_dict(), feature="pool3", device=dev)
+    n, bsz = 4096, 128
+    z = torch.randn(n, 100, 1, 1, device=dev)
+
+    def fid_pass():
+        feats = []
+        with torch.no_grad():
+            for i in range(0, n, bsz):
+                feats.append(ext.forward_generated(trainer.model_g(z[i:i + bsz]).float()))
+        return ops.feature_moments(torch.cat(feats).contiguous())
+    fid_pass()
+    torch.cuda.synchronize()
+    ev[0].record()
+    fid_pass()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1])
+    out["fid_eval"] = {"images_per_s": n / (ms * 1e-3), "ms": ms, "samples": n, "feature": "pool3 (2048-d)",
+                       "inception_tflops": 11.42e9 * n / (ms * 1e-3) / 1e12,
+                       "what": "G forward + Inception-v3 (94 tcgen05 implicit-GEMM convs, one CUDA graph per 128 images) + "
+                               "2048x2048 covariance, random-init weights"}
+    del ext
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 256, (50000, 32, 32, 3), dtype=np.uint8)
+    loader = DeviceImageLoader(data, None, 512, 64, [0.5] * 3, [0.5] * 3, shuffle=True)
+    for _ in loader:
+        pass
+    torch.cuda.synchronize()
+    ev[0].record()
+    cnt = 0
+    for x, _ in loader:
+        cnt += x.shape[0]
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1])
+    out["input_pipeline"] = {"images_per_s": cnt / (ms * 1e-3), "ms_per_epoch": ms, "samples": cnt,
+                             "what": "one epoch of a 50k x 32x32x3 uint8 set: seeded permutation gather + Pillow-exact "
+                                     "bilinear 32->64 + ToTensor/Normalize -> NCHW fp32, batches of 512"}
+    return out
+
+
 def run_b200(args):
     import torch
     import __graft_entry__ as entry
@@ -379,6 +436,11 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"oracle port of the reference step, 3 steps of 128 images on {cores} host "
                                           f"threads ({cms:.0f} ms/step)"}
+    if comm.world_size == 1 and not args.no_secondary:
+        try:
+            line["secondary"] = secondary_paths(torch, trainer, dev)
+        except Exception as e:                      # the headline never depends on the secondary paths
+            line["secondary"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if comm.world_size > 1:
