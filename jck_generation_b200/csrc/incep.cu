@@ -36,6 +36,7 @@ struct CGParams {
     int Hq, Wq, oy0, ox0, Ho, Wo, Hob, Wob, opy, opx, c_off, relu, out_f32;
     long long ldc;
     int stages, stage_bytes, vec_coef;
+    int resident;              // 1: the whole weight matrix (ksteps boxes of BN x 64) stays in shared memory; the ring carries A only
     const float* scale;
     const float* bias;
 };
@@ -47,11 +48,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * p.stage_bytes);
+    const int b_bytes = p.BN * 128;                                    // one K step of the weight tile
+    uint8_t* wres = smem + stages * p.stage_bytes;                     // resident weights (p.resident), else unused
+    uint64_t* full = reinterpret_cast<uint64_t*>(wres + (p.resident ? p.ksteps * b_bytes : 0));
     uint64_t* empty = full + kCGMaxStages;
     uint64_t* tfull = empty + kCGMaxStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* wfull = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -59,6 +63,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         prefetch_tmap(&mapB);
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        mbar_init(wfull, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * kCGAccCols);
@@ -70,7 +75,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t tx = kCGABytes + p.BN * 128;
+            const uint32_t tx = kCGABytes + (p.resident ? 0 : b_bytes);
+            if (p.resident) {                       // n_tiles == 1: every tile of this CTA uses the same weights
+                mbar_arrive_expect_tx(wfull, (uint32_t)(p.ksteps * b_bytes));
+                for (int ks = 0; ks < p.ksteps; ++ks) {
+                    const int tap = ks / p.csteps, cc = ks - tap * p.csteps;
+                    tma_load_2d(wres + ks * b_bytes, &mapB, wfull, tap * p.Cp + cc * 64, 0);
+                }
+            }
             int it = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int nt = t % p.n_tiles, mt = t / p.n_tiles;
@@ -83,12 +95,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     mbar_arrive_expect_tx(&full[s], tx);
                     const int tap = ks / p.csteps, cc = ks - tap * p.csteps;
                     tma_load_2d(sa, &mapA, &full[s], cc * 64, m0 + p.shift[tap]);
-                    tma_load_2d(sb, &mapB, &full[s], tap * p.Cp + cc * 64, n0);
+                    if (!p.resident) tma_load_2d(sb, &mapB, &full[s], tap * p.Cp + cc * 64, n0);
                 }
             }
         }
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(p.BN, 0, 0);
+        if (p.resident) {
+            mbar_wait(wfull, 0);
+            fence_after_sync();
+        }
         int it = 0, lt = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
             const int acc = lt & 1;
@@ -101,7 +117,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(smem + s * p.stage_bytes);
-                    const uint32_t b_addr = a_addr + kCGABytes;
+                    const uint32_t b_addr = p.resident ? smem_u32(wres + ks * b_bytes) : a_addr + kCGABytes;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(tmem_d, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024), idesc,
@@ -483,13 +499,17 @@ extern "C" int jck_conv_gemm(const void* act, long long lda, const void* w, cons
     p.n_tiles = (N + p.BN - 1) / p.BN;
     const int m_tiles = (M + 127) / 128;
     p.total_tiles = m_tiles * p.n_tiles;
-    p.stage_bytes = kCGABytes + p.BN * 128;
-    p.stages = (200 * 1024) / p.stage_bytes;
+    // small filter banks stay resident in shared memory for the CTA's whole tile walk (the stem / 1x1 layers would otherwise
+    // re-stream as many weight bytes as activation bytes); the ring then carries A only
+    const int w_bytes = p.ksteps * p.BN * 128;
+    p.resident = (p.n_tiles == 1 && w_bytes <= 96 * 1024 && getenv("JCK_CG_NO_RESIDENT") == nullptr) ? 1 : 0;
+    p.stage_bytes = kCGABytes + (p.resident ? 0 : p.BN * 128);
+    p.stages = (200 * 1024 - (p.resident ? w_bytes : 0)) / p.stage_bytes;
     if (p.stages > kCGMaxStages) p.stages = kCGMaxStages;
     p.scale = scale;
     p.bias = bias;
     p.vec_coef = (((uintptr_t)scale & 15) == 0 && ((uintptr_t)bias & 15) == 0) ? 1 : 0;
-    const int smem = p.stages * p.stage_bytes + 256 + 1024;
+    const int smem = p.stages * p.stage_bytes + (p.resident ? w_bytes : 0) + 256 + 1024;
     CUtensorMap mA, mB;
     int rc;
     if ((rc = encode_bf16_2d(&mA, act, (unsigned long long)C, (unsigned long long)rows_a, (unsigned long long)lda * 2, 64, 128))) return rc;
