@@ -39,13 +39,14 @@ SUPERCLASS = [
 
 class Metrics:
     def __init__(self, real_images=None, feature="logits", checkpoint=os.path.join('./save/iception_v3', 'loss_bset.pt'),
-                 cache=os.path.join('./data', 'metric_data.pikl'), batch=128):
+                 cache=os.path.join('./data', 'metric_data.pikl'), batch=128, comm=None):
         from torchvision import models
         from .inception import InceptionV3
         if not torch.cuda.is_available():
             raise RuntimeError("Metrics: the Inception-v3 forward runs on the jck sm_100a kernels; there is no CPU path")
         self.device = get_default_device()
         self.feature, self.batch = feature, batch
+        self.comm = comm                      # data-parallel evaluation (BASELINE configs[4]): see evaluate_generated
         self.class_to_superclass = {c: s for s, cs in enumerate(SUPERCLASS) for c in cs}
         torch.manual_seed(12345)
         # parameter container only (the reference's checkpoint format); the forward below is ours
@@ -87,13 +88,14 @@ class Metrics:
             feats.append(self.extractor.forward_generated(image) if generated else self.extractor.forward(image))
         return torch.cat(feats).float().contiguous()
 
-    def _moments(self, feats):
-        """(mean, covariance) as float64 numpy, taken on the device (ops.feature_moments)"""
+    def _moments(self, feats, sharded=False):
+        """(mean, covariance) as float64 numpy, taken on the device (ops.feature_moments).  `sharded`: `feats` holds this
+        rank's rows only; the column sums and the Gram matrix are all-reduced, every rank gets the moments of ALL rows."""
         from . import ops
         if not torch.is_tensor(feats):
             feats = torch.as_tensor(np.ascontiguousarray(feats), dtype=torch.float32)
         feats = feats.to(self.device).float().contiguous()
-        mean, cov = ops.feature_moments(feats)
+        mean, cov = ops.feature_moments(feats, self.comm if sharded else None)
         return mean.double().cpu().numpy(), cov.double().cpu().numpy()
 
     def _score(self, logits, n, splits):
@@ -109,7 +111,7 @@ class Metrics:
         n = len(images.dataset)
         return self._score(self._extract(images), n, splits)
 
-    def _fid_from(self, generated_features, intra_fid=False, label=0):
+    def _fid_from(self, generated_features, intra_fid=False, label=0, sharded=False):
         from scipy.linalg import sqrtm
         real = self.real_features
         if real is None:
@@ -117,7 +119,7 @@ class Metrics:
         if intra_fid:
             real = real[self.real_superclass_idx[label]]
         mu1, sigma1 = self._moments(real)
-        mu2, sigma2 = self._moments(generated_features)
+        mu2, sigma2 = self._moments(generated_features, sharded)
         diff = np.sum((mu1 - mu2) ** 2.0)
         covmean = sqrtm(sigma1.dot(sigma2))
         if np.iscomplexobj(covmean):
@@ -143,4 +145,22 @@ class Metrics:
         feats = self._extract(fake.split(self.batch), generated=True)
         score = self._score(feats, feats.shape[0], 10) if self.feature == "logits" else float("nan")
         fid = self._fid_from(feats) if self.real_features is not None else float("nan")
+        return score, fid
+
+    def evaluate_generated_sharded(self, fake_local):
+        """Data-parallel evaluation (BASELINE configs[4]: 50 k generated samples over 8 GPUs): every rank passes ITS rows of
+        the generated set (rank r = rows [r n/W, (r+1) n/W), n/W equal on all ranks); features are extracted locally, their
+        sums and Gram matrix all-reduced (2 x d + d x d floats), the d-wide logits all-gathered for the split scores.  Every
+        rank returns the same (score, fid) as one rank evaluating all n rows."""
+        import torch.distributed as dist
+        comm = self.comm
+        assert comm is not None and comm.world_size > 1, "construct Metrics(comm=...) under torchrun"
+        feats = self._extract(fake_local.to(self.device).float().split(self.batch), generated=True)
+        score = float("nan")
+        if self.feature == "logits":
+            parts = [torch.empty_like(feats) for _ in range(comm.world_size)]
+            dist.all_gather(parts, feats)
+            allf = torch.cat(parts)
+            score = self._score(allf, allf.shape[0], 10)
+        fid = self._fid_from(feats, sharded=True) if self.real_features is not None else float("nan")
         return score, fid

@@ -12,7 +12,7 @@ from jck_generation_b200.inception import InceptionV3
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    model = calibrated_inception(seed=1, calib_batch=1)
+    model = calibrated_inception(seed=1, calib_batch=2)
     flops = [0]
 
     def hook(m, i, o):
