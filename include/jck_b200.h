@@ -293,7 +293,7 @@ int jck_rng_advance(unsigned long long* counter_base, unsigned long long by, voi
  *
  * jck_conv_gemm: out = act(scale[n] * sum_{tap,c} A[m + shift[tap]][c] * W[n][tap*Cp + c] + bias[n]) on tcgen05.
  *   A: bf16 rows [rows_a][C], pitch lda (% 8 == 0); rows outside [0, rows_a) read as zero.  W: bf16 [N][ntaps*Cp],
- *   Cp = C rounded up to 64 (zero filled).  scale / bias: fp32 [N], nullable (1 / 0).  Row m of the M = B*Hq*Wq computed
+ *   Cp = C rounded up to 64, or 32 when C <= 32 (zero filled).  scale / bias: fp32 [N], nullable (1 / 0).  Row m of the M = B*Hq*Wq computed
  *   rows is grid position (b, Y, X); it is stored iff oy = Y - oy0 in [0, Ho) and ox = X - ox0 in [0, Wo), at
  *   out[((b*Hob + oy + opy)*Wob + ox + opx)*ldc + c_off + n], dtype JCK_BF16 or JCK_F32.
  *   geom = {M, N, C, ntaps, Hq, Wq, oy0, ox0, Ho, Wo, Hob, Wob, opy, opx, c_off, relu, out_dtype, rows_a, shift[ntaps]}

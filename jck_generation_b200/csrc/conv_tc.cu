@@ -50,12 +50,13 @@ EncodeTiledFn get_encode() {
 }
 
 int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+           const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return set_error(JCK_E_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims,
-                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(JCK_E_DRIVER, "cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
     return JCK_OK;
@@ -1768,11 +1769,12 @@ int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, void* C, const Gem
 
 // 2-D bf16 tensor map (dims / box innermost first, 128-byte swizzle) for the other translation units (incep.cu)
 int encode_bf16_2d(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long rows,
-                   unsigned long long pitch_bytes, unsigned box_inner, unsigned box_rows) {
+                   unsigned long long pitch_bytes, unsigned box_inner, unsigned box_rows, int swizzle64) {
     cuuint64_t dims[2] = {inner, rows};
     cuuint64_t str[1] = {pitch_bytes};
     cuuint32_t box[2] = {box_inner, box_rows};
-    return encode(m, base, 2, dims, str, box);
+    return encode(m, base, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 }  // namespace jck
 

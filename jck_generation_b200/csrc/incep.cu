@@ -18,7 +18,7 @@
 namespace jck {
 
 int encode_bf16_2d(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long rows,
-                   unsigned long long pitch_bytes, unsigned box_inner, unsigned box_rows);
+                   unsigned long long pitch_bytes, unsigned box_inner, unsigned box_rows, int swizzle64);
 
 namespace {
 using namespace tc;
@@ -26,12 +26,23 @@ using namespace tc;
 constexpr int kCGThreads = 192;
 constexpr int kCGMaxStages = 8;
 constexpr int kCGMaxTaps = 32;
-constexpr int kCGABytes = 128 * 64 * 2;
 constexpr int kCGAccCols = 256;
+
+// K-major operand tile [rows][kw bf16], kw = 64 (128-byte swizzle, layout 2) or 32 (64-byte swizzle, layout 4): 8-row groups
+// of rows x (2 kw) bytes, +32 bytes per UMMA_K = 16 step
+__device__ __forceinline__ uint64_t cg_sdesc(uint32_t smem_addr, int kw) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(((uint32_t)(kw * 16) >> 4) & 0x3FFFu) << 32;       // SBO: 8 rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(kw == 64 ? 2 : 4) << 61;
+    return d;
+}
 
 struct CGParams {
     int M, N, BN, n_tiles, total_tiles;
     int csteps, ksteps, Cp;
+    int kw, a_bytes;           // K chunk per stage: 64 channels (16 KB of A) or, for C <= 32, 32 channels (8 KB, 64-byte swizzle)
     int shift[kCGMaxTaps];
     int Hq, Wq, oy0, ox0, Ho, Wo, Hob, Wob, opy, opx, c_off, relu, out_f32;
     long long ldc;
@@ -48,7 +59,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    const int b_bytes = p.BN * 128;                                    // one K step of the weight tile
+    const int b_bytes = p.BN * 2 * p.kw;                               // one K step of the weight tile
     uint8_t* wres = smem + stages * p.stage_bytes;                     // resident weights (p.resident), else unused
     uint64_t* full = reinterpret_cast<uint64_t*>(wres + (p.resident ? p.ksteps * b_bytes : 0));
     uint64_t* empty = full + kCGMaxStages;
@@ -75,12 +86,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t tx = kCGABytes + (p.resident ? 0 : b_bytes);
+            const uint32_t tx = p.a_bytes + (p.resident ? 0 : b_bytes);
             if (p.resident) {                       // n_tiles == 1: every tile of this CTA uses the same weights
                 mbar_arrive_expect_tx(wfull, (uint32_t)(p.ksteps * b_bytes));
                 for (int ks = 0; ks < p.ksteps; ++ks) {
                     const int tap = ks / p.csteps, cc = ks - tap * p.csteps;
-                    tma_load_2d(wres + ks * b_bytes, &mapB, wfull, tap * p.Cp + cc * 64, 0);
+                    tma_load_2d(wres + ks * b_bytes, &mapB, wfull, tap * p.Cp + cc * p.kw, 0);
                 }
             }
             int it = 0;
@@ -91,11 +102,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const int s = it % stages;
                     mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
                     uint8_t* sa = smem + s * p.stage_bytes;
-                    uint8_t* sb = sa + kCGABytes;
+                    uint8_t* sb = sa + p.a_bytes;
                     mbar_arrive_expect_tx(&full[s], tx);
                     const int tap = ks / p.csteps, cc = ks - tap * p.csteps;
-                    tma_load_2d(sa, &mapA, &full[s], cc * 64, m0 + p.shift[tap]);
-                    if (!p.resident) tma_load_2d(sb, &mapB, &full[s], tap * p.Cp + cc * 64, n0);
+                    tma_load_2d(sa, &mapA, &full[s], cc * p.kw, m0 + p.shift[tap]);
+                    if (!p.resident) tma_load_2d(sb, &mapB, &full[s], tap * p.Cp + cc * p.kw, n0);
                 }
             }
         }
@@ -117,10 +128,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(smem + s * p.stage_bytes);
-                    const uint32_t b_addr = p.resident ? smem_u32(wres + ks * b_bytes) : a_addr + kCGABytes;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_d, make_sdesc(a_addr + k * 32, 0, 1024), make_sdesc(b_addr + k * 32, 0, 1024), idesc,
+                    const uint32_t b_addr = p.resident ? smem_u32(wres + ks * b_bytes) : a_addr + p.a_bytes;
+                    const int nk = p.kw >> 4;
+                    for (int k = 0; k < nk; ++k)
+                        umma_bf16(tmem_d, cg_sdesc(a_addr + k * 32, p.kw), cg_sdesc(b_addr + k * 32, p.kw), idesc,
                                   (ks > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty[s]);
                     if (ks == p.ksteps - 1) umma_commit(&tfull[acc]);
@@ -289,31 +300,39 @@ pool3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ ou
         const int c = (int)(i % cv) * 8;
         const long long m = i / cv;
         const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((long long)Wo * Ho));
+        // all nine 128-bit loads are issued before the first use (clamped addresses; windows cut by the border are masked)
+        uint4 u[9];
+        bool ok[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
+                ok[ky * 3 + kx] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+                const int cy = min(max(iy, 0), H - 1), cx = min(max(ix, 0), W - 1);
+                u[ky * 3 + kx] = __ldg(reinterpret_cast<const uint4*>(x + buf_at(gi, b, cy, cx) + c));
+            }
+        }
         float a[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = mode == 0 ? -INFINITY : 0.f;
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * stride + ky - pad;
-            if (iy < 0 || iy >= H) continue;
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * stride + kx - pad;
-                if (ix < 0 || ix >= W) continue;
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + buf_at(gi, b, iy, ix) + c));
-                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float f = __bfloat162float(h[j]);
-                    a[j] = mode == 0 ? fmaxf(a[j], f) : a[j] + f;
-                }
+        for (int t = 0; t < 9; ++t) {
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u[t]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float f = __bfloat162float(h[j]);
+                if (mode == 0) a[j] = ok[t] ? fmaxf(a[j], f) : a[j];
+                else a[j] += ok[t] ? f : 0.f;
             }
         }
         if (mode == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] *= (1.f / 9.f);
         }
-        uint4 u;
-        u.x = pack_bf16x2(a[0], a[1]); u.y = pack_bf16x2(a[2], a[3]); u.z = pack_bf16x2(a[4], a[5]); u.w = pack_bf16x2(a[6], a[7]);
-        *reinterpret_cast<uint4*>(out + buf_at(go, b, oy, ox) + c) = u;
+        uint4 r;
+        r.x = pack_bf16x2(a[0], a[1]); r.y = pack_bf16x2(a[2], a[3]); r.z = pack_bf16x2(a[4], a[5]); r.w = pack_bf16x2(a[6], a[7]);
+        *reinterpret_cast<uint4*>(out + buf_at(go, b, oy, ox) + c) = r;
     }
 }
 
@@ -484,8 +503,11 @@ extern "C" int jck_conv_gemm(const void* act, long long lda, const void* w, cons
         return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv_gemm: operand pitch / base not 16-byte aligned (lda=%lld)", lda);
     CGParams p;
     p.M = M; p.N = N;
-    p.csteps = (C + 63) / 64;
-    p.Cp = p.csteps * 64;
+    // K chunk: 64 channels; layers with at most 32 channels (the stem) use 32-wide chunks so that no box is half zero-fill
+    p.kw = (C <= 32 && getenv("JCK_CG_NO_K32") == nullptr) ? 32 : 64;
+    p.a_bytes = 128 * p.kw * 2;
+    p.csteps = (C + p.kw - 1) / p.kw;
+    p.Cp = C <= 32 ? 32 : (C + 63) / 64 * 64;      // the weight matrix's pitch per tap (the caller's packing)
     p.ksteps = ntaps * p.csteps;
     p.Hq = geom[4]; p.Wq = geom[5]; p.oy0 = geom[6]; p.ox0 = geom[7]; p.Ho = geom[8]; p.Wo = geom[9];
     p.Hob = geom[10]; p.Wob = geom[11]; p.opy = geom[12]; p.opx = geom[13]; p.c_off = geom[14]; p.relu = geom[15];
@@ -501,20 +523,27 @@ extern "C" int jck_conv_gemm(const void* act, long long lda, const void* w, cons
     p.total_tiles = m_tiles * p.n_tiles;
     // small filter banks stay resident in shared memory for the CTA's whole tile walk (the stem / 1x1 layers would otherwise
     // re-stream as many weight bytes as activation bytes); the ring then carries A only
-    const int w_bytes = p.ksteps * p.BN * 128;
+    const int w_bytes = p.ksteps * p.BN * 2 * p.kw;
     p.resident = (p.n_tiles == 1 && w_bytes <= 96 * 1024 && getenv("JCK_CG_NO_RESIDENT") == nullptr) ? 1 : 0;
-    p.stage_bytes = kCGABytes + (p.resident ? 0 : p.BN * 128);
+    p.stage_bytes = p.a_bytes + (p.resident ? 0 : p.BN * 2 * p.kw);
     p.stages = (200 * 1024 - (p.resident ? w_bytes : 0)) / p.stage_bytes;
     if (p.stages > kCGMaxStages) p.stages = kCGMaxStages;
     p.scale = scale;
     p.bias = bias;
     p.vec_coef = (((uintptr_t)scale & 15) == 0 && ((uintptr_t)bias & 15) == 0) ? 1 : 0;
-    const int smem = p.stages * p.stage_bytes + (p.resident ? w_bytes : 0) + 256 + 1024;
+    // always more than half of the SM's shared memory: ONE CTA per SM.  Two co-resident CTAs (possible with the 8 KB stages of
+    // the 32-channel mode; with programmatic dependent launch also a CTA of the NEXT launch) would serialise on the 512 TMEM
+    // columns each allocates and leave half of the SMs idle (measured: 6.0 -> 7.7 ms per 128 images)
+    int smem = p.stages * p.stage_bytes + (p.resident ? w_bytes : 0) + 256 + 1024;
+    if (smem < 120 * 1024) smem = 120 * 1024;
     CUtensorMap mA, mB;
     int rc;
-    if ((rc = encode_bf16_2d(&mA, act, (unsigned long long)C, (unsigned long long)rows_a, (unsigned long long)lda * 2, 64, 128))) return rc;
-    if ((rc = encode_bf16_2d(&mB, w, (unsigned long long)ntaps * p.Cp, (unsigned long long)N, (unsigned long long)ntaps * p.Cp * 2, 64,
-                             (unsigned)p.BN)))
+    const int sw64 = p.kw == 32;
+    if ((rc = encode_bf16_2d(&mA, act, (unsigned long long)C, (unsigned long long)rows_a, (unsigned long long)lda * 2, (unsigned)p.kw, 128,
+                             sw64)))
+        return rc;
+    if ((rc = encode_bf16_2d(&mB, w, (unsigned long long)ntaps * p.Cp, (unsigned long long)N, (unsigned long long)ntaps * p.Cp * 2,
+                             (unsigned)p.kw, (unsigned)p.BN, sw64)))
         return rc;
     static bool cfg = false;
     if (!cfg) {

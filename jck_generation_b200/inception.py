@@ -25,6 +25,11 @@ def _ceil(v, m):
     return (v + m - 1) // m * m
 
 
+def k_pitch(C):
+    """columns per filter tap of a jck_conv_gemm weight matrix: C rounded up to the kernel's K chunk (32 for C <= 32, else 64)"""
+    return 32 if C <= 32 else _ceil(C, 64)
+
+
 class Buf:
     """NHWC bf16 activation buffer with a zero border of (py, px) pixels; channel pitch ld >= C."""
 
@@ -58,13 +63,13 @@ class _Conv:
         self.implicit = self.stride == 1 and self.C % 8 == 0
         wt = w.permute(0, 2, 3, 1).contiguous()                         # [N][kh][kw][C]
         if self.implicit:
-            self.Cp = _ceil(self.C, 64)
+            self.Cp = k_pitch(self.C)
             wm = torch.zeros(self.N, self.kh * self.kw, self.Cp)
             wm[:, :, :self.C] = wt.view(self.N, self.kh * self.kw, self.C)
         else:
             K = self.kh * self.kw * self.C
             self.Kp = _ceil(K, 8)
-            wm = torch.zeros(self.N, _ceil(self.Kp, 64))
+            wm = torch.zeros(self.N, k_pitch(self.Kp))
             wm[:, :K] = wt.reshape(self.N, K)
         self.w = wm.reshape(self.N, -1).to(dtype).contiguous().to(device)
 

@@ -18,7 +18,7 @@ def _buf_index(geom, ld, B, H, W):
 def conv_gemm(act, lda, w, scale, bias, out, ldc, geom):
     M, N, C, ntaps, Hq, Wq, oy0, ox0, Ho, Wo, Hob, Wob, opy, opx, c_off, relu, out_dtype, rows_a = geom[:18]
     shifts = geom[18:18 + ntaps]
-    Cp = (C + 63) // 64 * 64
+    Cp = 32 if C <= 32 else (C + 63) // 64 * 64
     A = act.view(-1)[:rows_a * lda].view(rows_a, lda)[:, :C].float()
     Wm = w.view(N, ntaps * Cp).float()
     acc = torch.zeros(M, N)

@@ -12,8 +12,8 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     dev = torch.device("cuda")
-    for name, tf32, cl in (("fp32, TF32 off", False, False), ("fp32 storage, TF32 convs (torch default)", True, False),
-                           ("TF32 convs, channels_last", True, True)):
+    # (channels_last is not an option for the reference's code: compute_gradient_penalty's .view(B, -1), dcgan_trainer.py:125)
+    for name, tf32, cl in (("fp32, TF32 off", False, False), ("fp32 storage, TF32 convs (torch default)", True, False)):
         torch.backends.cudnn.allow_tf32 = tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
         torch.backends.cudnn.benchmark = True

@@ -53,8 +53,24 @@ def main():
             times.append((name, a, b, src, net.convs[name]))
             return r
         net._conv = timed
+        others = []
+        for meth in ("_stem", "_pool", "_head"):
+            fn = getattr(net, meth)
+
+            def wrap(*a, __fn=fn, __m=meth, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = __fn(*a, **k)
+                e1.record()
+                others.append((__m, e0, e1))
+                return r
+            setattr(net, meth, wrap)
         net.forward_generated(fake)
         torch.cuda.synchronize()
+        agg = {}
+        for m, e0, e1 in others:
+            agg[m] = agg.get(m, 0.0) + e0.elapsed_time(e1)
+        print("  " + "  ".join(f"{m}: {t * 1e3:.0f} us" for m, t in agg.items()))
         for name, a, b, src, cv in times:
             t = a.elapsed_time(b)
             Ho = (src.H + 2 * cv.pad[0] - cv.kh) // cv.stride + 1

@@ -33,7 +33,7 @@ def _conv_case(B, H, W, C, N, kh, kw, pad, border, out_border, c_off, ldc_extra,
     Ho, Wo = H + 2 * pad[0] - kh + 1, W + 2 * pad[1] - kw + 1
     dst = Buf(B, Ho, Wo, c_off + N + ldc_extra, out_border[0], out_border[1], device="cpu")
     dst.t.fill_(5.0)                                     # sentinel: whatever the kernel must not touch
-    Cp = (C + 63) // 64 * 64
+    Cp = 32 if C <= 32 else (C + 63) // 64 * 64
     w4 = torch.randn(N, C, kh, kw, generator=g) / (C * kh * kw) ** 0.5
     wm = torch.zeros(N, kh * kw, Cp)
     wm[:, :, :C] = w4.permute(0, 2, 3, 1).reshape(N, kh * kw, C)
@@ -60,7 +60,10 @@ def _conv_case(B, H, W, C, N, kh, kw, pad, border, out_border, c_off, ldc_extra,
     (2, 35, 35, 192, 48, 1, 1, (0, 0), (0, 0), (2, 2), 0, 0),          # 1x1 into a bordered buffer
     (2, 35, 35, 48, 64, 5, 5, (2, 2), (2, 2), (0, 0), 64, 128),        # 5x5 into a concat slice
     (2, 35, 35, 96, 96, 3, 3, (1, 1), (1, 1), (0, 0), 128, 32),        # 3x3, C = 96 (ragged 64-chunk)
-    (1, 149, 149, 32, 32, 3, 3, (0, 0), (0, 0), (1, 1), 0, 0),         # valid 3x3, C = 32
+    (1, 149, 149, 32, 32, 3, 3, (0, 0), (0, 0), (1, 1), 0, 0),         # valid 3x3, C = 32 (32-wide K chunks, 64-byte swizzle)
+    (2, 75, 75, 32, 64, 3, 3, (1, 1), (1, 1), (0, 0), 0, 0),           # 3x3 p1, C = 32 -> 64
+    (2, 40, 40, 24, 48, 3, 3, (1, 1), (1, 1), (0, 0), 16, 0),          # C = 24 (ragged 32-chunk)
+    (3, 30, 30, 32, 32, 1, 1, (0, 0), (0, 0), (0, 0), 0, 0),           # 1x1, one 32-wide K step
     (3, 17, 17, 160, 160, 1, 7, (0, 3), (0, 3), (3, 0), 0, 0),         # 1x7
     (3, 17, 17, 160, 192, 7, 1, (3, 0), (3, 0), (0, 0), 192, 384),     # 7x1 into a slice
     (4, 8, 8, 448, 384, 3, 3, (1, 1), (1, 1), (1, 1), 0, 0),           # N = 384 (two 192-column tiles)
