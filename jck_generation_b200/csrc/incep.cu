@@ -30,14 +30,15 @@ constexpr int kCGAccCols = 256;
 
 // K-major operand tile [rows][kw bf16], kw = 64 (128-byte swizzle, layout 2) or 32 (64-byte swizzle, layout 4): 8-row groups
 // of rows x (2 kw) bytes, +32 bytes per UMMA_K = 16 step
-__device__ __forceinline__ uint64_t cg_sdesc(uint32_t smem_addr, int kw) {
+// (the address-independent bits are built once per kernel: the single issuing thread must not spend its cycles on them)
+__device__ __forceinline__ uint64_t cg_sdesc_hi(int kw) {
     uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
     d |= (uint64_t)(((uint32_t)(kw * 16) >> 4) & 0x3FFFu) << 32;       // SBO: 8 rows
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)(kw == 64 ? 2 : 4) << 61;
     return d;
 }
+__device__ __forceinline__ uint64_t cg_sdesc(uint64_t hi, uint32_t smem_addr) { return hi | (uint64_t)((smem_addr >> 4) & 0x3FFFu); }
 
 struct CGParams {
     int M, N, BN, n_tiles, total_tiles;
@@ -112,6 +113,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(p.BN, 0, 0);
+        const uint64_t dhi = cg_sdesc_hi(p.kw);
+        const bool wide = p.kw == 64;
         if (p.resident) {
             mbar_wait(wfull, 0);
             fence_after_sync();
@@ -129,10 +132,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(smem + s * p.stage_bytes);
                     const uint32_t b_addr = p.resident ? smem_u32(wres + ks * b_bytes) : a_addr + p.a_bytes;
-                    const int nk = p.kw >> 4;
-                    for (int k = 0; k < nk; ++k)
-                        umma_bf16(tmem_d, cg_sdesc(a_addr + k * 32, p.kw), cg_sdesc(b_addr + k * 32, p.kw), idesc,
-                                  (ks > 0 || k > 0) ? 1u : 0u);
+                    if (wide) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_d, cg_sdesc(dhi, a_addr + k * 32), cg_sdesc(dhi, b_addr + k * 32), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            umma_bf16(tmem_d, cg_sdesc(dhi, a_addr + k * 32), cg_sdesc(dhi, b_addr + k * 32), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                    }
                     umma_commit(&empty[s]);
                     if (ks == p.ksteps - 1) umma_commit(&tfull[acc]);
                 }
