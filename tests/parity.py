@@ -218,16 +218,16 @@ def autocast_envelope(batch, nc=3, seed=12345, rng_seed=11):
     return {k: rel_err(b[k], a[k]) for k in a}
 
 
-def make_cgan_pair(dtype, lr, seed=12345):
+def make_cgan_pair(dtype, lr, seed=12345, nc=3, n_classes=100):
     from jck_generation_b200 import parallel
     from jck_generation_b200.model import CGAN
     from jck_generation_b200.train.cgan_step import CGANStep
     from jck_generation_b200.train.optim import FusedAdam
-    g_o, d_o = omodels.build("CGAN", seed=seed)
+    g_o, d_o = omodels.build("CGAN", seed=seed, nc=nc, n_classes=n_classes)
     osteps.inject_dropout(d_o)
     og, od = osteps.make_optimizers(g_o, d_o, lr)
-    g = CGAN.Generator(dtype=dtype).cuda()
-    d = CGAN.Discriminator(dtype=dtype).cuda()
+    g = CGAN.Generator(nc=nc, n_classes=n_classes, dtype=dtype).cuda()
+    d = CGAN.Discriminator(nc=nc, n_classes=n_classes, dtype=dtype).cuda()
     g.load_state_dict(g_o.state_dict(), strict=True)
     d.load_state_dict(d_o.state_dict(), strict=True)
     comm = parallel.LocalComm()
@@ -239,13 +239,13 @@ def make_cgan_pair(dtype, lr, seed=12345):
                                  lr=lr)
 
 
-def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11, real=None, labels=None, rng=None, sync_d=True):
+def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11, real=None, labels=None, rng=None, sync_d=True, nc=3, n_classes=100):
     """One CGAN step (incl. the back-propagated gradient penalty) vs the oracle.  Returns {name: rel err}."""
-    P = make_cgan_pair(dtype, lr)
-    real = real if real is not None else osteps.make_real(batch, n_steps=1)[0]
-    rng = rng if rng is not None else osteps.make_rng(batch, n_steps=1, seed=rng_seed, dropout_dim=256)[0]
+    P = make_cgan_pair(dtype, lr, nc=nc, n_classes=n_classes)
+    real = real if real is not None else osteps.make_real(batch, nc=nc, n_steps=1)[0]
+    rng = rng if rng is not None else osteps.make_rng(batch, nc=nc, n_steps=1, seed=rng_seed, dropout_dim=256)[0]
     if labels is None:
-        labels = osteps.one_hot(torch.randint(0, 100, (batch,), generator=torch.Generator().manual_seed(3)), 100)
+        labels = osteps.one_hot(torch.randint(0, n_classes, (batch,), generator=torch.Generator().manual_seed(3)), n_classes)
     want = osteps.cgan_step(P.g_o, P.d_o, P.og, P.od, real, labels, rng, capture=True)
     cap = want["capture"]
     r = to_cuda({k: v for k, v in rng.items() if k != "drop"})
@@ -257,7 +257,7 @@ def cgan_step_parity(dtype, batch=8, lr=2e-4, rng_seed=11, real=None, labels=Non
     for k in ("loss_d", "loss_g", "x_d", "z1_gd", "z2_gd", "gp", "err_real", "err_fake"):
         errs["scalar." + k] = abs(got[k] - want[k]) / max(abs(want[k]), 1e-6)
     errs["fake_raw"] = rel_err(P.step.last["fake_raw"], cap["fake_raw"])
-    errs["gp_grads"] = rel_err(nhwc_to_nchw(P.step.last["gp_grad_nhwc"], 3), cap["gp_grads"])
+    errs["gp_grads"] = rel_err(nhwc_to_nchw(P.step.last["gp_grad_nhwc"], nc), cap["gp_grads"])
     _kink_flips(P.step.last, cap["pre"], batch, errs)
     for (name, p) in P.d.named_parameters():
         errs["d_grad." + name] = rel_err(p.grad, cap["d_grads"][name])
