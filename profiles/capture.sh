@@ -19,3 +19,9 @@ ncu --set full --clock-control none --import-source on -k regex:'edge_up_scatter
 # spends parked in griddepcontrol.wait behind its predecessor
 JCK_PDL=0 python bench.py --no-cpu-baseline --kernel-table --steps 5 --warmup 3 > gpurun_out/ktable.log 2> gpurun_out/ktable.err
 tail -n 3 gpurun_out/ncu_list.log gpurun_out/ncu_conv.log gpurun_out/ncu_edge.log
+
+# Inception-v3 extractor (metrics.py path): launch list of two eager forwards, then --set full of the conv kernel
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_incep_r1.csv \
+    python tests/notes/incep_ncu.py > gpurun_out/ncu_incep_list.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_gemm --launch-skip 95 --launch-count 32 -f \
+    -o gpurun_out/prof_incep_r1 python tests/notes/incep_ncu.py > gpurun_out/ncu_incep.log 2>&1

@@ -67,3 +67,18 @@ def test_inception_score_emulator_matches_scipy():
         py = part.mean(0)
         want = np.exp(np.mean([entropy(part[i], py) for i in range(50)]))
         assert abs(float(scores[k]) - want) < 1e-4 * want
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour WITHOUT a CUDA device")
+def test_no_cpu_path_in_the_product(model, tmp_path, monkeypatch):
+    """the product has no CPU route: Metrics refuses to construct, and the extractor with the real backend refuses CPU tensors"""
+    from jck_generation_b200.inception import InceptionV3
+    from jck_generation_b200.metrics import Metrics
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Metrics(None)
+    net = InceptionV3(model.state_dict(), device="cpu", use_graph=False)          # K defaults to the C ABI
+    with pytest.raises(AssertionError, match="CUDA"):
+        net.forward(torch.zeros(1, 3, 299, 299))
+    with pytest.raises(AssertionError, match="bf16"):
+        InceptionV3(model.state_dict(), device="cpu", act_dtype=torch.float32)   # fp32 buffers exist only for the emulator
