@@ -48,10 +48,115 @@ struct CGParams {
     int Hq, Wq, oy0, ox0, Ho, Wo, Hob, Wob, opy, opx, c_off, relu, out_f32;
     long long ldc;
     int stages, stage_bytes, vec_coef;
+    // window mode (conv_gemm_window_kernel): the rows [m0 + smin, m0 + 128 + smax) of a tile are loaded ONCE per 64-channel
+    // chunk and every tap reads them at a row offset through its shared-memory descriptor
+    int smin, wboxes, win_bytes, wstages;
     int resident;              // 1: the whole weight matrix (ksteps boxes of BN x 64) stays in shared memory; the ring carries A only
     const float* scale;
     const float* bias;
 };
+
+// Epilogue warps (2..5) of both conv kernels: TMEM accumulator -> scale / bias / ReLU -> masked, re-mapped store.
+__device__ __forceinline__ void cg_epilogue(const CGParams& p, void* __restrict__ out, uint32_t tmem_base, uint64_t* tfull,
+                                            uint64_t* tempty, int warp, int lane) {
+    const int wq = warp & 3;
+    const int plane = p.Hq * p.Wq;
+    const int chunks = p.BN >> 4;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int m = mt * 128 + wq * 32 + lane, n0 = nt * p.BN;
+        const int b = m / plane, r = m - b * plane;
+        const int Y = r / p.Wq, X = r - Y * p.Wq;
+        const int oy = Y - p.oy0, ox = X - p.ox0;
+        const bool valid = m < p.M && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo;
+        const long long orow = (((long long)b * p.Hob + oy + p.opy) * p.Wob + ox + p.opx) * p.ldc + p.c_off;
+        const int acc = lt & 1;
+        const uint32_t tmem_d = tmem_base + acc * kCGAccCols + ((uint32_t)(wq * 32) << 16);
+        mbar_wait(&tfull[acc], (lt >> 1) & 1);
+        fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < chunks; ++c) {
+            const int nb = n0 + c * 16;
+            const bool full16 = nb + 16 <= p.N;
+            // this chunk's BatchNorm coefficients (L1-resident after the CTA's first tile), issued before the TMEM read
+            float4 sc[4], bi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sc[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+                bi[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (full16 && p.vec_coef) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (p.scale) sc[q] = __ldg(reinterpret_cast<const float4*>(p.scale + nb) + q);
+                    if (p.bias) bi[q] = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + q);
+                }
+            }
+            float v[16];
+            tmem_ld16(tmem_d + c * 16, v);
+            tmem_ld_wait();
+            if (c == chunks - 1) {
+                fence_before_sync();
+                mbar_arrive(&tempty[acc]);
+            }
+            if (!valid || nb >= p.N) continue;
+            if (full16 && p.vec_coef) {
+                const float* scf = reinterpret_cast<const float*>(sc);
+                const float* bif = reinterpret_cast<const float*>(bi);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float x = fmaf(v[i], scf[i], bif[i]);
+                    v[i] = p.relu ? fmaxf(x, 0.f) : x;
+                }
+                if (p.out_f32) {
+                    float* o = reinterpret_cast<float*>(out) + orow + nb;
+                    if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = v[i];
+                    }
+                } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow + nb;
+                    uint4 u0, u1;
+                    u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
+                    u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
+                    u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
+                    u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(o);
+                    if ((a & 31) == 0) {
+                        st_global_256(o, u0, u1);
+                    } else if ((a & 15) == 0) {
+                        reinterpret_cast<uint4*>(o)[0] = u0;
+                        reinterpret_cast<uint4*>(o)[1] = u1;
+                    } else {
+                        const __nv_bfloat16* h0 = reinterpret_cast<const __nv_bfloat16*>(&u0);
+                        const __nv_bfloat16* h1 = reinterpret_cast<const __nv_bfloat16*>(&u1);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { o[i] = h0[i]; o[8 + i] = h1[i]; }
+                    }
+                }
+            } else {
+                // ragged last chunk (the fc layer's N = 100) or unaligned coefficient vectors: element by element
+                const int nv = min(16, p.N - nb);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (i < nv) {
+                        const float s1 = p.scale ? __ldg(p.scale + nb + i) : 1.f;
+                        const float b1 = p.bias ? __ldg(p.bias + nb + i) : 0.f;
+                        float x = fmaf(v[i], s1, b1);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        if (p.out_f32) reinterpret_cast<float*>(out)[orow + nb + i] = x;
+                        else reinterpret_cast<__nv_bfloat16*>(out)[orow + nb + i] = __float2bfloat16_rn(x);
+                    }
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kCGThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void* __restrict__ out,
@@ -148,103 +253,154 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
     } else {
-        const int wq = warp & 3;
-        const int plane = p.Hq * p.Wq;
-        const int chunks = p.BN >> 4;
-        int lt = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-            const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-            const int m = mt * 128 + wq * 32 + lane, n0 = nt * p.BN;
-            const int b = m / plane, r = m - b * plane;
-            const int Y = r / p.Wq, X = r - Y * p.Wq;
-            const int oy = Y - p.oy0, ox = X - p.ox0;
-            const bool valid = m < p.M && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo;
-            const long long orow = (((long long)b * p.Hob + oy + p.opy) * p.Wob + ox + p.opx) * p.ldc + p.c_off;
-            const int acc = lt & 1;
-            const uint32_t tmem_d = tmem_base + acc * kCGAccCols + ((uint32_t)(wq * 32) << 16);
-            mbar_wait(&tfull[acc], (lt >> 1) & 1);
-            fence_after_sync();
-#pragma unroll 1
-            for (int c = 0; c < chunks; ++c) {
-                const int nb = n0 + c * 16;
-                const bool full16 = nb + 16 <= p.N;
-                // this chunk's BatchNorm coefficients (L1-resident after the CTA's first tile), issued before the TMEM read
-                float4 sc[4], bi[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    sc[q] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    bi[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cg_epilogue(p, out, tmem_base, tfull, tempty, warp, lane);
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 2 * kCGAccCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window variant.  The kernel above re-reads the activations once per filter tap (nine shifted boxes for a 3 x 3), which
+// makes every multi-tap layer L2 -> shared-memory bound (profiles/r01_ncu_incep.md).  Here the producer loads the row WINDOW
+// [m0 + smin, m0 + 128 + smax) of a tile once per channel chunk (wboxes boxes of 128 rows), and tap t is the SAME shared
+// memory read through a descriptor that starts (shift[t] - smin) rows further down.  Measured on sm_100a: the tensor core
+// applies the 128-byte (64-byte) swizzle to the ABSOLUTE shared-memory address, exactly as TMA wrote it, so a start address
+// that is not a multiple of the 8-row pattern needs NO base offset in the descriptor (leaving bits 49-51 zero gives exact
+// results for every shift; setting them to (address >> 7) & 7 gives wrong ones).  K order is chunk-major / tap-minor; the
+// weights are still indexed [tap][chunk].
+// Weights: resident (as above) or streamed through the `full / empty` ring, one BN x kw tile per (chunk, tap).
+// ------------------------------------------------------------------------------------------------
+constexpr int kCGMaxWin = 4;
+
+__global__ void __launch_bounds__(kCGThreads, 1)
+conv_gemm_window_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, void* __restrict__ out,
+                        const __grid_constant__ CGParams p) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages, wstages = p.wstages;
+    const int b_bytes = p.BN * 2 * p.kw;
+    const int ntaps = p.ksteps / p.csteps;
+    uint8_t* win = smem;                                              // [wstages][win_bytes]
+    uint8_t* bring = smem + wstages * p.win_bytes;                    // resident: [ksteps][b_bytes]; else ring [stages][b_bytes]
+    uint64_t* full = reinterpret_cast<uint64_t*>(bring + (p.resident ? p.ksteps : stages) * b_bytes);
+    uint64_t* empty = full + kCGMaxStages;
+    uint64_t* tfull = empty + kCGMaxStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wfull = tempty + 2;
+    uint64_t* winf = wfull + 1;
+    uint64_t* wine = winf + kCGMaxWin;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wine + kCGMaxWin);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < wstages; ++s) { mbar_init(&winf[s], 1); mbar_init(&wine[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * kCGAccCols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            if (p.resident) {
+                mbar_arrive_expect_tx(wfull, (uint32_t)(p.ksteps * b_bytes));
+                for (int ks = 0; ks < p.ksteps; ++ks) {
+                    const int tap = ks / p.csteps, cc = ks - tap * p.csteps;
+                    tma_load_2d(bring + ks * b_bytes, &mapB, wfull, tap * p.Cp + cc * p.kw, 0);
                 }
-                if (full16 && p.vec_coef) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (p.scale) sc[q] = __ldg(reinterpret_cast<const float4*>(p.scale + nb) + q);
-                        if (p.bias) bi[q] = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + q);
-                    }
-                }
-                float v[16];
-                tmem_ld16(tmem_d + c * 16, v);
-                tmem_ld_wait();
-                if (c == chunks - 1) {
-                    fence_before_sync();
-                    mbar_arrive(&tempty[acc]);
-                }
-                if (!valid || nb >= p.N) continue;
-                if (full16 && p.vec_coef) {
-                    const float* scf = reinterpret_cast<const float*>(sc);
-                    const float* bif = reinterpret_cast<const float*>(bi);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x = fmaf(v[i], scf[i], bif[i]);
-                        v[i] = p.relu ? fmaxf(x, 0.f) : x;
-                    }
-                    if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(out) + orow + nb;
-                        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = v[i];
-                        }
-                    } else {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow + nb;
-                        uint4 u0, u1;
-                        u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
-                        u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
-                        u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
-                        u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
-                        const uintptr_t a = reinterpret_cast<uintptr_t>(o);
-                        if ((a & 31) == 0) {
-                            st_global_256(o, u0, u1);
-                        } else if ((a & 15) == 0) {
-                            reinterpret_cast<uint4*>(o)[0] = u0;
-                            reinterpret_cast<uint4*>(o)[1] = u1;
-                        } else {
-                            const __nv_bfloat16* h0 = reinterpret_cast<const __nv_bfloat16*>(&u0);
-                            const __nv_bfloat16* h1 = reinterpret_cast<const __nv_bfloat16*>(&u1);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) { o[i] = h0[i]; o[8 + i] = h1[i]; }
-                        }
-                    }
-                } else {
-                    // ragged last chunk (the fc layer's N = 100) or unaligned coefficient vectors: element by element
-                    const int nv = min(16, p.N - nb);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (i < nv) {
-                            const float s1 = p.scale ? __ldg(p.scale + nb + i) : 1.f;
-                            const float b1 = p.bias ? __ldg(p.bias + nb + i) : 0.f;
-                            float x = fmaf(v[i], s1, b1);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            if (p.out_f32) reinterpret_cast<float*>(out)[orow + nb + i] = x;
-                            else reinterpret_cast<__nv_bfloat16*>(out)[orow + nb + i] = __float2bfloat16_rn(x);
+            }
+            // the window of job (tile, chunk) j + 1 is requested BEFORE the weight tiles of job j, so that its latency hides
+            // behind job j's MMAs instead of behind the weight ring's back-pressure
+            int iw = 0, ib = 0;
+            int tw = blockIdx.x, ccw = 0;
+            auto issue_window = [&]() {
+                if (tw >= p.total_tiles) return;
+                const int m0w = (tw / p.n_tiles) * 128;
+                const int ws = iw % wstages;
+                mbar_wait(&wine[ws], ((iw / wstages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&winf[ws], (uint32_t)(p.wboxes * p.a_bytes));
+                for (int bx = 0; bx < p.wboxes; ++bx)
+                    tma_load_2d(win + ws * p.win_bytes + bx * p.a_bytes, &mapA, &winf[ws], ccw * p.kw, m0w + p.smin + bx * 128);
+                ++iw;
+                if (++ccw == p.csteps) { ccw = 0; tw += gridDim.x; }
+            };
+            issue_window();
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int n0 = (t % p.n_tiles) * p.BN;
+                for (int cc = 0; cc < p.csteps; ++cc) {
+                    issue_window();
+                    if (!p.resident) {
+                        for (int tap = 0; tap < ntaps; ++tap, ++ib) {
+                            const int s = ib % stages;
+                            mbar_wait(&empty[s], ((ib / stages) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)b_bytes);
+                            tma_load_2d(bring + s * b_bytes, &mapB, &full[s], tap * p.Cp + cc * p.kw, n0);
                         }
                     }
                 }
             }
         }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(p.BN, 0, 0);
+        const uint64_t dhi = cg_sdesc_hi(p.kw);
+        const int row_bytes = 2 * p.kw;
+        const int nk = p.kw >> 4;
+        if (p.resident) {
+            mbar_wait(wfull, 0);
+            fence_after_sync();
+        }
+        int iw = 0, ib = 0, lt = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
+            const int acc = lt & 1;
+            mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);
+            fence_after_sync();
+            const uint32_t tmem_d = tmem_base + acc * kCGAccCols;
+            for (int cc = 0; cc < p.csteps; ++cc, ++iw) {
+                const int ws = iw % wstages;
+                mbar_wait(&winf[ws], (iw / wstages) & 1);
+                fence_after_sync();
+                const uint32_t w_addr = smem_u32(win + ws * p.win_bytes);
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    int s = 0;
+                    if (!p.resident) {
+                        s = ib % stages;
+                        mbar_wait(&full[s], (ib / stages) & 1);
+                        fence_after_sync();
+                        ++ib;
+                    }
+                    if (lane == 0) {
+                        const uint32_t a_addr = w_addr + (uint32_t)((p.shift[tap] - p.smin) * row_bytes);
+                        const uint32_t b_addr = smem_u32(bring + (p.resident ? (tap * p.csteps + cc) : s) * b_bytes);
+                        for (int k = 0; k < nk; ++k)
+                            umma_bf16(tmem_d, cg_sdesc(dhi, a_addr + k * 32), cg_sdesc(dhi, b_addr + k * 32), idesc,
+                                      (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        if (!p.resident) umma_commit(&empty[s]);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    umma_commit(&wine[ws]);
+                    if (cc == p.csteps - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        cg_epilogue(p, out, tmem_base, tfull, tempty, warp, lane);
     }
 
     fence_before_sync();
@@ -556,10 +712,39 @@ extern "C" int jck_conv_gemm(const void* act, long long lda, const void* w, cons
     static bool cfg = false;
     if (!cfg) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_gemm smem attr: %s", cudaGetErrorString(e));
         cfg = true;
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    // window kernel: multi-tap layers whose filter bank is resident (measured: the two 32-channel 3 x 3 stem layers 531 -> 480 and
+    // 547 -> 496 us per 128 images); with streamed weights it measured SLOWER than the tap-streaming kernel (Conv2d_4a 338 -> 398
+    // us) before the producer was reordered, so those layers stay on the kernel above unless JCK_CG_WINDOW=all; JCK_CG_WINDOW=0
+    // turns the window kernel off
+    const char* wenv = getenv("JCK_CG_WINDOW");
+    const bool win_all = wenv && wenv[0] == 'a';
+    const bool win_off = wenv && wenv[0] == '0';
+    if (ntaps > 1 && !win_off && (p.resident || win_all)) {
+        int smin = p.shift[0], smax = p.shift[0];
+        for (int t = 1; t < ntaps; ++t) { smin = p.shift[t] < smin ? p.shift[t] : smin; smax = p.shift[t] > smax ? p.shift[t] : smax; }
+        p.smin = smin;
+        p.wboxes = (128 + (smax - smin) + 127) / 128;
+        p.win_bytes = p.wboxes * p.a_bytes;
+        const int b_bytes = p.BN * 2 * p.kw;
+        p.stages = p.resident ? 1 : 4;                       // weight ring depth (unused when resident)
+        const int b_region = p.resident ? w_bytes : p.stages * b_bytes;
+        p.wstages = (200 * 1024 - b_region) / p.win_bytes;
+        if (p.wstages > kCGMaxWin) p.wstages = kCGMaxWin;
+        if (p.wstages >= 2) {
+            int wsmem = p.wstages * p.win_bytes + b_region + 256 + 1024;
+            if (wsmem < 120 * 1024) wsmem = 120 * 1024;
+            launch_pdl(conv_gemm_window_kernel, dim3(grid), dim3(kCGThreads), wsmem, as_stream(stream), mA, mB, out, p);
+            JCK_LAUNCH_CHECK("conv_gemm_window");
+            return JCK_OK;
+        }
+        p.stages = (200 * 1024 - (p.resident ? w_bytes : 0)) / p.stage_bytes;      // does not fit: the tap-streaming kernel
+        if (p.stages > kCGMaxStages) p.stages = kCGMaxStages;
+    }
     launch_pdl(conv_gemm_kernel, dim3(grid), dim3(kCGThreads), smem, as_stream(stream), mA, mB, out, p);
     JCK_LAUNCH_CHECK("conv_gemm");
     return JCK_OK;

@@ -1,6 +1,8 @@
 """Tensor-level wrappers over the C ABI (include/jck_b200.h).  PyTorch is plumbing here: it owns
 device memory and streams; every arithmetic kernel is ours.  Nothing in this module computes on
 the CPU or through torch operators."""
+import ctypes as _ct
+
 import torch
 
 from . import _lib
@@ -435,9 +437,6 @@ def bn_adj_param(asums, mr, dgamma, C, scale=1.0):
 
 
 # ---- Inception-v3 feature extractor (metrics.py) -----------------------------------------------------------------
-import ctypes as _ct
-
-
 def _ints(vals):
     return (_ct.c_int * len(vals))(*[int(v) for v in vals])
 
