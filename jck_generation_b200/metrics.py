@@ -137,15 +137,32 @@ class Metrics:
             total += self.fid(loader, intra_fid=True, label=sidx)
         return total / 100
 
-    def evaluate_generated(self, fake):
-        """The reference's eval branch (dcgan_trainer.py:198-211) on the device: `fake` is the generator's output in
-        [-1, 1]; de-normalise / resize to 299 / ImageNet-normalise are fused into the Inception stem kernel, the features
-        are extracted ONCE and feed both the score and the FID (the reference runs the network twice)."""
+    def evaluate_generated(self, fake, intra=False):
+        """The reference's eval branch (dcgan_trainer.py:198-211, cgan_trainer.py:221-235) on the device: `fake` is the
+        generator's output in [-1, 1]; de-normalise / resize to 299 / ImageNet-normalise are fused into the Inception stem
+        kernel, and the features are extracted ONCE and feed the score, the FID and -- with `intra` (CGAN: `fake` holds the
+        1000 class-ordered samples of cgan_trainer.py:146-153) -- the intra-FID; the reference runs the network 22 times.
+        Returns (score, fid) or (score, fid, intra_fid)."""
         fake = fake.to(self.device).float()
         feats = self._extract(fake.split(self.batch), generated=True)
         score = self._score(feats, feats.shape[0], 10) if self.feature == "logits" else float("nan")
         fid = self._fid_from(feats) if self.real_features is not None else float("nan")
-        return score, fid
+        if not intra:
+            return score, fid
+        return score, fid, self._intra_fid_from(feats)
+
+    def _intra_fid_from(self, feats):
+        """metrics.py:133-141 on already extracted features: the FID of every CIFAR-100 superclass's generated rows against
+        that superclass's real rows, summed and divided by 100 (sic)."""
+        if self.real_features is None or not self.real_superclass_idx:
+            return float("nan")
+        total = 0.0
+        for sidx in range(20):
+            rows = self.fake_superclass_idx[sidx]
+            if not rows or max(rows) >= feats.shape[0] or not self.real_superclass_idx.get(sidx):
+                return float("nan")           # not the 1000-sample class-ordered set / a superclass without real rows
+            total += self._fid_from(feats[rows], intra_fid=True, label=sidx)
+        return total / 100
 
     def evaluate_generated_sharded(self, fake_local):
         """Data-parallel evaluation (BASELINE configs[4]: 50 k generated samples over 8 GPUs): every rank passes ITS rows of

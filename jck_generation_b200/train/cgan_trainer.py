@@ -178,13 +178,15 @@ class CGANTrainer(Trainer):
                     flush()
                     with torch.no_grad():
                         fake = self.model_g(fixed_noise, fixed_labels).detach()
-                    inception_score, fid = self.metric.evaluate_generated(fake)
-                    intra_fid = float("nan")
+                    inception_score, fid, intra_fid = self.metric.evaluate_generated(fake, intra=True)
                     self.logger.debug(f'inception score: {inception_score}\tfid: {fid}\tintra fid: {intra_fid}')
                     denorm = (0.5 * fake + 0.5)[::10]
                     if low_fid > fid:
                         low_fid = fid
                         self.save_model('fid', iters, inception_score, fid, intra_fid, denorm)
+                    if low_intra_fid > intra_fid:            # cgan_trainer.py:242-245 (never true for a NaN intra-FID)
+                        low_intra_fid = intra_fid
+                        self.save_model('intra_fid', iters, inception_score, fid, intra_fid, denorm)
                     if high_is < inception_score:
                         high_is = inception_score
                         self.save_model('is', iters, inception_score, fid, intra_fid, denorm)
