@@ -58,3 +58,71 @@ def test_intra_fid_from_features_matches_reference_formula():
     assert np.isnan(m._intra_fid_from(gen[:64]))
     m.real_superclass_idx = {}
     assert np.isnan(m._intra_fid_from(gen))
+
+
+REF_ROOT = "/root/reference"
+
+
+def _load_reference_metrics():
+    """the reference's own metrics.py, imported from where it lies (never copied); its module-level imports need the
+    reference root on sys.path (`from utils import get_default_device`)"""
+    import importlib.util
+    import os
+    import sys
+    if not os.path.isfile(os.path.join(REF_ROOT, "metrics.py")):
+        return None
+    saved = {k: sys.modules.get(k) for k in ("utils", "metrics")}
+    sys.path.insert(0, REF_ROOT)
+    try:
+        spec = importlib.util.spec_from_file_location("_jck_ref_metrics", os.path.join(REF_ROOT, "metrics.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(REF_ROOT)
+        for k, v in saved.items():
+            if v is None:
+                m = sys.modules.get(k)
+                if m is not None and (getattr(m, "__file__", "") or "").startswith(REF_ROOT):
+                    del sys.modules[k]
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def test_formulas_against_the_live_reference_class():
+    """Pin against the reference ITSELF (metrics.py:96-141), run here: its unmodified `inception_score`, `fid` and
+    `intra_fid` methods on an instance whose private feature extractor is replaced by a table lookup (the constructor needs a
+    checkpoint and CIFAR-100, metrics.py:51,56), against ours on the same features with the device pieces stubbed."""
+    import pytest
+    ref = _load_reference_metrics()
+    if ref is None:
+        pytest.skip("/root/reference is not present on this machine")
+    rng = np.random.default_rng(1)
+    d = 8
+    real_targets = rng.integers(0, 100, 3000)
+    real = (rng.normal(size=(3000, d)) + real_targets[:, None] * 0.02).astype(np.float32)
+    logits = torch.from_numpy(rng.normal(size=(1000, d)).astype(np.float32) * 1.5 + 0.3)
+    ours = _stub_metrics(real, real_targets)
+
+    r = object.__new__(ref.Metrics)
+    r.real_features = real
+    r.real_superclass_idx, r.fake_superclass_idx = ours.real_superclass_idx, ours.fake_superclass_idx
+
+    def extract(images, real=False, softmax=False):            # images: DataLoader over ROW INDICES into `logits`
+        rows = torch.cat([b for b in images]).long()
+        f = logits[rows]
+        return torch.softmax(f, dim=1).numpy() if softmax else f.numpy()
+    r._Metrics__extract_features = extract
+    idx = torch.arange(1000)
+    loader = torch.utils.data.DataLoader(idx, batch_size=128)
+    want_is = r.inception_score(loader, splits=10)
+    want_fid = r.fid(loader)
+    want_intra = r.intra_fid(idx)
+
+    from tests import incep_emul as emu
+    scores = torch.zeros(10)
+    emu.inception_score(logits, 10, scores)                      # the score kernel's restatement (GPU test: kernel == scipy)
+    assert abs(float(scores.mean()) - want_is) <= 1e-5 * want_is
+    f64 = logits
+    assert abs(ours._fid_from(f64) - want_fid) <= 1e-6 * abs(want_fid)
+    assert abs(ours._intra_fid_from(f64) - want_intra) <= 1e-6 * abs(want_intra)
