@@ -92,7 +92,7 @@ class InceptionV3:
             self.fc_w = sd[fcw[0]].to(act_dtype).contiguous().to(self.device)              # [100][2048]
             self.fc_b = sd[fcw[0][:-len("weight")] + "bias"].float().contiguous().to(self.device)
         self._bufs = {}
-        self._graphs = {}          # one CUDA graph of the ~115 launches per input shape (the launches are 10-100 us each)
+        self._graphs = {}          # one CUDA graph of the 114 launches per input shape (the launches are 10-100 us each)
         self.use_graph = use_graph
         self.launches = 0
 
