@@ -7,8 +7,8 @@ so the reference's `./save/iception_v3/loss_bset.pt` loads unchanged -- runs as 
 `jck_conv_gemm` (tcgen05, bf16 operands, fp32 accumulation; eval-mode BatchNorm folded into the fp32 epilogue), 13 pooling
 launches, one global average pool and the fc GEMM.  Activations are NHWC bf16 buffers that carry the zero border their
 stride-1 consumer needs, so a kh x kw convolution is kh*kw shifted 2-D TMA boxes of the producer's buffer and the
-concatenations of the Inception blocks are channel slices of one output buffer; only the five stride-2 convolutions and the
-3-channel stem go through an explicit patch matrix (`jck_im2col`).
+concatenations of the Inception blocks are channel slices of one output buffer; only the five stride-2 convolutions go
+through an explicit patch matrix (`jck_im2col`; the 3-channel stem's comes straight from the un-resized images, `jck_stem_patches`).
 
 `K` is the kernel backend: `jck_generation_b200.ops` (the C ABI) -- there is no CPU path in the product.  The tests inject
 `tests/incep_emul.py`, a torch restatement of the SAME primitives, to check this host graph on a machine without a GPU.
