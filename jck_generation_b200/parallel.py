@@ -138,12 +138,22 @@ def init_from_env(backend=None):
     return comm
 
 
+def env_rank_world():
+    """(rank, world size) torchrun's environment describes; (0, 1) when launched plainly"""
+    return int(os.environ.get("RANK", "0")), max(1, int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def local_slice(n, rank, world):
+    """Rows of an n-row GLOBAL batch that rank `rank` of `world` trains on: n // world consecutive rows (SURVEY.md 8e: rank r
+    owns rows [r B/W, (r+1) B/W)); when world does not divide n the last n % world rows are dropped on every rank so that all
+    ranks keep the same local batch (SyncBN's sample count is static)."""
+    per = n // world
+    return slice(rank * per, (rank + 1) * per)
+
+
 def shard_rows(t, comm):
     """Rows of a global per-sample tensor owned by this rank."""
-    n = t.shape[0]
-    assert n % comm.world_size == 0, "global batch must divide by the world size"
-    per = n // comm.world_size
-    return t[comm.rank * per:(comm.rank + 1) * per]
+    return t[local_slice(t.shape[0], comm.rank, comm.world_size)]
 
 
 class FlatParams:

@@ -51,16 +51,21 @@ class CGANDataPreprocessor:
         self._logger.debug('data transform')
 
     def get_data_loader(self):
+        # data parallel (torchrun): args.batch_size is the GLOBAL batch.  The device and synthetic loaders hand every rank its
+        # own rows; the host DataLoader yields global batches and the trainer takes the rank's rows (`global_batches`).
+        from ..parallel import env_rank_world
+        rank, world = env_rank_world()
+        self.global_batches = self._u8 is None and not self.synthetic
         if self._u8 is not None:
             # Resize(64) / ToTensor / Normalize + OneHotEncoder (:49-62) and the loaders (:82-92) on the device
             from .device_pipeline import DeviceImageLoader
             data, targets = self._u8
             n_cls = self.n_classes if self.synthetic else len(self._trainset.classes)
             self.trainloader = DeviceImageLoader(data, targets, self.batch_size, 64, [0.5] * 3, [0.5] * 3, shuffle=True,
-                                                 n_classes=n_cls)
+                                                 n_classes=n_cls, rank=rank, world=world)
             self.inceptionloader = DeviceImageLoader(data, targets, 128, (299, 299), IMAGENET_MEAN, IMAGENET_STD, shuffle=False)
         elif self.synthetic:
-            self.trainloader = SyntheticLoader(self.batch_size, self.synthetic_batches, n_classes=self.n_classes)
+            self.trainloader = SyntheticLoader(self.batch_size, self.synthetic_batches, n_classes=self.n_classes, rank=rank, world=world)
             self.inceptionloader = None
         else:
             self.trainloader = torch.utils.data.DataLoader(self._trainset, self.batch_size, shuffle=True,

@@ -68,15 +68,21 @@ class DCGANDataPreprocessor:
         self._logger.debug('data transform')
 
     def get_data_loader(self):
+        # data parallel (torchrun): args.batch_size is the GLOBAL batch.  The device and synthetic loaders hand every rank its
+        # own rows; the host DataLoader yields global batches and the trainer takes the rank's rows (`global_batches`).
+        from ..parallel import env_rank_world
+        rank, world = env_rank_world()
+        self.global_batches = self._u8 is None and not self.synthetic
         if self._u8 is not None:
             # the reference's two transforms (:37-49) and loaders (:69-75) on the device, bit-identical results
             from .device_pipeline import DeviceImageLoader
             data, targets = self._u8
-            self.trainloader = DeviceImageLoader(data, targets, self.batch_size, 64, [0.5] * 3, [0.5] * 3, shuffle=True)
+            self.trainloader = DeviceImageLoader(data, targets, self.batch_size, 64, [0.5] * 3, [0.5] * 3, shuffle=True,
+                                                 rank=rank, world=world)
             self.inceptionloader = DeviceImageLoader(data, targets, self.batch_size * 2, (299, 299), IMAGENET_MEAN, IMAGENET_STD,
                                                      shuffle=False)
         elif self.synthetic:
-            self.trainloader = SyntheticLoader(self.batch_size, self.synthetic_batches)
+            self.trainloader = SyntheticLoader(self.batch_size, self.synthetic_batches, rank=rank, world=world)
             self.inceptionloader = None
         else:
             self.trainloader = torch.utils.data.DataLoader(self._trainset, self.batch_size, shuffle=True,

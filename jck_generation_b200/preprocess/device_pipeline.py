@@ -68,9 +68,12 @@ class DeviceImageLoader:
     """Iterable of (images fp32 [B, C, size_h, size_w] on the device, labels) with the reference loader's contract.
     labels: int64 one-hot [B, n_classes] when `n_classes` is given (CGAN), else int64 class indices [B]."""
 
-    def __init__(self, data_u8, targets, batch_size, size, mean, std, shuffle=True, n_classes=None, device="cuda"):
+    def __init__(self, data_u8, targets, batch_size, size, mean, std, shuffle=True, n_classes=None, device="cuda", rank=0, world=1):
+        """rank / world: data parallel -- `batch_size` is the GLOBAL batch; every rank draws the same index batch (same torch
+        seed on all ranks, main.py:34) and gathers only its own rows (parallel.local_slice), so no row is processed twice."""
         from .. import _lib
         self._lib = _lib
+        self.rank, self.world = rank, world
         data_u8 = np.ascontiguousarray(data_u8)
         assert data_u8.dtype == np.uint8 and data_u8.ndim == 4, "dataset must be uint8 [N, H, W, C]"
         self.N, self.Hi, self.Wi, self.C = data_u8.shape
@@ -119,5 +122,10 @@ class DeviceImageLoader:
         return out, onehot
 
     def __iter__(self):
+        from ..parallel import local_slice
         for index in self._index_loader:
+            if self.world > 1:
+                index = index[local_slice(index.numel(), self.rank, self.world)]
+                if index.numel() == 0:
+                    continue
             yield self.batch(index)

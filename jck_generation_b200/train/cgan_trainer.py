@@ -168,6 +168,8 @@ class CGANTrainer(Trainer):
         for epoch in range(self.epoch):
             for i, data in enumerate(DevicePrefetcher(real_images_loader, self.device)):
                 real_data, labels_data = data
+                if getattr(self.data_pre, "global_batches", False):      # host DataLoader under torchrun: this rank's rows
+                    real_data, labels_data = parallel.shard_rows(real_data, self.comm), parallel.shard_rows(labels_data, self.comm)
                 real_data = real_data.contiguous().float()
                 scal = self.train_step(real_data, labels_data)
                 pending.append((epoch, i, scal if not self.use_graph else scal.clone()))

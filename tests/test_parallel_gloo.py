@@ -110,3 +110,23 @@ def test_flat_params_keep_module_semantics():
     assert torch.equal(lin.weight.detach(), before["weight"] * 2)
     lin.load_state_dict(before)            # in-place copy keeps the views alive
     assert torch.equal(flat.views(flat.flat)[0], before["weight"])
+
+
+def test_rank_rows_of_a_global_batch():
+    """data parallel loaders: the batch size is the GLOBAL batch, rank r owns rows [r B/W, (r+1) B/W); the ranks'
+    rows tile the global batch without overlap, a remainder is dropped on every rank"""
+    import torch
+    from jck_generation_b200 import parallel
+    from jck_generation_b200.preprocess.synthetic import SyntheticLoader
+    for n, world in ((512, 8), (128, 4), (37, 2), (5, 8)):
+        rows = [list(range(n))[parallel.local_slice(n, r, world)] for r in range(world)]
+        assert all(len(x) == n // world for x in rows)
+        flat = [i for x in rows for i in x]
+        assert flat == list(range((n // world) * world))
+    full = list(SyntheticLoader(16, 2, n_classes=10, pin=False))
+    parts = [list(SyntheticLoader(16, 2, n_classes=10, pin=False, rank=r, world=4)) for r in range(4)]
+    for b in range(2):
+        assert torch.equal(torch.cat([parts[r][b][0] for r in range(4)]), full[b][0])
+        assert torch.equal(torch.cat([parts[r][b][1] for r in range(4)]), full[b][1])
+    plain = list(SyntheticLoader(16, 1, pin=False, rank=1, world=2))
+    assert plain[0][0].shape[0] == 8 and plain[0][1].shape[0] == 8
