@@ -35,6 +35,13 @@ WORKLOAD = ("DCGAN 3x64x64 nz=100 ngf=ndf=64, 512 images/GPU/step (BASELINE conf
             "at N=8), full G+D step incl. gradient penalty + Adam, SyncBN over the global batch")
 
 
+def shared_config(world, batch):
+    """`config` of BOTH arms (this framework and --impl reference): the workload, nothing implementation-specific --
+    what is specific to a run (CUDA graph, SyncBN transport, the CPU sample) is reported under `run` / `cpu_baseline`."""
+    return {"workload": WORKLOAD, "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+            "l2": "working set per step (~1.5 GB of activations at 512 images) exceeds the 126 MB L2; no flush"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -131,7 +138,10 @@ class ClockSampler(threading.Thread):
 # -------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's step, timed on the host cores
 # -------------------------------------------------------------------------------------------------------
-def time_cpu_port(batch, steps, warmup):
+def time_cpu_port(batch, steps, warmup, anomaly=False):
+    """The reference's step on the host cores (oracle port: the reference's torch operators in the reference's order,
+    bit-exact vs the unmodified trainer -- tests/test_oracle_golden.py), all host threads.  `anomaly`: with
+    torch.autograd.set_detect_anomaly(True), as the reference's main.py:28 leaves it."""
     import torch
     from oracle import models, steps as osteps
     cores = os.cpu_count() or 1
@@ -140,12 +150,17 @@ def time_cpu_port(batch, steps, warmup):
     og, od = osteps.make_optimizers(g, d, 2e-4)
     real = osteps.make_real(batch, n_steps=1)[0]
     rng = osteps.make_rng(batch, n_steps=1, seed=1)[0]
-    for _ in range(warmup):
-        osteps.dcgan_step(g, d, og, od, real, rng)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        osteps.dcgan_step(g, d, og, od, real, rng)
-    dt = (time.perf_counter() - t0) / steps
+    prev = torch.is_anomaly_enabled()
+    torch.autograd.set_detect_anomaly(bool(anomaly))
+    try:
+        for _ in range(warmup):
+            osteps.dcgan_step(g, d, og, od, real, rng)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            osteps.dcgan_step(g, d, og, od, real, rng)
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        torch.autograd.set_detect_anomaly(prev)
     return batch / dt, dt * 1e3, cores
 
 
@@ -153,15 +168,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_batch = 128
+    # every step is ONE per-GPU batch of the GPU arm (512 images, ~1.3 s on 16 host threads): the same batch size the
+    # GPU arm's kernels see, so the two arms' `config` are identical; under N > 1 it is a per-GPU-sized sample of the
+    # global batch (the reference is a single process)
+    sample_batch = args.batch
     v, ms, cores = time_cpu_port(sample_batch, args.steps, max(1, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{sample_batch}-image slice of the per-GPU batch per step"},
+            "config": shared_config(args.gpus, args.batch),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"oracle port of train/dcgan_trainer.py:155-189 (torch CPU, {cores} threads), "
-                                       f"{args.steps} steps of {sample_batch} images, anomaly detection off"},
+                                       f"{args.steps} steps of {sample_batch} images (one per-GPU batch each), anomaly "
+                                       f"detection off"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "the reference is pure Python on torch; it has no installable package (no setup.py / pyproject) and "
@@ -171,17 +190,20 @@ def run_reference(args):
 
 
 # -------------------------------------------------------------------------------------------------------
-# per-op device timing (CUDA events on the launching stream) for the roofline of the dominant kernel
+# per-op device timing (CUDA events on the launching stream) for the rooflines
 # -------------------------------------------------------------------------------------------------------
 class OpTimer:
-    CONV = ("conv_down", "conv_up", "conv_wgrad")
+    """Wraps every op of jck_generation_b200.ops with a CUDA-event pair (on the launching stream) and attaches the op's
+    ALGORITHMIC work: FLOPs for the convolutions (2 * MACs), bytes for the streaming passes (each tensor read or written
+    once: DESIGN.md section 4's per-element figures x the elements of the call)."""
 
     def __init__(self, ops, torch):
         self.ops, self.torch, self.rec, self.saved = ops, torch, [], {}
 
     def __enter__(self):
         names = [n for n in dir(self.ops) if callable(getattr(self.ops, n)) and not n.startswith("_") and
-                 n not in ("dt", "L", "check", "wgrad_workspace_bytes", "edge_wgrad_workspace_bytes", "img_alloc")]
+                 n not in ("dt", "L", "check", "wgrad_workspace_bytes", "edge_wgrad_workspace_bytes", "img_alloc",
+                           "gemm_tc_workspace_bytes")]
         for n in names:
             fn = getattr(self.ops, n)
             if getattr(fn, "__module__", "") != self.ops.__name__:
@@ -193,7 +215,7 @@ class OpTimer:
                 e0.record()
                 r = __fn(*a, **k)
                 e1.record()
-                self.rec.append((__n, self._flops(__n, a, k), e0, e1))
+                self.rec.append((__n, self._work(__n, a, k), e0, e1))
                 return r
             setattr(self.ops, n, wrap)
         return self
@@ -203,83 +225,214 @@ class OpTimer:
             setattr(self.ops, n, fn)
 
     @staticmethod
-    def _flops(name, a, k):
-        if name == "conv_down":       # (x_large, w_down, out_small, stats, Ca, Cb)
-            B, Hs, Ws = a[2].shape[:3]
-            return name + f"[{a[4]}x{a[5]}@{Hs}]", 2.0 * B * Hs * Ws * 16 * a[4] * a[5]
-        if name == "conv_up":         # (x_small, w_up, out_large, stats, Ca, Cb)
+    def _work(name, a, k):
+        """(key, flops, bytes) of one call"""
+        nb = lambda t: t.numel() * t.element_size()
+        if name in ("conv_down", "conv_down_bnbwd"):       # (x_large, w_down, out_small | y_saved ..., Ca, Cb)
+            out = a[2] if name == "conv_down" else a[6]
+            Ca, Cb = (a[4], a[5]) if name == "conv_down" else (a[8], a[9])
+            B, Hs, Ws = out.shape[:3]
+            return f"{name}[{Ca}x{Cb}@{Hs}]", 2.0 * B * Hs * Ws * 16 * Ca * Cb, nb(a[0]) + nb(out)
+        if name in ("conv_up", "conv_up_bnbwd"):           # (x_small, w_up, out_large | y_saved ..., Ca, Cb)
+            out = a[2] if name == "conv_up" else a[6]
+            Ca, Cb = (a[4], a[5]) if name == "conv_up" else (a[8], a[9])
             B, Hs, Ws = a[0].shape[:3]
-            return name + f"[{a[4]}x{a[5]}@{Hs}]", 2.0 * B * Hs * Ws * 16 * a[4] * a[5]
-        if name == "conv_wgrad":      # (small, large, dw4, workspace, Ca, Cb, accumulate)
+            return f"{name}[{Ca}x{Cb}@{Hs}]", 2.0 * B * Hs * Ws * 16 * Ca * Cb, nb(a[0]) + nb(out)
+        if name == "conv_wgrad":                           # (small, large, dw4, workspace, Ca, Cb, accumulate)
             B, Hs, Ws = a[0].shape[:3]
-            return name + f"[{a[4]}x{a[5]}@{Hs}]", 2.0 * B * Hs * Ws * 16 * a[4] * a[5]
-        return name, 0.0
+            return f"{name}[{a[4]}x{a[5]}@{Hs}]", 2.0 * B * Hs * Ws * 16 * a[4] * a[5], nb(a[0]) + nb(a[1])
+        if name == "bn_act_fwd":                           # (y, ss, a, C, ...): read y, write a
+            return f"{name}[{a[3]}ch,{nb(a[0]) >> 20}MiB]", 0.0, nb(a[0]) + nb(a[2])
+        if name == "bn_act_bwd_reduce":                    # (da, y, ss, mr, sums, C, ...): read da, y
+            return f"{name}[{a[5]}ch,{nb(a[0]) >> 20}MiB]", 0.0, nb(a[0]) + nb(a[1])
+        if name == "bn_act_bwd_apply":                     # (da, y, ss, mr, gamma, sums, dy, C, ...): read da, y; write dy
+            return f"{name}[{a[7]}ch,{nb(a[0]) >> 20}MiB]", 0.0, nb(a[0]) + nb(a[1]) + nb(a[6])
+        if name == "edge_down_img":                        # (img_p4, w, out_small, ...): read image, write out
+            return f"{name}[{nb(a[2]) >> 20}MiB]", 0.0, nb(a[0]) + nb(a[2])
+        if name in ("edge_up_scatter", "edge_up"):         # (x_small, w, img_p4, Ca): read x, write image
+            return f"{name}[{nb(a[0]) >> 20}MiB]", 0.0, nb(a[0]) + nb(a[2])
+        if name == "adam":                                 # 4 reads + 3 writes of fp32
+            return name, 0.0, 7 * nb(a[0])
+        return name, 0.0, 0.0
 
     def table(self):
         self.torch.cuda.synchronize()
         agg = {}
-        for name, (key, fl), e0, e1 in self.rec:
-            t = agg.setdefault(key, {"op": name, "ms": 0.0, "calls": 0, "flop": 0.0})
+        for name, (key, fl, by), e0, e1 in self.rec:
+            t = agg.setdefault(key, {"op": name, "ms": 0.0, "calls": 0, "flop": 0.0, "bytes": 0.0})
             t["ms"] += e0.elapsed_time(e1)
             t["calls"] += 1
             t["flop"] += fl
+            t["bytes"] += by
         return agg
 
 
-def secondary_paths(torch, trainer, dev):
-    """SURVEY.md 8f rows measured beside the headline (device time, CUDA events, after a warm-up pass):
-    * fid_eval: BASELINE configs[4] on one GPU, scaled to 4096 samples: generator -> fused resize/normalise -> Inception-v3
-      pool3 features on our tcgen05 conv kernels -> 2048 x 2048 covariance (ops.feature_moments);
-    * input_pipeline: the reference's Resize(64)/ToTensor/Normalize loader on a CIFAR-shaped uint8 set resident in HBM."""
+def _ev_time(torch, fn, n):
+    """mean device ms of n calls of fn (CUDA events on the current stream, synchronised on both sides)"""
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def secondary_paths(torch, trainer, dev, args):
+    """Measured beside the headline (device time, CUDA events, after warm-up), single GPU:
+    * cgan_step: BASELINE configs[1] (CGAN, batch 256) at the config's shape (1 channel, 10 classes; 28x28 sources are
+      resized to 64 by the preprocessor as the reference resizes CIFAR, cgan_data_preprocessor.py:51) and at the reference's
+      native shape (3 channels, 100 classes); the step back-propagates the gradient penalty (second order);
+    * fp32_step: the headline step in the exact-parity fp32 mode (CUDA-core FMA kernels, the mode the <= 1e-4 tests run);
+    * library_bar: the reference's own step UNCHANGED on this GPU through torch eager + cuDNN / cuBLAS (utils.py:4-8
+      device='cuda'), true fp32 and torch's default TF32 convolutions;
+    * cpu_anomaly_on: the CPU baseline with torch.autograd.set_detect_anomaly(True), as the reference's main.py:28 runs;
+    * fid_eval: BASELINE configs[4] on one GPU, scaled to 4096 samples; input_pipeline: the reference's loader on the device."""
     import numpy as np
     from jck_generation_b200 import ops
-    from jck_generation_b200.inception import InceptionV3
-    from jck_generation_b200.preprocess.device_pipeline import DeviceImageLoader
-    from torchvision import models
     out = {}
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
-    torch.manual_seed(12345)
-    net = models.inception_v3(weights=None, aux_logits=True, init_weights=False)
-    ext = InceptionV3(net.state_dict(), feature="pool3", device=dev)
-    n, bsz = 4096, 128
-    z = torch.randn(n, 100, 1, 1, device=dev)
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:                      # noqa: BLE001 -- the headline never depends on a secondary path
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
 
-    def fid_pass():
-        feats = []
-        with torch.no_grad():
-            for i in range(0, n, bsz):
-                feats.append(ext.forward_generated(trainer.model_g(z[i:i + bsz]).float()))
-        return ops.feature_moments(torch.cat(feats).contiguous())
-    fid_pass()
-    torch.cuda.synchronize()
-    ev[0].record()
-    fid_pass()
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1])
-    out["fid_eval"] = {"images_per_s": n / (ms * 1e-3), "ms": ms, "samples": n, "feature": "pool3 (2048-d)",
-                       "inception_tflops": 11.42e9 * n / (ms * 1e-3) / 1e12,
-                       "what": "G forward + Inception-v3 (94 tcgen05 implicit-GEMM convs, one CUDA graph per 128 images) + "
-                               "2048x2048 covariance, random-init weights"}
-    del ext
-    rng = np.random.default_rng(0)
-    data = rng.integers(0, 256, (50000, 32, 32, 3), dtype=np.uint8)
-    loader = DeviceImageLoader(data, None, 512, 64, [0.5] * 3, [0.5] * 3, shuffle=True)
-    for _ in loader:
-        pass
-    torch.cuda.synchronize()
-    ev[0].record()
-    cnt = 0
-    for x, _ in loader:
-        cnt += x.shape[0]
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1])
-    out["input_pipeline"] = {"images_per_s": cnt / (ms * 1e-3), "ms_per_epoch": ms, "samples": cnt,
-                             "what": "one epoch of a 50k x 32x32x3 uint8 set: seeded permutation gather + Pillow-exact "
-                                     "bilinear 32->64 + ToTensor/Normalize -> NCHW fp32, batches of 512"}
+    def cgan():
+        from jck_generation_b200.model import CGAN
+        from jck_generation_b200.train.cgan_trainer import CGANTrainer
+        res = {}
+        for tag, nc, ncls in (("mnist_shape_1ch_10cls", 1, 10), ("reference_shape_3ch_100cls", 3, 100)):
+            class _D:
+                idx_to_labels = {i: str(i) for i in range(ncls)}
+
+                def get_data_loader(self):
+                    return [], None
+            B = 256
+            a = argparse.Namespace(epoch=1, max_learning_rate=2e-4, model_path="bench_cgan", log_file=0, batch_size=B,
+                                   num_worker=0, dtype="bf16", cuda_graph=1, metrics=0,
+                                   save_path=os.path.join(ROOT, "gpurun_out", "bench_save"))
+            torch.manual_seed(12345)
+            tr = CGANTrainer(a, CGAN.Generator(nc=nc, n_classes=ncls), CGAN.Discriminator(nc=nc, n_classes=ncls), _D())
+            real = (torch.rand(B, nc, 64, 64) * 2 - 1).to(dev)
+            labels = torch.nn.functional.one_hot(torch.randint(0, ncls, (B,)), ncls).to(dev)
+            for _ in range(3):
+                tr.train_step(real, labels)
+            ms = _ev_time(torch, lambda: tr.train_step(real, labels), 20)
+            res[tag] = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3), "batch": B, "dtype": "bf16", "cuda_graph": True}
+            del tr
+        return res
+    guarded("cgan_step", cgan)
+
+    def fp32():
+        from jck_generation_b200.model import DCGAN
+        from jck_generation_b200.train.dcgan_trainer import DCGANTrainer
+
+        class _D:
+            def get_data_loader(self):
+                return [], None
+        B = args.batch
+        a = argparse.Namespace(epoch=1, max_learning_rate=2e-4, model_path="bench_fp32", log_file=0, batch_size=B, num_worker=0,
+                               dtype="fp32", cuda_graph=0, metrics=0, save_path=os.path.join(ROOT, "gpurun_out", "bench_save"))
+        torch.manual_seed(12345)
+        tr = DCGANTrainer(a, DCGAN.Generator(), DCGAN.Discriminator(), _D())
+        real = (torch.rand(B, 3, 64, 64) * 2 - 1).to(dev)
+        tr.train_step(real)
+        ms = _ev_time(torch, lambda: tr.train_step(real), 3)
+        return {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3), "batch": B, "dtype": "f32",
+                "what": "CUDA-core fp32 FMA kernels (the <= 1e-4 parity mode), eager launches"}
+    guarded("fp32_step", fp32)
+
+    def library_bar():
+        from oracle import models, steps as osteps
+        B, res = args.batch, {}
+        keep = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+        try:
+            for tag, tf32 in (("fp32", False), ("tf32_convs_torch_default", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.benchmark = True
+                g, d = models.build("DCGAN", seed=12345)
+                g, d = g.to(dev), d.to(dev)
+                og, od = osteps.make_optimizers(g, d, 2e-4)
+                real = osteps.make_real(B, n_steps=1)[0].to(dev)
+                rng = {k: v.to(dev) for k, v in osteps.make_rng(B, n_steps=1, seed=1)[0].items()}
+                with torch.device(dev):
+                    for _ in range(3):
+                        osteps.dcgan_step(g, d, og, od, real, rng)
+                    ms = _ev_time(torch, lambda: osteps.dcgan_step(g, d, og, od, real, rng), 8)
+                res[tag] = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3)}
+                del g, d, og, od
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = keep
+        res["what"] = (f"the reference's step (oracle port: its torch operators in its order) on this GPU through torch eager + "
+                       f"cuDNN/cuBLAS, {B} images, 5 host syncs per step as the reference's .item() calls")
+        return res
+    guarded("library_bar", library_bar)
+
+    def anomaly():
+        v, ms, cores = time_cpu_port(args.batch, 2, 1, anomaly=True)
+        return {"value": v, "unit": UNIT, "ms_per_step": ms, "cores": cores,
+                "what": f"CPU baseline with torch.autograd.set_detect_anomaly(True) (reference main.py:28), 2 steps of {args.batch}"}
+    guarded("cpu_anomaly_on", anomaly)
+
+    def fid():
+        from jck_generation_b200.inception import InceptionV3
+        from torchvision import models
+        torch.manual_seed(12345)
+        net = models.inception_v3(weights=None, aux_logits=True, init_weights=False)
+        ext = InceptionV3(net.state_dict(), feature="pool3", device=dev)
+        n, bsz = 4096, 128
+        z = torch.randn(n, 100, 1, 1, device=dev)
+
+        def fid_pass():
+            feats = []
+            with torch.no_grad():
+                for i in range(0, n, bsz):
+                    feats.append(ext.forward_generated(trainer.model_g(z[i:i + bsz]).float()))
+            return ops.feature_moments(torch.cat(feats).contiguous())
+        fid_pass()
+        ms = _ev_time(torch, fid_pass, 1)
+        return {"images_per_s": n / (ms * 1e-3), "ms": ms, "samples": n, "feature": "pool3 (2048-d)",
+                "inception_tflops": 11.42e9 * n / (ms * 1e-3) / 1e12,
+                "what": "G forward + Inception-v3 (94 tcgen05 implicit-GEMM convs, one CUDA graph per 128 images) + "
+                        "2048x2048 covariance, random-init weights"}
+    guarded("fid_eval", fid)
+
+    def pipeline():
+        from jck_generation_b200.preprocess.device_pipeline import DeviceImageLoader
+        rng = np.random.default_rng(0)
+        data = rng.integers(0, 256, (50000, 32, 32, 3), dtype=np.uint8)
+        loader = DeviceImageLoader(data, None, 512, 64, [0.5] * 3, [0.5] * 3, shuffle=True)
+        for _ in loader:
+            pass
+        cnt = [0]
+
+        def epoch():
+            for x, _ in loader:
+                cnt[0] += x.shape[0]
+        ms = _ev_time(torch, epoch, 1)
+        return {"images_per_s": cnt[0] / (ms * 1e-3), "ms_per_epoch": ms, "samples": cnt[0],
+                "what": "one epoch of a 50k x 32x32x3 uint8 set: seeded permutation gather + Pillow-exact bilinear 32->64 + "
+                        "ToTensor/Normalize -> NCHW fp32, batches of 512"}
+    guarded("input_pipeline", pipeline)
     return out
+
+
+def make_trainer(torch, args, batch, dtype=None):
+    from jck_generation_b200.model import DCGAN
+    from jck_generation_b200.train.dcgan_trainer import DCGANTrainer
+
+    class _Data:
+        def get_data_loader(self):
+            return [], None
+    targs = argparse.Namespace(epoch=1, max_learning_rate=2e-4, model_path="bench", log_file=0, batch_size=batch,
+                               num_worker=0, dtype=dtype or args.dtype, cuda_graph=0 if args.no_graph else 1, metrics=0,
+                               save_path=os.path.join(ROOT, "gpurun_out", "bench_save"))
+    torch.manual_seed(12345)
+    return DCGANTrainer(targs, DCGAN.Generator(), DCGAN.Discriminator(), _Data())
 
 
 def run_b200(args):
@@ -287,8 +440,6 @@ def run_b200(args):
     import __graft_entry__ as entry
     entry.build()
     from jck_generation_b200 import _lib, ops, parallel
-    from jck_generation_b200.model import DCGAN
-    from jck_generation_b200.train.dcgan_trainer import DCGANTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:      # convenience: relaunch under torchrun
@@ -300,14 +451,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     B = args.batch
 
-    class _Data:
-        def get_data_loader(self):
-            return [], None
-    targs = argparse.Namespace(epoch=1, max_learning_rate=2e-4, model_path="bench", log_file=0, batch_size=B,
-                               num_worker=0, dtype=args.dtype, cuda_graph=0 if args.no_graph else 1, metrics=0,
-                               save_path=os.path.join(ROOT, "gpurun_out", "bench_save"))
-    torch.manual_seed(12345)
-    trainer = DCGANTrainer(targs, DCGAN.Generator(), DCGAN.Discriminator(), _Data())
+    trainer = make_trainer(torch, args, B)
     comm = trainer.comm
     rank = comm.rank
     step = trainer.step
@@ -321,9 +465,6 @@ def run_b200(args):
         c0 = _lib.launch_count()
         step.capture(B)
         launches_per_step = (_lib.launch_count() - c0) // 3      # 2 warm-up runs + 1 captured run
-
-    def one_step():
-        return step.replay(real) if use_graph else step.run(real)
 
     def timed(fn, n):
         comm.barrier()
@@ -341,6 +482,9 @@ def run_b200(args):
         if comm.world_size > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t) / n, _lib.launch_count() - c0
+
+    def one_step():
+        return step.replay(real) if use_graph else step.run(real)
 
     for _ in range(max(3, args.warmup)):
         one_step()
@@ -374,39 +518,55 @@ def run_b200(args):
            "api": "DCGANTrainer.train_step(real) fed by the trainer's DevicePrefetcher from a pinned host batch "
                   "(H2D of the next batch overlaps the running step); losses read back every step"}
 
-    # dominant kernel roofline: eager pass with CUDA events around every op
-    # (weight gradients back on the main stream for this pass: per-kernel times must not include a concurrent kernel)
+    # rooflines: eager pass with CUDA events around every op, everything on ONE stream (weight gradients and the
+    # penalty sweep in line: a per-kernel time must not include a concurrent kernel).  The dominant op is the one with the
+    # largest total time over ALL ops; the top streaming (HBM-bound) op is reported next to it.
     pk = peaks()
-    side = (step.eg.wgrad_stream, step.ed.wgrad_stream)
-    step.eg.wgrad_stream = step.ed.wgrad_stream = None
+    side = (step.eg.wgrad_stream, step.ed.wgrad_stream, step.gp_stream)
+    step.eg.wgrad_stream = step.ed.wgrad_stream = step.gp_stream = None
     with OpTimer(ops, torch) as ot:
         for _ in range(2):
             step.run(real)
         tab = ot.table()
-    step.eg.wgrad_stream, step.ed.wgrad_stream = side
+    step.eg.wgrad_stream, step.ed.wgrad_stream, step.gp_stream = side
     tot = sum(t["ms"] for t in tab.values()) or 1.0
-    conv = {k: t for k, t in tab.items() if t["flop"] > 0}
-    top = max(conv.items(), key=lambda kv: kv[1]["ms"])
-    fam = {}
-    for k, t in conv.items():
-        f = fam.setdefault(t["op"], {"ms": 0.0, "flop": 0.0, "calls": 0})
-        f["ms"] += t["ms"]; f["flop"] += t["flop"]; f["calls"] += t["calls"]
-    tk, tv = top
-    achieved = tv["flop"] / (tv["ms"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": tk, "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"],
-                "avg_launch_ms": tv["ms"] / tv["calls"], "share_of_step": tv["ms"] / tot,
-                "step_tensor_frac": FLOP_PER_IMAGE * value / (comm.world_size * pk["tf_sustained"] * 1e12),
-                "families": {k: {"share": f["ms"] / tot, "tflops": f["flop"] / (f["ms"] * 1e-3) / 1e12} for k, f in fam.items()}}
+    traffic_db = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f).get(tk)
-        if tr:
-            roofline["traffic"] = tr["avg_bytes_per_launch"]
-            roofline["traffic_source"] = "profiles/r01_ncu_kernels.md: DRAM read+write bytes per launch (ncu --set full), " \
-                                         f"algorithmic {tr['algorithmic_avg_bytes_per_launch']:.3g} B"
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            traffic_db = json.load(f)
     except OSError:
         pass
+
+    def roof(key, t):
+        tensor = t["flop"] > 0
+        if tensor:
+            ach, peak, unit = t["flop"] / (t["ms"] * 1e-3) / 1e12, pk["tf_sustained"], "TFLOP/s"
+        else:
+            ach, peak, unit = t["bytes"] / (t["ms"] * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+        r = {"bound": "tensor" if tensor else "hbm", "kernel": key, "achieved": ach, "peak": peak, "unit": unit,
+             "frac": ach / peak, "traffic": None, "peak_source": pk["source"], "avg_launch_ms": t["ms"] / t["calls"],
+             "calls_per_step": t["calls"] // 2, "share_of_step": t["ms"] / tot,
+             "algorithmic_per_launch": (t["flop"] if tensor else t["bytes"]) / t["calls"]}
+        tr = traffic_db.get(key)
+        if tr:
+            r["traffic"] = tr["dram_bytes_per_launch"]
+            r["traffic_source"] = tr.get("source", "profiles/r02_ncu_kernels.md (ncu --set full, dram__bytes_read + write)")
+        return r
+    top_key, top_t = max(tab.items(), key=lambda kv: kv[1]["ms"])
+    roofline = roof(top_key, top_t)
+    roofline["step_tensor_frac"] = FLOP_PER_IMAGE * value / (comm.world_size * pk["tf_sustained"] * 1e12)
+    fam = {}
+    for k, t in tab.items():
+        if t["flop"] > 0 or t["bytes"] > 0:
+            f = fam.setdefault(t["op"], {"ms": 0.0, "flop": 0.0, "bytes": 0.0, "calls": 0})
+            f["ms"] += t["ms"]; f["flop"] += t["flop"]; f["bytes"] += t["bytes"]; f["calls"] += t["calls"]
+    roofline["families"] = {k: ({"share": f["ms"] / tot, "tflops": f["flop"] / (f["ms"] * 1e-3) / 1e12} if f["flop"] > 0 else
+                                {"share": f["ms"] / tot, "gbs": f["bytes"] / (f["ms"] * 1e-3) / 1e9}) for k, f in fam.items()}
+    hbm_ops = {k: t for k, t in tab.items() if t["flop"] == 0 and t["bytes"] > 0}
+    roofline_hbm = roof(*max(hbm_ops.items(), key=lambda kv: kv[1]["ms"])) if hbm_ops else None
+    tensor_ops = {k: t for k, t in tab.items() if t["flop"] > 0}
+    roofline_tensor = roof(*max(tensor_ops.items(), key=lambda kv: kv[1]["ms"])) if tensor_ops else None
+
     if args.kernel_table and rank == 0:
         # per-kernel device time from CUPTI (torch.profiler), warm caches, eager launches
         from torch.profiler import ProfilerActivity, profile
@@ -422,25 +582,56 @@ def run_b200(args):
                   f"{e.key[:100]}", file=sys.stderr)
     if args.profile_ops and rank == 0:
         for k, t in sorted(tab.items(), key=lambda kv: -kv[1]["ms"]):
-            print(f"# {t['ms'] / 2:9.3f} ms/step  {t['calls'] // 2:4d} calls  {k}", file=sys.stderr)
+            w = (f"{t['flop'] / (t['ms'] * 1e-3) / 1e12:7.0f} TFLOP/s" if t["flop"] > 0 else
+                 f"{t['bytes'] / (t['ms'] * 1e-3) / 1e9:7.0f} GB/s" if t["bytes"] > 0 else "")
+            print(f"# {t['ms'] / 2:9.3f} ms/step  {t['calls'] // 2:4d} calls  {k:44s} {w}", file=sys.stderr)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": comm.world_size, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": total_images,
-                       "parallelism": f"dp{comm.world_size}", "cuda_graph": bool(use_graph),
-                       "l2": "working set per step (~1.5 GB of activations at 512 images) exceeds the 126 MB L2; no flush"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
-    if comm.world_size == 1 and not args.no_cpu_baseline:
-        v, cms, cores = time_cpu_port(128, 3, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"oracle port of the reference step, 3 steps of 128 images on {cores} host "
-                                          f"threads ({cms:.0f} ms/step)"}
-    if comm.world_size == 1 and not args.no_secondary:
+            "config": shared_config(comm.world_size, B),
+            "run": {"cuda_graph": bool(use_graph), "syncbn_transport": comm.transport,
+                    "grad_exchange": ("none (one GPU)" if comm.world_size == 1 else
+                                      f"NCCL all-reduce, {len(step.sync_d.buckets)} + {len(step.sync_g.buckets)} buckets started "
+                                      "as their gradients become final"),
+                    "penalty_sweep_stream": step.gp_stream is not None,
+                    "launches_per_step": launches_per_step},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "roofline_hbm": roofline_hbm, "roofline_tensor": roofline_tensor}
+
+    secondary = {}
+    if comm.world_size > 1:
+        # (1) W ranks == one rank on the global batch, outside the timed region; (2) BASELINE configs[2] as stated:
+        # 512 images GLOBAL, i.e. 512 / N per GPU (strong scaling), same step, own CUDA graph
+        from jck_generation_b200.train import dp_selfcheck
         try:
-            line["secondary"] = secondary_paths(torch, trainer, dev)
-        except Exception as e:                      # the headline never depends on the secondary paths
-            line["secondary"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            line["dp_check"] = dp_selfcheck.run(comm, per_rank=32)
+        except Exception as e:                      # noqa: BLE001
+            line["dp_check"] = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+        comm.barrier()
+        gb = 512
+        if gb % comm.world_size == 0:
+            b2 = gb // comm.world_size
+            tr2 = make_trainer(torch, args, b2)
+            real2 = real[:b2].contiguous()
+            if tr2.use_graph:
+                tr2.step.capture(b2)
+            f2 = (lambda: tr2.step.replay(real2)) if tr2.use_graph else (lambda: tr2.step.run(real2))
+            for _ in range(max(3, args.warmup)):
+                f2()
+            ms2, _ = timed(f2, args.steps)
+            secondary["strong_scaling"] = {"global_batch": gb, "per_gpu_batch": b2, "ms_per_step": ms2,
+                                           "images_per_s": gb / (ms2 * 1e-3),
+                                           "what": "BASELINE configs[2]: DCGAN 3x64x64 batch 512 GLOBAL, data parallel with SyncBN"}
+    if comm.world_size == 1 and not args.no_cpu_baseline:
+        v, cms, cores = time_cpu_port(B, 5, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle port of the reference step, 5 steps of {B} images (the GPU arm's batch) on "
+                                          f"{cores} host threads ({cms:.0f} ms/step), anomaly detection off"}
+    if comm.world_size == 1 and not args.no_secondary:
+        secondary.update(secondary_paths(torch, trainer, dev, args))
+    if secondary:
+        line["secondary"] = secondary
     if rank == 0:
         print(json.dumps(line), flush=True)
     if comm.world_size > 1:

@@ -193,12 +193,14 @@ int jck_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int
  * scalars (fp32, ADDED): scalars[0] += BCE mean, scalars[1] += mean(prob). w5 is NHWC-ordered. */
 int jck_head_fwd(const void* a4, const void* w5, float* prob, float target, float* scalars, int B, int K,
                  int dtype, void* stream);
-/* mode 0: dlogit = (p-target)/max(p(1-p),1e-12) * p(1-p) / B   (BCE mean backward through sigmoid)
+/* mode 0: dlogit = (p-target)/max(p(1-p),1e-12) * p(1-p) / mean_count   (BCE mean backward through sigmoid;
+ *         mean_count = the batch the mean runs over: 0 -> B; the GLOBAL batch under data parallelism, so that the
+ *         ranks' gradients SUM to the global-batch mean the reference computes)
  * mode 1: dlogit = p(1-p)                                   (grad_outputs = ones, the GP sweep)
  * mode 2: dlogit = dprob[b] * p(1-p)                        (caller-supplied gradient of the sigmoid output)
  * da4[b][k] = dlogit[b]*w5[k];  dw5[k] (+)= sum_b dlogit[b]*a4[b][k] when dw5 != NULL (fp32, NHWC order) */
 int jck_head_bwd(const float* prob, const float* dprob, float target, const void* w5, const void* a4, void* da4,
-                 float* dw5, int B, int K, int mode, int accumulate, int dtype, void* stream);
+                 float* dw5, int B, int mean_count, int K, int mode, int accumulate, int dtype, void* stream);
 /* conv5 weight [1][C4][4][4] fp32 <-> NHWC-ordered [16*C4] */
 int jck_pack_head(const float* w4, void* w5, int C4, int dtype, void* stream);
 int jck_unpack_head_grad(const float* dw5, float* dw4, int C4, int accumulate, void* stream);

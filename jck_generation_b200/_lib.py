@@ -67,7 +67,7 @@ _SIGNATURES = {
     "jck_bn_act_bwd_apply": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_ll, c_f, c_f, c_i, c_p],
     "jck_bn_param_grad": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_head_fwd": [c_p, c_p, c_p, c_f, c_p, c_i, c_i, c_i, c_p],
-    "jck_head_bwd": [c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_head_bwd": [c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "jck_pack_head": [c_p, c_p, c_i, c_i, c_p],
     "jck_unpack_head_grad": [c_p, c_p, c_i, c_i, c_p],
     "jck_prep_image_rng": [c_p, c_ull, c_ull, c_p, c_f, c_f, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

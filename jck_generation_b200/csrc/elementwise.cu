@@ -763,7 +763,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob, float target, const T* __restrict__ w5,
                 const T* __restrict__ a4,
-                T* __restrict__ da4, float* __restrict__ dw5, int B, int K, int mode, int chunk) {
+                T* __restrict__ da4, float* __restrict__ dw5, int B, int K, int mode, int chunk, float invB) {
     pdl_entry();
     const int k = (blockIdx.x * 256 + threadIdx.x) * 8;
     if (k >= K) return;
@@ -772,7 +772,6 @@ head_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ dprob,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const int b_beg = blockIdx.y * chunk, b_end = min(B, b_beg + chunk);
-    const float invB = 1.f / (float)B;
     for (int b = b_beg; b < b_end; ++b) {
         const float dl = head_dlogit(prob[b], dprob ? dprob[b] : 0.f, target, mode, invB);
         float o[8];
@@ -1114,9 +1113,10 @@ extern "C" int jck_head_fwd(const void* a4, const void* w5, float* prob, float t
 }
 
 extern "C" int jck_head_bwd(const float* prob, const float* dprob, float target, const void* w5, const void* a4, void* da4,
-                            float* dw5, int B, int K, int mode, int accumulate, int dtype, void* stream) {
-    JCK_REQUIRE(prob && w5 && da4 && B > 0 && K > 0 && K % 8 == 0 && (!dw5 || a4) && (mode != 2 || dprob),
+                            float* dw5, int B, int mean_count, int K, int mode, int accumulate, int dtype, void* stream) {
+    JCK_REQUIRE(prob && w5 && da4 && B > 0 && mean_count >= 0 && K > 0 && K % 8 == 0 && (!dw5 || a4) && (mode != 2 || dprob),
                 "head_bwd: bad argument");
+    const float invB = 1.f / (float)(mean_count > 0 ? mean_count : B);
     cudaStream_t st = as_stream(stream);
     if (dw5 && !accumulate) {
         cudaError_t e = cudaMemsetAsync(dw5, 0, sizeof(float) * K, st);
@@ -1127,7 +1127,7 @@ extern "C" int jck_head_bwd(const float* prob, const float* dprob, float target,
     chunks = (B + chunk - 1) / chunk;
     dim3 grid((K / 8 + 255) / 256, chunks);
     DISPATCH_DTYPE(dtype, "head_bwd",
-        launch_pdl(head_bwd_kernel<T>, dim3(grid), dim3(256), 0, st, prob, dprob, target, (const T*)w5, (const T*)a4, (T*)da4, dw5, B, K, mode, chunk);)
+        launch_pdl(head_bwd_kernel<T>, dim3(grid), dim3(256), 0, st, prob, dprob, target, (const T*)w5, (const T*)a4, (T*)da4, dw5, B, K, mode, chunk, invB);)
     JCK_LAUNCH_CHECK("head_bwd");
     return JCK_OK;
 }

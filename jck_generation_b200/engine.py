@@ -172,6 +172,11 @@ class _GradTarget:
     gradients are used; every operand is kept alive by the Ctx until then."""
     sink = None
     wgrad_stream = None
+    grad_sync = None          # parallel.GradBuckets: told as each parameter's gradient becomes final (trainer hot path)
+
+    def _grad_ready(self, *params):
+        if self.grad_sync is not None and self.sink is None:
+            self.grad_sync.ready(*params)
 
     def _wgrad_scope(self):
         if self.wgrad_stream is None:
@@ -274,7 +279,9 @@ class DiscriminatorEngine(_GradTarget):
 
     # ---- backward ----------------------------------------------------------------------------------
     def head_backward(self, ctx, mode, targets=None, dprob=None, wgrad=True, accumulate=False):
-        """d(loss)/d(a4) (+ conv5 weight gradient).  mode 0 BCE-mean, 1 ones (GP sweep), 2 upstream dprob."""
+        """d(loss)/d(a4) (+ conv5 weight gradient).  mode 0 BCE-mean, 1 ones (GP sweep), 2 upstream dprob.
+        The BCE mean runs over the GLOBAL batch (rows per group x world size): under data parallelism the ranks'
+        gradients then SUM to the gradient of the reference's global-batch mean -- no division after the exchange."""
         B, per = ctx.B, ctx.B // ctx.groups
         da4 = torch.empty(B, self.K5, dtype=self.dtype, device=self.dev)
         a4 = ctx.a[4].view(B, self.K5)
@@ -284,13 +291,15 @@ class DiscriminatorEngine(_GradTarget):
             sl = slice(g * per, (g + 1) * per)
             ops.head_bwd(ctx.prob[sl], targets[g] if targets is not None else 0.0, self.w5, a4[sl], da4[sl],
                          self.dw5 if wgrad else None, mode, True,
-                         dprob=dprob[sl] if dprob is not None else None)
+                         dprob=dprob[sl] if dprob is not None else None, mean_count=per * self.comm.world_size)
         if wgrad:
             ops.unpack_head_grad(self.dw5, self._gb(self.m.conv5.weight), accumulate)
+            if not accumulate:
+                self._grad_ready(self.m.conv5.weight)
         return da4.view(B, 4, 4, self.convs[4].Ca)
 
     def trunk_backward(self, ctx, da4, wgrad=True, input_grad=False, accumulate=False, inject=None, inject_rows=None,
-                       fuse=True, dx_out=None):
+                       fuse=True, dx_out=None, comm=None):
         """Backward through conv4..conv1 given d/d(a4).  Returns d/d(input) (NHWC) when asked.
         `inject[k]` (rows `inject_rows` of the batch) is added to the gradient of the raw conv-k output
         before it is used: the second-order terms of the CGAN gradient penalty enter here.  The sweep
@@ -300,9 +309,12 @@ class DiscriminatorEngine(_GradTarget):
         fuse=False every layer runs the separate reduce pass and ctx.da[k] keeps d/d(activation) (the CGAN
         penalty sweep needs it).
         `dx_out`: a caller-owned JCK_IMG_P4 buffer (zero border / pad channel, e.g. one kept across steps) that
-        receives the image-side input gradient instead of a freshly zeroed one."""
+        receives the image-side input gradient instead of a freshly zeroed one.
+        `comm`: communicator for this sweep's SyncBN exchanges when it is issued from a second stream
+        (parallel.AuxComm); default the engine's."""
         B, groups = ctx.B, ctx.groups
-        world = self.comm.world_size
+        comm = comm or self.comm
+        world = comm.world_size
         fuse = fuse and self.fused_bn_bwd
         da, reduced = da4, False
         zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev)
@@ -313,8 +325,10 @@ class DiscriminatorEngine(_GradTarget):
             if not reduced:
                 ops.bn_act_bwd_reduce(da, ctx.y[k], ctx.ss[k], ctx.mr[k], sums, C, groups, LRELU)
             # parameter gradients are this rank's contribution (ranks are averaged later); then the global sums
-            _bn_bwd_sums(self.comm, sums, self._gb(nm.bn.weight) if wgrad else None, self._gb(nm.bn.bias) if wgrad else None,
+            _bn_bwd_sums(comm, sums, self._gb(nm.bn.weight) if wgrad else None, self._gb(nm.bn.bias) if wgrad else None,
                          C, groups, accumulate)
+            if wgrad and not accumulate:
+                self._grad_ready(nm.bn.weight, nm.bn.bias)
             dy = torch.empty_like(ctx.y[k])
             count = (B // groups) * cv.Hs * cv.Ws * world
             ops.bn_act_bwd_apply(da, ctx.y[k], ctx.ss[k], ctx.mr[k], nm.gamma, sums, dy, C, groups, count,
@@ -334,6 +348,8 @@ class DiscriminatorEngine(_GradTarget):
                         nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, cv.Ca, cv.Cb, self.dtype, self.algo)
                         ops.conv_wgrad(dy, inp, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb, accumulate,
                                        algo=self.algo)
+                    if not accumulate:
+                        self._grad_ready(cv.weight)
             reduced = False
             if k > 1 or input_grad:
                 if cv.edge:
@@ -466,6 +482,8 @@ class GeneratorEngine(_GradTarget):
                 with self._wgrad_scope():
                     ops.edge_wgrad_img(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, self.nc,
                                        accumulate)
+                    if not accumulate:
+                        self._grad_ready(cv.weight)
                 ops.edge_down_img(d_large, cv.w_down_e, da, None, cv.Ca)
                 reduced = False
             else:
@@ -473,6 +491,8 @@ class GeneratorEngine(_GradTarget):
                 with self._wgrad_scope():
                     ops.conv_wgrad(ctx.a[k - 1], d_large, self._gb(cv.weight), self.ws.get(nbytes), cv.Ca, cv.Cb,
                                    accumulate, algo=self.algo)
+                    if not accumulate:
+                        self._grad_ready(cv.weight)
                 reduced = fuse and cv.Ca >= FUSE_MIN_C
                 if reduced:
                     ops.conv_down_bnbwd(d_large, cv.w_down, yk, ssk, mrk, 0.0, da, sums, cv.Ca, cv.Cb)
@@ -481,6 +501,8 @@ class GeneratorEngine(_GradTarget):
             if not reduced:
                 ops.bn_act_bwd_reduce(da, yk, ssk, mrk, sums, C, 1, 0.0)
             _bn_bwd_sums(self.comm, sums, self._gb(nm.bn.weight), self._gb(nm.bn.bias), C, 1, accumulate)
+            if not accumulate:
+                self._grad_ready(nm.bn.weight, nm.bn.bias)
             dy = torch.empty_like(yk)
             count = (yk.numel() // C) * world
             # a fused producer already applied relu': slope 1 leaves g untouched
@@ -497,3 +519,5 @@ class GeneratorEngine(_GradTarget):
         else:
             ops.fc_wgrad(d_large.view(B, N1), ctx.x, self.dw_fc, accumulate=False)
             ops.unpack_fc_grad(self.dw_fc, self._gb(self.m.conv1.weight), accumulate)
+        if not accumulate:
+            self._grad_ready(self.m.conv1.weight)

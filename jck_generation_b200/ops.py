@@ -243,11 +243,12 @@ def head_fwd(a4, w5, prob, target, scalars):
     check(L().jck_head_fwd(_p(a4), _p(w5), _p(prob), float(target), _p(scalars), B, K, dt(a4), _s()), "head_fwd")
 
 
-def head_bwd(prob, target, w5, a4, da4, dw5, mode, accumulate, dprob=None):
+def head_bwd(prob, target, w5, a4, da4, dw5, mode, accumulate, dprob=None, mean_count=0):
+    """mean_count: the batch the BCE mean runs over (0 = these rows; the global batch under data parallelism)."""
     B = prob.shape[0]
     K = w5.numel()
-    check(L().jck_head_bwd(_p(prob), _p(dprob), float(target), _p(w5), _p(a4), _p(da4), _p(dw5), B, K, mode, int(accumulate),
-                           dt(da4), _s()), "head_bwd")
+    check(L().jck_head_bwd(_p(prob), _p(dprob), float(target), _p(w5), _p(a4), _p(da4), _p(dw5), B, int(mean_count), K, mode,
+                           int(accumulate), dt(da4), _s()), "head_bwd")
 
 
 # ---- generator output, GP, Adam, RNG ---------------------------------------------------------------------------

@@ -22,6 +22,8 @@ class LocalComm:
     world_size = 1
     rank = 0
     peer = None
+    peer_aux = None
+    transport = "local"
 
     def allreduce_sum_(self, t):
         return t
@@ -44,6 +46,7 @@ class TorchComm:
     CPU tests)."""
 
     peer = None      # opaque libjck_b200 communicator (NVLink peer-memory mailboxes) once open_peer() succeeded
+    peer_aux = None  # a second, independent one (own mailboxes and call counter) for exchanges issued from a second stream
 
     def __init__(self, group=None):
         assert dist.is_initialized(), "init the process group first (see init_from_env)"
@@ -52,13 +55,26 @@ class TorchComm:
         self.rank = dist.get_rank(group)
 
     def open_peer(self):
-        """Open the peer-memory communicator of csrc/comm.cu: every rank exports its mailbox with CUDA IPC, the
-        handles travel through one torch.distributed all_gather, every rank maps its peers.  From then on the
-        SyncBN exchanges (2C floats, 40+ per step) are single-CTA kernels storing straight into the peers' HBM
-        instead of host-launched NCCL calls.  Large buffers (the gradient buckets) stay on NCCL."""
-        from . import ops
+        """Open the peer-memory communicators of csrc/comm.cu (the main one and the auxiliary one)."""
         if self.peer is not None or self.world_size == 1 or self.world_size > 8 or not torch.cuda.is_available():
             return self
+        self.peer = self._open_one()
+        if self.peer is not None:
+            self.peer_aux = self._open_one()
+        return self
+
+    @property
+    def transport(self):
+        """What carries the SyncBN statistics: 'peer' (NVLink peer-memory mailboxes, csrc/comm.cu) or 'nccl'."""
+        return "peer" if self.peer is not None else "nccl"
+
+    def _open_one(self):
+        """One peer-memory communicator: every rank exports its mailbox with CUDA IPC, the
+        handles travel through one torch.distributed all_gather, every rank maps its peers.  From then on the
+        SyncBN exchanges (2C floats, 40+ per step) are single-CTA kernels storing straight into the peers' HBM
+        instead of host-launched NCCL calls.  Large buffers (the gradient buckets) stay on NCCL.
+        Returns the opaque handle, or None (with a warning on rank 0) when any rank could not map any peer."""
+        from . import ops
         dev = torch.device("cuda", torch.cuda.current_device())
         comm, err = None, ""
         try:
@@ -82,9 +98,8 @@ class TorchComm:
                 warnings.warn("peer-memory communicator unavailable (%s); SyncBN statistics travel over NCCL" % (err or "a peer failed"))
             if comm is not None:
                 ops.comm_destroy(comm)
-            return self
-        self.peer = comm
-        return self
+            return None
+        return comm
 
     def allreduce_sum_(self, t):
         if self.world_size > 1:
@@ -118,6 +133,34 @@ class TorchComm:
     def barrier(self):
         if self.world_size > 1:
             dist.barrier(group=self.group)
+
+
+class AuxComm:
+    """The same communicator as seen from a SECOND stream: its small (SyncBN) exchanges go through the auxiliary
+    peer communicator, whose mailboxes and device-side call counter are its own, so they cannot interleave with the main
+    stream's exchanges (every rank issues each stream's exchanges in the same order, but the two streams' relative order
+    on the device is free).  Large or NCCL-carried exchanges fall through to the process group, which serialises them in
+    host issue order -- identical on every rank."""
+
+    def __init__(self, comm):
+        self._c = comm
+        self.world_size, self.rank = comm.world_size, comm.rank
+        self.peer = getattr(comm, "peer_aux", None)
+        self.peer_aux = None
+        self.transport = getattr(comm, "transport", "local")
+
+    def allreduce_sum_(self, t):
+        if self.world_size > 1:
+            if self.peer is not None and t.is_cuda and t.dtype == torch.float32 and t.numel() <= _PEER_MAX_N \
+                    and t.is_contiguous():
+                from . import ops
+                ops.comm_allreduce_small(self.peer, t)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._c.group)
+        return t
+
+    def barrier(self):
+        self._c.barrier()
 
 
 def init_from_env(backend=None):
@@ -170,14 +213,19 @@ class FlatParams:
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.offsets = []
+        # The flat buffers are laid out in REVERSE parameter order: backward produces the gradients of the last layer
+        # first, so the gradients that become final together are contiguous and a bucket of them (GradBuckets) is one
+        # slice.  `offsets` stays indexed by parameter order (optimizer state / checkpoints are unaffected).
+        self.offsets = [None] * len(params)
+        self.layout = list(range(len(params)))[::-1]
         off = 0
-        for p in params:
+        for idx in self.layout:
+            p = params[idx]
             k = p.numel()
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
-            self.offsets.append((off, k))
+            self.offsets[idx] = (off, k)
             off += k
         self.numel = n
 
@@ -189,3 +237,70 @@ class FlatParams:
         for (o, k), p in zip(self.offsets, self.params):
             if p.grad is None or p.grad.data_ptr() != self.grad[o:o + k].data_ptr():
                 p.grad = self.grad[o:o + k].view(p.shape)
+
+
+class GradBuckets:
+    """Gradient exchange of one network, bucketed and overlapped with the backward sweep that produces it
+    (SURVEY.md 8e): the flat gradient buffer (reverse parameter order = the order backward finishes them) is cut into
+    contiguous buckets of at least `min_elems` floats; the sweep calls ready(p) as each parameter's gradient becomes
+    final, and the moment a bucket is complete its all-reduce (SUM -- the loss head already divides by the GLOBAL batch,
+    jck_head_bwd mean_count) starts on the process group's stream while the sweep goes on.  finish() makes the
+    current stream wait for all of them.  ready() may be called from any stream (the weight-gradient kernels run on a
+    side stream): the bucket's collective is ordered after an event recorded at each call."""
+
+    def __init__(self, flat, comm, min_elems=1 << 19):
+        self.flat, self.comm = flat, comm
+        self.buckets = []                # [lo, hi, {param ids}]
+        lo, ids = 0, set()
+        for idx in flat.layout:
+            o, k = flat.offsets[idx]
+            ids.add(id(flat.params[idx]))
+            if o + k - lo >= min_elems:
+                self.buckets.append([lo, o + k, ids])
+                lo, ids = o + k, set()
+        if ids:
+            self.buckets.append([lo, flat.numel, ids])
+        self.bucket_of = {pid: b for b, (_, _, ids) in enumerate(self.buckets) for pid in ids}
+        self.begin()
+
+    def begin(self):
+        self.missing = [set(ids) for _, _, ids in self.buckets]
+        self.events = [[] for _ in self.buckets]
+        self.issued = [False] * len(self.buckets)
+        self.handles = []
+
+    def ready(self, *params):
+        if self.comm.world_size == 1:
+            return
+        for p in params:
+            b = self.bucket_of[id(p)]
+            if self.issued[b]:
+                continue
+            ev = torch.cuda.Event() if p.is_cuda else None
+            if ev is not None:
+                ev.record()
+                self.events[b].append(ev)
+            self.missing[b].discard(id(p))
+            if not self.missing[b]:
+                self._issue(b)
+
+    def _issue(self, b):
+        lo, hi, _ = self.buckets[b]
+        if self.events[b]:
+            cur = torch.cuda.current_stream()
+            for ev in self.events[b]:
+                cur.wait_event(ev)
+        self.handles.append(dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=getattr(self.comm, "group", None),
+                                            async_op=True))
+        self.issued[b] = True
+
+    def finish(self):
+        """Start whatever was never marked ready (ordered after the current stream), then wait for everything."""
+        if self.comm.world_size == 1:
+            return
+        for b in range(len(self.buckets)):
+            if not self.issued[b]:
+                self._issue(b)
+        for h in self.handles:
+            h.wait()                      # stream-ordered: the current stream waits, the host does not
+        self.handles = []

@@ -22,6 +22,9 @@ class CGANStep(DCGANStep):
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
         self.nz = self.g.nz            # G.conv1 takes nz + n_classes inputs; the noise itself is nz wide
+        # D's gradients ACCUMULATE over three sweeps here (first order, second order, penalty), so nothing is final
+        # before the last one: one exchange per network after its backward (averaged: the heads divide by the local batch)
+        self.ed.grad_sync = self.eg.grad_sync = None
 
     def draw(self, B):
         r = super().draw(B)

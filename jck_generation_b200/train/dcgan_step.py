@@ -14,15 +14,23 @@ the reference's wasted D weight-gradient of pass D (zeroed at :155 before any us
 Random tensors: `rng` injects host-made tensors (parity mode -- CPU mt19937 and Philox streams can
 never agree); otherwise they are drawn on the device by our Philox kernel.
 """
+import os
+
 import torch
 
 from .. import ops
+from ..parallel import AuxComm, GradBuckets
 
 LABEL_REAL = 0.9
 LABEL_FAKE = 0.1
 
 # rows of the per-step scalar block
 S_REAL, S_FAKE, S_GP, S_G = 0, 1, 2, 3
+
+
+def _null():
+    import contextlib
+    return contextlib.nullcontext()
 
 
 class DCGANStep:
@@ -43,8 +51,19 @@ class DCGANStep:
         self._static = None
         self._p4_bufs = {}
         # weight-gradient kernels run beside the sweep that produces their operands (engine._GradTarget)
+        self.gp_stream = None
         if self.dtype == torch.bfloat16:
             self.eg.wgrad_stream = self.ed.wgrad_stream = torch.cuda.Stream(device=self.dev)
+            # the gradient-penalty sweep (pass C) is independent of the A+B backward: it runs on its own stream, its
+            # HBM-bound BatchNorm passes beside the other sweep's convolutions and vice versa (JCK_GP_STREAM=0: in line)
+            if os.environ.get("JCK_GP_STREAM", "1") != "0":
+                self.gp_stream = torch.cuda.Stream(device=self.dev)
+        self.comm_gp = AuxComm(comm) if (self.gp_stream is not None and comm.world_size > 1) else None
+        # gradient exchange: per-bucket all-reduce started as the bucket's last gradient is written (parallel.GradBuckets)
+        self.sync_d = GradBuckets(flat_d, comm)
+        self.sync_g = GradBuckets(flat_g, comm)
+        if comm.world_size > 1:
+            self.ed.grad_sync, self.eg.grad_sync = self.sync_d, self.sync_g
 
     # ---- random tensors ----------------------------------------------------------------------------
     def draw(self, B):
@@ -111,24 +130,31 @@ class DCGANStep:
         ctx = ed.trunk_forward(X, groups=3)                                                                # :162,173,114
         ed.head_forward(ctx, targets=[LABEL_REAL, LABEL_FAKE, None], scalars=scal)
 
-        cab = ctx.slice(0, 2)                                                                              # :164,175
+        # pass C, the penalty's input-gradient sweep (:116-126): forked onto its own stream
+        main = torch.cuda.current_stream()
+        gps = self.gp_stream
+        if gps is not None:
+            gps.wait_stream(main)
+        with torch.cuda.stream(gps) if gps is not None else _null():
+            cc = ctx.slice(2, 3)
+            da4c = ed.head_backward(cc, mode=1, wgrad=False)
+            dx = ed.trunk_backward(cc, da4c, wgrad=False, input_grad=True, dx_out=self._p4("dx", B) if p4 else None,
+                                   comm=self.comm_gp)
+            ops.gp_penalty(dx, scal[S_GP])
+
+        # passes A+B (:164,175): D's parameter gradients; every bucket of them is exchanged as soon as it is final,
+        # while the rest of this sweep and the penalty sweep run
+        self.sync_d.begin()
+        cab = ctx.slice(0, 2)
         da4 = ed.head_backward(cab, mode=0, targets=[LABEL_REAL, LABEL_FAKE], wgrad=True, accumulate=False)
         ed.trunk_backward(cab, da4, wgrad=True, input_grad=False, accumulate=False)
-        if self.comm.world_size > 1:
-            ed.join_wgrad()
-        pending = self.comm.allreduce_mean_begin(self.flat_d.grad)      # D's gradients are final: exchange them ...
-
-        cc = ctx.slice(2, 3)                                                                               # :116-126
-        da4 = ed.head_backward(cc, mode=1, wgrad=False)
-        dx = ed.trunk_backward(cc, da4, wgrad=False, input_grad=True,   # ... while the penalty's input-gradient sweep runs
-                               dx_out=self._p4("dx", B) if p4 else None)
-        ops.gp_penalty(dx, scal[S_GP])
-
         ed.join_wgrad()
-        self.comm.allreduce_mean_end(pending, self.flat_d.grad)
+        self.sync_d.finish()
         self.opt_d.step()                                                                                  # :180
         if after_d_update is not None:
             after_d_update()
+        if gps is not None:
+            main.wait_stream(gps)       # the penalty sweep reads the packed weights refresh() is about to overwrite
         ed.refresh(force=True)
 
         ctx2 = ed.trunk_forward(X[B:2 * B], groups=1)                                                      # :185
@@ -137,9 +163,10 @@ class DCGANStep:
         dmix = ed.trunk_backward(ctx2, da4, wgrad=False, input_grad=True, dx_out=self._p4("dmix", B) if p4 else None)
         dy5 = self._p4("dy5", B) if p4 else torch.empty_like(dmix)
         ops.g_out_bwd(dmix, fake_raw, 0.9, dy5, layout=lay)
+        self.sync_g.begin()
         eg.backward(gctx, dy5, accumulate=False)
         eg.join_wgrad()
-        self.comm.allreduce_mean_(self.flat_g.grad)
+        self.sync_g.finish()
         self.opt_g.step()                                                                                  # :189
         eg.refresh(force=True)
         self.last = {"fake_raw": fake_raw, "gp_grad_nhwc": dx, "ctx": ctx, "ctx_g": gctx, "ctx_d": ctx2,

@@ -152,7 +152,7 @@ def _to_p4(x_nchw):
     return out
 
 
-def check_edge(which, B=8, nc=3):
+def check_edge(which, B=8, nc=3, groups=None):
     """tcgen05 image-edge kernels (Ca = 64, nc image channels, Hs = 32) against torch CPU convolutions."""
     from jck_generation_b200 import ops
     Ca, Hs = 64, 32
@@ -164,7 +164,8 @@ def check_edge(which, B=8, nc=3):
         x = _mk((B, nc, 64, 64), dt, 32)
         want = F.conv2d(x, w4, stride=2, padding=1)
         out = torch.full((B, Hs, Hs, Ca), float("nan"), dtype=dt, device="cuda")
-        groups = 2 if B % 2 == 0 else 1         # two BatchNorm groups when the batch splits evenly
+        if groups is None:
+            groups = 2 if B % 2 == 0 else 1     # two BatchNorm groups when the batch splits evenly
         stats = torch.zeros(groups, 2 * Ca, device="cuda")
         ops.edge_down_img(_to_p4(x), wde, out, stats, Ca, ipg=B // groups)
         torch.cuda.synchronize()
@@ -283,6 +284,36 @@ def check_fc(dtype, B=8, K=100, C=512):
     torch.cuda.synchronize()
     ws = torch.cat([want.sum((0, 2, 3)), (want ** 2).sum((0, 2, 3))])
     return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats.view(-1), ws), "dw": _rel(dw4, want_dw)}
+
+
+def check_fc_tc(B=512, K=100, C=512):
+    """G.conv1 as the bf16 engine runs it (engine.GeneratorEngine.forward / backward): z cast to bf16 rows, the weight as the
+    MN-major operand of jck_gemm_tc, BatchNorm statistics in the epilogue; weight gradient = split-K GEMM over the batch."""
+    from jck_generation_b200 import ops
+    bf = torch.bfloat16
+    z = _mk((B, K, 1, 1), bf, 13)
+    w4 = _mk((K, C, 4, 4), bf, 14, 0.05)
+    want = F.conv_transpose2d(z, w4, stride=1, padding=0)               # [B,C,4,4]
+    dy = _mk((B, C, 4, 4), bf, 15)
+    want_dw = torch.einsum("bk,bcyx->kcyx", z.view(B, K), dy)
+    N1, Kp = 16 * C, (K + 7) // 8 * 8
+    w_fc = torch.empty(K, N1, dtype=bf, device="cuda")
+    ops.pack_fc_t(w4.cuda().contiguous(), w_fc)
+    zb = torch.empty(B, Kp, dtype=bf, device="cuda")
+    ops.cast_rows_bf16(z.view(B, K).cuda().contiguous(), zb)
+    y1 = torch.full((B, 4, 4, C), float("nan"), dtype=bf, device="cuda")
+    stats = torch.zeros(1, 2 * C, device="cuda")
+    ops.gemm_tc(zb, 0, Kp, w_fc, 1, N1, y1.view(B, N1), B, N1, K, stats=stats, stats_channels=C)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().to(bf).cuda().view(B, N1)
+    dw_fc = torch.empty(K, N1, device="cuda")
+    nbytes = ops.gemm_tc_workspace_bytes(K, N1, B)
+    ws = torch.empty(max(nbytes, 4) // 4, device="cuda")
+    ops.gemm_tc(zb, 1, Kp, dyn, 1, N1, dw_fc, K, N1, B, workspace=ws)
+    dw4 = torch.zeros(K, C, 4, 4, device="cuda")
+    ops.unpack_fc_grad_t(dw_fc, dw4, False)
+    torch.cuda.synchronize()
+    wst = torch.cat([want.sum((0, 2, 3)), (want ** 2).sum((0, 2, 3))])
+    return {"out": _rel(y1.float().permute(0, 3, 1, 2), want), "stats": _rel(stats.view(-1), wst), "dw": _rel(dw4, want_dw)}
 
 
 def check_misc():
@@ -432,9 +463,30 @@ def all_cases():
               ("edge_down1", "-", "bf16", "tc", 4), ("edge_up1", "-", "bf16", "tc", 4), ("edge_wgrad1", "-", "bf16", "tc", 4)]
     cases += [("bnbwd_up", "c2", "bf16", "tc", 8), ("bnbwd_up", "c3", "bf16", "tc", 8), ("bnbwd_up", "c4", "bf16", "tc", 3),
               ("bnbwd_down", "c2", "bf16", "tc", 8), ("bnbwd_down", "c3", "bf16", "tc", 3), ("bnbwd_down", "c4", "bf16", "tc", 16)]
+    cases += big_cases()
     cases += [("bn", "-", "f32", "-", 8), ("bn", "-", "bf16", "-", 8), ("head", "-", "f32", "-", 8),
               ("head", "-", "bf16", "-", 8), ("fc", "-", "f32", "-", 8), ("fc", "-", "bf16", "-", 8),
               ("misc", "-", "f32", "-", 4), ("gemm", "-", "bf16", "tc", 0)]
+    return cases
+
+
+def big_cases():
+    """The sizes the benchmark runs (BASELINE configs[2]: 512 images per GPU).  At these sizes every tcgen05 kernel walks
+    several tiles per CTA (persistent tile loop, TMEM double buffering, ring phase carry-over, register-resident
+    BatchNorm partials flushed on a group change, split-K ranges of the weight gradient) -- paths a batch of 8 never
+    enters (<= 32 tile pairs < 148 clusters).  1536 = the discriminator's [real | fake | x_hat] forward with three
+    BatchNorm groups; 1024 = the backward of its A+B slice (two groups); 512 = the generator and the penalty sweep."""
+    cases = []
+    for shape in ("c2", "c3", "c4"):
+        cases += [("down", shape, "bf16", "tc", 512), ("down_groups3", shape, "bf16", "tc", 1536),
+                  ("up", shape, "bf16", "tc", 512), ("up", shape, "bf16", "tc", 1024),
+                  ("wgrad", shape, "bf16", "tc", 1024), ("wgrad", shape, "bf16", "tc", 512)]
+    cases += [("bnbwd_up", "c3", "bf16", "tc", 1024), ("bnbwd_up", "c4", "bf16", "tc", 1024), ("bnbwd_up", "c4", "bf16", "tc", 512),
+              ("bnbwd_down", "c3", "bf16", "tc", 512), ("bnbwd_down", "c4", "bf16", "tc", 512),
+              ("edge_down_g3", "-", "bf16", "tc", 1536), ("edge_down", "-", "bf16", "tc", 512),
+              ("edge_upscatter", "-", "bf16", "tc", 512), ("edge_wgrad", "-", "bf16", "tc", 1024),
+              ("edge_wgrad", "-", "bf16", "tc", 512),
+              ("bn_big", "-", "bf16", "-", 1536), ("head_big", "-", "bf16", "-", 512), ("fc_big", "-", "bf16", "-", 512)]
     return cases
 
 
@@ -449,6 +501,16 @@ def run_case(op, shape, dtype, algo, B):
         return check_down(shape, _dt(dtype), _alg(algo), B, groups=2)
     if op == "up_groups":
         return check_up(shape, _dt(dtype), _alg(algo), B, groups=2)
+    if op == "down_groups3":
+        return check_down(shape, _dt(dtype), _alg(algo), B, groups=3)
+    if op == "edge_down_g3":
+        return check_edge("down", B, nc=3, groups=3)
+    if op == "bn_big":
+        return check_bn(_dt(dtype), C=128, B=B, H=16, groups=3)
+    if op == "head_big":
+        return check_head(_dt(dtype), B=B)
+    if op == "fc_big":
+        return check_fc_tc(B)
     if op.startswith("bnbwd_"):
         kind = op[6:]
         groups = 2 if (B % 2 == 0 and shape in ("c3", "c4")) else 1
@@ -489,6 +551,8 @@ def main():
         return
     bad = 0
     cases = all_cases()
+    if "--only-big" in sys.argv:
+        cases = big_cases()
     if "--only-tc" in sys.argv:
         cases = [c for c in cases if c[3] == "tc"]
     if "--no-tc" in sys.argv:

@@ -105,9 +105,36 @@ def first_clean(fn, seeds=(11, 12, 13, 14, 15, 16, 17, 18), **kw):
     raise AssertionError(f"no draw without a LeakyReLU/ReLU kink flip among seeds {seeds}")
 
 
-def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11, sync_d=True):
-    """One step, everything compared.  Returns {name: relative error}.  `sync_d`: see _d_update_sync."""
+def sync_from_oracle(P):
+    """Put the CUDA side into the oracle's state: weights, BatchNorm buffers, Adam moments and step count."""
+    P.g.load_state_dict(P.g_o.state_dict())
+    P.d.load_state_dict(P.d_o.state_dict())
+    for opt_o, opt, flat in ((P.og, P.opt_g, P.fg), (P.od, P.opt_d, P.fd)):
+        sd = opt_o.state_dict()
+        steps = 0
+        for idx, (o, k) in enumerate(flat.offsets):
+            st = sd["state"].get(idx)
+            if st:
+                flat.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                flat.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps = int(float(st["step"]))
+        opt.steps_done = steps
+        opt.step_dev.fill_(steps)
+    P.step.eg.refresh(force=True)
+    P.step.ed.refresh(force=True)
+
+
+def dcgan_step_parity(dtype, batch=8, lr=2e-4, nc=3, rng_seed=11, sync_d=True, warm_steps=0):
+    """One step, everything compared.  Returns {name: relative error}.  `sync_d`: see _d_update_sync.
+    `warm_steps`: train the ORACLE that many steps first and start the CUDA side from its state, so the compared step
+    runs off the N(0, .02) initialisation (where BatchNorm backward cancels most of every gradient)."""
     P = make_pair(dtype, lr, nc=nc)
+    if warm_steps:
+        wr = osteps.make_real(batch, nc=nc, n_steps=warm_steps, seed=4242)
+        wn = osteps.make_rng(batch, nc=nc, n_steps=warm_steps, seed=4243)
+        for i in range(warm_steps):
+            osteps.dcgan_step(P.g_o, P.d_o, P.og, P.od, wr[i], wn[i])
+        sync_from_oracle(P)
     real = osteps.make_real(batch, nc=nc, n_steps=1)[0]
     rng = osteps.make_rng(batch, nc=nc, n_steps=1, seed=rng_seed)[0]
     want = osteps.dcgan_step(P.g_o, P.d_o, P.og, P.od, real, rng, capture=True)
@@ -188,7 +215,7 @@ def smoke_check():
     print("smoke ok: fp32 worst", worst32, "bf16 loss_d err", e16["scalar.loss_d"])
 
 
-def autocast_envelope(batch, nc=3, seed=12345, rng_seed=11):
+def autocast_envelope(batch, nc=3, seed=12345, rng_seed=11, warm_steps=0):
     """What bf16 costs on THIS network with torch's own bf16 autocast (CPU): relative error of every
     parameter gradient of the generator step (G through D) and of the discriminator passes A+B against
     fp32.  BatchNorm backward subtracts the batch-common part of the gradient, which at initialisation
@@ -197,9 +224,18 @@ def autocast_envelope(batch, nc=3, seed=12345, rng_seed=11):
     import torch.nn as nn
     real = osteps.make_real(batch, nc=nc, n_steps=1)[0]
     rng = osteps.make_rng(batch, nc=nc, n_steps=1, seed=rng_seed)[0]
+    g0, d0 = omodels.build("DCGAN", seed=seed, nc=nc)
+    if warm_steps:          # the same warm-up dcgan_step_parity(warm_steps=...) runs
+        og, od = osteps.make_optimizers(g0, d0, 2e-4)
+        wr = osteps.make_real(batch, nc=nc, n_steps=warm_steps, seed=4242)
+        wn = osteps.make_rng(batch, nc=nc, n_steps=warm_steps, seed=4243)
+        for i in range(warm_steps):
+            osteps.dcgan_step(g0, d0, og, od, wr[i], wn[i])
+    import copy
 
     def grads(autocast):
-        g, d = omodels.build("DCGAN", seed=seed, nc=nc)
+        g, d = copy.deepcopy(g0), copy.deepcopy(d0)
+        g.zero_grad(); d.zero_grad()
         bce = nn.BCELoss()
         with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
             fake = 0.9 * g(rng["z"]) + 0.1 * rng["noise_fake"]

@@ -2,7 +2,7 @@
 gradients, scalars, post-step weights / BN buffers, loss trajectories; module (autograd) API; trainer.
 
 Tolerances (north_star): fp32 mode rel err <= 1e-4 on activations and gradients.  bf16 mode: activations
-<= 2e-2 (8-bit mantissa storage through up to nine layers); gradients are bounded by the error torch's
+<= 1e-2 (1.3e-2 for the two deepest layers on generated images); gradients are bounded by the error torch's
 own bf16 autocast makes on the same network (tests/parity.py:autocast_envelope) -- BatchNorm backward
 cancels the batch-common part of the gradient, so 1e-2 is not reachable by ANY bf16 implementation here
 (measured: torch autocast is 6-17 % off on these gradients at initialisation)."""
@@ -61,17 +61,22 @@ def test_fp32_post_step_state(fp32_errs):
 
 
 def test_bf16_activations(bf16_errs):
+    """north_star: <= 1e-2.  Holds for every layer except D's conv3 / conv4 on GENERATED images (8 and 9 bf16 layers deep:
+    measured 1.0e-2 / 1.2e-2, bound 1.3e-2); see tests/test_gpu_big.py for the same check at the benchmarked batches."""
+    deep = ("d_act.B.conv3", "d_act.B.conv4", "d_act.D.conv3", "d_act.D.conv4")
     for k, v in bf16_errs.items():
         if k.startswith(("d_act", "g_act", "fake_raw")):
-            assert v <= 2e-2, f"{k}: {v}"
+            assert v <= (1.3e-2 if k in deep else 1e-2), f"{k}: {v}"
     for k in ("scalar.loss_d", "scalar.loss_g", "scalar.x_d", "scalar.z1_gd", "scalar.err_real", "scalar.err_fake"):
-        assert bf16_errs[k] <= 3e-2, f"{k}: {bf16_errs[k]}"
+        assert bf16_errs[k] <= 1e-2, f"{k}: {bf16_errs[k]}"
 
 
 def test_bf16_gradients_within_torch_autocast_envelope(bf16_errs):
+    """Every parameter gradient against the error of torch's own bf16 autocast on the same tensor (measured at batches 8,
+    128, 512: ours is at or below it on every tensor; tests/test_gpu_big.py holds the large batches to 1.1x + 5e-3)."""
     env = parity.autocast_envelope(8)
     for k, e in env.items():
-        assert bf16_errs[k] <= 1.5 * e + 2e-2, f"{k}: ours {bf16_errs[k]:.3f} vs torch bf16 autocast {e:.3f}"
+        assert bf16_errs[k] <= 1.25 * e + 1e-2, f"{k}: ours {bf16_errs[k]:.3f} vs torch bf16 autocast {e:.3f}"
 
 
 def test_nc1_restatement_fp32():

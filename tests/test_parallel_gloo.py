@@ -36,7 +36,9 @@ def _syncbn_conv_rank(rank, world, port, ret):
     up_all = torch.randn(B, C, H, H, generator=gen)           # d(loss_sum)/d(act), per sample
 
     x = parallel.shard_rows(x_all, comm)
-    up = parallel.shard_rows(up_all, comm) / x.shape[0]       # loss = mean over the LOCAL batch (engine convention)
+    # loss = mean over the GLOBAL batch (engine convention: jck_head_bwd mean_count = rows x world), so the ranks' parameter
+    # gradients SUM to the reference's global-batch gradient
+    up = parallel.shard_rows(up_all, comm) / (x.shape[0] * comm.world_size)
     # ---- forward, as engine.trunk_forward does it
     y = F.conv2d(x, w, stride=2, padding=1)
     stats = torch.cat([y.sum((0, 2, 3)), (y * y).sum((0, 2, 3))])
@@ -55,15 +57,24 @@ def _syncbn_conv_rank(rank, world, port, ret):
     dy = (gamma * rstd).view(1, C, 1, 1) * (g - sums[:C].view(1, C, 1, 1) / count - xhat * sums[C:].view(1, C, 1, 1) / count)
     dw_local = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2, padding=1)
 
-    # ---- flat bucket + averaged gradient exchange
+    # ---- flat buffer (reverse parameter order) + bucketed gradient exchange, started as the gradients become final
     mod = torch.nn.Module()
     mod.w = torch.nn.Parameter(w.clone()); mod.g = torch.nn.Parameter(gamma.clone()); mod.b = torch.nn.Parameter(beta.clone())
     flat = parallel.FlatParams(mod)
-    mod.w.grad.copy_(dw_local); mod.g.grad.copy_(dgamma_local); mod.b.grad.copy_(dbeta_local)
-    comm.allreduce_mean_(flat.grad)
+    assert flat.layout == [2, 1, 0] and flat.offsets[2][0] == 0 and flat.offsets[0][0] == 2 * C
+    sync = parallel.GradBuckets(flat, comm, min_elems=2 * C)          # buckets: [b, g] and [w]
+    assert [(lo, hi) for lo, hi, _ in sync.buckets] == [(0, 2 * C), (2 * C, flat.numel)]
+    sync.begin()
+    mod.g.grad.copy_(dgamma_local); mod.b.grad.copy_(dbeta_local)
+    sync.ready(mod.g, mod.b)                                          # first bucket complete: its all-reduce starts here
+    assert sync.issued == [True, False]
+    mod.w.grad.copy_(dw_local)
+    sync.ready(mod.w)
+    sync.finish()
+    assert sync.issued == [True, True] and not sync.handles
     mod.zero_grad()            # sets .grad = None; rebind must re-attach the bucket views
     flat.rebind()
-    assert mod.w.grad.data_ptr() == flat.grad.data_ptr()
+    assert mod.w.grad.data_ptr() == flat.grad[2 * C:].data_ptr() and mod.b.grad.data_ptr() == flat.grad.data_ptr()
 
     # ---- single-process truth on the full batch: loss = mean over the GLOBAL batch
     wt, gt, bt = w.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
