@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the FID-eval / input-pipeline side measurements")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the side measurements (CGAN step, fp32 step, library bar, FID eval ...)")
+    ap.add_argument("--secondary-only", action="store_true", help="(internal) run only the side measurements, print their JSON")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device time table")
     ap.add_argument("--kernel-table", action="store_true", help="print per-kernel device time (CUPTI via torch.profiler)")
     return ap.parse_args()
@@ -629,7 +630,17 @@ def run_b200(args):
                                 "sample": f"oracle port of the reference step, 5 steps of {B} images (the GPU arm's batch) on "
                                           f"{cores} host threads ({cms:.0f} ms/step), anomaly detection off"}
     if comm.world_size == 1 and not args.no_secondary:
-        secondary.update(secondary_paths(torch, trainer, dev, args))
+        # in a child process: a fault in a side path (they exercise other kernels: CGAN, Inception, fp32 mode) must not take
+        # the headline down with it, and their allocations / cudnn autotuning must not disturb it either
+        del trainer, step
+        torch.cuda.empty_cache()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--secondary-only", "--batch", str(B), "--dtype", args.dtype],
+                               capture_output=True, text=True, timeout=900)
+            got = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            secondary.update(json.loads(got[-1]) if got else {"error": (r.stderr or r.stdout)[-300:]})
+        except Exception as e:                      # noqa: BLE001
+            secondary["error"] = f"{type(e).__name__}: {e}"[:300]
     if secondary:
         line["secondary"] = secondary
     if rank == 0:
@@ -644,10 +655,22 @@ def run_b200(args):
         os._exit(0)
 
 
+def run_secondary_only(args):
+    import torch
+    import __graft_entry__ as entry
+    entry.build()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    trainer = make_trainer(torch, args, args.batch)
+    print(json.dumps(secondary_paths(torch, trainer, dev, args)), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.secondary_only:
+        run_secondary_only(args)
     else:
         run_b200(args)
 

@@ -204,12 +204,16 @@ class FlatParams:
     nn.Parameter API intact): Adam becomes one launch per network and the gradient exchange one
     all-reduce per network."""
 
+    ALIGN = 32       # floats
+
     def __init__(self, module):
         params = [p for p in module.parameters()]
         self.params = params
-        n = sum(p.numel() for p in params)
+        # every parameter starts on a 128-byte boundary (the kernels read parameters and gradients with 128-bit
+        # accesses); the padding elements stay zero in all four buffers
+        n = sum(-(-p.numel() // self.ALIGN) * self.ALIGN for p in params)
         dev = params[0].device
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -226,7 +230,7 @@ class FlatParams:
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
             self.offsets[idx] = (off, k)
-            off += k
+            off += -(-k // self.ALIGN) * self.ALIGN
         self.numel = n
 
     def views(self, flat):
@@ -254,10 +258,11 @@ class GradBuckets:
         lo, ids = 0, set()
         for idx in flat.layout:
             o, k = flat.offsets[idx]
+            end = o + -(-k // flat.ALIGN) * flat.ALIGN          # padded end = the next parameter's offset
             ids.add(id(flat.params[idx]))
-            if o + k - lo >= min_elems:
-                self.buckets.append([lo, o + k, ids])
-                lo, ids = o + k, set()
+            if end - lo >= min_elems:
+                self.buckets.append([lo, end, ids])
+                lo, ids = end, set()
         if ids:
             self.buckets.append([lo, flat.numel, ids])
         self.bucket_of = {pid: b for b, (_, _, ids) in enumerate(self.buckets) for pid in ids}

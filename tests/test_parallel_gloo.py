@@ -61,9 +61,10 @@ def _syncbn_conv_rank(rank, world, port, ret):
     mod = torch.nn.Module()
     mod.w = torch.nn.Parameter(w.clone()); mod.g = torch.nn.Parameter(gamma.clone()); mod.b = torch.nn.Parameter(beta.clone())
     flat = parallel.FlatParams(mod)
-    assert flat.layout == [2, 1, 0] and flat.offsets[2][0] == 0 and flat.offsets[0][0] == 2 * C
-    sync = parallel.GradBuckets(flat, comm, min_elems=2 * C)          # buckets: [b, g] and [w]
-    assert [(lo, hi) for lo, hi, _ in sync.buckets] == [(0, 2 * C), (2 * C, flat.numel)]
+    A = flat.ALIGN                                                    # every parameter starts on a 128-byte boundary
+    assert flat.layout == [2, 1, 0] and flat.offsets[2][0] == 0 and flat.offsets[1][0] == A and flat.offsets[0][0] == 2 * A
+    sync = parallel.GradBuckets(flat, comm, min_elems=2 * A)          # buckets: [b, g] and [w]
+    assert [(lo, hi) for lo, hi, _ in sync.buckets] == [(0, 2 * A), (2 * A, flat.numel)]
     sync.begin()
     mod.g.grad.copy_(dgamma_local); mod.b.grad.copy_(dbeta_local)
     sync.ready(mod.g, mod.b)                                          # first bucket complete: its all-reduce starts here
@@ -74,7 +75,7 @@ def _syncbn_conv_rank(rank, world, port, ret):
     assert sync.issued == [True, True] and not sync.handles
     mod.zero_grad()            # sets .grad = None; rebind must re-attach the bucket views
     flat.rebind()
-    assert mod.w.grad.data_ptr() == flat.grad[2 * C:].data_ptr() and mod.b.grad.data_ptr() == flat.grad.data_ptr()
+    assert mod.w.grad.data_ptr() == flat.grad[2 * A:].data_ptr() and mod.b.grad.data_ptr() == flat.grad.data_ptr()
 
     # ---- single-process truth on the full batch: loss = mean over the GLOBAL batch
     wt, gt, bt = w.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
@@ -114,7 +115,7 @@ def test_flat_params_keep_module_semantics():
     lin = torch.nn.Linear(4, 3)
     before = {k: v.clone() for k, v in lin.state_dict().items()}
     flat = parallel.FlatParams(lin)
-    assert flat.numel == 15
+    assert flat.numel == 2 * flat.ALIGN            # weight (12) and bias (3), each padded to a 128-byte boundary
     for k, v in lin.state_dict().items():
         assert torch.equal(v, before[k])
     flat.flat.mul_(2)                      # the parameters are views of the bucket
