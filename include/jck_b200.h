@@ -349,6 +349,9 @@ int jck_one_hot_i64(const long long* labels, const long long* index, long long* 
 int jck_comm_create(int rank, int world, void** comm_out, void* ipc_handle_out /* JCK_COMM_HANDLE_BYTES */);
 int jck_comm_connect(void* comm, const void* all_handles /* world x JCK_COMM_HANDLE_BYTES, rank order */);
 int jck_comm_destroy(void* comm);
+/* *flag_out <- 1 if any exchange on this communicator ever timed out waiting for a peer (JCK_COMM_TIMEOUT_S seconds,
+ * default 120; the timed-out exchange returned NaN instead of a sum), else 0.  Synchronises with the device. */
+int jck_comm_error(void* comm, int* flag_out);
 /* data[0..n) <- sum over ranks, in place, n <= JCK_COMM_MAX_N; identical bits on every rank */
 int jck_comm_allreduce_small(void* comm, float* data, int n, void* stream);
 /* SyncBN forward: all-reduce stats[groups][2C] in place, then exactly jck_bn_finalize (count = GLOBAL samples) */

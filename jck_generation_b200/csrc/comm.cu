@@ -10,7 +10,12 @@
 // (fixed summation order).  `seq` is a device-side counter the kernel advances itself, so the launch sequence
 // is CUDA-graph capturable.  A slot is reused after kSlots calls; a rank can only be kSlots calls ahead of a
 // peer if that peer has delivered its values for the calls in between, i.e. has finished reading the slot.
-// Every spin is bounded: a protocol bug traps instead of hanging the GPU.
+// Every spin is bounded (JCK_COMM_TIMEOUT_S seconds, default 120 -- generous, like NCCL's watchdog: legitimate rank
+// skew can be seconds when rank 0 alone writes a checkpoint or runs an evaluation while its peers already wait in the
+// next step's exchange).  A timeout does NOT trap (that would destroy the CUDA context of a job that may be recoverable):
+// the kernel prints a diagnostic, raises a sticky error flag the host reads with jck_comm_error(), and poisons its result
+// with NaN so that nothing downstream can mistake it for a sum.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace jck {
@@ -23,6 +28,8 @@ constexpr int kMaxN = JCK_COMM_MAX_N;
 struct CommDev {
     unsigned long long* peer[kMaxWorld];   // mailbox base of every rank (own included), as mapped in THIS process
     unsigned int* seq;                     // local call counter
+    unsigned int* err;                     // sticky error flag (device memory, read back by jck_comm_error)
+    long long timeout_cycles;              // spin bound
     int rank, world;
 };
 
@@ -62,9 +69,11 @@ __device__ void allreduce_block(const CommDev& c, float* __restrict__ data, int 
             if ((unsigned int)(v >> 32) != seq) {
                 const long long t0 = clock64();
                 do {
-                    if (clock64() - t0 > 8000000000LL) {   // ~4 s: a peer never arrived
-                        printf("jck: comm all-reduce timed out (rank %d waits for rank %d, call %u)\n", c.rank, r, seq);
-                        __trap();
+                    if (clock64() - t0 > c.timeout_cycles) {   // a peer never arrived
+                        if (atomicExch(c.err, 1u) == 0u)
+                            printf("jck: comm all-reduce timed out (rank %d waits for rank %d, call %u)\n", c.rank, r, seq);
+                        v = ((unsigned long long)seq << 32) | 0x7FC00000ull;   // NaN: poison, do not pretend
+                        break;
                     }
                     v = ld_sys_u64(w);
                 } while ((unsigned int)(v >> 32) != seq);
@@ -144,6 +153,12 @@ extern "C" int jck_comm_create(int rank, int world, void** comm_out, void* ipc_h
     cm->dev.world = world;
     cudaError_t e = cudaGetDevice(&cm->device);
     const size_t bytes = mailbox_words() * sizeof(unsigned long long) + 256;
+    {
+        const char* t = getenv("JCK_COMM_TIMEOUT_S");
+        double secs = t ? atof(t) : 120.0;
+        if (!(secs > 0.0)) secs = 120.0;
+        cm->dev.timeout_cycles = (long long)(secs * 2.0e9);            // clock64 ticks at ~2 GHz
+    }
     if (e == cudaSuccess) e = cudaMalloc(&cm->local, bytes);
     if (e == cudaSuccess) e = cudaMemset(cm->local, 0, bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -156,6 +171,7 @@ extern "C" int jck_comm_create(int rank, int world, void** comm_out, void* ipc_h
     memcpy(ipc_handle_out, &h, sizeof(h));
     cm->dev.peer[rank] = reinterpret_cast<unsigned long long*>(cm->local);
     cm->dev.seq = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(cm->local) + mailbox_words() * sizeof(unsigned long long));
+    cm->dev.err = cm->dev.seq + 16;
     *comm_out = cm;
     return JCK_OK;
 }
@@ -173,6 +189,16 @@ extern "C" int jck_comm_connect(void* comm, const void* all_handles) {
         cm->opened[r] = p;
         cm->dev.peer[r] = reinterpret_cast<unsigned long long*>(p);
     }
+    return JCK_OK;
+}
+
+extern "C" int jck_comm_error(void* comm, int* flag_out) {
+    JCK_REQUIRE(comm && flag_out, "comm_error: bad argument");
+    Comm* cm = static_cast<Comm*>(comm);
+    unsigned int f = 0;
+    cudaError_t e = cudaMemcpy(&f, cm->dev.err, sizeof(f), cudaMemcpyDeviceToHost);      // synchronises with the device
+    if (e != cudaSuccess) return set_error(JCK_E_CUDA, "comm_error: %s", cudaGetErrorString(e));
+    *flag_out = (int)f;
     return JCK_OK;
 }
 

@@ -743,6 +743,299 @@ int launch_conv_tc_persist(const CUtensorMap& mA, const CUtensorMap& mB, void* o
     return JCK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Up conv with an in-shared-memory input WINDOW and a RESIDENT filter bank (the 64-channel layer: G.conv4 forward,
+// D.conv2 input gradient; Ca <= 128 -> Cb = 64).
+// The tap-streaming kernels above re-load the activation tile once per (output parity, tap): 16 boxes of 16 KB per
+// 128 input pixels and 64-channel chunk, which pins the 64-channel layer (only 4 KB of weights per box to amortise
+// them) to the L2 -> shared-memory stream at ~600-700 TFLOP/s.  Here
+//  * a tile is 8 x 16 input pixels of ONE image and its 10 x 18 pixel neighbourhood (1-pixel halo; out-of-image pixels
+//    are zero-filled by TMA = the padding) is loaded ONCE per channel chunk: 180 rows of 128 bytes, 128B-swizzled.
+//    Every one of the 16 (parity, tap) products reads its shifted 8 x 16 sub-window straight from that buffer through
+//    the MMA's shared-memory descriptor:   operand row (yl, xl) = window row (yl + 1 + dy) * 10 + (xl + 1 + dx),
+//    i.e. start address = window + ((1 + dy) * 10 + 1 + dx) * 128 B with the 8-row groups (one image row each) 1280 B
+//    apart (the descriptor's stride-byte-offset field).  The swizzle is a function of the absolute shared-memory
+//    address on sm_100a (see incep.cu), so a start address off the 1 KB swizzle atom needs no base-offset bits.
+//    Activation traffic drops 11x (23 KB instead of 256 KB per tile and chunk);
+//  * two CTAs of a cluster (cta_group::2, M = 256) take the two 8-pixel halves of a 16-pixel-wide strip, and each keeps
+//    ITS HALF of the layer's whole filter bank (all 16 (parity, tap) x chunk tiles of [32 out][64 k], 128 KB) resident
+//    for its entire tile walk: after the prologue the only shared-memory traffic from L2 is the 46 KB window per tile,
+//    and the main loop is 128 back-to-back MMAs per tile with no operand barrier in between;
+//  * products that read the SAME window shift are issued as ONE MMA over the concatenated output columns of the parities
+//    that use it: the centre shift serves all four parities (N = 256), three of the four edge shifts serve two parities
+//    whose accumulators are adjacent in the column order P00 | P01 | P11 | P10 (N = 128), the rest are N = 64 -- ten
+//    MMAs per 16-deep K step instead of sixteen N = 64 ones (measured: a stream of N = 64 MMAs keeps the tensor pipe
+//    at 40 % -- the per-instruction A-operand fetch is not amortised);
+//  * windows and the four 64-column parity accumulators are double buffered (2 x 256 TMEM columns), so the epilogue of
+//    tile i (each thread writes its input pixel's 2 x 2 output block: two runs of 256 contiguous bytes; BatchNorm
+//    sums over the four parities before ONE pair of warp transposes per 32 channels) overlaps the MMAs of tile i + 1.
+// One CTA pair per SM pair (the resident bank + two windows fill the 227 KB).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWinTW = 8, kWinTH = 16;                       // tile: 8 x 16 input pixels = 128 MMA rows per CTA
+constexpr int kWinBW = kWinTW + 2, kWinBH = kWinTH + 2;      // with the halo
+constexpr int kWinBytes = kWinBW * kWinBH * 128;             // 23,040 B per 64-channel chunk
+constexpr int kWinPitch = 23 * 1024;                         // chunk buffers on 1 KB boundaries
+constexpr int kWinMaxChunks = 2;                             // Ca <= 128
+constexpr int kWinWTile = 32 * 128;                          // this CTA's half of one [64 out][64 k] weight tile
+constexpr int kWinWOff = 2 * kWinMaxChunks * kWinPitch;      // after the two window buffers
+constexpr int kWinBarOff = kWinWOff + 16 * kWinMaxChunks * kWinWTile;
+constexpr int kWinRedOff = kWinBarOff + 256;
+constexpr int kWinSmem = kWinRedOff + 4 * 2 * 64 * 4 + 1024;
+
+struct ConvWinParams { int B, Hs, Ws, Ca, tiles_x, tiles_img, ipg; };
+
+// accumulator column order P00 | P01 | P11 | P10 (a Gray cycle: neighbours share an output-row or output-column parity, so
+// the parities that read one edge shift of the window are adjacent) -> output parity index py * 2 + px
+__host__ __device__ __forceinline__ int win_slot_phase(int slot) { return slot == 2 ? 3 : (slot == 3 ? 2 : slot); }
+
+__global__ void __launch_bounds__(192, 1)
+conv_up_win_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvWinParams p, const int total_pairs) {
+    pdl_trigger();
+    constexpr int Cb = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + kWinBarOff);   // [2]  leader: both CTAs' window bytes have landed
+    uint64_t* a_empty = a_full + 2;                                      // [2]  each CTA: the tile's MMAs have read the window
+    uint64_t* tfull = a_empty + 2;                                       // [2]  each CTA: accumulators complete
+    uint64_t* tempty = tfull + 2;                                        // [2]  leader: accumulators drained by both epilogues
+    uint64_t* w_full = tempty + 2;                                       // leader: both CTAs' filter-bank halves have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    float* red = reinterpret_cast<float*>(smem + kWinRedOff);            // [4 warps][2][64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int cchunks = p.Ca / kBK;
+    const int wtiles = 16 * cchunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&a_full[a], 1);
+            mbar_init(&a_empty[a], 1);
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 2 * 128);
+        }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+    fence_before_sync();
+    cluster_sync_all();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    // tile of pair-tile tp for this CTA: the two CTAs take x-adjacent tiles (tiles_x is even)
+    auto decode = [&](int tp, int& n, int& x0, int& y0) {
+        const int t = 2 * tp + rank;
+        n = t / p.tiles_img;
+        const int rem = t - n * p.tiles_img;
+        x0 = (rem % p.tiles_x) * kWinTW;
+        y0 = (rem / p.tiles_x) * kWinTH;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer (both CTAs) ----------------
+            // resident filter bank, per channel chunk 64 KB = this CTA's half (cta_group::2: rows [r N/2, (r+1) N/2) of every
+            // MMA's B tile) of the ten MMA groups, as sixteen [32 out][64 k] boxes -- see the group table at the MMA issuer
+            if (rank == 0) mbar_arrive_expect_tx(w_full, 2 * wtiles * kWinWTile);
+            for (int cc = 0; cc < cchunks; ++cc) {
+                for (int q = 0; q < 16; ++q) {
+                    int slot, half, tap;               // accumulator slot (column order), which 32-row half of it, filter tap
+                    if (q < 4) { slot = 2 * rank + (q >> 1); half = q & 1; tap = 0; }             // centre shift, N = 256
+                    else if (q < 6) { slot = 0 + rank; half = q & 1; tap = 2; }                 // (-1, 0): slots 0,1
+                    else if (q < 8) { slot = 1 + rank; half = q & 1; tap = 1; }                 // (0, +1): slots 1,2
+                    else if (q < 10) { slot = 2 + rank; half = q & 1; tap = 2; }                // (+1, 0): slots 2,3
+                    else if (q == 10) { slot = 3; half = rank; tap = 1; }                       // (0, -1): slot 3
+                    else if (q == 11) { slot = 0; half = rank; tap = 1; }                       // (0, -1): slot 0
+                    else { slot = q - 12; half = rank; tap = 3; }                               // the four corners
+                    const int phase = win_slot_phase(slot);
+                    tma_load_2d_2cta(smem + kWinWOff + (cc * 16 + q) * kWinWTile, &mapB, w_full, tap * p.Ca + cc * kBK,
+                                     phase * Cb + half * 32);
+                }
+            }
+            int lt = 0;
+            for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
+                int n, x0, y0;
+                decode(tp, n, x0, y0);
+                const int buf = lt & 1;
+                mbar_wait(&a_empty[buf], ((lt >> 1) & 1) ^ 1);     // the MMAs of the tile two back have read this window
+                if (rank == 0) mbar_arrive_expect_tx(&a_full[buf], 2 * cchunks * kWinBytes);
+                for (int cc = 0; cc < cchunks; ++cc)
+                    tma_load_4d_2cta(smem + (buf * kWinMaxChunks + cc) * kWinPitch, &mapA, &a_full[buf], cc * kBK, x0 - 1, y0 - 1, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            // ---------------- MMA issuer: ONE thread of the leader CTA, 128 MMAs per tile back to back ----------------
+            constexpr uint32_t idesc64 = make_idesc(64, 0, 0, 256), idesc128 = make_idesc(128, 0, 0, 256),
+                               idesc256 = make_idesc(256, 0, 0, 256);
+            const uint64_t a_desc0 = make_sdesc(smem_u32(smem), 0, kWinBW * 128);
+            const uint64_t b_desc0 = make_sdesc(smem_u32(smem + kWinWOff), 0, 1024);
+            mbar_wait(w_full, 0);
+            int lt = 0;
+            for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);      // accumulator set drained by both CTAs' epilogues
+                mbar_wait(&a_full[buf], (lt >> 1) & 1);
+                fence_after_sync();
+                const uint32_t tmem_d = tmem_base + buf * 256;
+                for (int cc = 0; cc < cchunks; ++cc) {
+                    const uint64_t a_c = a_desc0 + (uint64_t)(((buf * kWinMaxChunks + cc) * kWinPitch) >> 4);
+                    const uint64_t b_c = b_desc0 + (uint64_t)((cc * 16 * kWinWTile) >> 4);
+                    // group: window shift (dy, dx) | first accumulator slot | N | offset of its B tile in the chunk's bank
+                    auto group = [&](int dy, int dx, int slot, int n, int b_off, uint32_t idesc_n, bool first) {
+                        const uint64_t a_d = a_c + (uint64_t)((((1 + dy) * kWinBW + 1 + dx) * 128) >> 4);
+                        const uint64_t b_d = b_c + (uint64_t)(b_off >> 4);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_bf16_2cta(tmem_d + slot * Cb, a_d + (uint64_t)(k * 2), b_d + (uint64_t)(k * 2), idesc_n,
+                                           (first && cc == 0 && k == 0) ? 0u : 1u);
+                        (void)n;
+                    };
+                    group(0, 0, 0, 256, 0, idesc256, true);                 // centre: P00 | P01 | P11 | P10, tap (0,0)
+                    group(-1, 0, 0, 128, 4 * kWinWTile, idesc128, false);   // rows above: P00 | P01, tap (1,0)
+                    group(0, 1, 1, 128, 6 * kWinWTile, idesc128, false);    // right: P01 | P11, tap (0,1)
+                    group(1, 0, 2, 128, 8 * kWinWTile, idesc128, false);    // below: P11 | P10, tap (1,0)
+                    group(0, -1, 3, 64, 10 * kWinWTile, idesc64, false);    // left: P10, tap (0,1)
+                    group(0, -1, 0, 64, 11 * kWinWTile, idesc64, false);    // left: P00, tap (0,1)
+                    group(-1, -1, 0, 64, 12 * kWinWTile, idesc64, false);   // corners, tap (1,1)
+                    group(-1, 1, 1, 64, 13 * kWinWTile, idesc64, false);
+                    group(1, 1, 2, 64, 14 * kWinWTile, idesc64, false);
+                    group(1, -1, 3, 64, 15 * kWinWTile, idesc64, false);
+                }
+                umma_commit_2cta(&a_empty[buf], 3);
+                umma_commit_2cta(&tfull[buf], 3);
+            }
+        }
+    } else {
+        // ---------------- epilogue: thread = one input pixel (yl, xl) of this CTA's tile, its 2 x 2 output block ----------------
+        const int wq = warp & 3;
+        const int r = wq * 32 + lane;
+        const int yl = r >> 3, xl = r & 7;
+        const int e = threadIdx.x - 64;                      // flushes column e of [sum | sum of squares] x 64
+        float acc_stat = 0.f;
+        int acc_group = -1;
+        int lt = 0;
+        for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
+            int n, x0, y0;
+            decode(tp, n, x0, y0);
+            const int buf = lt & 1;
+            mbar_wait(&tfull[buf], (lt >> 1) & 1);
+            fence_after_sync();
+            const uint32_t tmem_d = tmem_base + buf * 256 + ((uint32_t)(wq * 32) << 16);
+            const size_t Wo = 2 * (size_t)p.Ws;
+            __nv_bfloat16* o00 = out + (((size_t)n * 2 * p.Hs + 2 * (y0 + yl)) * Wo + 2 * (x0 + xl)) * Cb;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {                    // 32-column halves of the 64 output channels
+                float s1[32], s2[32];
+#pragma unroll 1
+                for (int slot = 0; slot < 4; ++slot) {
+                    const int phase = win_slot_phase(slot);
+                    float v[32];
+                    tmem_ld32(tmem_d + slot * Cb + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == 1 && slot == 3) {               // last read of this accumulator set: hand it back to the leader
+                        fence_before_sync();
+                        mbar_arrive_leader(&tempty[buf]);
+                    }
+                    uint4 u[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        u[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                        u[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                        u[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                        u[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                    }
+                    __nv_bfloat16* orow = o00 + ((size_t)(phase >> 1) * Wo + (phase & 1)) * Cb + c * 32;
+                    st_global_256(orow, u[0], u[1]);
+                    st_global_256(orow + 16, u[2], u[3]);
+                    if (stats != nullptr) {
+                        if (slot == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { s1[i] = v[i]; s2[i] = v[i] * v[i]; }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
+                        }
+                    }
+                }
+                if (stats != nullptr) {
+                    const float a1 = warp_transpose_sum(s1, lane);
+                    const float a2 = warp_transpose_sum(s2, lane);
+                    red[(wq * 2 + 0) * Cb + c * 32 + lane] = a1;
+                    red[(wq * 2 + 1) * Cb + c * 32 + lane] = a2;
+                }
+            }
+            if (stats != nullptr) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int g = n / p.ipg;
+                if (g != acc_group) {
+                    if (acc_group >= 0) atomicAdd(stats + (size_t)acc_group * 2 * Cb + e, acc_stat);
+                    acc_group = g;
+                    acc_stat = 0.f;
+                }
+                const int which = e / Cb, cc = e % Cb;
+                acc_stat += red[(0 * 2 + which) * Cb + cc] + red[(1 * 2 + which) * Cb + cc] +
+                            red[(2 * 2 + which) * Cb + cc] + red[(3 * 2 + which) * Cb + cc];
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // red[] is rewritten by the next tile
+            }
+        }
+        if (stats != nullptr && acc_group >= 0) atomicAdd(stats + (size_t)acc_group * 2 * Cb + e, acc_stat);
+    }
+
+    fence_before_sync();
+    cluster_sync_all();                    // the peer may still be signalling this CTA's barriers / reading its smem
+    if (warp == 1) {
+        fence_after_sync();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
+bool conv_up_win_supported(int B, int Hs, int Ws, int Ca, int Cb) {
+    static const bool enabled = [] { const char* e = getenv("JCK_UP_WIN"); return !(e && e[0] == '0'); }();
+    return enabled && B > 0 && Cb == 64 && Ca % kBK == 0 && Ca / kBK <= kWinMaxChunks && Ws % (2 * kWinTW) == 0 &&
+           Hs % kWinTH == 0;
+}
+
+int conv_up_win(const void* in, const void* w, void* out, float* stats, int B, int Hs, int Ws, int Ca, int ipg, cudaStream_t st) {
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, kWinBW, kWinBH, 1))) return rc;
+    if ((rc = map_matrix(&mB, w, 4 * 64, 4 * Ca, 32))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_up_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmem);
+        if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_up_win smem attr: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    ConvWinParams p{B, Hs, Ws, Ca, Ws / kWinTW, (Ws / kWinTW) * (Hs / kWinTH), ipg};
+    const int total_pairs = B * p.tiles_img / 2;
+    const int clusters = total_pairs < kNumSMs / 2 ? total_pairs : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = kWinSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_up_win_kernel, mA, mB, (__nv_bfloat16*)out, stats, p, total_pairs);
+    if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_up_win launch: %s", cudaGetErrorString(e));
+    JCK_LAUNCH_CHECK("conv_up_win");
+    return JCK_OK;
+}
+
 bool tc_conv_supported(int B, int Hs, int Ws, int Ca, int Cb, int ipg, bool up, PatchGeom* g) {
     const int Cin = up ? Ca : Cb, Cout = up ? Cb : Ca;
     if (Cin % 64 != 0 || Cout % 64 != 0) return false;
@@ -757,6 +1050,7 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
     PatchGeom g;
     if (!tc_conv_supported(B, Hs, Ws, Ca, Cb, ipg, kUp, &g))
         return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv tc: unsupported shape B=%d Hs=%d Ws=%d Ca=%d Cb=%d", B, Hs, Ws, Ca, Cb);
+    if (kUp && !bb && conv_up_win_supported(B, Hs, Ws, Ca, Cb)) return conv_up_win(in, w, out, stats, B, Hs, Ws, Ca, ipg, st);
     const int Cout = kUp ? Cb : Ca;
     const int bn = (Cout % 128 == 0) ? 128 : 64;
     ConvTcParams p{B, Hs, Ws, Ca, Cb, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, ipg};

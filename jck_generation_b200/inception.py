@@ -106,6 +106,10 @@ class InceptionV3:
     def _scratch(self, key, numel, dtype):
         k = (key, dtype)
         if k not in self._bufs or self._bufs[k].numel() < numel:
+            # growing a scratch buffer frees the old one, whose address is baked into every CUDA graph captured so far: drop
+            # those graphs (they are re-captured on their next use) instead of letting a replay write into freed memory
+            if k in self._bufs:
+                self._graphs.clear()
             self._bufs[k] = torch.zeros(numel, dtype=dtype, device=self.device)
         return self._bufs[k]
 

@@ -39,7 +39,7 @@ SUPERCLASS = [
 
 class Metrics:
     def __init__(self, real_images=None, feature="logits", checkpoint=os.path.join('./save/iception_v3', 'loss_bset.pt'),
-                 cache=os.path.join('./data', 'metric_data.pikl'), batch=128, comm=None):
+                 cache=os.path.join('./data', 'metric_data.pikl'), batch=128, comm=None, allow_random_weights=None):
         from torchvision import models
         from .inception import InceptionV3
         if not torch.cuda.is_available():
@@ -48,13 +48,27 @@ class Metrics:
         self.feature, self.batch = feature, batch
         self.comm = comm                      # data-parallel evaluation (BASELINE configs[4]): see evaluate_generated
         self.class_to_superclass = {c: s for s, cs in enumerate(SUPERCLASS) for c in cs}
-        torch.manual_seed(12345)
-        # parameter container only (the reference's checkpoint format); the forward below is ours
-        self.inception_model = models.inception_v3(weights=None, aux_logits=True, init_weights=False)
-        self.inception_model.aux_logits = False
-        self.inception_model.fc = nn.Sequential(nn.Linear(self.inception_model.fc.in_features, 100))
+        # parameter container only (the reference's checkpoint format); the forward below is ours.  Built under a forked RNG:
+        # constructing the container must not disturb the global torch RNG the loaders' shuffle order comes from.
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(12345)
+            self.inception_model = models.inception_v3(weights=None, aux_logits=True, init_weights=False)
+            self.inception_model.aux_logits = False
+            self.inception_model.fc = nn.Sequential(nn.Linear(self.inception_model.fc.in_features, 100))
         if os.path.exists(checkpoint):
             self.inception_model.load_state_dict(torch.load(checkpoint, map_location="cpu"))
+        else:
+            # the reference raises here (metrics.py:51 torch.load of a missing file).  Scores from a random-weight network
+            # are meaningless for model selection, so that is opt-in only (throughput benchmarks, plumbing tests).
+            if allow_random_weights is None:
+                allow_random_weights = os.environ.get("JCK_METRICS_RANDOM_WEIGHTS", "0") == "1"
+            if not allow_random_weights:
+                raise FileNotFoundError(f"Metrics: Inception-v3 checkpoint {checkpoint} not found (the reference's metrics.py:51 "
+                                        "loads it unconditionally); pass allow_random_weights=True / JCK_METRICS_RANDOM_WEIGHTS=1 "
+                                        "to run the evaluation plumbing on seeded random weights")
+            import warnings
+            warnings.warn(f"Metrics: {checkpoint} missing -- IS / FID below come from a RANDOM-WEIGHT Inception-v3 and are "
+                          "meaningless as quality scores")
         self.inception_model.eval()
         self.extractor = InceptionV3(self.inception_model.state_dict(), feature=feature, device=self.device)
 
@@ -76,6 +90,14 @@ class Metrics:
             loader = real_images if is_loader else \
                 torch.utils.data.DataLoader(real_images, batch, shuffle=False, num_workers=0, pin_memory=True)
             self.real_features = self._extract(loader, real=True).cpu().numpy()
+            if feature == "logits" and (comm is None or getattr(comm, "rank", 0) == 0):
+                # the reference pickles the real-image features after the first extraction (metrics.py:70-77)
+                try:
+                    os.makedirs(os.path.dirname(cache) or ".", exist_ok=True)
+                    with open(cache, 'wb') as f:
+                        pickle.dump(self.real_features, f)
+                except OSError:
+                    pass
 
     @torch.no_grad()
     def _extract(self, images, real=False, generated=False):

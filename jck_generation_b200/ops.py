@@ -194,6 +194,14 @@ def comm_connect(comm, all_handles):
     check(L().jck_comm_connect(comm, all_handles), "comm_connect")
 
 
+def comm_error(comm):
+    """True when an exchange on this peer communicator ever timed out waiting for a peer (synchronises with the device)."""
+    import ctypes
+    flag = ctypes.c_int(0)
+    check(L().jck_comm_error(comm, ctypes.byref(flag)), "comm_error")
+    return bool(flag.value)
+
+
 def comm_destroy(comm):
     check(L().jck_comm_destroy(comm), "comm_destroy")
 

@@ -40,6 +40,9 @@ class LocalComm:
     def barrier(self):
         pass
 
+    def check_health(self):
+        pass
+
 
 class TorchComm:
     """Collectives through an initialised torch.distributed process group (nccl on GPUs, gloo in the
@@ -133,6 +136,16 @@ class TorchComm:
     def barrier(self):
         if self.world_size > 1:
             dist.barrier(group=self.group)
+
+    def check_health(self):
+        """Raise if a peer-memory exchange ever timed out (csrc/comm.cu: the exchange then returned NaN and raised a sticky
+        flag instead of trapping).  Synchronises with the device: call it where the host syncs anyway (the trainers do,
+        every 100 steps).  JCK_SYNCBN=nccl selects the NCCL transport, whose watchdog handles stragglers itself."""
+        from . import ops
+        for tag, c in (("main", self.peer), ("auxiliary", self.peer_aux)):
+            if c is not None and ops.comm_error(c):
+                raise RuntimeError(f"rank {self.rank}: a SyncBN exchange on the {tag} peer-memory communicator timed out waiting "
+                                   "for a peer (JCK_COMM_TIMEOUT_S, default 120 s); the step's statistics were poisoned with NaN")
 
 
 class AuxComm:

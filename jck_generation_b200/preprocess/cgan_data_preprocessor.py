@@ -4,7 +4,7 @@ as in the reference :90, returns the inception *dataset*, not a loader)."""
 import torch
 
 from ..logger.main_logger import MainLogger
-from .dcgan_data_preprocessor import _cifar_available, u8_source, IMAGENET_MEAN, IMAGENET_STD
+from .dcgan_data_preprocessor import _cifar100, u8_source, IMAGENET_MEAN, IMAGENET_STD
 from .synthetic import SyntheticLoader
 
 
@@ -24,14 +24,16 @@ class CGANDataPreprocessor:
         self.batch_size = args.batch_size
         self.num_worker = getattr(args, "num_worker", 0)
         self.n_classes = int(getattr(args, "n_classes", 100))
-        self.synthetic = bool(getattr(args, "synthetic", 0)) or not _cifar_available()
+        # synthetic images ONLY on request (args.synthetic / --synthetic); otherwise the reference's behaviour: CIFAR-100 from
+        # ./data, downloaded when missing (download=True, :20-21), and an error when that fails -- never a silent stand-in
+        self.synthetic = bool(getattr(args, "synthetic", 0))
         self.synthetic_batches = int(getattr(args, "synthetic_batches", 391))
         self._trainset = self._inceptionset = None
         self.idx_to_labels = {i: str(i) for i in range(self.n_classes)}
         if not self.synthetic:
             import torchvision
-            self._trainset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
-            self._inceptionset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
+            self._trainset = _cifar100(torchvision)
+            self._inceptionset = _cifar100(torchvision)
             self.idx_to_labels = {v: k for k, v in self._trainset.class_to_idx.items()}
         self._u8 = u8_source(self, args, self.n_classes)
         self._logger.debug('data preprocessor init' + (' (synthetic source)' if self.synthetic else '') +

@@ -1,11 +1,11 @@
 """Drop-in for the reference's preprocess/dcgan_data_preprocessor.py: `DCGANDataPreprocessor(args)`,
 `.transform_data()`, `.get_data_loader() -> (train_loader, inception_loader)`.
 
-With CIFAR-100 already on disk under ./data the behaviour is the reference's (torchvision dataset,
+The behaviour is the reference's (torchvision CIFAR-100 under ./data, downloaded when missing,
 Resize(64)/ToTensor/Normalize(.5,.5) for training, Resize(299)/ImageNet-normalise for the metric
-loader, shuffle=True, pin_memory=True; dcgan_data_preprocessor.py:37-75).  Without it -- there is no
-network here, and the reference's download=True cannot work -- or with args.synthetic=1, a synthetic
-source with the same contract is used (preprocess/synthetic.py)."""
+loader, shuffle=True, pin_memory=True; dcgan_data_preprocessor.py:20-21,37-75); a missing dataset that
+cannot be downloaded raises.  Only with args.synthetic=1 (an explicit request: benchmarks, smoke runs) a
+synthetic source with the same contract is used (preprocess/synthetic.py)."""
 import os
 
 import torch
@@ -39,18 +39,30 @@ def _cifar_available(root="./data"):
     return os.path.isdir(os.path.join(root, "cifar-100-python"))
 
 
+def _cifar100(torchvision, root="./data"):
+    """torchvision.datasets.CIFAR100(root, train=True, download=True) as the reference builds it
+    (preprocess/dcgan_data_preprocessor.py:20-21); a failed download is an error that names the way out."""
+    try:
+        return torchvision.datasets.CIFAR100(root, train=True, download=not _cifar_available(root), transform=None)
+    except Exception as e:      # noqa: BLE001 -- no network, bad archive ...
+        raise RuntimeError(f"CIFAR-100 is not under {root}/cifar-100-python and could not be downloaded ({e}); put the dataset "
+                           "there, or pass --synthetic 1 to train on synthetic images (benchmarks / smoke runs only)") from e
+
+
 class DCGANDataPreprocessor:
     def __init__(self, args):
         self._logger = MainLogger(args)
         self.batch_size = args.batch_size
         self.num_worker = getattr(args, "num_worker", 0)
-        self.synthetic = bool(getattr(args, "synthetic", 0)) or not _cifar_available()
+        # synthetic images ONLY on request (args.synthetic / --synthetic); otherwise the reference's behaviour: CIFAR-100 from
+        # ./data, downloaded when missing (download=True, :20-21), and an error when that fails -- never a silent stand-in
+        self.synthetic = bool(getattr(args, "synthetic", 0))
         self.synthetic_batches = int(getattr(args, "synthetic_batches", 391))   # 50000 / 128
         self._trainset = self._inceptionset = None
         if not self.synthetic:
             import torchvision
-            self._trainset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
-            self._inceptionset = torchvision.datasets.CIFAR100("./data", train=True, download=False, transform=None)
+            self._trainset = _cifar100(torchvision)
+            self._inceptionset = _cifar100(torchvision)
         self._u8 = u8_source(self, args)
         self._logger.debug('data preprocessor init' + (' (synthetic source)' if self.synthetic else '') +
                            (' (device pipeline)' if self._u8 is not None else ''))

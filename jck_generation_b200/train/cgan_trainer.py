@@ -153,6 +153,7 @@ class CGANTrainer(Trainer):
         def flush():
             if not pending:
                 return
+            self.comm.check_health()
             block = torch.stack([p[2] for p in pending])
             self.comm.allreduce_mean_(block)
             for (ep, i, _), s in zip(pending, block.cpu()):
@@ -165,6 +166,7 @@ class CGANTrainer(Trainer):
             pending.clear()
 
         done = False
+        self.comm.barrier()        # ranks enter the first step (and its graph capture / peer-memory exchanges) together
         for epoch in range(self.epoch):
             for i, data in enumerate(DevicePrefetcher(real_images_loader, self.device)):
                 real_data, labels_data = data
@@ -192,6 +194,7 @@ class CGANTrainer(Trainer):
                     if high_is < inception_score:
                         high_is = inception_score
                         self.save_model('is', iters, inception_score, fid, intra_fid, denorm)
+                    self.comm.barrier()    # rank 0 alone wrote checkpoints / plots: do not let the others run ahead into SyncBN
                 iters += 1
                 if self.max_iters and iters >= self.max_iters:
                     done = True

@@ -157,6 +157,7 @@ class DCGANTrainer(Trainer):
         def flush():
             if not pending:
                 return
+            self.comm.check_health()
             block = torch.stack([p[2] for p in pending])             # one D2H for up to 100 steps
             self.comm.allreduce_mean_(block)
             host = block.cpu()
@@ -170,6 +171,7 @@ class DCGANTrainer(Trainer):
             pending.clear()
 
         done = False
+        self.comm.barrier()        # ranks enter the first step (and its graph capture / peer-memory exchanges) together
         for epoch in range(self.epoch):
             for i, data in enumerate(DevicePrefetcher(real_images_loader, self.device)):
                 real_data = data[0]
@@ -194,6 +196,7 @@ class DCGANTrainer(Trainer):
                         high_is = inception_score
                         self.logger.debug(f"{iters} highest is")
                         self.save_model('is', iters, high_is, fake.cpu())
+                    self.comm.barrier()    # rank 0 alone wrote checkpoints / plots: do not let the others run ahead into SyncBN
                 iters += 1
                 if self.max_iters and iters >= self.max_iters:
                     done = True

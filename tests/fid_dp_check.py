@@ -28,7 +28,7 @@ def main():
     fake = torch.tanh(torch.randn(512, 3, 64, 64, generator=g))
     ok = True
     for feature in ("logits", "pool3"):
-        m = Metrics(real, feature=feature, comm=comm)
+        m = Metrics(real, feature=feature, comm=comm, allow_random_weights=True)
         s1, f1 = m.evaluate_generated(fake)                               # all rows on this rank
         sw, fw = m.evaluate_generated_sharded(parallel.shard_rows(fake, comm))
         scale = float(np.trace(np.cov(m.real_features.astype(np.float64), rowvar=False)))

@@ -12,7 +12,9 @@ import torch
 import torch.nn.functional as F
 
 # (Ca, Cb, Hs): the three GEMM-shaped layer geometries + the image-edge geometry
-SHAPES = {"c2": (128, 64, 16), "c3": (256, 128, 8), "c4": (512, 256, 4), "edge": (64, 3, 32)}
+SHAPES = {"c2": (128, 64, 16), "c3": (256, 128, 8), "c4": (512, 256, 4), "edge": (64, 3, 32),
+          # extra geometries of the windowed 64-channel up-conv kernel (conv_up_win_kernel): one channel chunk; a 32 x 32 map
+          "w64": (64, 64, 16), "w32": (128, 64, 32)}
 
 
 def _rel(got, want):
@@ -53,7 +55,7 @@ def check_down(shape, dtype, algo, B=8, groups=1):
     return {"out": _rel(out.float().permute(0, 3, 1, 2), want), "stats": _rel(stats, ws)}
 
 
-def check_up(shape, dtype, algo, B=8, groups=1):
+def check_up(shape, dtype, algo, B=8, groups=1, stats=True):
     from jck_generation_b200 import ops
     Ca, Cb, Hs = SHAPES[shape]
     x = _mk((B, Ca, Hs, Hs), dtype, 3)
@@ -62,6 +64,10 @@ def check_up(shape, dtype, algo, B=8, groups=1):
     _, wu = _packed(w4, dtype)
     xin = x.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
     out = torch.full((B, 2 * Hs, 2 * Hs, Cb), float("nan"), dtype=dtype, device="cuda")
+    if not stats:                # the input-gradient use: no BatchNorm statistics
+        ops.conv_up(xin, wu, out, None, Ca, Cb, ipg=B, algo=algo)
+        torch.cuda.synchronize()
+        return {"out": _rel(out.float().permute(0, 3, 1, 2), want)}
     stats = torch.zeros(groups, 2 * Cb, device="cuda")
     ops.conv_up(xin, wu, out, stats, Ca, Cb, ipg=B // groups, algo=algo)
     torch.cuda.synchronize()
@@ -447,12 +453,14 @@ def _dt(name):
 def all_cases():
     cases = []
     for op in ("down", "up", "wgrad"):
-        for shape in SHAPES:
+        for shape in ("c2", "c3", "c4", "edge"):
             cases.append((op, shape, "f32", "simt", 8))
             cases.append((op, shape, "bf16", "simt", 8))
             if shape != "edge":
                 cases.append((op, shape, "bf16", "tc", 8))
                 cases.append((op, shape, "bf16", "tc", 3))      # ragged: batch not a multiple of the tile
+    cases += [("up", "w64", "bf16", "tc", 5), ("up", "w32", "bf16", "tc", 3), ("up_groups", "c2", "bf16", "tc", 6),
+              ("up_groups", "w32", "bf16", "tc", 4), ("up_nostats", "c2", "bf16", "tc", 9)]
     cases += [("down_groups", "c3", "bf16", "tc", 8), ("up_groups", "c4", "bf16", "tc", 16),
               ("down_groups", "c4", "f32", "simt", 6)]
     cases += [("edge_down", "-", "bf16", "tc", 8), ("edge_down", "-", "bf16", "tc", 3), ("edge_down", "-", "bf16", "tc", 150),
@@ -501,6 +509,8 @@ def run_case(op, shape, dtype, algo, B):
         return check_down(shape, _dt(dtype), _alg(algo), B, groups=2)
     if op == "up_groups":
         return check_up(shape, _dt(dtype), _alg(algo), B, groups=2)
+    if op == "up_nostats":
+        return check_up(shape, _dt(dtype), _alg(algo), B, stats=False)
     if op == "down_groups3":
         return check_down(shape, _dt(dtype), _alg(algo), B, groups=3)
     if op == "edge_down_g3":
@@ -553,6 +563,9 @@ def main():
     cases = all_cases()
     if "--only-big" in sys.argv:
         cases = big_cases()
+    if "--match" in sys.argv:                      # e.g. --match up:c2  (op prefix : shape)
+        op, _, shape = sys.argv[sys.argv.index("--match") + 1].partition(":")
+        cases = [c for c in cases if c[0].startswith(op) and (not shape or c[1] == shape)]
     if "--only-tc" in sys.argv:
         cases = [c for c in cases if c[3] == "tc"]
     if "--no-tc" in sys.argv:

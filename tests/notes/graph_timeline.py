@@ -1,6 +1,7 @@
 """Timeline of ONE CUDA-graph replay of the DCGAN step (CUPTI kernel records via torch.profiler): start, duration, stream of
 every kernel, idle gaps on the main stream and overlap with the side stream.  Run with JCK_PDL=0 so that a kernel's
-duration does not include the time it is parked behind its predecessor.  Usage: python tests/notes/graph_timeline.py [batch]"""
+duration does not include the time it is parked behind its predecessor.  Usage: python tests/notes/graph_timeline.py [batch]
+(under torchrun: the data-parallel step, NCCL / peer-memory kernels included, as rank 0 sees it)."""
 import argparse, json, os, sys, tempfile
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -29,6 +30,9 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     tr.train_step(real)
     torch.cuda.synchronize()
+if tr.comm.rank != 0:            # under torchrun: rank 0 reports
+    tr.comm.barrier()
+    os._exit(0)
 path = os.path.join(tempfile.mkdtemp(), "t.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy")]
@@ -51,3 +55,7 @@ for e in ev:
         end_main = max(end_main, e["ts"] + e["dur"])
     print(f"{(e['ts'] - t0):9.1f} {e['dur']:7.1f} {'M' if s == main else 'S'} {name}{gap}")
 print(f"idle on the main stream: {gap_total:.1f} us")
+if tr.comm.world_size > 1:
+    sys.stdout.flush()
+    tr.comm.barrier()
+    os._exit(0)
