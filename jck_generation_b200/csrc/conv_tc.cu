@@ -430,7 +430,7 @@ struct PairSmem {
 };
 
 template <int BN_, int STAGES, int MODE, int EPIM>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, BN_ == 256 ? 1 : 2)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvTcParams p,
                     const int n_tiles, const int total_pairs, const BnBwdEpi bb) {
@@ -692,7 +692,8 @@ int launch_pair_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, flo
         configured = true;
     }
     const int total_pairs = ((m_tiles + 1) / 2) * n_tiles * (MODE == kUpM ? 4 : 1);
-    const int clusters = total_pairs < kNumSMs ? total_pairs : kNumSMs;     // 2 co-resident CTAs per SM
+    const int max_clusters = BN_ == 256 ? kNumSMs / 2 : kNumSMs;            // BN = 256 fills TMEM: one CTA per SM; else two
+    const int clusters = total_pairs < max_clusters ? total_pairs : max_clusters;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(192);
@@ -780,7 +781,8 @@ constexpr int kWinWTile = 32 * 128;                          // this CTA's half 
 constexpr int kWinWOff = 2 * kWinMaxChunks * kWinPitch;      // after the two window buffers
 constexpr int kWinBarOff = kWinWOff + 16 * kWinMaxChunks * kWinWTile;
 constexpr int kWinRedOff = kWinBarOff + 256;
-constexpr int kWinSmem = kWinRedOff + 4 * 2 * 64 * 4 + 1024;
+constexpr int kWinCoefOff = kWinRedOff + 4 * 2 * 64 * 4;     // [scale | shift | mean | rstd][64]  (fused BatchNorm-backward epilogue)
+constexpr int kWinSmem = kWinCoefOff + 4 * 64 * 4 + 1024;
 
 struct ConvWinParams { int B, Hs, Ws, Ca, tiles_x, tiles_img, ipg; };
 
@@ -788,9 +790,15 @@ struct ConvWinParams { int B, Hs, Ws, Ca, tiles_x, tiles_img, ipg; };
 // the parities that read one edge shift of the window are adjacent) -> output parity index py * 2 + px
 __host__ __device__ __forceinline__ int win_slot_phase(int slot) { return slot == 2 ? 3 : (slot == 3 ? 2 : slot); }
 
-__global__ void __launch_bounds__(192, 1)
+// EPIM = 1: the BatchNorm-backward reduction of the layer this convolution's output feeds (see BnBwdEpi) in the epilogue:
+// g = acc * act'(y * scale + shift) is stored instead of acc and stats receives (sum g, sum g * xhat) per group.  The saved
+// y has the output's layout, so a thread reads exactly the 64-byte runs it is about to write; the epilogue of this kernel
+// waits for the MMAs most of the time (it is not the critical path), which is what makes the fusion pay here.
+template <int EPIM>
+__global__ void __launch_bounds__(320, 1)
 conv_up_win_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvWinParams p, const int total_pairs) {
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ stats, const ConvWinParams p, const int total_pairs,
+                   const BnBwdEpi bb) {
     pdl_trigger();
     constexpr int Cb = 64;
     extern __shared__ uint8_t smem_raw[];
@@ -802,6 +810,7 @@ conv_up_win_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     uint64_t* w_full = tempty + 2;                                       // leader: both CTAs' filter-bank halves have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     float* red = reinterpret_cast<float*>(smem + kWinRedOff);            // [4 warps][2][64]
+    float* cf = reinterpret_cast<float*>(smem + kWinCoefOff);            // [4][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -816,7 +825,7 @@ conv_up_win_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             mbar_init(&a_full[a], 1);
             mbar_init(&a_empty[a], 1);
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 2 * 128);
+            mbar_init(&tempty[a], 2 * 256);
         }
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -913,79 +922,143 @@ conv_up_win_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             }
         }
     } else {
-        // ---------------- epilogue: thread = one input pixel (yl, xl) of this CTA's tile, its 2 x 2 output block ----------------
+        // ---------------- epilogue: EIGHT warps.  A thread = one input pixel (yl, xl) of this CTA's tile = one TMEM lane, its 2 x 2
+        // output block, and ONE 32-channel half of the 64 output channels (warps 2..5 the first half, 6..9 the second: two warps
+        // share a TMEM lane quarter, warp % 4).  Four warps could not keep up with the MMAs once the epilogue also does the
+        // BatchNorm-backward arithmetic (~10 operations per element). ----------------
         const int wq = warp & 3;
+        const int c = (warp - 2) >> 2;                       // which 32-channel half
         const int r = wq * 32 + lane;
         const int yl = r >> 3, xl = r & 7;
-        const int e = threadIdx.x - 64;                      // flushes column e of [sum | sum of squares] x 64
+        const int e = threadIdx.x - 64;                      // 0..255; threads < 128 flush column e of [sum | sum of squares] x 64
         float acc_stat = 0.f;
-        int acc_group = -1;
+        int acc_group = -1, cf_group = -1;
         int lt = 0;
         for (int tp = cid; tp < total_pairs; tp += ncl, ++lt) {
             int n, x0, y0;
             decode(tp, n, x0, y0);
             const int buf = lt & 1;
+            const int grp = n / p.ipg;
+            if constexpr (EPIM == 1) {
+                if (grp != cf_group) {                       // this group's BatchNorm coefficients (rarely changes: tiles walk images in order)
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    {
+                        const int which = e / Cb, ch = e - which * Cb;
+                        cf[e] = ((which < 2) ? bb.ss : bb.mr)[(size_t)grp * 2 * Cb + (which & 1) * Cb + ch];
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    cf_group = grp;
+                }
+            }
+            const uint32_t tmem_d = tmem_base + buf * 256 + ((uint32_t)(wq * 32) << 16) + c * 32;
+            const size_t Wo = 2 * (size_t)p.Ws;
+            const size_t o00_off = (((size_t)n * 2 * p.Hs + 2 * (y0 + yl)) * Wo + 2 * (x0 + xl)) * Cb + c * 32;
+            __nv_bfloat16* o00 = out + o00_off;
+            auto out_off = [&](int slot) {
+                const int phase = win_slot_phase(slot);
+                return ((size_t)(phase >> 1) * Wo + (phase & 1)) * Cb;
+            };
+            if constexpr (EPIM == 1) {
+                // the NEXT tile's saved y -> L2 now (its registers-loads then pay an L2 hit, not an HBM round trip)
+                if (tp + ncl < total_pairs) {
+                    int n2, x2, y2;
+                    decode(tp + ncl, n2, x2, y2);
+                    const __nv_bfloat16* yn = bb.y + (((size_t)n2 * 2 * p.Hs + 2 * (y2 + yl)) * Wo + 2 * (x2 + xl)) * Cb + c * 32;
+#pragma unroll
+                    for (int slot = 0; slot < 4; ++slot)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(yn + out_off(slot)));
+                }
+            }
+            // EPIM = 1: the saved y of this thread's four 64-byte runs.  The first two are requested BEFORE the accumulator wait
+            // (they do not depend on the MMAs), each register buffer is re-filled two iterations ahead of its next use (ten warps
+            // per CTA cap a thread at 168 registers: two buffers, not four)
+            uint4 yr[2][4];
+            if constexpr (EPIM == 1) {
+#pragma unroll
+                for (int slot = 0; slot < 2; ++slot) {
+                    const __nv_bfloat16* ys = bb.y + o00_off + out_off(slot);
+                    ld_global_nc_256(ys, yr[slot][0], yr[slot][1]);
+                    ld_global_nc_256(ys + 16, yr[slot][2], yr[slot][3]);
+                }
+            }
             mbar_wait(&tfull[buf], (lt >> 1) & 1);
             fence_after_sync();
-            const uint32_t tmem_d = tmem_base + buf * 256 + ((uint32_t)(wq * 32) << 16);
-            const size_t Wo = 2 * (size_t)p.Ws;
-            __nv_bfloat16* o00 = out + (((size_t)n * 2 * p.Hs + 2 * (y0 + yl)) * Wo + 2 * (x0 + xl)) * Cb;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {                    // 32-column halves of the 64 output channels
-                float s1[32], s2[32];
-#pragma unroll 1
-                for (int slot = 0; slot < 4; ++slot) {
-                    const int phase = win_slot_phase(slot);
-                    float v[32];
-                    tmem_ld32(tmem_d + slot * Cb + c * 32, v);
-                    tmem_ld_wait();
-                    if (c == 1 && slot == 3) {               // last read of this accumulator set: hand it back to the leader
-                        fence_before_sync();
-                        mbar_arrive_leader(&tempty[buf]);
-                    }
-                    uint4 u[4];
+            float s1[32], s2[32];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        u[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                        u[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                        u[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                        u[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                    }
-                    __nv_bfloat16* orow = o00 + ((size_t)(phase >> 1) * Wo + (phase & 1)) * Cb + c * 32;
-                    st_global_256(orow, u[0], u[1]);
-                    st_global_256(orow + 16, u[2], u[3]);
-                    if (stats != nullptr) {
-                        if (slot == 0) {
+            for (int slot = 0; slot < 4; ++slot) {
+                float v[32];
+                tmem_ld32(tmem_d + slot * Cb, v);
+                tmem_ld_wait();
+                if (slot == 3) {                             // last read of this accumulator set: hand it back to the leader
+                    fence_before_sync();
+                    mbar_arrive_leader(&tempty[buf]);
+                }
+                if constexpr (EPIM == 1) {
+                    const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(yr[slot & 1]);
+                    const float4* sc4 = reinterpret_cast<const float4*>(cf + c * 32);          // 128-bit broadcast reads
+                    const float4* sh4 = reinterpret_cast<const float4*>(cf + Cb + c * 32);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) { s1[i] = v[i]; s2[i] = v[i] * v[i]; }
-                        } else {
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 sc = sc4[q], sh = sh4[q];
+                        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = q * 4 + j;
+                            const float yv = __bfloat162float(yb[i]);
+                            const float pre = fmaf(yv, scv[j], shv[j]);
+                            const float gg = pre > 0.f ? v[i] : v[i] * bb.slope;
+                            v[i] = gg;
+                            // sum g (y - mean) rstd = rstd (sum g y - mean sum g): mean and rstd once per column below
+                            if (slot == 0) { s1[i] = gg; s2[i] = gg * yv; } else { s1[i] += gg; s2[i] = fmaf(gg, yv, s2[i]); }
                         }
                     }
+                    if (slot < 2) {
+                        const __nv_bfloat16* ys = bb.y + o00_off + out_off(slot + 2);
+                        ld_global_nc_256(ys, yr[slot & 1][0], yr[slot & 1][1]);
+                        ld_global_nc_256(ys + 16, yr[slot & 1][2], yr[slot & 1][3]);
+                    }
+                } else if (stats != nullptr) {
+                    if (slot == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { s1[i] = v[i]; s2[i] = v[i] * v[i]; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
+                    }
                 }
-                if (stats != nullptr) {
-                    const float a1 = warp_transpose_sum(s1, lane);
-                    const float a2 = warp_transpose_sum(s2, lane);
-                    red[(wq * 2 + 0) * Cb + c * 32 + lane] = a1;
-                    red[(wq * 2 + 1) * Cb + c * 32 + lane] = a2;
+                uint4 u[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    u[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                    u[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                    u[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                    u[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
                 }
+                __nv_bfloat16* orow = o00 + out_off(slot);
+                st_global_256(orow, u[0], u[1]);
+                st_global_256(orow + 16, u[2], u[3]);
             }
             if (stats != nullptr) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int g = n / p.ipg;
-                if (g != acc_group) {
-                    if (acc_group >= 0) atomicAdd(stats + (size_t)acc_group * 2 * Cb + e, acc_stat);
-                    acc_group = g;
-                    acc_stat = 0.f;
+                const float a1 = warp_transpose_sum(s1, lane);
+                float a2 = warp_transpose_sum(s2, lane);
+                if constexpr (EPIM == 1) a2 = (a2 - cf[2 * Cb + c * 32 + lane] * a1) * cf[3 * Cb + c * 32 + lane];
+                red[(wq * 2 + 0) * Cb + c * 32 + lane] = a1;
+                red[(wq * 2 + 1) * Cb + c * 32 + lane] = a2;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (e < 2 * Cb) {
+                    if (grp != acc_group) {
+                        if (acc_group >= 0) atomicAdd(stats + (size_t)acc_group * 2 * Cb + e, acc_stat);
+                        acc_group = grp;
+                        acc_stat = 0.f;
+                    }
+                    const int which = e / Cb, cc = e % Cb;
+                    acc_stat += red[(0 * 2 + which) * Cb + cc] + red[(1 * 2 + which) * Cb + cc] +
+                                red[(2 * 2 + which) * Cb + cc] + red[(3 * 2 + which) * Cb + cc];
                 }
-                const int which = e / Cb, cc = e % Cb;
-                acc_stat += red[(0 * 2 + which) * Cb + cc] + red[(1 * 2 + which) * Cb + cc] +
-                            red[(2 * 2 + which) * Cb + cc] + red[(3 * 2 + which) * Cb + cc];
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // red[] is rewritten by the next tile
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // red[] is rewritten by the next tile
             }
         }
-        if (stats != nullptr && acc_group >= 0) atomicAdd(stats + (size_t)acc_group * 2 * Cb + e, acc_stat);
+        if (stats != nullptr && e < 2 * Cb && acc_group >= 0) atomicAdd(stats + (size_t)acc_group * 2 * Cb + e, acc_stat);
     }
 
     fence_before_sync();
@@ -1002,14 +1075,16 @@ bool conv_up_win_supported(int B, int Hs, int Ws, int Ca, int Cb) {
            Hs % kWinTH == 0;
 }
 
-int conv_up_win(const void* in, const void* w, void* out, float* stats, int B, int Hs, int Ws, int Ca, int ipg, cudaStream_t st) {
+int conv_up_win(const void* in, const void* w, void* out, float* stats, int B, int Hs, int Ws, int Ca, int ipg, cudaStream_t st,
+                const BnBwdEpi* bb) {
     CUtensorMap mA, mB;
     int rc;
     if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, kWinBW, kWinBH, 1))) return rc;
     if ((rc = map_matrix(&mB, w, 4 * 64, 4 * Ca, 32))) return rc;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_up_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmem);
+        cudaError_t e = cudaFuncSetAttribute(conv_up_win_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_up_win_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmem);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_up_win smem attr: %s", cudaGetErrorString(e));
         configured = true;
     }
@@ -1018,7 +1093,7 @@ int conv_up_win(const void* in, const void* w, void* out, float* stats, int B, i
     const int clusters = total_pairs < kNumSMs / 2 ? total_pairs : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(320);
     cfg.dynamicSmemBytes = kWinSmem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -1030,7 +1105,9 @@ int conv_up_win(const void* in, const void* w, void* out, float* stats, int B, i
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_up_win_kernel, mA, mB, (__nv_bfloat16*)out, stats, p, total_pairs);
+    const BnBwdEpi none{nullptr, nullptr, nullptr, 0.f};
+    cudaError_t e = bb ? cudaLaunchKernelEx(&cfg, conv_up_win_kernel<1>, mA, mB, (__nv_bfloat16*)out, stats, p, total_pairs, *bb)
+                       : cudaLaunchKernelEx(&cfg, conv_up_win_kernel<0>, mA, mB, (__nv_bfloat16*)out, stats, p, total_pairs, none);
     if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_up_win launch: %s", cudaGetErrorString(e));
     JCK_LAUNCH_CHECK("conv_up_win");
     return JCK_OK;
@@ -1050,7 +1127,7 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
     PatchGeom g;
     if (!tc_conv_supported(B, Hs, Ws, Ca, Cb, ipg, kUp, &g))
         return set_error(JCK_E_UNSUPPORTED_SHAPE, "conv tc: unsupported shape B=%d Hs=%d Ws=%d Ca=%d Cb=%d", B, Hs, Ws, Ca, Cb);
-    if (kUp && !bb && conv_up_win_supported(B, Hs, Ws, Ca, Cb)) return conv_up_win(in, w, out, stats, B, Hs, Ws, Ca, ipg, st);
+    if (kUp && conv_up_win_supported(B, Hs, Ws, Ca, Cb)) return conv_up_win(in, w, out, stats, B, Hs, Ws, Ca, ipg, st, bb);
     const int Cout = kUp ? Cb : Ca;
     const int bn = (Cout % 128 == 0) ? 128 : 64;
     ConvTcParams p{B, Hs, Ws, Ca, Cb, g.bw, g.bh, g.nb, Ws / g.bw, Hs / g.bh, ipg};
@@ -1067,6 +1144,17 @@ int conv_tc(const void* in, const void* w, void* out, float* stats, int B, int H
     }
     const BnBwdEpi none{nullptr, nullptr, nullptr, 0.f};
     constexpr int M_ = kUp ? kUpM : kDown;
+    // JCK_BN256: 0 = never, 1 = always, unset = where it measured faster (>= 1024 images: 5-10 % on the 256- / 512-channel
+    // layers of the discriminator's three-group forward; +-1 us at 512 images)
+    static const int bn256 = [] { const char* e = getenv("JCK_BN256"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    if (Cout % 256 == 0 && (bn256 == 1 || (bn256 < 0 && B >= 1024))) {
+        // 256-column tiles: 131 FLOP per byte staged instead of 87; both accumulators fill TMEM, one CTA pair per SM pair
+        CUtensorMap mB2;
+        if (!kUp) { if ((rc = map_matrix(&mB2, w, Ca, 16 * Cb, 128))) return rc; }
+        else { if ((rc = map_matrix(&mB2, w, 4 * Cb, 4 * Ca, 128))) return rc; }
+        if (bb) return launch_pair_cfg<256, 6, M_, 1>(mA, mB2, out, stats, p, m_tiles, Cout / 256, *bb, st);
+        return launch_pair_cfg<256, 6, M_, 0>(mA, mB2, out, stats, p, m_tiles, Cout / 256, none, st);
+    }
     if (bn == 128) {
         if (bb) return launch_pair_cfg<128, 4, M_, 1>(mA, mB, out, stats, p, m_tiles, Cout / 128, *bb, st);
         return launch_pair_cfg<128, 4, M_, 0>(mA, mB, out, stats, p, m_tiles, Cout / 128, none, st);

@@ -108,6 +108,13 @@ __device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uin
                  : "memory");
 }
 
+// 256-bit read-only global load (LDG.E.256, sm_100): one whole 32-byte sector per thread.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+
 // ---- tcgen05 -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

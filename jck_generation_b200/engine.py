@@ -28,6 +28,20 @@ LRELU = 0.2
 # TMA stream already saturates, so it only beats the separate streaming pass where the K loop is long -- layers
 # whose output has >= 256 channels (+3..6 us vs a 8..14 us reduce pass); at 64 / 128 channels it loses (+18..46 us).
 FUSE_MIN_C = 256
+
+
+def fuse_up_bnbwd(cv):
+    """Does the input-gradient (up) convolution of layer `cv` run the BatchNorm-backward reduction of the layer below in
+    its epilogue?  Only for >= 256 output channels (above).  The windowed 64-channel kernel (conv_up_win_kernel) has the
+    fused epilogue too (jck_conv_up_bnbwd, parity-tested), but measured at 512 images it takes 61 us against 31 us for the
+    plain kernel + 34 us for the streaming reduce pass it would replace: ~10 extra operations per element on the eight
+    epilogue warps a 168-register budget allows make the epilogue, not the MMAs, the critical path (JCK_FUSE_WIN=1 to try)."""
+    import os
+    if cv.Cb == 64 and os.environ.get("JCK_FUSE_WIN", "0") == "1":
+        return cv.Ca <= 128 and cv.Hs % 16 == 0 and cv.Ws % 16 == 0
+    return cv.Cb >= FUSE_MIN_C
+
+
 BN_EPS = 1e-5
 BN_MOM = 0.1
 
@@ -356,7 +370,7 @@ class DiscriminatorEngine(_GradTarget):
                     # border / pad channel of the P4 image stay zero (the kernel writes interior pixels only)
                     da = dx_out if dx_out is not None else torch.zeros_like(inp)
                     _edge_up(cv, dy, da)
-                elif fuse and k > 1 and cv.Cb >= FUSE_MIN_C:
+                elif fuse and k > 1 and fuse_up_bnbwd(cv):
                     da = torch.empty_like(inp)
                     ops.conv_up_bnbwd(dy, cv.w_up, ctx.y[k - 1], ctx.ss[k - 1], ctx.mr[k - 1], LRELU, da, zeros[k - 2],
                                       cv.Ca, cv.Cb, ipg=B // groups)

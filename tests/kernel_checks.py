@@ -489,7 +489,8 @@ def big_cases():
         cases += [("down", shape, "bf16", "tc", 512), ("down_groups3", shape, "bf16", "tc", 1536),
                   ("up", shape, "bf16", "tc", 512), ("up", shape, "bf16", "tc", 1024),
                   ("wgrad", shape, "bf16", "tc", 1024), ("wgrad", shape, "bf16", "tc", 512)]
-    cases += [("bnbwd_up", "c3", "bf16", "tc", 1024), ("bnbwd_up", "c4", "bf16", "tc", 1024), ("bnbwd_up", "c4", "bf16", "tc", 512),
+    cases += [("bnbwd_up", "c2", "bf16", "tc", 1024), ("bnbwd_up", "c2", "bf16", "tc", 512), ("bnbwd_up", "w32", "bf16", "tc", 6),
+              ("bnbwd_up", "c3", "bf16", "tc", 1024), ("bnbwd_up", "c4", "bf16", "tc", 1024), ("bnbwd_up", "c4", "bf16", "tc", 512),
               ("bnbwd_down", "c3", "bf16", "tc", 512), ("bnbwd_down", "c4", "bf16", "tc", 512),
               ("edge_down_g3", "-", "bf16", "tc", 1536), ("edge_down", "-", "bf16", "tc", 512),
               ("edge_upscatter", "-", "bf16", "tc", 512), ("edge_wgrad", "-", "bf16", "tc", 1024),
@@ -523,7 +524,7 @@ def run_case(op, shape, dtype, algo, B):
         return check_fc_tc(B)
     if op.startswith("bnbwd_"):
         kind = op[6:]
-        groups = 2 if (B % 2 == 0 and shape in ("c3", "c4")) else 1
+        groups = 2 if B % 2 == 0 else 1
         return check_bnbwd(kind, shape, B, groups=groups, slope=0.0 if kind != "up" else 0.2)
     if op.startswith("edge_"):
         return check_edge(op[5:].rstrip("1"), B, nc=1 if op.endswith("1") else 3)
