@@ -349,6 +349,10 @@ int jck_one_hot_i64(const long long* labels, const long long* index, long long* 
 int jck_comm_create(int rank, int world, void** comm_out, void* ipc_handle_out /* JCK_COMM_HANDLE_BYTES */);
 int jck_comm_connect(void* comm, const void* all_handles /* world x JCK_COMM_HANDLE_BYTES, rank order */);
 int jck_comm_destroy(void* comm);
+/* early_dependents = 0 (the default): this communicator's kernels never execute griddepcontrol.launch_dependents (their
+ * dependents start when the exchange has completed).  At most ONE communicator of a process may have it on when exchanges
+ * are issued from more than one stream -- see csrc/comm.cu for the cross-rank deadlock this prevents. */
+int jck_comm_configure(void* comm, int early_dependents);
 /* *flag_out <- 1 if any exchange on this communicator ever timed out waiting for a peer (JCK_COMM_TIMEOUT_S seconds,
  * default 120; the timed-out exchange returned NaN instead of a sum), else 0.  Synchronises with the device. */
 int jck_comm_error(void* comm, int* flag_out);

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "jck_comm_create": [c_i, c_i, ctypes.POINTER(c_p), c_p],
     "jck_comm_connect": [c_p, c_p],
     "jck_comm_destroy": [c_p],
+    "jck_comm_configure": [c_p, c_i],
     "jck_comm_error": [c_p, ctypes.POINTER(c_i)],
     "jck_comm_allreduce_small": [c_p, c_p, c_i, c_p],
     "jck_bn_finalize_sync": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_f, c_p],

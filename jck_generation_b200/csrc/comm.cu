@@ -15,6 +15,16 @@
 // next step's exchange).  A timeout does NOT trap (that would destroy the CUDA context of a job that may be recoverable):
 // the kernel prints a diagnostic, raises a sticky error flag the host reads with jck_comm_error(), and poisons its result
 // with NaN so that nothing downstream can mistake it for a sum.
+//
+// Programmatic dependent launch and spin-waits on a REMOTE peer: a kernel that has executed launch_dependents lets its
+// dependents become resident early; they then sit in griddepcontrol.wait holding registers / thread slots on every SM
+// while this kernel waits for the peer.  With ONE stream of exchanges that is harmless (the peer's counterpart only has
+// ordinary kernels in front of it).  With TWO streams issuing exchanges (the penalty sweep runs on its own stream with its
+// own communicator, parallel.AuxComm) it deadlocks across ranks: rank 0 spins in a main-stream exchange whose dependents
+// fill the GPU, so its auxiliary exchange cannot get an SM, while rank 1 spins in the auxiliary exchange whose dependents
+// starve its main one (seen at 2 GPUs with 1024-thread exchange kernels).  So by default a communicator NEVER triggers
+// early: its dependents start only when the exchange has completed (jck_comm_configure can turn early launch on for ONE
+// communicator of a process; measured, it does not pay).  The kernels are 512 threads (half an SM's registers) for the same reason.
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -31,7 +41,13 @@ struct CommDev {
     unsigned int* err;                     // sticky error flag (device memory, read back by jck_comm_error)
     long long timeout_cycles;              // spin bound
     int rank, world;
+    int early_dependents;                  // execute griddepcontrol.launch_dependents on entry (see above)
 };
+
+__device__ __forceinline__ void comm_entry(const CommDev& c) {
+    if (c.early_dependents) pdl_trigger();
+    pdl_wait();
+}
 
 struct Comm {
     CommDev dev;
@@ -86,18 +102,20 @@ __device__ void allreduce_block(const CommDev& c, float* __restrict__ data, int 
     if (threadIdx.x == 0) *c.seq = seq;
 }
 
-__global__ void __launch_bounds__(1024) comm_allreduce_kernel(const CommDev c, float* __restrict__ data, int n) {
-    pdl_entry();
+constexpr int kCommThreads = 512;
+
+__global__ void __launch_bounds__(kCommThreads) comm_allreduce_kernel(const CommDev c, float* __restrict__ data, int n) {
+    comm_entry(c);
     allreduce_block(c, data, n);
 }
 
 // SyncBN forward: exchange [groups][2C] statistics, then what jck_bn_finalize does (same arithmetic).
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kCommThreads)
 bn_finalize_sync_kernel(const CommDev c, float* __restrict__ stats, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                         long long* __restrict__ nbt, float* __restrict__ scale_shift, float* __restrict__ mean_rstd, int C,
                         int groups, float count, float eps, float momentum) {
-    pdl_entry();
+    comm_entry(c);
     allreduce_block(c, stats, groups * 2 * C);
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
         float rm = running_mean ? running_mean[ch] : 0.f, rv = running_var ? running_var[ch] : 0.f;
@@ -123,10 +141,10 @@ bn_finalize_sync_kernel(const CommDev c, float* __restrict__ stats, const float*
 }
 
 // SyncBN backward: this rank's share of dgamma / dbeta from its LOCAL sums, then exchange the sums.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kCommThreads)
 bn_bwd_sums_sync_kernel(const CommDev c, float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                         int C, int groups, int accumulate) {
-    pdl_entry();
+    comm_entry(c);
     if (dgamma != nullptr) {
         for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
             float sb = 0.f, sg = 0.f;
@@ -151,6 +169,7 @@ extern "C" int jck_comm_create(int rank, int world, void** comm_out, void* ipc_h
     Comm* cm = new Comm();
     cm->dev.rank = rank;
     cm->dev.world = world;
+    cm->dev.early_dependents = 0;          // measured at 2 GPUs: early launch buys nothing here (2.82 vs 2.75 ms/step) and is unsafe with two streams
     cudaError_t e = cudaGetDevice(&cm->device);
     const size_t bytes = mailbox_words() * sizeof(unsigned long long) + 256;
     {
@@ -192,6 +211,12 @@ extern "C" int jck_comm_connect(void* comm, const void* all_handles) {
     return JCK_OK;
 }
 
+extern "C" int jck_comm_configure(void* comm, int early_dependents) {
+    JCK_REQUIRE(comm, "comm_configure: bad argument");
+    static_cast<Comm*>(comm)->dev.early_dependents = early_dependents ? 1 : 0;
+    return JCK_OK;
+}
+
 extern "C" int jck_comm_error(void* comm, int* flag_out) {
     JCK_REQUIRE(comm && flag_out, "comm_error: bad argument");
     Comm* cm = static_cast<Comm*>(comm);
@@ -215,7 +240,7 @@ extern "C" int jck_comm_destroy(void* comm) {
 extern "C" int jck_comm_allreduce_small(void* comm, float* data, int n, void* stream) {
     JCK_REQUIRE(comm && data && n > 0 && n <= kMaxN, "comm_allreduce_small: n=%d (max %d)", n, kMaxN);
     Comm* cm = static_cast<Comm*>(comm);
-    launch_pdl(comm_allreduce_kernel, dim3(1), dim3(1024), 0, as_stream(stream), cm->dev, data, n);
+    launch_pdl(comm_allreduce_kernel, dim3(1), dim3(kCommThreads), 0, as_stream(stream), cm->dev, data, n);
     JCK_LAUNCH_CHECK("comm_allreduce_small");
     return JCK_OK;
 }
@@ -226,7 +251,7 @@ extern "C" int jck_bn_finalize_sync(void* comm, float* stats, const float* gamma
     JCK_REQUIRE(comm && stats && gamma && beta && scale_shift && mean_rstd && C > 0 && groups > 0 && count > 0 &&
                 groups * 2 * C <= kMaxN, "bn_finalize_sync: bad argument");
     Comm* cm = static_cast<Comm*>(comm);
-    launch_pdl(bn_finalize_sync_kernel, dim3(1), dim3(1024), 0, as_stream(stream), cm->dev, stats, gamma, beta, running_mean, running_var,
+    launch_pdl(bn_finalize_sync_kernel, dim3(1), dim3(kCommThreads), 0, as_stream(stream), cm->dev, stats, gamma, beta, running_mean, running_var,
                                                              num_batches_tracked, scale_shift, mean_rstd, C, groups, count,
                                                              eps, momentum);
     JCK_LAUNCH_CHECK("bn_finalize_sync");
@@ -238,7 +263,7 @@ extern "C" int jck_bn_bwd_sums_sync(void* comm, float* sums, float* dgamma, floa
     JCK_REQUIRE(comm && sums && C > 0 && groups > 0 && groups * 2 * C <= kMaxN && ((dgamma == nullptr) == (dbeta == nullptr)),
                 "bn_bwd_sums_sync: bad argument");
     Comm* cm = static_cast<Comm*>(comm);
-    launch_pdl(bn_bwd_sums_sync_kernel, dim3(1), dim3(1024), 0, as_stream(stream), cm->dev, sums, dgamma, dbeta, C, groups, accumulate);
+    launch_pdl(bn_bwd_sums_sync_kernel, dim3(1), dim3(kCommThreads), 0, as_stream(stream), cm->dev, sums, dgamma, dbeta, C, groups, accumulate);
     JCK_LAUNCH_CHECK("bn_bwd_sums_sync");
     return JCK_OK;
 }

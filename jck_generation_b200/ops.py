@@ -194,6 +194,10 @@ def comm_connect(comm, all_handles):
     check(L().jck_comm_connect(comm, all_handles), "comm_connect")
 
 
+def comm_configure(comm, early_dependents):
+    check(L().jck_comm_configure(comm, int(early_dependents)), "comm_configure")
+
+
 def comm_error(comm):
     """True when an exchange on this peer communicator ever timed out waiting for a peer (synchronises with the device)."""
     import ctypes

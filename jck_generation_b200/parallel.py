@@ -63,7 +63,7 @@ class TorchComm:
             return self
         self.peer = self._open_one()
         if self.peer is not None:
-            self.peer_aux = self._open_one()
+            self.peer_aux = self._open_one()       # for exchanges issued from a second stream (AuxComm)
         return self
 
     @property

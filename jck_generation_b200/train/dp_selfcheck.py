@@ -15,7 +15,10 @@ from .dcgan_step import DCGANStep
 from .optim import FusedAdam
 
 TOL = {  # dtype -> (forward / statistics, D gradients, pass-D-derived gradients)
-    torch.float32: (1e-4, 1e-3, 2e-2),
+    # fp32 D gradients are bimodal between ANY two runs of the same binary: ~2e-6 when no LeakyReLU pre-activation sits within
+    # summation-order noise of zero, 4e-4 .. 2e-3 when one or two do and take the other branch on one side (the per-channel
+    # statistics are summed in a different order across ranks; DESIGN.md section 2, "kink flips")
+    torch.float32: (1e-4, 5e-3, 2e-2),
     torch.bfloat16: (1e-1, 1e-1, 2e-1),
 }
 

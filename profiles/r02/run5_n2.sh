@@ -1,4 +1,5 @@
 set -x
+export JCK_COMM_TIMEOUT_S=20
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 timeout 300 $TR --master-port 29541 -m tests.comm_check > gpurun_out/r2_n2_comm.log 2>&1; tail -2 gpurun_out/r2_n2_comm.log
 timeout 300 $TR --master-port 29542 -m tests.dp_check > gpurun_out/r2_n2_dp.log 2>&1; tail -3 gpurun_out/r2_n2_dp.log
