@@ -1178,10 +1178,13 @@ struct WgradTcParams {
     int b_tiles;               // Cb / BNW
 };
 
+// Pipeline: two stages of 64 pixels (80 KB each).  Four stages of 32 pixels (same 160 KB, deeper prefetch) measured SLOWER
+// (c3 at 512 images: 52 vs 44 us; c4: 58 vs 48 us): twice the barrier round trips and TMA boxes per MMA outweigh the prefetch.
+constexpr int kWgradKPix = 64;                           // K step of the image-edge weight gradient (wgrad_edge_direct_kernel)
 constexpr int kWgradStages = 2;
-constexpr int kWgradKPix = 64;
-constexpr int kWgradABytes = 2 * kWgradKPix * 128;       // two 64-channel atoms of `a`
-constexpr int kWgradBBytes = 8 * kWgradKPix * 128;       // G * BNW / 64 = 8 atoms
+constexpr int kWgTcKPix = 64;
+constexpr int kWgradABytes = 2 * kWgTcKPix * 128;       // two 64-channel atoms of `a`
+constexpr int kWgradBBytes = 8 * kWgTcKPix * 128;       // G * BNW / 64 = 8 atoms
 constexpr int kWgradStage = kWgradABytes + kWgradBBytes; // 80 KB
 constexpr int kWgradSmem = kWgradStages * kWgradStage + 256 + 1024;
 
@@ -1236,7 +1239,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant_
                 const int ys = ((st / p.kx_tiles) % p.ky_tiles) * p.kbh;
                 const int ns = (st / (p.kx_tiles * p.ky_tiles)) * p.knb;
                 tma_load_4d(sa, &mapS, &full[s], a_tile * 128, xs, ys, ns);
-                tma_load_4d(sa + kWgradKPix * 128, &mapS, &full[s], a_tile * 128 + 64, xs, ys, ns);
+                tma_load_4d(sa + kWgTcKPix * 128, &mapS, &full[s], a_tile * 128 + 64, xs, ys, ns);
 #pragma unroll 1
                 for (int g = 0; g < G; ++g) {
                     const int tap = tap0 + g;
@@ -1244,7 +1247,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant_
                     const int dy = (ky - 1) >> 1, qy = (ky - 1) & 1;
                     const int dx = (kx - 1) >> 1, qx = (kx - 1) & 1;
                     for (int at = 0; at < ATOMS_B; ++at)
-                        tma_load_5d(sb + (g * ATOMS_B + at) * (kWgradKPix * 128), &mapL, &full[s],
+                        tma_load_5d(sb + (g * ATOMS_B + at) * (kWgTcKPix * 128), &mapL, &full[s],
                                     qx * p.Cb + b_tile * BNW + at * 64, xs + dx, qy, ys + dy, ns);
                 }
             }
@@ -1267,10 +1270,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant_
 #pragma unroll 1
                 for (int g = 0; g < kGroups; ++g) {
 #pragma unroll
-                    for (int k = 0; k < kWgradKPix / 16; ++k) {
-                        const uint64_t da = make_sdesc(a_addr + k * 2048, kWgradKPix * 128, 1024);
-                        const uint64_t db = make_sdesc(b_addr + g * 2 * (kWgradKPix * 128) + k * 2048,
-                                                       kWgradKPix * 128, 1024);
+                    for (int k = 0; k < kWgTcKPix / 16; ++k) {
+                        const uint64_t da = make_sdesc(a_addr + k * 2048, kWgTcKPix * 128, 1024);
+                        const uint64_t db = make_sdesc(b_addr + g * 2 * (kWgTcKPix * 128) + k * 2048,
+                                                       kWgTcKPix * 128, 1024);
                         umma_bf16(tmem_base + g * 128, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
                     }
                 }
@@ -1343,7 +1346,7 @@ WgradPlan wgrad_plan(int B, int Hs, int Ws, int Ca, int Cb) {
     WgradPlan pl{};
     pl.ok = false;
     if (Ca % 128 != 0 || Cb % 64 != 0) return pl;
-    if (!patch_geom(Hs, Ws, kWgradKPix, &pl.g)) return pl;
+    if (!patch_geom(Hs, Ws, kWgTcKPix, &pl.g)) return pl;
     pl.bnw = (Cb % 128 == 0) ? 128 : 64;
     pl.G = 512 / pl.bnw;
     const int tiles = (Ca / 128) * (Cb / pl.bnw) * (16 / pl.G);
