@@ -161,6 +161,15 @@ int jck_unpack_fc_grad(const float* dw_fc, float* dw4, int K, int C, int accumul
 int jck_pack_fc_t(const float* w4, void* w_t_bf16, int K, int C, void* stream);
 int jck_unpack_fc_grad_t(const float* dw_t, float* dw4, int K, int C, int accumulate, void* stream);
 int jck_cast_rows_bf16(const float* x, void* out_bf16, int M, int K, int ldo, void* stream);
+/* out[m] = [a[m][0:K1] | b[m][0:K2] | 0 ...] (row pitch ldo), b fp32 or int64 (b_is_i64), out fp32 or bf16: the CGAN generator
+ * input cat([z, labels.reshape(-1, n_classes, 1, 1)], 1) (model/CGAN.py:154-155) written straight into the operand of the
+ * conv1 matrix product -- no torch.cat, no separate int64 -> float or fp32 -> bf16 pass. */
+int jck_concat_rows(const float* a, const void* b, int b_is_i64, void* out, int M, int K1, int K2, int ldo, int dtype,
+                    void* stream);
+/* stream-ordered memset to zero (one graph memset node): the per-step accumulator arena (BatchNorm statistics / backward sums /
+ * logged scalars), gradient buffers that accumulate.  Replaces torch.zeros / .zero_() inside the captured step. */
+int jck_zero(void* p, size_t bytes, void* stream);
+int jck_copy_f32(const float* src, float* dst, long long n, void* stream);
 
 /* ---- BatchNorm2d (train mode) + activation ---------------------------------------------------
  * Replaces nn.BatchNorm2d + nn.LeakyReLU(0.2)/nn.ReLU model/DCGAN.py:11-12,43-44 (forward) and

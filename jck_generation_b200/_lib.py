@@ -50,6 +50,9 @@ _SIGNATURES = {
     "jck_pack_fc_t": [c_p, c_p, c_i, c_i, c_p],
     "jck_unpack_fc_grad_t": [c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_cast_rows_bf16": [c_p, c_p, c_i, c_i, c_i, c_p],
+    "jck_concat_rows": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_zero": [c_p, c_sz, c_p],
+    "jck_copy_f32": [c_p, c_p, c_ll, c_p],
     "jck_axpy": [c_p, c_p, c_f, c_ll, c_i, c_p],
     "jck_gp_seed": [c_p, c_p, c_p, c_i, c_ll, c_f, c_i, c_p],
     "jck_pack_linear": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],

@@ -475,6 +475,27 @@ __global__ void unpack_fc_grad_t_kernel(const float* __restrict__ dw_t, float* _
         dw4[idx] = accumulate ? dw4[idx] + v : v;
     }
 }
+// out[m][0:K1] = a[m][:], out[m][K1:K1+K2] = b[m][:] (b fp32, or int64 when b_is_i64), zero up to ldo; bf16 or fp32 output
+template <typename TO>
+__global__ void concat_rows_kernel(const float* __restrict__ a, const void* __restrict__ b, TO* __restrict__ out, int M, int K1,
+                                   int K2, int ldo, int b_is_i64) {
+    pdl_entry();
+    const long long total = (long long)M * ldo;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(o % ldo);
+        const long long m = o / ldo;
+        float v = 0.f;
+        if (k < K1) v = a[m * K1 + k];
+        else if (k < K1 + K2)
+            v = b_is_i64 ? (float)reinterpret_cast<const long long*>(b)[m * K2 + (k - K1)]
+                         : reinterpret_cast<const float*>(b)[m * K2 + (k - K1)];
+        st_act(out + o, v);
+    }
+}
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+    pdl_entry();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 __global__ void cast_rows_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int M, int K, int ldo) {
     pdl_entry();
     const long long total = (long long)M * ldo;
@@ -1007,6 +1028,27 @@ extern "C" int jck_cast_rows_bf16(const float* x, void* out_bf16, int M, int K, 
     launch_pdl(cast_rows_bf16_kernel, dim3(grid_for((long long)M * ldo, 256)), dim3(256), 0, as_stream(stream), x,
                (__nv_bfloat16*)out_bf16, M, K, ldo);
     JCK_LAUNCH_CHECK("cast_rows_bf16");
+    return JCK_OK;
+}
+extern "C" int jck_concat_rows(const float* a, const void* b, int b_is_i64, void* out, int M, int K1, int K2, int ldo, int dtype,
+                               void* stream) {
+    JCK_REQUIRE(a && b && out && M > 0 && K1 > 0 && K2 > 0 && ldo >= K1 + K2, "concat_rows: bad argument");
+    DISPATCH_DTYPE(dtype, "concat_rows",
+        launch_pdl(concat_rows_kernel<T>, dim3(grid_for((long long)M * ldo, 256)), dim3(256), 0, as_stream(stream), a, b, (T*)out, M, K1,
+                   K2, ldo, b_is_i64);)
+    JCK_LAUNCH_CHECK("concat_rows");
+    return JCK_OK;
+}
+extern "C" int jck_zero(void* p, size_t bytes, void* stream) {
+    JCK_REQUIRE(p && bytes > 0, "zero: bad argument");
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, as_stream(stream));
+    if (e != cudaSuccess) return set_error(JCK_E_CUDA, "zero: %s", cudaGetErrorString(e));
+    return JCK_OK;
+}
+extern "C" int jck_copy_f32(const float* src, float* dst, long long n, void* stream) {
+    JCK_REQUIRE(src && dst && n > 0, "copy_f32: bad argument");
+    launch_pdl(copy_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), src, dst, n);
+    JCK_LAUNCH_CHECK("copy_f32");
     return JCK_OK;
 }
 extern "C" int jck_pack_head(const float* w4, void* w5, int C4, int dtype, void* stream) {

@@ -132,10 +132,13 @@ class Ctx:
         return s
 
 
-def _zero_blocks(groups, channels, device):
-    """One memset for all the [groups][2C] fp32 accumulators of a pass (stats / backward sums)."""
+def _zero_blocks(groups, channels, device, arena=None):
+    """All the [groups][2C] fp32 accumulators of a pass (stats / backward sums), zeroed: slices of the step's arena
+    (ops.ZeroArena: one memset per STEP) when the step provides one, else one torch.zeros for the pass (module API)."""
     total = sum(groups * 2 * c for c in channels)
-    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    flat = arena.take(total) if arena is not None else None
+    if flat is None:
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
     out, off = [], 0
     for c in channels:
         out.append(flat[off:off + groups * 2 * c].view(groups, 2 * c))
@@ -186,6 +189,7 @@ class _GradTarget:
     gradients are used; every operand is kept alive by the Ctx until then."""
     sink = None
     wgrad_stream = None
+    arena = None              # ops.ZeroArena of the running step (set by the step; None: accumulators come from torch.zeros)
     grad_sync = None          # parallel.GradBuckets: told as each parameter's gradient becomes final (trainer hot path)
 
     def _grad_ready(self, *params):
@@ -259,7 +263,7 @@ class DiscriminatorEngine(_GradTarget):
         ctx.x, ctx.groups, ctx.B = x_nhwc, groups, B
         cur = x_nhwc
         world = self.comm.world_size
-        zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev)
+        zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev, self.arena)
         for k in range(1, 5):
             cv, nm = self.convs[k], self.norms[k]
             y = torch.empty(B, cv.Hs, cv.Ws, cv.Ca, dtype=self.dtype, device=self.dev)
@@ -300,7 +304,7 @@ class DiscriminatorEngine(_GradTarget):
         da4 = torch.empty(B, self.K5, dtype=self.dtype, device=self.dev)
         a4 = ctx.a[4].view(B, self.K5)
         if wgrad:
-            self.dw5.zero_()
+            ops.zero(self.dw5)
         for g in range(ctx.groups):
             sl = slice(g * per, (g + 1) * per)
             ops.head_bwd(ctx.prob[sl], targets[g] if targets is not None else 0.0, self.w5, a4[sl], da4[sl],
@@ -331,7 +335,7 @@ class DiscriminatorEngine(_GradTarget):
         world = comm.world_size
         fuse = fuse and self.fused_bn_bwd
         da, reduced = da4, False
-        zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev)
+        zeros = _zero_blocks(groups, [self.convs[k].Ca for k in range(1, 5)], self.dev, self.arena)
         for k in range(4, 0, -1):
             cv, nm = self.convs[k], self.norms[k]
             C = cv.Ca
@@ -440,21 +444,36 @@ class GeneratorEngine(_GradTarget):
         ctx.y[k], ctx.a[k], ctx.ss[k], ctx.mr[k] = y, a, ss, mr
         return a
 
-    def forward(self, z2d, update_running=True, y5_out=None):
+    def forward(self, z2d, update_running=True, y5_out=None, labels=None):
         """z2d: [B, K1] fp32 (z, or cat(z, one-hot) for CGAN).  Returns ctx; ctx.y[5] is the raw conv5
         output [B,64,64,nc] (tanh is applied by ops.g_out_fwd at the image edge).  `y5_out`: caller-owned
-        JCK_IMG_P4 buffer for it (zero border / pad channel), else a freshly zeroed one."""
+        JCK_IMG_P4 buffer for it (zero border / pad channel), else a freshly zeroed one.
+        `labels` ([B, n_classes] fp32 or int64, CGAN): z2d then holds the nz noise columns only and the reference's
+        cat([z, labels], 1) (model/CGAN.py:154-155) is written straight into conv1's operand by ONE kernel
+        (jck_concat_rows: concat + int64 -> float + fp32 -> bf16), not materialised by torch.cat."""
         self.refresh()
         B = z2d.shape[0]
         ctx = Ctx()
+        zb_ready = False
+        if labels is not None:
+            assert z2d.shape[1] + labels.shape[1] == self.K1
+            if self.tc_fc:
+                ctx.zb = torch.empty(B, self.K1p, dtype=torch.bfloat16, device=self.dev)
+                ops.concat_rows(z2d.contiguous(), labels.contiguous(), ctx.zb)
+                zb_ready = True
+            else:
+                full = torch.empty(B, self.K1, dtype=torch.float32, device=self.dev)
+                ops.concat_rows(z2d.contiguous(), labels.contiguous(), full)
+                z2d = full
         ctx.x, ctx.B, ctx.groups = z2d, B, 1
         y1 = torch.empty(B, 4, 4, self.C1, dtype=self.dtype, device=self.dev)
-        zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev)
+        zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev, self.arena)
         stats = zeros[0]
         N1 = 16 * self.C1
         if self.tc_fc:
-            ctx.zb = torch.empty(B, self.K1p, dtype=torch.bfloat16, device=self.dev)
-            ops.cast_rows_bf16(z2d.contiguous(), ctx.zb)
+            if not zb_ready:
+                ctx.zb = torch.empty(B, self.K1p, dtype=torch.bfloat16, device=self.dev)
+                ops.cast_rows_bf16(z2d.contiguous(), ctx.zb)
             ops.gemm_tc(ctx.zb, 0, self.K1p, self.w_fc, 1, N1, y1.view(B, N1), B, N1, self.K1, stats=stats, stats_channels=self.C1)
         else:
             ops.fc_fwd(z2d, self.w_fc, y1, stats, self.C1)
@@ -482,7 +501,7 @@ class GeneratorEngine(_GradTarget):
         B = ctx.B
         world = self.comm.world_size
         d_large = dy5
-        zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev)
+        zeros = _zero_blocks(1, [self.norms[k].C for k in range(1, 5)], self.dev, self.arena)
         fuse = self.dtype == torch.bfloat16 and self.algo != ops.ALGO_SIMT
         for k in range(5, 1, -1):
             cv = self.convs[k]

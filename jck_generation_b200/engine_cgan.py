@@ -174,8 +174,8 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
     def flush_linear1_grad(self, accumulate):
         """dw1a / dw1b (kernel layout) -> linear1.weight.grad (reference layout), then clear them."""
         ops.unpack_linear_grad(self.dw1a, self.dw1b, self._gb(self.m.linear1.weight), self.C4, 16, accumulate)
-        self.dw1a.zero_()
-        self.dw1b.zero_()
+        ops.zero(self.dw1a)
+        ops.zero(self.dw1b)
 
     # ---- gradient-penalty sweeps ---------------------------------------------------------------------------------
     def head_gp_seed(self, ctx):
@@ -213,7 +213,9 @@ class CganDiscriminatorEngine(DiscriminatorEngine):
                 ops.conv_down(abar, cv.w_down, dbar, None, C, cv.Cb, algo=self.algo)
                 nbytes = ops.wgrad_workspace_bytes(B, cv.Hs, cv.Ws, C, cv.Cb, self.dtype, self.algo)
                 ops.conv_wgrad(ctx.dy[k], abar, self._gb(cv.weight), self.ws.get(nbytes), C, cv.Cb, True, algo=self.algo)
-            asums = torch.zeros(3 * C, dtype=torch.float32, device=self.dev)
+            asums = self.arena.take(3 * C) if self.arena is not None else None
+            if asums is None:
+                asums = torch.zeros(3 * C, dtype=torch.float32, device=self.dev)
             count = B * cv.Hs * cv.Ws * world
             ops.bn_adj_reduce(dbar, ctx.da[k], ctx.y[k], ctx.ss[k], ctx.mr[k], ctx.bsum[k], asums, C, count, LRELU)
             ops.bn_adj_param(asums, ctx.mr[k], self._gb(nm.bn.weight), C)          # this rank's share of dgamma

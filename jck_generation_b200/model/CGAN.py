@@ -178,16 +178,14 @@ class Generator(nn.Module):
 
     def concat_inputs(self, z, labels):
         """cat([z, labels.reshape(-1, n_classes, 1, 1)], 1) of the reference (CGAN.py:154-155) as a [B, nz + n_classes]
-        fp32 matrix: pure data movement plus the int64 -> float conversion kernel."""
+        fp32 matrix, by one kernel (jck_concat_rows: concat + int64 -> float).  The trainer's step does not even materialise it:
+        GeneratorEngine.forward(z, labels=...) writes the concatenation straight into conv1's bf16 operand."""
         B = z.shape[0]
         out = torch.empty(B, self.nz + self.n_classes, dtype=torch.float32, device=z.device)
-        out[:, :self.nz].copy_(z.detach().reshape(B, self.nz))
-        if labels.dtype == torch.float32:
-            out[:, self.nz:].copy_(labels.reshape(B, self.n_classes))
-        else:
-            lab = torch.empty(B, self.n_classes, dtype=torch.float32, device=z.device)
-            ops.i64_to_f32(labels.contiguous(), lab)
-            out[:, self.nz:].copy_(lab)
+        lab = labels.reshape(B, self.n_classes)
+        if lab.dtype not in (torch.float32, torch.int64):
+            lab = lab.float()
+        ops.concat_rows(z.detach().reshape(B, self.nz).float().contiguous(), lab.contiguous(), out)    # one kernel
         return out
 
     def forward(self, x, labels):

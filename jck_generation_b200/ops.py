@@ -374,6 +374,48 @@ def unpack_fc_grad_t(dw_t, dw4, accumulate):
     check(L().jck_unpack_fc_grad_t(_p(dw_t), _p(dw4), dw4.shape[0], dw4.shape[1], int(accumulate), _s()), "unpack_fc_grad_t")
 
 
+def concat_rows(a, b, out):
+    """out[m] = [a[m] | b[m] | 0 ...]: a fp32 [M,K1], b fp32 or int64 [M,K2], out fp32 / bf16 [M, ldo >= K1 + K2]"""
+    M, K1 = a.shape
+    K2 = b.shape[1]
+    assert a.dtype == torch.float32 and b.dtype in (torch.float32, torch.int64) and a.is_contiguous() and b.is_contiguous()
+    check(L().jck_concat_rows(_p(a), _p(b), int(b.dtype == torch.int64), _p(out), M, K1, K2, out.shape[1], dt(out), _s()),
+          "concat_rows")
+
+
+def zero(t):
+    """stream-ordered memset of a contiguous tensor (one memset node in a captured graph)"""
+    assert t.is_contiguous()
+    check(L().jck_zero(_p(t), t.numel() * t.element_size(), _s()), "zero")
+
+
+def copy_f32(src, dst):
+    assert src.dtype == torch.float32 and dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    check(L().jck_copy_f32(_p(src), _p(dst), src.numel(), _s()), "copy_f32")
+
+
+class ZeroArena:
+    """The fp32 accumulators of one train step (BatchNorm statistics and backward sums of every pass, the logged scalars)
+    as slices of ONE buffer zeroed by ONE memset at the start of the step, instead of a torch.zeros fill kernel per pass."""
+
+    def __init__(self, device, numel=1 << 16):
+        self.buf = torch.empty(numel, dtype=torch.float32, device=device)
+        self.cursor = 0
+
+    def reset(self):
+        self.cursor = 0
+        zero(self.buf)
+
+    def take(self, n):
+        """n zeroed floats, or None when the arena is exhausted (the caller falls back to torch.zeros)"""
+        n_pad = -(-n // 32) * 32
+        if self.cursor + n_pad > self.buf.numel():
+            return None
+        out = self.buf[self.cursor:self.cursor + n]
+        self.cursor += n_pad
+        return out
+
+
 def cast_rows_bf16(x, out):
     M, K = x.shape
     check(L().jck_cast_rows_bf16(_p(x), _p(out), M, K, out.shape[1], _s()), "cast_rows_bf16")

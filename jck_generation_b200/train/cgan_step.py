@@ -43,6 +43,7 @@ class CGANStep(DCGANStep):
         r = rng if rng is not None else self.draw(B)
         self.flat_d.rebind()
         self.flat_g.rebind()
+        self.arena.reset()
         lay = ed.img_layout
         if labels.dtype != torch.float32:
             lab = torch.empty(B, labels.shape[1], dtype=torch.float32, device=dev)
@@ -59,8 +60,9 @@ class CGANStep(DCGANStep):
                                out_nchw=real_n, layout=lay)                                                       # :182
         else:
             ops.prep_image(real, out_nhwc=X[0:B], m1=r["noise_real"], a1=0.9, b1=0.1, out_nchw=real_n, layout=lay)
-        z2d = self.g.concat_inputs(r["z"], lab)
-        gctx = eg.forward(z2d, y5_out=self._p4("y5", B) if eg.img_layout == ops.IMG_P4 else None)                 # :190
+        # :190 -- cat([z, labels]) goes straight into conv1's operand (GeneratorEngine.forward, jck_concat_rows)
+        gctx = eg.forward(r["z"].reshape(B, self.nz).contiguous(), labels=lab,
+                          y5_out=self._p4("y5", B) if eg.img_layout == ops.IMG_P4 else None)
         fake_raw = torch.empty(B, self.nc, 64, 64, dtype=torch.float32, device=dev)
         fake_n = torch.empty_like(fake_raw)
         if drawn:
@@ -71,7 +73,7 @@ class CGANStep(DCGANStep):
             ops.g_out_fwd(gctx.y[5], r["noise_fake"], 0.9, 0.1, fake_raw, fake_n, X[B:2 * B], (B, self.nc, 64, 64), layout=lay)
         ops.prep_image(real_n, out_nhwc=X[2 * B:3 * B], a1=1.0, x2=fake_n, alpha=r["alpha"].reshape(B), layout=lay)  # :115
 
-        scal = torch.zeros(4, 2, dtype=torch.float32, device=dev)
+        scal = self.arena.take(8).view(4, 2)               # valid until the next step's reset (callers clone to keep it)
         masks = r.get("drop_abc")
         if masks is None:                                  # injected masks: three separate [B,256] blocks
             masks = torch.cat([m.reshape(B, 256).float() for m in r["drop"][:3]]).contiguous()
@@ -79,7 +81,7 @@ class CGANStep(DCGANStep):
         ed.head_forward(ctx, lab, masks, targets=[LABEL_REAL, LABEL_FAKE, None], scalars=scal)
 
         # ---- D update: first + second order ------------------------------------------------------------------
-        self.flat_d.grad.zero_()                           # everything below accumulates
+        ops.zero(self.flat_d.grad)                         # everything below accumulates
         cc = ctx.slice(2, 3)
         cc.head = {k: (v[2 * B:3 * B] if (torch.is_tensor(v) and v.shape[0] == 3 * B) else v) for k, v in ctx.head.items()}
         g_a4 = ed.head_gp_seed(cc)
@@ -92,7 +94,7 @@ class CGANStep(DCGANStep):
         dls = torch.empty(3 * B, dtype=torch.float32, device=dev)
         ops.logit_grad(ctx.prob[0:B], dls[0:B], mode=0, target=LABEL_REAL, scale=1.0 / B)
         ops.logit_grad(ctx.prob[B:2 * B], dls[B:2 * B], mode=0, target=LABEL_FAKE, scale=1.0 / B)
-        dls[2 * B:3 * B].copy_(sbar)
+        ops.copy_f32(sbar.contiguous(), dls[2 * B:3 * B])
         da4 = ed.head_backward(ctx, dls, wgrad=True)
         ed.flush_linear1_grad(accumulate=True)
         ed.trunk_backward(ctx, da4, wgrad=True, input_grad=False, accumulate=True, inject=ybar, inject_rows=(2 * B, 3 * B))  # :203

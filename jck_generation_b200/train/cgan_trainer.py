@@ -174,7 +174,7 @@ class CGANTrainer(Trainer):
                     real_data, labels_data = parallel.shard_rows(real_data, self.comm), parallel.shard_rows(labels_data, self.comm)
                 real_data = real_data.contiguous().float()
                 scal = self.train_step(real_data, labels_data)
-                pending.append((epoch, i, scal if not self.use_graph else scal.clone()))
+                pending.append((epoch, i, scal.clone()))       # the block lives in the step's arena: keep a copy
                 if len(pending) >= 100:
                     flush()
                 last = (epoch == self.epoch - 1) and (i == len(real_images_loader) - 1)

@@ -50,6 +50,9 @@ class DCGANStep:
         self._graph = None
         self._static = None
         self._p4_bufs = {}
+        # every fp32 accumulator of a step lives in one arena zeroed by one memset (no torch fill kernels in the step)
+        self.arena = ops.ZeroArena(self.dev)
+        self.eg.arena = self.ed.arena = self.arena
         # weight-gradient kernels run beside the sweep that produces their operands (engine._GradTarget)
         self.gp_stream = None
         if self.dtype == torch.bfloat16:
@@ -101,6 +104,7 @@ class DCGANStep:
         r = rng if rng is not None else self.draw(B)
         self.flat_d.rebind()
         self.flat_g.rebind()
+        self.arena.reset()
 
         lay = ed.img_layout
         p4 = lay == ops.IMG_P4
@@ -126,7 +130,7 @@ class DCGANStep:
         ops.prep_image(real_n, out_nhwc=X[2 * B:3 * B], a1=1.0, x2=fake_n, alpha=r["alpha"].reshape(B),
                        layout=lay)                                                                         # :112
 
-        scal = torch.zeros(4, 2, dtype=torch.float32, device=dev)
+        scal = self.arena.take(8).view(4, 2)               # valid until the next step's reset (callers clone to keep it)
         ctx = ed.trunk_forward(X, groups=3)                                                                # :162,173,114
         ed.head_forward(ctx, targets=[LABEL_REAL, LABEL_FAKE, None], scalars=scal)
 

@@ -177,7 +177,7 @@ class DCGANTrainer(Trainer):
                 real_data = data[0]
                 real_data = parallel.shard_rows(real_data, self.comm) if getattr(self.data_pre, "global_batches", False) else real_data
                 scal = self.train_step(real_data.contiguous().float())
-                pending.append((epoch, i, scal if not self.use_graph else scal.clone()))
+                pending.append((epoch, i, scal.clone()))       # the block lives in the step's arena: keep a copy
                 if len(pending) >= 100:
                     flush()
 
