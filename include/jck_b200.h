@@ -62,6 +62,16 @@ extern "C" {
 #define JCK_ALGO_SIMT 1  /* CUDA-core fp32-FMA implicit GEMM (exact-fp32 parity mode; edge layers) */
 #define JCK_ALGO_TC 2    /* tcgen05 / TMEM / TMA implicit GEMM; error if unsupported */
 
+/* Traversal order of the streaming BatchNorm passes (a scheduling hint, never a change of the result).  A tensor that
+ * does not fit the 126 MB L2 is walked by all thread blocks together as ONE front, ascending or descending, so that a
+ * pass which starts where its producer stopped finds the producer's last ~40 MB still in L2 and leaves its own tail
+ * where a consumer walking the other way begins.  Convolutions write ascending; the step runs bn_act_fwd and
+ * bn_act_bwd_reduce descending, bn_act_bwd_apply ascending after a reduce pass / descending after a fused convolution.
+ * JCK_ORDER_SLAB keeps the per-block contiguous slabs used for small tensors. */
+#define JCK_ORDER_ASC 0
+#define JCK_ORDER_DESC 1
+#define JCK_ORDER_SLAB 2
+
 int jck_version(void);
 const char* jck_last_error_string(void);
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
@@ -183,15 +193,16 @@ int jck_bn_finalize(const float* stats, const float* gamma, const float* beta, f
                     void* stream);
 /* a = act(scale*y + shift); slope 0 -> ReLU, 0.2 -> LeakyReLU.  pix_per_group pixels per group. */
 int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, long long npix, int C,
-                   long long pix_per_group, float slope, int dtype, void* stream);
+                   long long pix_per_group, float slope, int dtype, int order, void* stream);
 /* g = da * act'(scale*y+shift); sums[g] += {sum g, sum g*xhat} (caller zeroes sums [groups][2C]) */
 int jck_bn_act_bwd_reduce(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
                           float* sums, long long npix, int C, long long pix_per_group, float slope,
-                          int dtype, void* stream);
+                          int dtype, int order, void* stream);
 /* dy = gamma*rstd*(g - sum_g/count - xhat*sum_gx/count) */
 int jck_bn_act_bwd_apply(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
                          const float* gamma, const float* sums, void* dy, long long npix, int C,
-                         long long pix_per_group, float count, float slope, int dtype, void* stream);
+                         long long pix_per_group, float count, float slope, int dtype, int order,
+                         void* stream);
 /* dgamma (+)= sum over groups of sum_gx ; dbeta (+)= sum over groups of sum_g */
 int jck_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int groups, int accumulate,
                       void* stream);

@@ -65,9 +65,9 @@ _SIGNATURES = {
     "jck_pack_fc": [c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_unpack_fc_grad": [c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_bn_finalize": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_f, c_p],
-    "jck_bn_act_fwd": [c_p, c_p, c_p, c_ll, c_i, c_ll, c_f, c_i, c_p],
-    "jck_bn_act_bwd_reduce": [c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_ll, c_f, c_i, c_p],
-    "jck_bn_act_bwd_apply": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_ll, c_f, c_f, c_i, c_p],
+    "jck_bn_act_fwd": [c_p, c_p, c_p, c_ll, c_i, c_ll, c_f, c_i, c_i, c_p],
+    "jck_bn_act_bwd_reduce": [c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_ll, c_f, c_i, c_i, c_p],
+    "jck_bn_act_bwd_apply": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_i, c_ll, c_f, c_f, c_i, c_i, c_p],
     "jck_bn_param_grad": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_head_fwd": [c_p, c_p, c_p, c_f, c_p, c_i, c_i, c_i, c_p],
     "jck_head_bwd": [c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

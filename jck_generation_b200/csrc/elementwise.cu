@@ -728,6 +728,189 @@ bn_act_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ y, const
         one(Vec8<T>::load_raw(pd), Vec8<T>::load_raw(py), po);
 }
 
+// ---- coherent-front variants for tensors larger than the L2 -------------------------------------------------------
+// The slab kernels above give every block its own contiguous slab: 600-900 parallel sweeps, so what is left in the
+// 126 MB L2 when the kernel ends is the tail of EVERY slab, and what the producer left there (the last ~40-50 MB a
+// convolution wrote, measured as the gap between its output size and its DRAM write bytes) has been evicted by the time
+// a slab reaches it.  Here all blocks walk the tensor together, one 16 KB chunk (kBnUnroll row steps) per block per
+// iteration, grid-strided, ascending or DESCENDING: a kernel that starts where its producer stopped reads the
+// producer's tail from L2, and leaves its own last output where a consumer walking the other way starts.  The train
+// step alternates directions along each chain (convolutions ascend; bn_act_fwd and bn_act_bwd_reduce descend;
+// bn_act_bwd_apply ascends after a reduce pass and descends after a fused convolution).  Loads of tensors that are dead
+// after the pass (or not needed again before the L2 has turned over) carry L2::evict_first so they do not displace the
+// output.  Groups are contiguous pixel ranges, so a block reloads its per-channel coefficients when its chunk crosses
+// into another group (and the reduce pass flushes its partial sums there).  Results are identical to the slab kernels.
+template <typename T> struct Vec8Stream;
+template <> struct Vec8Stream<float> {
+    static __device__ __forceinline__ typename Vec8<float>::Raw load(const float* p) { return Vec8<float>::load_raw(p); }
+};
+template <> struct Vec8Stream<__nv_bfloat16> {
+    static __device__ __forceinline__ uint4 load(const __nv_bfloat16* p) {
+        uint64_t pol;     // fractional L2 policy: the whole access evict_first (hoisted out of the loop by the compiler)
+        asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        uint4 u;
+        asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p), "l"(pol));
+        return u;
+    }
+};
+constexpr int kBnChunkElems = kBnUnroll * kBnRowElems;     // 8192 elements per block per iteration
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_front_kernel(const T* __restrict__ y, const float* __restrict__ scale_shift, T* __restrict__ a, int C,
+                        unsigned chunks_per_group, unsigned total_chunks, int descending, float slope) {
+    pdl_entry();
+    typedef typename Vec8<T>::Raw Raw;
+    const unsigned cv = C / 8;
+    const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv, c0 = myc * 8;
+    float sc[8], sh[8];
+    unsigned cur_g = 0xffffffffu;
+    for (unsigned i = blockIdx.x; i < total_chunks; i += gridDim.x) {
+        const unsigned c = descending ? total_chunks - 1 - i : i;
+        const unsigned g = c / chunks_per_group;
+        if (g != cur_g) {
+            Vec8<float>::load(scale_shift + (size_t)g * 2 * C + c0, sc);
+            Vec8<float>::load(scale_shift + (size_t)g * 2 * C + C + c0, sh);
+            cur_g = g;
+        }
+        const size_t off = (size_t)c * kBnChunkElems + (size_t)myr * C + c0;
+        Raw r[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) r[u] = Vec8Stream<T>::load(y + off + u * kBnRowElems);   // y: next read in backward
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            float v[8];
+            Vec8<T>::unpack(r[u], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float pre = fmaf(v[j], sc[j], sh[j]);
+                v[j] = pre > 0.f ? pre : pre * slope;
+            }
+            Vec8<T>::store(a + off + u * kBnRowElems, v);
+        }
+    }
+}
+
+template <typename T, int MINB>       // MINB: resident blocks per SM the register budget is cut for (2: 128, 3: 80 registers)
+__global__ void __launch_bounds__(256, MINB)
+bn_act_bwd_reduce_front_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
+                               const float* __restrict__ mean_rstd, float* __restrict__ sums, int C,
+                               unsigned chunks_per_group, unsigned total_chunks, int descending, float slope) {
+    pdl_entry();
+    typedef typename Vec8<T>::Raw Raw;
+    __shared__ float red[256][17];
+    const unsigned cv = C / 8, rows = 256 / cv;
+    const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv, c0 = myc * 8;
+    float sc[8], sh[8], mu[8], s1[8], s2[8];
+    unsigned cur_g = 0xffffffffu;
+    auto flush = [&](unsigned g) {      // block-uniform: every thread of the block changes group in the same iteration
+        float rs[8];
+        Vec8<float>::load(mean_rstd + (size_t)g * 2 * C + C + c0, rs);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s1[j]; red[threadIdx.x][8 + j] = s2[j] * rs[j]; }
+        __syncthreads();
+        for (int col = threadIdx.x; col < 2 * C; col += 256) {
+            const int which = col / C, ch = col % C;
+            const int vc = ch / 8, j = ch % 8;
+            float s = 0.f;
+            for (unsigned r = 0; r < rows; ++r) s += red[r * cv + vc][which * 8 + j];
+            atomicAdd(sums + (size_t)g * 2 * C + which * C + ch, s);
+        }
+        __syncthreads();
+    };
+    for (unsigned i = blockIdx.x; i < total_chunks; i += gridDim.x) {
+        const unsigned c = descending ? total_chunks - 1 - i : i;
+        const unsigned g = c / chunks_per_group;
+        if (g != cur_g) {
+            if (cur_g != 0xffffffffu) flush(cur_g);
+            Vec8<float>::load(scale_shift + (size_t)g * 2 * C + c0, sc);
+            Vec8<float>::load(scale_shift + (size_t)g * 2 * C + C + c0, sh);
+            Vec8<float>::load(mean_rstd + (size_t)g * 2 * C + c0, mu);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+            cur_g = g;
+        }
+        const size_t off = (size_t)c * kBnChunkElems + (size_t)myr * C + c0;
+        Raw rd[kBnUnroll], ry[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {        // both are read again by the apply pass that follows: default policy
+            rd[u] = Vec8<T>::load_raw(da + off + u * kBnRowElems);
+            ry[u] = Vec8<T>::load_raw(y + off + u * kBnRowElems);
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            float d[8], v[8];
+            Vec8<T>::unpack(rd[u], d);
+            Vec8<T>::unpack(ry[u], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float pre = fmaf(v[j], sc[j], sh[j]);
+                const float gg = pre > 0.f ? d[j] : d[j] * slope;
+                s1[j] += gg;
+                s2[j] = fmaf(gg, v[j] - mu[j], s2[j]);
+            }
+        }
+    }
+    if (cur_g != 0xffffffffu) flush(cur_g);
+}
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bn_act_bwd_apply_front_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale_shift,
+                              const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                              const float* __restrict__ sums, T* __restrict__ dy, int C, unsigned chunks_per_group,
+                              unsigned total_chunks, int descending, float inv_count, float slope) {
+    pdl_entry();
+    typedef typename Vec8<T>::Raw Raw;
+    const unsigned cv = C / 8;
+    const unsigned myc = threadIdx.x % cv, myr = threadIdx.x / cv, c0 = myc * 8;
+    float sc[8], sh[8], k1[8], k3[8], k4[8];
+    unsigned cur_g = 0xffffffffu;
+    for (unsigned i = blockIdx.x; i < total_chunks; i += gridDim.x) {
+        const unsigned c = descending ? total_chunks - 1 - i : i;
+        const unsigned g = c / chunks_per_group;
+        if (g != cur_g) {
+            float mu[8], rs[8], ga[8], sg[8], sgx[8];
+            const size_t gofs = (size_t)g * 2 * C;
+            Vec8<float>::load(scale_shift + gofs + c0, sc);
+            Vec8<float>::load(scale_shift + gofs + C + c0, sh);
+            Vec8<float>::load(mean_rstd + gofs + c0, mu);
+            Vec8<float>::load(mean_rstd + gofs + C + c0, rs);
+            Vec8<float>::load(gamma + c0, ga);
+            Vec8<float>::load(sums + gofs + c0, sg);
+            Vec8<float>::load(sums + gofs + C + c0, sgx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                k1[j] = ga[j] * rs[j];
+                k3[j] = k1[j] * rs[j] * sgx[j] * inv_count;
+                k4[j] = k3[j] * mu[j] - k1[j] * sg[j] * inv_count;
+            }
+            cur_g = g;
+        }
+        const size_t off = (size_t)c * kBnChunkElems + (size_t)myr * C + c0;
+        Raw rd[kBnUnroll], ry[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {        // da and y are dead after this pass: do not let them displace dy
+            rd[u] = Vec8Stream<T>::load(da + off + u * kBnRowElems);
+            ry[u] = Vec8Stream<T>::load(y + off + u * kBnRowElems);
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            float d[8], v[8];
+            Vec8<T>::unpack(rd[u], d);
+            Vec8<T>::unpack(ry[u], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float pre = fmaf(v[j], sc[j], sh[j]);
+                const float gg = pre > 0.f ? d[j] : d[j] * slope;
+                d[j] = fmaf(k1[j], gg, fmaf(-k3[j], v[j], k4[j]));
+            }
+            Vec8<T>::store(dy + off + u * kBnRowElems, d);
+        }
+    }
+}
+
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      int C, int groups, int accumulate) {
     pdl_entry();
@@ -1092,14 +1275,50 @@ static dim3 bn_grid(long long pix_per_group, int groups, int C, int waves, unsig
     return dim3((unsigned)bpg, (unsigned)groups);
 }
 
+// Coherent-front kernels (above): for tensors that do not fit the L2 anyway (>= kBnFrontMinBytes) whose groups are whole
+// numbers of 8192-element chunks; JCK_ORDER_SLAB (or JCK_BN_FRONT=0 in the environment, for A/B timing) keeps the slabs.
+constexpr long long kBnFrontMinBytes = 24LL << 20;
+static bool bn_front_enabled() {
+    static const bool on = [] { const char* e = getenv("JCK_BN_FRONT"); return !(e && e[0] == '0'); }();
+    return on;
+}
+static bool bn_front(long long npix, int C, long long pix_per_group, int dtype, int order, unsigned* cpg, unsigned* total) {
+    if (order == JCK_ORDER_SLAB || !bn_front_enabled()) return false;
+    const long long elems = npix * C, per_group = pix_per_group * C;
+    const long long bytes = elems * (dtype == JCK_BF16 ? 2 : 4);
+    if (bytes < kBnFrontMinBytes || per_group % kBnChunkElems != 0 || elems / kBnChunkElems >= (1LL << 31)) return false;
+    *cpg = (unsigned)(per_group / kBnChunkElems);
+    *total = (unsigned)(elems / kBnChunkElems);
+    return true;
+}
+// resident blocks per SM of the two backward passes (JCK_BN_OCC=2|3): 40 coefficient + 32 data registers per thread do not
+// fit the 64 a 4-block budget allows -- ptxas then sinks each load pair to its use and only 2 x 16 B per thread are in flight
+static int bn_front_occ() {
+    static const int occ = [] { const char* e = getenv("JCK_BN_OCC"); return (e && e[0] == '2') ? 2 : 3; }();
+    return occ;
+}
+static unsigned bn_front_grid(unsigned total_chunks, int waves) {
+    const unsigned g = (unsigned)(waves * kNumSMs);
+    return total_chunks < g ? total_chunks : g;
+}
+
 #define BN_COMMON_CHECKS(name)                                                                                   \
     JCK_REQUIRE(npix > 0 && pix_per_group > 0 && npix % pix_per_group == 0 && npix < (1LL << 31), name ": bad size"); \
     if (!bn_c_ok(C)) return set_error(JCK_E_UNSUPPORTED_SHAPE, name ": C=%d (need C/8 dividing 256)", C);
 
 extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, long long npix, int C, long long pix_per_group,
-                              float slope, int dtype, void* stream) {
+                              float slope, int dtype, int order, void* stream) {
     JCK_REQUIRE(y && scale_shift && a, "bn_act_fwd: bad argument");
     BN_COMMON_CHECKS("bn_act_fwd")
+    unsigned cpg, total;
+    if (bn_front(npix, C, pix_per_group, dtype, order, &cpg, &total)) {
+        const unsigned grid = bn_front_grid(total, 6);
+        DISPATCH_DTYPE(dtype, "bn_act_fwd",
+            launch_pdl(bn_act_fwd_front_kernel<T>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)y, scale_shift, (T*)a, C, cpg,
+                       total, (int)(order == JCK_ORDER_DESC), slope);)
+        JCK_LAUNCH_CHECK("bn_act_fwd");
+        return JCK_OK;
+    }
     unsigned slab;
     const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 6, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_fwd",
@@ -1111,9 +1330,25 @@ extern "C" int jck_bn_act_fwd(const void* y, const float* scale_shift, void* a, 
 
 extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
                                      float* sums, long long npix, int C, long long pix_per_group, float slope, int dtype,
-                                     void* stream) {
+                                     int order, void* stream) {
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && sums, "bn_act_bwd_reduce: bad argument");
     BN_COMMON_CHECKS("bn_act_bwd_reduce")
+    unsigned cpg, total;
+    if (bn_front(npix, C, pix_per_group, dtype, order, &cpg, &total)) {
+        const int occ = bn_front_occ();
+        const unsigned grid = bn_front_grid(total, occ);
+        if (occ == 2) {
+            DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
+                launch_pdl(bn_act_bwd_reduce_front_kernel<T, 2>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y,
+                           scale_shift, mean_rstd, sums, C, cpg, total, (int)(order == JCK_ORDER_DESC), slope);)
+        } else {
+            DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
+                launch_pdl(bn_act_bwd_reduce_front_kernel<T, 3>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y,
+                           scale_shift, mean_rstd, sums, C, cpg, total, (int)(order == JCK_ORDER_DESC), slope);)
+        }
+        JCK_LAUNCH_CHECK("bn_act_bwd_reduce");
+        return JCK_OK;
+    }
     unsigned slab;
     const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 4, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_reduce",
@@ -1125,9 +1360,27 @@ extern "C" int jck_bn_act_bwd_reduce(const void* da, const void* y, const float*
 
 extern "C" int jck_bn_act_bwd_apply(const void* da, const void* y, const float* scale_shift, const float* mean_rstd,
                                     const float* gamma, const float* sums, void* dy, long long npix, int C,
-                                    long long pix_per_group, float count, float slope, int dtype, void* stream) {
+                                    long long pix_per_group, float count, float slope, int dtype, int order, void* stream) {
     JCK_REQUIRE(da && y && scale_shift && mean_rstd && gamma && sums && dy && count > 0, "bn_act_bwd_apply: bad argument");
     BN_COMMON_CHECKS("bn_act_bwd_apply")
+    unsigned cpg, total;
+    if (bn_front(npix, C, pix_per_group, dtype, order, &cpg, &total)) {
+        const int occ = bn_front_occ();
+        const unsigned grid = bn_front_grid(total, occ);
+        if (occ == 2) {
+            DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
+                launch_pdl(bn_act_bwd_apply_front_kernel<T, 2>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y,
+                           scale_shift, mean_rstd, gamma, sums, (T*)dy, C, cpg, total, (int)(order == JCK_ORDER_DESC), 1.f / count,
+                           slope);)
+        } else {
+            DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",
+                launch_pdl(bn_act_bwd_apply_front_kernel<T, 3>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)da, (const T*)y,
+                           scale_shift, mean_rstd, gamma, sums, (T*)dy, C, cpg, total, (int)(order == JCK_ORDER_DESC), 1.f / count,
+                           slope);)
+        }
+        JCK_LAUNCH_CHECK("bn_act_bwd_apply");
+        return JCK_OK;
+    }
     unsigned slab;
     const dim3 grid = bn_grid(pix_per_group, (int)(npix / pix_per_group), C, 4, &slab);
     DISPATCH_DTYPE(dtype, "bn_act_bwd_apply",

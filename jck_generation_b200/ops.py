@@ -227,21 +227,27 @@ def bn_bwd_sums_sync(comm, sums, dgamma, dbeta, C, groups, accumulate):
           "bn_bwd_sums_sync")
 
 
-def bn_act_fwd(y, scale_shift, a, C, groups, slope):
+# traversal order of the streaming BatchNorm passes on tensors larger than the L2 (include/jck_b200.h: JCK_ORDER_*)
+ORDER_ASC, ORDER_DESC, ORDER_SLAB = 0, 1, 2
+
+
+def bn_act_fwd(y, scale_shift, a, C, groups, slope, order=ORDER_DESC):
+    """default DESC: the producer (a convolution) wrote y ascending, the consumer (the next convolution) reads a ascending"""
     npix = y.numel() // C
-    check(L().jck_bn_act_fwd(_p(y), _p(scale_shift), _p(a), npix, C, npix // groups, slope, dt(y), _s()), "bn_act_fwd")
+    check(L().jck_bn_act_fwd(_p(y), _p(scale_shift), _p(a), npix, C, npix // groups, slope, dt(y), order, _s()), "bn_act_fwd")
 
 
-def bn_act_bwd_reduce(da, y, scale_shift, mean_rstd, sums, C, groups, slope):
+def bn_act_bwd_reduce(da, y, scale_shift, mean_rstd, sums, C, groups, slope, order=ORDER_DESC):
     npix = y.numel() // C
     check(L().jck_bn_act_bwd_reduce(_p(da), _p(y), _p(scale_shift), _p(mean_rstd), _p(sums), npix, C,
-                                    npix // groups, slope, dt(y), _s()), "bn_act_bwd_reduce")
+                                    npix // groups, slope, dt(y), order, _s()), "bn_act_bwd_reduce")
 
 
-def bn_act_bwd_apply(da, y, scale_shift, mean_rstd, gamma, sums, dy, C, groups, count, slope):
+def bn_act_bwd_apply(da, y, scale_shift, mean_rstd, gamma, sums, dy, C, groups, count, slope, order=ORDER_ASC):
+    """default ASC: it follows a descending reduce pass over the same two tensors"""
     npix = y.numel() // C
     check(L().jck_bn_act_bwd_apply(_p(da), _p(y), _p(scale_shift), _p(mean_rstd), _p(gamma), _p(sums), _p(dy),
-                                   npix, C, npix // groups, float(count), slope, dt(y), _s()), "bn_act_bwd_apply")
+                                   npix, C, npix // groups, float(count), slope, dt(y), order, _s()), "bn_act_bwd_apply")
 
 
 def bn_param_grad(sums, dgamma, dbeta, C, groups, accumulate):

@@ -101,6 +101,8 @@ def test_trainer_with_device_pipeline_and_metrics(tmp_path, monkeypatch):
     with the eval branch live (Metrics on the jck Inception extractor, real features from the device metric loader)."""
     import argparse
     monkeypatch.chdir(tmp_path)
+    # no Inception checkpoint offline: Metrics raises like the reference unless random weights are asked for explicitly
+    monkeypatch.setenv("JCK_METRICS_RANDOM_WEIGHTS", "1")
     from jck_generation_b200.model import DCGAN
     from jck_generation_b200.preprocess.dcgan_data_preprocessor import DCGANDataPreprocessor
     from jck_generation_b200.train.dcgan_trainer import DCGANTrainer
