@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the side measurements (CGAN step, fp32 step, library bar, FID eval ...)")
     ap.add_argument("--secondary-only", action="store_true", help="(internal) run only the side measurements, print their JSON")
+    ap.add_argument("--quick", action="store_true", help="(A/B timing) only the device-timed step: no e2e, rooflines or side paths")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device time table")
     ap.add_argument("--kernel-table", action="store_true", help="print per-kernel device time (CUPTI via torch.profiler)")
     return ap.parse_args()
@@ -497,6 +498,17 @@ def run_b200(args):
     total_images = B * comm.world_size
     value = total_images / (ms * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": comm.world_size, "steps": args.steps,
+                              "ms_per_step": ms, "clocks": clocks, "quick": True}), flush=True)
+        if comm.world_size > 1:
+            comm.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
+        return
+
     # end to end through the public API: pinned host batch -> H2D -> step -> D2H of the step's scalars.  The
     # trainer's own input pipeline (train/prefetch.py) copies batch i+1 on a side stream while step i runs, as
     # DCGANTrainer.train() does; every timed step still pays one H2D of a full batch and one D2H of its losses.
@@ -527,6 +539,11 @@ def run_b200(args):
     step.eg.wgrad_stream = step.ed.wgrad_stream = step.gp_stream = None
     with OpTimer(ops, torch) as ot:
         for _ in range(2):
+            # The host needs ~30 us per eager launch (ctypes call, tensor-map encode, two event records), many kernels
+            # run 5-40 us: with an empty stream every start event would fire before its kernel has even been launched
+            # and the interval would measure the host.  Park the stream behind a ~12 ms spin so the whole step is queued
+            # before the GPU reaches it; the event pairs then bracket back-to-back device work only.
+            torch.cuda._sleep(24_000_000)
             step.run(real)
         tab = ot.table()
     step.eg.wgrad_stream, step.ed.wgrad_stream, step.gp_stream = side

@@ -1275,9 +1275,12 @@ static dim3 bn_grid(long long pix_per_group, int groups, int C, int waves, unsig
     return dim3((unsigned)bpg, (unsigned)groups);
 }
 
-// Coherent-front kernels (above): for tensors that do not fit the L2 anyway (>= kBnFrontMinBytes) whose groups are whole
-// numbers of 8192-element chunks; JCK_ORDER_SLAB (or JCK_BN_FRONT=0 in the environment, for A/B timing) keeps the slabs.
-constexpr long long kBnFrontMinBytes = 24LL << 20;
+// Coherent-front kernels (above): for tensors of >= kBnFrontMinBytes whose groups are whole numbers of 8192-element
+// chunks; JCK_ORDER_SLAB (or JCK_BN_FRONT=0 in the environment, for A/B timing) keeps the slabs.  Measured on the 512-image
+// step (profiles/r02/run16-18.sh): 2.60 -> 2.51 ms (40-step runs at 1965 MHz), 2.72 -> 2.61 ms (200-step runs under the
+// power cap); DRAM traffic per step 6.51 -> 5.65 GB (ncu --cache-control none, profiles/r02_ncu_launches_warmL2_summary.md).
+// Threshold 8 / 24 / 48 MB and 2 / 3 resident blocks per SM for the backward passes are within run-to-run noise of each other.
+constexpr long long kBnFrontMinBytes = 8LL << 20;
 static bool bn_front_enabled() {
     static const bool on = [] { const char* e = getenv("JCK_BN_FRONT"); return !(e && e[0] == '0'); }();
     return on;
@@ -1286,15 +1289,20 @@ static bool bn_front(long long npix, int C, long long pix_per_group, int dtype, 
     if (order == JCK_ORDER_SLAB || !bn_front_enabled()) return false;
     const long long elems = npix * C, per_group = pix_per_group * C;
     const long long bytes = elems * (dtype == JCK_BF16 ? 2 : 4);
-    if (bytes < kBnFrontMinBytes || per_group % kBnChunkElems != 0 || elems / kBnChunkElems >= (1LL << 31)) return false;
+    static const long long min_bytes = [] {
+        const char* e = getenv("JCK_BN_FRONT_MIN_MB");
+        return e ? (long long)atoi(e) << 20 : kBnFrontMinBytes;
+    }();
+    if (bytes < min_bytes || per_group % kBnChunkElems != 0 || elems / kBnChunkElems >= (1LL << 31)) return false;
     *cpg = (unsigned)(per_group / kBnChunkElems);
     *total = (unsigned)(elems / kBnChunkElems);
     return true;
 }
-// resident blocks per SM of the two backward passes (JCK_BN_OCC=2|3): 40 coefficient + 32 data registers per thread do not
-// fit the 64 a 4-block budget allows -- ptxas then sinks each load pair to its use and only 2 x 16 B per thread are in flight
+// resident blocks per SM of the two backward passes (JCK_BN_OCC=2|3, default 2): 40 coefficient + 32 data registers per
+// thread do not fit the 64 a 4-block budget allows -- ptxas then sinks each load pair to its use and only 2 x 16 B per thread
+// are in flight; at 128 registers (2 blocks, 512 threads x 8 x 16 B = 64 KB per SM) every load of a chunk is issued up front
 static int bn_front_occ() {
-    static const int occ = [] { const char* e = getenv("JCK_BN_OCC"); return (e && e[0] == '2') ? 2 : 3; }();
+    static const int occ = [] { const char* e = getenv("JCK_BN_OCC"); return (e && e[0] == '3') ? 3 : 2; }();
     return occ;
 }
 static unsigned bn_front_grid(unsigned total_chunks, int waves) {

@@ -208,17 +208,6 @@ class _GradTarget:
             torch.cuda.current_stream().wait_stream(self.wgrad_stream)
             self._wgrad_pending = False
 
-    # ---- packed-weight refresh beside the first kernels that do not need it -------------------------------------
-    # Re-packing the updated weights (one small kernel per layer, ~6-8 us each, serial) sits on the critical path
-    # right after an optimizer step.  refresh_overlapped() queues the packs on `side` (a stream that is idle at that
-    # point) and records which layer is the first to need them; _await_packs() makes the current stream wait there.
-    _packs_on = None
-
-    def _await_packs(self):
-        if self._packs_on is not None:
-            torch.cuda.current_stream().wait_stream(self._packs_on)
-            self._packs_on = None
-
     def _gb(self, p):
         if self.sink is not None:
             buf = self.sink.get(id(p))
@@ -265,22 +254,6 @@ class DiscriminatorEngine(_GradTarget):
                 ops.pack_head(w.detach(), self.w5)
                 self._w5_seen = key
 
-    def refresh_overlapped(self, side):
-        """refresh(force=True) after optimizer_d.step() with only conv1's packing on the current stream: conv2..4 and the
-        head are packed on `side` while conv1 + its BatchNorm run; trunk_forward waits for them before conv2."""
-        if side is None:
-            return self.refresh(force=True)
-        self.convs[1].refresh(True)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for k in range(2, 5):
-                self.convs[k].refresh(True)
-            if self.has_head:
-                w = self.m.conv5.weight
-                ops.pack_head(w.detach(), self.w5)
-                self._w5_seen = (w._version, w.data_ptr())
-        self._packs_on = side
-
     # ---- forward -----------------------------------------------------------------------------------
     def trunk_forward(self, x_nhwc, groups=1, update_running=True):
         self.refresh()
@@ -295,8 +268,6 @@ class DiscriminatorEngine(_GradTarget):
             cv, nm = self.convs[k], self.norms[k]
             y = torch.empty(B, cv.Hs, cv.Ws, cv.Ca, dtype=self.dtype, device=self.dev)
             stats = zeros[k - 1]
-            if k == 2:
-                self._await_packs()
             if cv.edge:
                 ops.edge_down_img(cur, cv.w_down_e, y, stats, cv.Ca, ipg=B // groups)   # patch matrix only if wgrad needs it
             else:
@@ -463,23 +434,6 @@ class GeneratorEngine(_GradTarget):
         for c in self.convs.values():
             c.refresh(force)
 
-    def refresh_overlapped(self, side):
-        """refresh(force=True) with every pack on `side`; forward() waits for them before its first kernel that reads a
-        weight.  The step calls this at its START (the previous step's optimizer_g.step() left the caches stale, see
-        invalidate()), so the packs run beside the random draws and the instance-noise pass of the real batch."""
-        if side is None:
-            return self.refresh(force=True)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            self.refresh(force=True)
-        self._packs_on = side
-
-    def invalidate(self):
-        """mark the packed caches stale without re-packing (the next forward() / refresh() packs them)"""
-        self._w1_seen = None
-        for c in self.convs.values():
-            c._seen = None
-
     def _bn_relu(self, ctx, k, y, stats, groups, update_running):
         nm = self.norms[k]
         C = nm.C
@@ -499,10 +453,7 @@ class GeneratorEngine(_GradTarget):
         `labels` ([B, n_classes] fp32 or int64, CGAN): z2d then holds the nz noise columns only and the reference's
         cat([z, labels], 1) (model/CGAN.py:154-155) is written straight into conv1's operand by ONE kernel
         (jck_concat_rows: concat + int64 -> float + fp32 -> bf16), not materialised by torch.cat."""
-        if self._packs_on is not None:
-            self._await_packs()
-        else:
-            self.refresh()
+        self.refresh()
         B = z2d.shape[0]
         ctx = Ctx()
         zb_ready = False

@@ -61,8 +61,6 @@ class DCGANStep:
             # HBM-bound BatchNorm passes beside the other sweep's convolutions and vice versa (JCK_GP_STREAM=0: in line)
             if os.environ.get("JCK_GP_STREAM", "1") != "0":
                 self.gp_stream = torch.cuda.Stream(device=self.dev)
-        # packed-weight refreshes overlapped with the kernels that do not need them (JCK_PACK_OVERLAP=0: in line)
-        self.overlap_packs = self.eg.wgrad_stream is not None and os.environ.get("JCK_PACK_OVERLAP", "1") != "0"
         self.comm_gp = AuxComm(comm) if (self.gp_stream is not None and comm.world_size > 1) else None
         # gradient exchange: per-bucket all-reduce started as the bucket's last gradient is written (parallel.GradBuckets)
         self.sync_d = GradBuckets(flat_d, comm)
@@ -103,13 +101,9 @@ class DCGANStep:
         ed, eg = self.ed, self.eg
         B = real.shape[0]
         dev, dt = self.dev, self.dtype
+        r = rng if rng is not None else self.draw(B)
         self.flat_d.rebind()
         self.flat_g.rebind()
-        # the generator's packed weights (stale since the previous step's optimizer_g.step()) are re-packed on the side
-        # stream beside the random draws and the instance-noise pass of the real batch; eg.forward() waits for them
-        if self.overlap_packs:
-            eg.refresh_overlapped(eg.wgrad_stream)
-        r = rng if rng is not None else self.draw(B)
         self.arena.reset()
 
         lay = ed.img_layout
@@ -165,10 +159,7 @@ class DCGANStep:
             after_d_update()
         if gps is not None:
             main.wait_stream(gps)       # the penalty sweep reads the packed weights refresh() is about to overwrite
-        if self.overlap_packs:
-            ed.refresh_overlapped(ed.wgrad_stream)      # conv2..4 + head packed beside conv1 of pass D
-        else:
-            ed.refresh(force=True)
+        ed.refresh(force=True)
 
         ctx2 = ed.trunk_forward(X[B:2 * B], groups=1)                                                      # :185
         ed.head_forward(ctx2, targets=[LABEL_REAL], scalars=scal[S_G:S_G + 1])
@@ -181,10 +172,7 @@ class DCGANStep:
         eg.join_wgrad()
         self.sync_g.finish()
         self.opt_g.step()                                                                                  # :189
-        if self.overlap_packs:
-            eg.invalidate()             # re-packed at the start of the next step (or by the next G.forward())
-        else:
-            eg.refresh(force=True)
+        eg.refresh(force=True)
         self.last = {"fake_raw": fake_raw, "gp_grad_nhwc": dx, "ctx": ctx, "ctx_g": gctx, "ctx_d": ctx2,
                      "dmix": dmix, "dy5": dy5}
         return scal
