@@ -342,6 +342,22 @@ int jck_resize_norm(const float* in_nchw, void* out_nhwc, int B, int C, int Hi, 
  * (bf16, row pitch 32, columns 27..31 zero) of the Hr x Wr resized, normalised 3-channel image, never materialised. */
 int jck_stem_patches(const float* in_nchw, void* patches, int B, int Hi, int Wi, int Hr, int Wr, float a, float b,
                      const float* mean3, const float* std3, void* stream);
+/* ---- split-precision mode of the extractor (fp32-grade features on the bf16 tensor cores) --------------------------
+ * Every activation is kept as TWO bf16 planes, value = hi + lo with hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits),
+ * the low plane a fixed element offset behind the high one; weights are split the same way on the host.  A product is
+ * hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM (lo*lo, 2^-18 relative, is dropped).  No new GEMM kernel is needed:
+ * with the two planes stacked along the row dimension of A, "the low plane at tap shift s" is simply the shift s + R
+ * (R = rows of one plane), so the caller passes 3*ntaps taps {s, s, s + R} against the weight blocks {W_hi, W_lo, W_hi}.
+ * jck_conv_gemm writes a split OUTPUT when geom carries one more entry after the shifts:
+ *     geom[18 + ntaps] = rows of one output plane   (low plane at out + that * ldc; bf16 output only).
+ * The streaming kernels take the plane offsets (in elements, multiples of 8; 0 = plain bf16 tensor): */
+int jck_pool3_split(const void* x, const int* in_geom, long long ldx, long long x_lo, void* out, const int* out_geom,
+                    long long ldo, long long out_lo, int B, int H, int W, int C, int stride, int pad, int Ho, int Wo, int mode,
+                    void* stream);
+int jck_global_avgpool_split(const void* x, long long x_lo, float* out_f32, void* out_bf16, long long out_lo, int B, int HW,
+                             int C, void* stream);
+int jck_stem_patches_split(const float* in_nchw, void* patches, long long patches_lo, int B, int Hi, int Wi, int Hr, int Wr,
+                           float a, float b, const float* mean3, const float* std3, void* stream);
 /* metrics.py:96-110: scores[k] = exp(mean_i KL(softmax(logits_i) || mean_i softmax(logits_i))) over rows
  * [k*(n/splits), (k+1)*(n/splits)) of fp32 logits [n][d] */
 int jck_inception_score(const float* logits, int n, int d, int splits, float* scores, void* stream);

@@ -89,6 +89,9 @@ _SIGNATURES = {
     "jck_global_avgpool": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "jck_resize_norm": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
     "jck_stem_patches": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
+    "jck_pool3_split": [c_p, c_p, c_ll, c_ll, c_p, c_p, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "jck_global_avgpool_split": [c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_i, c_p],
+    "jck_stem_patches_split": [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
     "jck_inception_score": [c_p, c_i, c_i, c_i, c_p, c_p],
     "jck_u8_resize_norm": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p],
     "jck_one_hot_i64": [c_p, c_p, c_p, c_i, c_i, c_p],

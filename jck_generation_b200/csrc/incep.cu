@@ -25,7 +25,7 @@ using namespace tc;
 
 constexpr int kCGThreads = 192;
 constexpr int kCGMaxStages = 8;
-constexpr int kCGMaxTaps = 32;
+constexpr int kCGMaxTaps = 96;      // 5 x 5 taps x 3 (split-precision mode: hi*hi, hi*lo, lo*hi)
 constexpr int kCGAccCols = 256;
 
 // K-major operand tile [rows][kw bf16], kw = 64 (128-byte swizzle, layout 2) or 32 (64-byte swizzle, layout 4): 8-row groups
@@ -47,6 +47,7 @@ struct CGParams {
     int shift[kCGMaxTaps];
     int Hq, Wq, oy0, ox0, Ho, Wo, Hob, Wob, opy, opx, c_off, relu, out_f32;
     long long ldc;
+    long long lo_out;          // split-precision output (bf16 only): element offset of the LOW plane of `out`; 0 = plain bf16
     int stages, stage_bytes, vec_coef;
     // window mode (conv_gemm_window_kernel): the rows [m0 + smin, m0 + 128 + smax) of a tile are loaded ONCE per 64-channel
     // chunk and every tap reads them at a row offset through its shared-memory descriptor
@@ -55,6 +56,27 @@ struct CGParams {
     const float* scale;
     const float* bias;
 };
+
+// 16 consecutive bf16 outputs of one row: 256-bit, 2 x 128-bit or element stores, whatever the address allows
+__device__ __forceinline__ void cg_store16(__nv_bfloat16* o, const float (&v)[16]) {
+    uint4 u0, u1;
+    u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
+    u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
+    u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
+    u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(o);
+    if ((a & 31) == 0) {
+        st_global_256(o, u0, u1);
+    } else if ((a & 15) == 0) {
+        reinterpret_cast<uint4*>(o)[0] = u0;
+        reinterpret_cast<uint4*>(o)[1] = u1;
+    } else {
+        const __nv_bfloat16* h0 = reinterpret_cast<const __nv_bfloat16*>(&u0);
+        const __nv_bfloat16* h1 = reinterpret_cast<const __nv_bfloat16*>(&u1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i] = h0[i]; o[8 + i] = h1[i]; }
+    }
+}
 
 // Epilogue warps (2..5) of both conv kernels: TMEM accumulator -> scale / bias / ReLU -> masked, re-mapped store.
 __device__ __forceinline__ void cg_epilogue(const CGParams& p, void* __restrict__ out, uint32_t tmem_base, uint64_t* tfull,
@@ -121,22 +143,12 @@ __device__ __forceinline__ void cg_epilogue(const CGParams& p, void* __restrict_
                     }
                 } else {
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + orow + nb;
-                    uint4 u0, u1;
-                    u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
-                    u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
-                    u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
-                    u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
-                    const uintptr_t a = reinterpret_cast<uintptr_t>(o);
-                    if ((a & 31) == 0) {
-                        st_global_256(o, u0, u1);
-                    } else if ((a & 15) == 0) {
-                        reinterpret_cast<uint4*>(o)[0] = u0;
-                        reinterpret_cast<uint4*>(o)[1] = u1;
-                    } else {
-                        const __nv_bfloat16* h0 = reinterpret_cast<const __nv_bfloat16*>(&u0);
-                        const __nv_bfloat16* h1 = reinterpret_cast<const __nv_bfloat16*>(&u1);
+                    cg_store16(o, v);
+                    if (p.lo_out) {
+                        // split precision: the value is kept as hi + lo, hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { o[i] = h0[i]; o[8 + i] = h1[i]; }
+                        for (int i = 0; i < 16; ++i) v[i] -= __bfloat162float(__float2bfloat16_rn(v[i]));
+                        cg_store16(o + p.lo_out, v);
                     }
                 }
             } else {
@@ -149,8 +161,14 @@ __device__ __forceinline__ void cg_epilogue(const CGParams& p, void* __restrict_
                         const float b1 = p.bias ? __ldg(p.bias + nb + i) : 0.f;
                         float x = fmaf(v[i], s1, b1);
                         if (p.relu) x = fmaxf(x, 0.f);
-                        if (p.out_f32) reinterpret_cast<float*>(out)[orow + nb + i] = x;
-                        else reinterpret_cast<__nv_bfloat16*>(out)[orow + nb + i] = __float2bfloat16_rn(x);
+                        if (p.out_f32) {
+                            reinterpret_cast<float*>(out)[orow + nb + i] = x;
+                        } else {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                            reinterpret_cast<__nv_bfloat16*>(out)[orow + nb + i] = h;
+                            if (p.lo_out)
+                                reinterpret_cast<__nv_bfloat16*>(out)[orow + nb + i + p.lo_out] = __float2bfloat16_rn(x - __bfloat162float(h));
+                        }
                     }
                 }
             }
@@ -456,7 +474,7 @@ im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ o
 // divisor 9 (F.avg_pool2d default count_include_pad=True, torchvision inception.py branch_pool)
 __global__ void __launch_bounds__(256)
 pool3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, BufGeom gi, BufGeom go, int B, int H, int W, int C,
-             int stride, int pad, int Ho, int Wo, int mode) {
+             int stride, int pad, int Ho, int Wo, int mode, long long x_lo, long long out_lo) {
     pdl_entry();
     const int cv = C / 8;
     const long long total = (long long)B * Ho * Wo * cv;
@@ -465,7 +483,7 @@ pool3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ ou
         const long long m = i / cv;
         const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((long long)Wo * Ho));
         // all nine 128-bit loads are issued before the first use (clamped addresses; windows cut by the border are masked)
-        uint4 u[9];
+        uint4 u[9], ul[9];
         bool ok[9];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -474,7 +492,9 @@ pool3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ ou
                 const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
                 ok[ky * 3 + kx] = iy >= 0 && iy < H && ix >= 0 && ix < W;
                 const int cy = min(max(iy, 0), H - 1), cx = min(max(ix, 0), W - 1);
-                u[ky * 3 + kx] = __ldg(reinterpret_cast<const uint4*>(x + buf_at(gi, b, cy, cx) + c));
+                const __nv_bfloat16* src = x + buf_at(gi, b, cy, cx) + c;
+                u[ky * 3 + kx] = __ldg(reinterpret_cast<const uint4*>(src));
+                ul[ky * 3 + kx] = x_lo ? __ldg(reinterpret_cast<const uint4*>(src + x_lo)) : make_uint4(0, 0, 0, 0);   // split: value = hi + lo
             }
         }
         float a[8];
@@ -483,9 +503,10 @@ pool3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ ou
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u[t]);
+            const __nv_bfloat16* l = reinterpret_cast<const __nv_bfloat16*>(&ul[t]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float f = __bfloat162float(h[j]);
+                const float f = __bfloat162float(h[j]) + __bfloat162float(l[j]);
                 if (mode == 0) a[j] = ok[t] ? fmaxf(a[j], f) : a[j];
                 else a[j] += ok[t] ? f : 0.f;
             }
@@ -496,23 +517,37 @@ pool3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ ou
         }
         uint4 r;
         r.x = pack_bf16x2(a[0], a[1]); r.y = pack_bf16x2(a[2], a[3]); r.z = pack_bf16x2(a[4], a[5]); r.w = pack_bf16x2(a[6], a[7]);
-        *reinterpret_cast<uint4*>(out + buf_at(go, b, oy, ox) + c) = r;
+        __nv_bfloat16* dst = out + buf_at(go, b, oy, ox) + c;
+        *reinterpret_cast<uint4*>(dst) = r;
+        if (out_lo) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] -= __bfloat162float(__float2bfloat16_rn(a[j]));
+            r.x = pack_bf16x2(a[0], a[1]); r.y = pack_bf16x2(a[2], a[3]); r.z = pack_bf16x2(a[4], a[5]); r.w = pack_bf16x2(a[6], a[7]);
+            *reinterpret_cast<uint4*>(dst + out_lo) = r;
+        }
     }
 }
 
 // mean over the HW pixels of a dense [B][HW][C] bf16 tensor -> fp32 [B][C] and bf16 [B][C] (either nullable)
 __global__ void __launch_bounds__(256)
 global_avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int B,
-                      int HW, int C) {
+                      int HW, int C, long long x_lo, long long out_lo) {
     pdl_entry();
     const long long total = (long long)B * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C), b = (int)(i / C);
         float s = 0.f;
-        for (int q = 0; q < HW; ++q) s += __bfloat162float(x[((long long)b * HW + q) * C + c]);
+        for (int q = 0; q < HW; ++q) {
+            const long long at = ((long long)b * HW + q) * C + c;
+            s += __bfloat162float(x[at]) + (x_lo ? __bfloat162float(x[at + x_lo]) : 0.f);
+        }
         s /= (float)HW;
         if (out_f32) out_f32[i] = s;
-        if (out_bf16) out_bf16[i] = __float2bfloat16_rn(s);
+        if (out_bf16) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(s);
+            out_bf16[i] = h;
+            if (out_lo) out_bf16[i + out_lo] = __float2bfloat16_rn(s - __bfloat162float(h));
+        }
     }
 }
 
@@ -552,7 +587,7 @@ resize_norm_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out
 // the same values resize_norm_kernel + im2col_kernel would produce (each resized pixel is rounded to bf16 first).
 __global__ void __launch_bounds__(256)
 stem_patches_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Hi, int Wi, int Hr, int Wr, int Ho, int Wo,
-                    float a, float bb, float m0, float m1, float m2, float s0, float s1, float s2) {
+                    float a, float bb, float m0, float m1, float m2, float s0, float s1, float s2, long long out_lo) {
     pdl_entry();
     const long long total = (long long)B * Ho * Wo;
     const float ry = (float)Hi / (float)Hr, rx = (float)Wi / (float)Wr;
@@ -560,7 +595,7 @@ stem_patches_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ ou
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho), b = (int)(i / ((long long)Wo * Ho));
         const float* img = in + (long long)b * 3 * Hi * Wi;
-        __align__(16) __nv_bfloat16 row[32];
+        __align__(16) __nv_bfloat16 row[32], row_lo[32];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const float fy = fmaxf(ry * ((float)(2 * oy + ky) + 0.5f) - 0.5f, 0.f);
@@ -578,16 +613,25 @@ stem_patches_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ ou
                     const float v10 = __ldg(pl + y1 * Wi + x0), v11 = __ldg(pl + y1 * Wi + x1);
                     const float top = v00 + wx * (v01 - v00), bot = v10 + wx * (v11 - v10);
                     const float v = top + wy * (bot - top);
-                    row[(ky * 3 + kx) * 3 + c] = __float2bfloat16_rn((a * v + bb - mean[c]) * istd[c]);
+                    const float val = (a * v + bb - mean[c]) * istd[c];
+                    const __nv_bfloat16 h = __float2bfloat16_rn(val);
+                    row[(ky * 3 + kx) * 3 + c] = h;
+                    row_lo[(ky * 3 + kx) * 3 + c] = __float2bfloat16_rn(val - __bfloat162float(h));
                 }
             }
         }
 #pragma unroll
-        for (int k = 27; k < 32; ++k) row[k] = __float2bfloat16_rn(0.f);
+        for (int k = 27; k < 32; ++k) row[k] = row_lo[k] = __float2bfloat16_rn(0.f);
         uint4* o = reinterpret_cast<uint4*>(out + i * 32);
         const uint4* r = reinterpret_cast<const uint4*>(row);
 #pragma unroll
         for (int q = 0; q < 4; ++q) o[q] = r[q];
+        if (out_lo) {
+            uint4* ol = reinterpret_cast<uint4*>(out + out_lo + i * 32);
+            const uint4* rl = reinterpret_cast<const uint4*>(row_lo);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ol[q] = rl[q];
+        }
     }
 }
 
@@ -680,6 +724,9 @@ extern "C" int jck_conv_gemm(const void* act, long long lda, const void* w, cons
     JCK_REQUIRE(p.Hq > 0 && p.Wq > 0 && M % (p.Hq * p.Wq) == 0 && rows_a > 0, "conv_gemm: row space %d is not B x %d x %d", M, p.Hq, p.Wq);
     for (int t = 0; t < ntaps; ++t) p.shift[t] = geom[18 + t];
     p.ldc = ldc;
+    // optional trailing entry: split-precision output, the LOW plane lies geom[18 + ntaps] output rows behind the high one
+    p.lo_out = (ngeom > 18 + ntaps) ? (long long)geom[18 + ntaps] * ldc : 0;
+    JCK_REQUIRE(p.lo_out == 0 || (!p.out_f32 && p.lo_out > 0 && p.lo_out % 8 == 0), "conv_gemm: split output needs bf16 and an 8-element aligned plane offset");
     const int nt = (N + 255) / 256;
     p.BN = (((N + nt - 1) / nt) + 15) / 16 * 16;
     p.n_tiles = (N + p.BN - 1) / p.BN;
@@ -728,6 +775,7 @@ extern "C" int jck_conv_gemm(const void* act, long long lda, const void* w, cons
         int smin = p.shift[0], smax = p.shift[0];
         for (int t = 1; t < ntaps; ++t) { smin = p.shift[t] < smin ? p.shift[t] : smin; smax = p.shift[t] > smax ? p.shift[t] : smax; }
         p.smin = smin;
+        if (smax - smin > 8192) smax = smin + (1 << 20);     // split-precision taps reach into the low plane: no window fits (falls through)
         p.wboxes = (128 + (smax - smin) + 127) / 128;
         p.win_bytes = p.wboxes * p.a_bytes;
         const int b_bytes = p.BN * 2 * p.kw;
@@ -772,22 +820,34 @@ extern "C" int jck_im2col(const void* x, const int* in_geom, long long ldx, void
 
 extern "C" int jck_pool3(const void* x, const int* in_geom, long long ldx, void* out, const int* out_geom, long long ldo, int B, int H,
                          int W, int C, int stride, int pad, int Ho, int Wo, int mode, void* stream) {
+    return jck_pool3_split(x, in_geom, ldx, 0, out, out_geom, ldo, 0, B, H, W, C, stride, pad, Ho, Wo, mode, stream);
+}
+
+extern "C" int jck_pool3_split(const void* x, const int* in_geom, long long ldx, long long x_lo, void* out, const int* out_geom,
+                               long long ldo, long long out_lo, int B, int H, int W, int C, int stride, int pad, int Ho, int Wo, int mode,
+                               void* stream) {
     JCK_REQUIRE(x && out && in_geom && out_geom && B > 0 && H > 0 && W > 0 && C > 0 && (mode == 0 || mode == 1), "pool3: bad argument");
+    JCK_REQUIRE(x_lo >= 0 && out_lo >= 0 && x_lo % 8 == 0 && out_lo % 8 == 0, "pool3: plane offsets must be multiples of 8 elements");
     const BufGeom gi = geom_of(in_geom, ldx), go = geom_of(out_geom, ldo);
     if (C % 8 != 0 || ldx % 8 != 0 || ldo % 8 != 0 || gi.c_off % 8 != 0 || go.c_off % 8 != 0)
         return set_error(JCK_E_UNSUPPORTED_SHAPE, "pool3: channels / pitches must be multiples of 8 (C=%d)", C);
     JCK_REQUIRE(mode == 1 || (pad == 0 && (Ho - 1) * stride + 3 <= H && (Wo - 1) * stride + 3 <= W), "pool3: max window leaves the image");
     const long long total = (long long)B * Ho * Wo * (C / 8);
     launch_pdl(pool3_kernel, dim3(grid_for(total, 256)), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)x, (__nv_bfloat16*)out, gi,
-               go, B, H, W, C, stride, pad, Ho, Wo, mode);
+               go, B, H, W, C, stride, pad, Ho, Wo, mode, x_lo, out_lo);
     JCK_LAUNCH_CHECK("pool3");
     return JCK_OK;
 }
 
 extern "C" int jck_global_avgpool(const void* x, float* out_f32, void* out_bf16, int B, int HW, int C, void* stream) {
-    JCK_REQUIRE(x && (out_f32 || out_bf16) && B > 0 && HW > 0 && C > 0, "global_avgpool: bad argument");
+    return jck_global_avgpool_split(x, 0, out_f32, out_bf16, 0, B, HW, C, stream);
+}
+
+extern "C" int jck_global_avgpool_split(const void* x, long long x_lo, float* out_f32, void* out_bf16, long long out_lo, int B, int HW,
+                                        int C, void* stream) {
+    JCK_REQUIRE(x && (out_f32 || out_bf16) && B > 0 && HW > 0 && C > 0 && x_lo >= 0 && out_lo >= 0, "global_avgpool: bad argument");
     launch_pdl(global_avgpool_kernel, dim3(grid_for((long long)B * C, 256)), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)x,
-               out_f32, (__nv_bfloat16*)out_bf16, B, HW, C);
+               out_f32, (__nv_bfloat16*)out_bf16, B, HW, C, x_lo, out_lo);
     JCK_LAUNCH_CHECK("global_avgpool");
     return JCK_OK;
 }
@@ -805,11 +865,17 @@ extern "C" int jck_resize_norm(const float* in_nchw, void* out_nhwc, int B, int 
 
 extern "C" int jck_stem_patches(const float* in_nchw, void* patches, int B, int Hi, int Wi, int Hr, int Wr, float a, float b,
                                 const float* mean3, const float* std3, void* stream) {
-    JCK_REQUIRE(in_nchw && patches && mean3 && std3 && B > 0 && Hi > 0 && Wi > 0 && Hr >= 3 && Wr >= 3, "stem_patches: bad argument");
+    return jck_stem_patches_split(in_nchw, patches, 0, B, Hi, Wi, Hr, Wr, a, b, mean3, std3, stream);
+}
+
+extern "C" int jck_stem_patches_split(const float* in_nchw, void* patches, long long patches_lo, int B, int Hi, int Wi, int Hr, int Wr,
+                                      float a, float b, const float* mean3, const float* std3, void* stream) {
+    JCK_REQUIRE(in_nchw && patches && mean3 && std3 && B > 0 && Hi > 0 && Wi > 0 && Hr >= 3 && Wr >= 3 && patches_lo >= 0 &&
+                patches_lo % 8 == 0, "stem_patches: bad argument");
     const int Ho = (Hr - 3) / 2 + 1, Wo = (Wr - 3) / 2 + 1;
     launch_pdl(stem_patches_kernel, dim3(grid_for((long long)B * Ho * Wo, 256)), dim3(256), 0, as_stream(stream), in_nchw,
                (__nv_bfloat16*)patches, B, Hi, Wi, Hr, Wr, Ho, Wo, a, b, mean3[0], mean3[1], mean3[2], 1.f / std3[0], 1.f / std3[1],
-               1.f / std3[2]);
+               1.f / std3[2], patches_lo);
     JCK_LAUNCH_CHECK("stem_patches");
     return JCK_OK;
 }

@@ -31,26 +31,48 @@ def k_pitch(C):
 
 
 class Buf:
-    """NHWC bf16 activation buffer with a zero border of (py, px) pixels; channel pitch ld >= C."""
+    """NHWC bf16 activation buffer with a zero border of (py, px) pixels; channel pitch ld >= C.
+    planes = 2 (split-precision mode): a second, identically laid out plane `lo` elements further on holds the low halves,
+    value = hi + lo; R = rows (bordered pixels) of one plane, so in the GEMM's row space the low plane starts at row R."""
 
-    def __init__(self, B, H, W, C, py=0, px=0, ld=None, device="cuda", dtype=torch.bfloat16):
+    def __init__(self, B, H, W, C, py=0, px=0, ld=None, device="cuda", dtype=torch.bfloat16, planes=1):
         self.B, self.H, self.W, self.C, self.py, self.px = B, H, W, C, py, px
         self.ld = ld or C
         self.Hb, self.Wb = H + 2 * py, W + 2 * px
-        self.t = torch.zeros(B * self.Hb * self.Wb * self.ld, dtype=dtype, device=device)
+        self.R = B * self.Hb * self.Wb
+        self.planes = planes
+        self.lo = self.R * self.ld if planes == 2 else 0
+        self.t = torch.zeros(planes * self.R * self.ld, dtype=dtype, device=device)
 
     def geom(self, c_off=0):
         return [self.Hb, self.Wb, self.py, self.px, c_off]
 
+    def _view(self, plane):
+        n = self.R * self.ld
+        return self.t[plane * n:(plane + 1) * n].view(self.B, self.Hb, self.Wb, self.ld)
+
     def interior(self):
-        """[B, H, W, C] view of the logical tensor (tests)."""
-        return self.t.view(self.B, self.Hb, self.Wb, self.ld)[:, self.py:self.py + self.H, self.px:self.px + self.W, :self.C]
+        """[B, H, W, C] view of the logical tensor (tests); the HIGH plane in split mode."""
+        return self._view(0)[:, self.py:self.py + self.H, self.px:self.px + self.W, :self.C]
+
+    def value(self):
+        """[B, H, W, C] fp32 values (hi + lo in split mode) -- tests"""
+        v = self.interior().float()
+        if self.planes == 2:
+            v = v + self._view(1)[:, self.py:self.py + self.H, self.px:self.px + self.W, :self.C].float()
+        return v
+
+
+def split_bf16(w):
+    """fp32 -> (hi, lo) bf16 with hi + lo = w to 16 mantissa bits"""
+    hi = w.to(torch.bfloat16)
+    return hi, (w - hi.float()).to(torch.bfloat16)
 
 
 class _Conv:
     """One BasicConv2d: packed bf16 weight matrix + folded BatchNorm (fp32 scale, bias)."""
 
-    def __init__(self, name, sd, device, dtype=torch.bfloat16):
+    def __init__(self, name, sd, device, dtype=torch.bfloat16, split=False):
         w = sd[name + ".conv.weight"].float()
         self.N, self.C, self.kh, self.kw = w.shape
         self.stride = 2 if name in STRIDE2 else 1
@@ -71,25 +93,44 @@ class _Conv:
             self.Kp = _ceil(K, 8)
             wm = torch.zeros(self.N, k_pitch(self.Kp))
             wm[:, :K] = wt.reshape(self.N, K)
-        self.w = wm.reshape(self.N, -1).to(dtype).contiguous().to(device)
+        if split:
+            # [W_hi | W_lo | W_hi] along the tap axis: pairs with the activation taps {hi, hi, lo} (InceptionV3._conv)
+            wm3 = wm.reshape(self.N, -1, wm.shape[-1])
+            hi, lo = split_bf16(wm3)
+            self.w = torch.cat([hi, lo, hi], dim=1).reshape(self.N, -1).contiguous().to(device)
+        else:
+            self.w = wm.reshape(self.N, -1).to(dtype).contiguous().to(device)
 
 
 class InceptionV3:
     """forward(images) -> fp32 features [B, 100] (feature='logits', the reference's) or [B, 2048] ('pool3')."""
 
-    def __init__(self, state_dict, feature="logits", device="cuda", K=None, act_dtype=torch.bfloat16, use_graph=True):
+    def __init__(self, state_dict, feature="logits", device="cuda", K=None, act_dtype=torch.bfloat16, use_graph=True,
+                 precision="bf16"):
+        """precision: "bf16" -- activations and weights rounded to bf16 (fastest; 0.2-0.7 % per layer), or "split" -- every
+        activation and weight kept as hi + lo bf16 pairs and every product formed as hi*hi + hi*lo + lo*hi on the same tcgen05
+        kernel (3x the MMAs, 2x the activation bytes): fp32-grade features, the mode whose free-running features are pinned
+        against torchvision fp32 (tests/test_gpu_incep.py)."""
         if K is None:
             from . import ops as K          # the C ABI; raises if libjck_b200.so is missing
             assert act_dtype == torch.bfloat16, "the kernels store activations in bf16 (fp32 is the emulator's check mode)"
+        assert precision in ("bf16", "split"), precision
+        assert precision == "bf16" or act_dtype == torch.bfloat16, "split precision is a pair of bf16 planes"
+        self.split = precision == "split"
+        self.planes = 2 if self.split else 1
         self.K, self.device, self.feature, self.dtype = K, torch.device(device), feature, act_dtype
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
         names = sorted({k[:-len(".conv.weight")] for k in sd if k.endswith(".conv.weight") and not k.startswith("AuxLogits")})
-        self.convs = {n: _Conv(n, sd, self.device, act_dtype) for n in names}
+        self.convs = {n: _Conv(n, sd, self.device, act_dtype, self.split) for n in names}
         self.fc_w = self.fc_b = None
         fcw = [k for k in sd if k.startswith("fc") and k.endswith("weight")]
         if feature == "logits":
             assert fcw, "state_dict has no fc layer"
-            self.fc_w = sd[fcw[0]].to(act_dtype).contiguous().to(self.device)              # [100][2048]
+            if self.split:
+                hi, lo = split_bf16(sd[fcw[0]].float())
+                self.fc_w = torch.cat([hi, lo, hi], dim=1).contiguous().to(self.device)      # [100][3 * 2048]
+            else:
+                self.fc_w = sd[fcw[0]].to(act_dtype).contiguous().to(self.device)          # [100][2048]
             self.fc_b = sd[fcw[0][:-len("weight")] + "bias"].float().contiguous().to(self.device)
         self._bufs = {}
         self._graphs = {}          # one CUDA graph of the 114 launches per input shape (the launches are 10-100 us each)
@@ -100,7 +141,7 @@ class InceptionV3:
     def _buf(self, key, B, H, W, C, py=0, px=0, ld=None):
         k = (key, B)
         if k not in self._bufs:
-            self._bufs[k] = Buf(B, H, W, C, py, px, ld, self.device, self.dtype)
+            self._bufs[k] = Buf(B, H, W, C, py, px, ld, self.device, self.dtype, self.planes)
         return self._bufs[k]
 
     def _scratch(self, key, numel, dtype):
@@ -124,26 +165,41 @@ class InceptionV3:
         if cv.implicit:
             assert src.py >= cv.pad[0] and src.px >= cv.pad[1], (name, "source border too small")
             shifts = [(ky - cv.pad[0]) * src.Wb + (kx - cv.pad[1]) for ky in range(cv.kh) for kx in range(cv.kw)]
-            rows = B * src.Hb * src.Wb
-            geom = [rows, cv.N, cv.C, len(shifts), src.Hb, src.Wb, src.py, src.px, Ho, Wo,
-                    dst.Hb, dst.Wb, dst.py, dst.px, c_off, 1, 1, rows] + shifts
+            rows = src.R
+            taps, rows_a, tail = self._split_taps(shifts, rows, dst)
+            geom = [rows, cv.N, cv.C, len(taps), src.Hb, src.Wb, src.py, src.px, Ho, Wo,
+                    dst.Hb, dst.Wb, dst.py, dst.px, c_off, 1, 1, rows_a] + taps + tail
             K.conv_gemm(src.t, src.ld, cv.w, cv.scale, cv.bias, dst.t, dst.ld, geom)
             self.launches += 1
         else:
             M = B * Ho * Wo
-            patches = self._scratch("patches", M * cv.Kp, self.dtype)
-            K.im2col(src.t, src.geom(), src.ld, patches, B, src.H, src.W, src.C, cv.kh, cv.kw, cv.stride, cv.stride,
-                     cv.pad[0], cv.pad[1], Ho, Wo, cv.Kp)
-            geom = [M, cv.N, cv.Kp, 1, Ho, Wo, 0, 0, Ho, Wo, dst.Hb, dst.Wb, dst.py, dst.px, c_off, 1, 1, M, 0]
+            patches = self._scratch("patches", self.planes * M * cv.Kp, self.dtype)
+            for pl in range(self.planes):           # split mode: the patch matrices of the two planes, stacked by rows
+                K.im2col(src.t[pl * src.lo:], src.geom(), src.ld, patches[pl * M * cv.Kp:], B, src.H, src.W, src.C, cv.kh, cv.kw,
+                         cv.stride, cv.stride, cv.pad[0], cv.pad[1], Ho, Wo, cv.Kp)
+            taps, rows_a, tail = self._split_taps([0], M, dst)
+            geom = [M, cv.N, cv.Kp, len(taps), Ho, Wo, 0, 0, Ho, Wo, dst.Hb, dst.Wb, dst.py, dst.px, c_off, 1, 1, rows_a] + taps + tail
             K.conv_gemm(patches, cv.Kp, cv.w, cv.scale, cv.bias, dst.t, dst.ld, geom)
-            self.launches += 2
+            self.launches += 1 + self.planes
         return dst
+
+    def _split_taps(self, shifts, rows, dst):
+        """(tap shifts, rows of A, trailing geom) of a jck_conv_gemm call.  Split precision: the low plane of A starts `rows`
+        rows behind the high one, so the three partial products hi*W_hi, hi*W_lo, lo*W_hi are the taps {s}, {s}, {rows + s}
+        against the weight blocks [W_hi | W_lo | W_hi] (_Conv), and the output's own low plane lies dst.R rows behind."""
+        if not self.split:
+            return list(shifts), rows, []
+        return list(shifts) + list(shifts) + [rows + s for s in shifts], 2 * rows, ([dst.R] if dst is not None else [])
 
     def _pool(self, src, dst, c_off, stride, pad, mode):
         Ho = (src.H + 2 * pad - 3) // stride + 1
         Wo = (src.W + 2 * pad - 3) // stride + 1
         assert (Ho, Wo) == (dst.H, dst.W)
-        self.K.pool3(src.t, src.geom(), src.ld, dst.t, dst.geom(c_off), dst.ld, src.B, src.H, src.W, src.C, stride, pad, Ho, Wo, mode)
+        if self.split:
+            self.K.pool3(src.t, src.geom(), src.ld, dst.t, dst.geom(c_off), dst.ld, src.B, src.H, src.W, src.C, stride, pad, Ho, Wo,
+                         mode, x_lo=src.lo, out_lo=dst.lo)
+        else:
+            self.K.pool3(src.t, src.geom(), src.ld, dst.t, dst.geom(c_off), dst.ld, src.B, src.H, src.W, src.C, stride, pad, Ho, Wo, mode)
         self.launches += 1
         return dst
 
@@ -223,10 +279,14 @@ class InceptionV3:
         assert C == 3, "Inception-v3 takes 3-channel images"
         cv = self.convs["Conv2d_1a_3x3"]
         M = B * 149 * 149
-        patches = self._scratch("patches", M * 32, self.dtype)
-        self.K.stem_patches(images, patches, B, Hi, Wi, 299, 299, a, b, mean, std)
+        patches = self._scratch("patches", self.planes * M * 32, self.dtype)
+        if self.split:
+            self.K.stem_patches(images, patches, B, Hi, Wi, 299, 299, a, b, mean, std, patches_lo=M * 32)
+        else:
+            self.K.stem_patches(images, patches, B, Hi, Wi, 299, 299, a, b, mean, std)
         dst = self._buf("c1a", B, 149, 149, 32)
-        geom = [M, cv.N, 32, 1, 149, 149, 0, 0, 149, 149, dst.Hb, dst.Wb, 0, 0, 0, 1, 1, M, 0]
+        taps, rows_a, tail = self._split_taps([0], M, dst)
+        geom = [M, cv.N, 32, len(taps), 149, 149, 0, 0, 149, 149, dst.Hb, dst.Wb, 0, 0, 0, 1, 1, rows_a] + taps + tail
         self.K.conv_gemm(patches, 32, cv.w, cv.scale, cv.bias, dst.t, dst.ld, geom)
         self.launches += 2
         return dst
@@ -293,14 +353,18 @@ class InceptionV3:
     def _head(self, x):
         B = x.B
         pooled = torch.empty(B, 2048, dtype=torch.float32, device=self.device)
-        pooled_bf = self._scratch("pooled_bf", B * 2048, self.dtype)
-        self.K.global_avgpool(x.t, pooled, pooled_bf, B, x.H * x.W, 2048)
+        pooled_bf = self._scratch("pooled_bf", self.planes * B * 2048, self.dtype)
+        if self.split:
+            self.K.global_avgpool(x.t, pooled, pooled_bf, B, x.H * x.W, 2048, x_lo=x.lo, out_lo=B * 2048)
+        else:
+            self.K.global_avgpool(x.t, pooled, pooled_bf, B, x.H * x.W, 2048)
         self.launches += 1
         if self.feature == "pool3":
             return pooled
         n = self.fc_w.shape[0]
         logits = torch.empty(B, n, dtype=torch.float32, device=self.device)
-        geom = [B, n, 2048, 1, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 0, B, 0]
+        taps, rows_a, _ = self._split_taps([0], B, None)
+        geom = [B, n, 2048, len(taps), 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 0, rows_a] + taps
         self.K.conv_gemm(pooled_bf, 2048, self.fc_w, None, self.fc_b, logits, n, geom)
         self.launches += 1
         return logits

@@ -39,7 +39,8 @@ SUPERCLASS = [
 
 class Metrics:
     def __init__(self, real_images=None, feature="logits", checkpoint=os.path.join('./save/iception_v3', 'loss_bset.pt'),
-                 cache=os.path.join('./data', 'metric_data.pikl'), batch=128, comm=None, allow_random_weights=None):
+                 cache=os.path.join('./data', 'metric_data.pikl'), batch=128, comm=None, allow_random_weights=None,
+                 precision=None):
         from torchvision import models
         from .inception import InceptionV3
         if not torch.cuda.is_available():
@@ -70,7 +71,14 @@ class Metrics:
             warnings.warn(f"Metrics: {checkpoint} missing -- IS / FID below come from a RANDOM-WEIGHT Inception-v3 and are "
                           "meaningless as quality scores")
         self.inception_model.eval()
-        self.extractor = InceptionV3(self.inception_model.state_dict(), feature=feature, device=self.device)
+        # "split" (default): activations / weights as hi + lo bf16 pairs, fp32-grade features -- the reference runs the network
+        # in fp32 (metrics.py:87), and this is the mode pinned against torchvision fp32 free running (tests/test_gpu_incep.py:
+        # <= 2e-3 at logits / pool3 of a random-weight network, where plain bf16 is 15 % off).  "bf16" (JCK_INCEPTION_PRECISION
+        # =bf16): one third of the tensor work, for throughput runs.
+        if precision is None:
+            precision = os.environ.get("JCK_INCEPTION_PRECISION", "split")
+        self.precision = precision
+        self.extractor = InceptionV3(self.inception_model.state_dict(), feature=feature, device=self.device, precision=precision)
 
         real_targets = getattr(real_images, "targets", None)
         fake_targets = [i for i in range(100) for _ in range(10)]

@@ -515,13 +515,21 @@ def im2col(x, in_geom, ldx, patches, B, H, W, C, kh, kw, sy, sx, py, px, Ho, Wo,
           "im2col")
 
 
-def pool3(x, in_geom, ldx, out, out_geom, ldo, B, H, W, C, stride, pad, Ho, Wo, mode):
+def pool3(x, in_geom, ldx, out, out_geom, ldo, B, H, W, C, stride, pad, Ho, Wo, mode, x_lo=0, out_lo=0):
+    """x_lo / out_lo: element offsets of the low planes in split-precision mode (include/jck_b200.h), 0 = plain bf16"""
     gi, go = _ints(in_geom), _ints(out_geom)
+    if x_lo or out_lo:
+        check(L().jck_pool3_split(_p(x), _ct.cast(gi, _ct.c_void_p), ldx, x_lo, _p(out), _ct.cast(go, _ct.c_void_p), ldo, out_lo,
+                                  B, H, W, C, stride, pad, Ho, Wo, mode, _s()), "pool3_split")
+        return
     check(L().jck_pool3(_p(x), _ct.cast(gi, _ct.c_void_p), ldx, _p(out), _ct.cast(go, _ct.c_void_p), ldo, B, H, W, C, stride, pad,
                         Ho, Wo, mode, _s()), "pool3")
 
 
-def global_avgpool(x, out_f32, out_bf16, B, HW, C):
+def global_avgpool(x, out_f32, out_bf16, B, HW, C, x_lo=0, out_lo=0):
+    if x_lo or out_lo:
+        check(L().jck_global_avgpool_split(_p(x), x_lo, _p(out_f32), _p(out_bf16), out_lo, B, HW, C, _s()), "global_avgpool_split")
+        return
     check(L().jck_global_avgpool(_p(x), _p(out_f32), _p(out_bf16), B, HW, C, _s()), "global_avgpool")
 
 
@@ -531,8 +539,12 @@ def resize_norm(x_nchw, out_nhwc, B, C, Hi, Wi, Ho, Wo, ldo, a, b, mean3, std3):
                               _ct.cast(s, _ct.c_void_p), _s()), "resize_norm")
 
 
-def stem_patches(x_nchw, patches, B, Hi, Wi, Hr, Wr, a, b, mean3, std3):
+def stem_patches(x_nchw, patches, B, Hi, Wi, Hr, Wr, a, b, mean3, std3, patches_lo=0):
     m, s = (_ct.c_float * 3)(*mean3), (_ct.c_float * 3)(*std3)
+    if patches_lo:
+        check(L().jck_stem_patches_split(_p(x_nchw), _p(patches), patches_lo, B, Hi, Wi, Hr, Wr, a, b, _ct.cast(m, _ct.c_void_p),
+                                         _ct.cast(s, _ct.c_void_p), _s()), "stem_patches_split")
+        return
     check(L().jck_stem_patches(_p(x_nchw), _p(patches), B, Hi, Wi, Hr, Wr, a, b, _ct.cast(m, _ct.c_void_p),
                                _ct.cast(s, _ct.c_void_p), _s()), "stem_patches")
 

@@ -105,17 +105,25 @@ class CGANTrainer(Trainer):
         plt.savefig(os.path.join(path, f'{iters}_fake_image.png'))
         plt.close()
 
+    def _gp_counter(self):
+        if getattr(self, "_gp_rng_counter", None) is None:
+            self._gp_rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        return self._gp_rng_counter
+
     def compute_gradient_penalty(self, real_data, fake_data, labels_data, alpha=None, dropout_mask=None):
         """mean((||d D(x_hat, y)/d x_hat||_2 - 1)^2) (reference :114-131) as a plain tensor.  Inside `train()`
         the penalty's gradient comes from CGANStep's second-order sweep, not from this method."""
         ed = self.model_d.engine()
         B = real_data.size(0)
         if alpha is None:
+            # a draw of this public method must neither collide with the step's Philox streams (ids 16*rank + 1..5) nor move
+            # the training counter: private counter, stream ids from a disjoint range
             alpha = torch.empty(B, 1, 1, 1, device=self.device)
-            ops.rand(alpha, self.step.seed, 99, self.step.rng_counter)
+            ops.rand(alpha, self.step.seed, (1 << 20) + 1, self._gp_counter())
+            ops.rng_advance(self._gp_counter(), (B + 3) // 4)
         if dropout_mask is None:
             dropout_mask = torch.empty(B, 256, dtype=torch.float32, device=self.device)
-            ops.dropout_mask(dropout_mask, 0.25, self.step.seed, 98, self.step.rng_counter)
+            ops.dropout_mask(dropout_mask, 0.25, self.step.seed, (1 << 20) + 2, self._gp_counter())
         x_hat = ops.img_alloc(B, ed.nc, 64, 64, ed.dtype, self.device, ed.img_layout)
         ops.prep_image(real_data.detach().contiguous().float(), out_nhwc=x_hat, a1=1.0,
                        x2=fake_data.detach().contiguous().float(), alpha=alpha.reshape(B).contiguous(), layout=ed.img_layout)

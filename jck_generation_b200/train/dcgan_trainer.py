@@ -112,6 +112,11 @@ class DCGANTrainer(Trainer):
             plt.savefig(os.path.join(save_path, f'{iters}_fake_image.png'))
         self.logger.debug(f'{iters} model save')
 
+    def _gp_counter(self):
+        if getattr(self, "_gp_rng_counter", None) is None:
+            self._gp_rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        return self._gp_rng_counter
+
     def compute_gradient_penalty(self, real_data, fake_data, alpha=None):
         """mean((||d D(x_hat)/d x_hat||_2 - 1)^2), x_hat = alpha*real + (1-alpha)*fake  (reference :110-127).
         Runs D forward (train mode) + the input-gradient sweep on our kernels.  The result is a plain
@@ -119,8 +124,11 @@ class DCGANTrainer(Trainer):
         ed = self.model_d.engine()
         B = real_data.size(0)
         if alpha is None:
+            # a draw of this public method must neither collide with the step's Philox streams (ids 16*rank + 1..5) nor move
+            # the training counter: private counter, stream ids from a disjoint range
             alpha = torch.empty(B, 1, 1, 1, device=self.device)
-            ops.rand(alpha, self.step.seed, 99, self.step.rng_counter)
+            ops.rand(alpha, self.step.seed, (1 << 20) + 1, self._gp_counter())
+            ops.rng_advance(self._gp_counter(), (B + 3) // 4)
         x_hat = ops.img_alloc(B, ed.nc, 64, 64, ed.dtype, self.device, ed.img_layout)
         ops.prep_image(real_data.detach().contiguous().float(), out_nhwc=x_hat, a1=1.0,
                        x2=fake_data.detach().contiguous().float(), alpha=alpha.reshape(B).contiguous(),

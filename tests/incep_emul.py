@@ -41,7 +41,11 @@ def conv_gemm(act, lda, w, scale, bias, out, ldc, geom):
     ok = (oy >= 0) & (oy < Ho) & (ox >= 0) & (ox < Wo)
     orow = ((b * Hob + oy + opy) * Wob + ox + opx) * ldc + c_off
     dst = orow[ok].view(-1, 1) + torch.arange(N).view(1, N)
-    out.view(-1)[dst.reshape(-1)] = acc[ok].reshape(-1).to(out.dtype)
+    hi = acc[ok].reshape(-1).to(out.dtype)
+    out.view(-1)[dst.reshape(-1)] = hi
+    if len(geom) > 18 + ntaps:                  # split-precision output: low plane geom[18 + ntaps] rows behind
+        lo_off = geom[18 + ntaps] * ldc
+        out.view(-1)[dst.reshape(-1) + lo_off] = (acc[ok].reshape(-1) - hi.float()).to(out.dtype)
 
 
 def im2col(x, in_geom, ldx, patches, B, H, W, C, kh, kw, sy, sx, py, px, Ho, Wo, Kp):
@@ -63,25 +67,40 @@ def im2col(x, in_geom, ldx, patches, B, H, W, C, kh, kw, sy, sx, py, px, Ho, Wo,
     patches.view(-1)[:B * Ho * Wo * Kp] = P.view(-1)
 
 
-def pool3(x, in_geom, ldx, out, out_geom, ldo, B, H, W, C, stride, pad, Ho, Wo, mode):
+def pool3(x, in_geom, ldx, out, out_geom, ldo, B, H, W, C, stride, pad, Ho, Wo, mode, x_lo=0, out_lo=0):
     src = x.view(-1)
     base = _buf_index(in_geom, ldx, B, H, W)
-    X = src[(base.unsqueeze(-1) + torch.arange(C)).reshape(-1)].view(B, H, W, C).float().permute(0, 3, 1, 2)
+    idx = (base.unsqueeze(-1) + torch.arange(C)).reshape(-1)
+    X = src[idx].float()
+    if x_lo:
+        X = X + src[idx + x_lo].float()
+    X = X.view(B, H, W, C).permute(0, 3, 1, 2)
     if mode == 0:
         Y = torch.nn.functional.max_pool2d(X, 3, stride)
     else:
         Y = torch.nn.functional.avg_pool2d(X, 3, stride, pad)
     assert Y.shape[2:] == (Ho, Wo)
     obase = _buf_index(out_geom, ldo, B, Ho, Wo)
-    out.view(-1)[(obase.unsqueeze(-1) + torch.arange(C)).reshape(-1)] = Y.permute(0, 2, 3, 1).reshape(-1).to(out.dtype)
+    oidx = (obase.unsqueeze(-1) + torch.arange(C)).reshape(-1)
+    yv = Y.permute(0, 2, 3, 1).reshape(-1)
+    hi = yv.to(out.dtype)
+    out.view(-1)[oidx] = hi
+    if out_lo:
+        out.view(-1)[oidx + out_lo] = (yv - hi.float()).to(out.dtype)
 
 
-def global_avgpool(x, out_f32, out_bf16, B, HW, C):
-    m = x.view(-1)[:B * HW * C].view(B, HW, C).float().mean(1)
+def global_avgpool(x, out_f32, out_bf16, B, HW, C, x_lo=0, out_lo=0):
+    v = x.view(-1)[:B * HW * C].float()
+    if x_lo:
+        v = v + x.view(-1)[x_lo:x_lo + B * HW * C].float()
+    m = v.view(B, HW, C).mean(1)
     if out_f32 is not None:
         out_f32.view(-1)[:B * C] = m.reshape(-1)
     if out_bf16 is not None:
-        out_bf16.view(-1)[:B * C] = m.reshape(-1).to(out_bf16.dtype)
+        hi = m.reshape(-1).to(out_bf16.dtype)
+        out_bf16.view(-1)[:B * C] = hi
+        if out_lo:
+            out_bf16.view(-1)[out_lo:out_lo + B * C] = (m.reshape(-1) - hi.float()).to(out_bf16.dtype)
 
 
 def resize_norm(x_nchw, out_nhwc, B, C, Hi, Wi, Ho, Wo, ldo, a, b, mean3, std3):
@@ -94,10 +113,18 @@ def resize_norm(x_nchw, out_nhwc, B, C, Hi, Wi, Ho, Wo, ldo, a, b, mean3, std3):
     out_nhwc.view(-1)[:o.numel()] = o.view(-1).to(out_nhwc.dtype)
 
 
-def stem_patches(x_nchw, patches, B, Hi, Wi, Hr, Wr, a, b, mean3, std3):
+def stem_patches(x_nchw, patches, B, Hi, Wi, Hr, Wr, a, b, mean3, std3, patches_lo=0):
+    Ho, Wo = (Hr - 3) // 2 + 1, (Wr - 3) // 2 + 1
+    if patches_lo:                              # split precision: the resized image in fp32, its hi / lo bf16 planes
+        f32 = torch.zeros(B * Hr * Wr * 4, dtype=torch.float32)
+        resize_norm(x_nchw, f32, B, 3, Hi, Wi, Hr, Wr, 4, a, b, mean3, std3)
+        hi = f32.to(patches.dtype)
+        lo = (f32 - hi.float()).to(patches.dtype)
+        im2col(hi, [Hr, Wr, 0, 0, 0], 4, patches, B, Hr, Wr, 3, 3, 3, 2, 2, 0, 0, Ho, Wo, 32)
+        im2col(lo, [Hr, Wr, 0, 0, 0], 4, patches.view(-1)[patches_lo:], B, Hr, Wr, 3, 3, 3, 2, 2, 0, 0, Ho, Wo, 32)
+        return
     img = torch.zeros(B * Hr * Wr * 4, dtype=patches.dtype)
     resize_norm(x_nchw, img, B, 3, Hi, Wi, Hr, Wr, 4, a, b, mean3, std3)
-    Ho, Wo = (Hr - 3) // 2 + 1, (Wr - 3) // 2 + 1
     im2col(img, [Hr, Wr, 0, 0, 0], 4, patches, B, Hr, Wr, 3, 3, 3, 2, 2, 0, 0, Ho, Wo, 32)
 
 

@@ -76,8 +76,11 @@ def test_metrics_and_input_entry_points_validate_arguments(lib):
     assert lib.jck_conv_gemm(None, 64, None, None, None, None, 64, None, 0, None) == -1 and "conv_gemm" in err()
     g19 = [128, 64, 64, 1, 8, 16, 0, 0, 8, 16, 8, 16, 0, 0, 0, 1, 1, 128, 0]
     assert lib.jck_conv_gemm(p, 64, p, None, None, p, 64, geom(*g19[:10]), 10, None) == -1
-    bad = list(g19); bad[3] = 40
-    assert lib.jck_conv_gemm(p, 64, p, None, None, p, 64, geom(*(bad + [0] * 40)), 59, None) == -1 and "geometry" in err()
+    bad = list(g19); bad[3] = 100                   # more than the 96 taps (5 x 5 taps x 3 partial products of the split mode)
+    assert lib.jck_conv_gemm(p, 64, p, None, None, p, 64, geom(*(bad + [0] * 100)), 119, None) == -1 and "geometry" in err()
+    # split-precision output asks for bf16 and an aligned plane offset
+    assert lib.jck_conv_gemm(p, 64, p, None, None, p, 63, geom(*(g19 + [3])), 20, None) == -1 and "split output" in err()
+    assert lib.jck_pool3_split(p, geom(8, 8, 0, 0, 0), 64, 4, p, geom(8, 8, 0, 0, 0), 64, 0, 1, 8, 8, 64, 1, 1, 8, 8, 1, None) == -1
     assert lib.jck_conv_gemm(p, 60, p, None, None, p, 64, geom(*g19), 19, None) == -2 and "aligned" in err()
     bad = list(g19); bad[0] = 100
     assert lib.jck_conv_gemm(p, 64, p, None, None, p, 64, geom(*bad), 19, None) == -1 and "row space" in err()

@@ -38,6 +38,43 @@ def test_graph_matches_torchvision_fp32(model):
             assert float(full[:, :b.py].abs().sum() + full[:, :, :b.px].abs().sum()) == 0.0
 
 
+def test_split_precision_graph_free_running_matches_torchvision(model):
+    """precision="split": activations and weights as hi + lo bf16 pairs, products hi*hi + hi*lo + lo*hi (the tap list and
+    the weight blocks tripled by the host graph, jck_conv_gemm itself unchanged).  FREE RUNNING against torchvision fp32:
+    5e-4 at the logits, <= 3e-3 at every block -- where plain bf16 storage is 17 % off at the logits of this (random-weight,
+    chaotic) test network.  This is the mode that pins the extractor against the reference's arithmetic end to end."""
+    from jck_generation_b200.inception import InceptionV3
+    x = torch.randn(1, 3, 299, 299, generator=torch.Generator().manual_seed(0))
+    acts = {}
+    hooks = [getattr(model, n).register_forward_hook(lambda m, i, o, n=n: acts.__setitem__(n, o))
+             for n in ("Conv2d_2b_3x3", "Mixed_5d", "Mixed_6e", "Mixed_7c")]
+    with torch.no_grad():
+        ref = model(x)
+    for h in hooks:
+        h.remove()
+    net = InceptionV3(model.state_dict(), device="cpu", K=emu, precision="split")
+    out = net.forward(x)
+    for n, r in acts.items():
+        mine = net._bufs[({"Conv2d_2b_3x3": "c2b"}.get(n, n + ".out"), 1)].value().permute(0, 3, 1, 2)
+        assert float((mine - r).norm() / r.norm()) < 5e-3, n
+    assert float((out - ref).norm() / ref.norm()) < 1.5e-3
+    assert net.launches == 94 + 2 * 4 + 1 + 13 + 1 + 1      # each stride-2 patch matrix once per plane
+    plain = InceptionV3(model.state_dict(), device="cpu", K=emu).forward(x)
+    assert float((plain - ref).norm() / ref.norm()) > 20 * float((out - ref).norm() / ref.norm())
+    # pool3 features and the generated-image entry (stem fused with resize / normalise) in split mode
+    p3 = InceptionV3(model.state_dict(), feature="pool3", device="cpu", K=emu, precision="split")
+    fake = torch.tanh(torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(2)))
+    f = p3.forward_generated(fake)
+    pre = torch.nn.functional.interpolate(0.5 * fake + 0.5, size=(299, 299), mode="bilinear", align_corners=False)
+    pre = (pre - torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    feats = {}
+    h = model.avgpool.register_forward_hook(lambda m, i, o: feats.__setitem__("p", o.flatten(1)))
+    with torch.no_grad():
+        model(pre)
+    h.remove()
+    assert float((f - feats["p"]).norm() / feats["p"].norm()) < 3e-3
+
+
 def test_pool3_features_and_generated_entry(model):
     from jck_generation_b200.inception import InceptionV3
     net = InceptionV3(model.state_dict(), feature="pool3", device="cpu", K=emu, act_dtype=torch.float32)
