@@ -544,12 +544,20 @@ def run_b200(args):
     side = (step.eg.wgrad_stream, step.ed.wgrad_stream, step.gp_stream)
     step.eg.wgrad_stream = step.ed.wgrad_stream = step.gp_stream = None
     with OpTimer(ops, torch) as ot:
+        # The host needs 50-100 us per eager launch (ctypes call, tensor-map encode, allocations, two event records), many
+        # kernels run 5-40 us: with an empty stream every start event would fire before its kernel has even been launched
+        # and the interval would measure the host.  So: time the host side of one eager step, then park the stream behind
+        # a device spin 1.5x that long before each measured step -- the whole step is queued before the GPU reaches it and
+        # the event pairs bracket back-to-back device work only.
+        torch.cuda.synchronize()
+        h0 = time.perf_counter()
+        step.run(real)
+        host_s = time.perf_counter() - h0
+        torch.cuda.synchronize()
+        ot.rec.clear()
+        spin = int(1.5 * host_s * 2.0e9) + 4_000_000
         for _ in range(2):
-            # The host needs ~30 us per eager launch (ctypes call, tensor-map encode, two event records), many kernels
-            # run 5-40 us: with an empty stream every start event would fire before its kernel has even been launched
-            # and the interval would measure the host.  Park the stream behind a ~12 ms spin so the whole step is queued
-            # before the GPU reaches it; the event pairs then bracket back-to-back device work only.
-            torch.cuda._sleep(24_000_000)
+            torch.cuda._sleep(spin)
             step.run(real)
         tab = ot.table()
     step.eg.wgrad_stream, step.ed.wgrad_stream, step.gp_stream = side
