@@ -264,10 +264,12 @@ class GradBuckets:
     jck_head_bwd mean_count) starts on the process group's stream while the sweep goes on.  finish() makes the
     current stream wait for all of them.  ready() may be called from any stream (the weight-gradient kernels run on a
     side stream): the bucket's collective is ordered after an event recorded at each call.
-    Issue order (= execution order on the process group's stream, identical on every rank): a bucket completed from a SIDE
-    stream -- a weight gradient, which lags behind the sweep -- is held back one step, so that a bucket completed next on
-    the home stream goes first.  For the generator that turns (conv2.w 8.4 MB, late) -> (conv1.w, ready earlier) into
-    conv1.w first: the small bucket no longer queues behind the wait for the slowest weight gradient."""
+    Each collective is issued from a dedicated ISSUE stream that waits for exactly the events of its bucket and nothing
+    else.  (Round-2 timeline at two GPUs, profiles/r02_scale_timeline.md: issued from whatever stream was current, the
+    collective was ordered behind everything already queued there -- a bucket completed by conv3's weight gradient waited
+    for conv2's, queued after it on the same side stream, so all three generator buckets ran back to back AFTER the last
+    weight gradient, 100 us in front of Adam; issued from the home stream it made the sweep itself wait for the lagging
+    weight-gradient stream.)  Issue order = completion order in host program order, identical on every rank."""
 
     def __init__(self, flat, comm, min_elems=1 << 19):
         self.flat, self.comm = flat, comm
@@ -283,6 +285,7 @@ class GradBuckets:
         if ids:
             self.buckets.append([lo, flat.numel, ids])
         self.bucket_of = {pid: b for b, (_, _, ids) in enumerate(self.buckets) for pid in ids}
+        self.issue_stream = torch.cuda.Stream(device=flat.grad.device) if (flat.grad.is_cuda and comm.world_size > 1) else None
         self.begin()
 
     def begin(self):
@@ -290,8 +293,6 @@ class GradBuckets:
         self.events = [[] for _ in self.buckets]
         self.issued = [False] * len(self.buckets)
         self.handles = []
-        self.deferred = None
-        self.home = torch.cuda.current_stream() if self.flat.grad.is_cuda else None
 
     def ready(self, *params):
         if self.comm.world_size == 1:
@@ -306,39 +307,35 @@ class GradBuckets:
                 self.events[b].append(ev)
             self.missing[b].discard(id(p))
             if not self.missing[b]:
-                late = self.home is not None and torch.cuda.current_stream() != self.home
-                if late:                                   # hold it back; whatever was held before goes now
-                    if self.deferred is not None:
-                        self._issue(self.deferred)
-                    self.deferred = b
-                else:
-                    self._issue(b)
-                    if self.deferred is not None:
-                        self._issue(self.deferred)
-                        self.deferred = None
+                self._issue(b)
 
     def _issue(self, b):
         if self.issued[b]:
             return
         lo, hi, _ = self.buckets[b]
-        if self.events[b]:
-            cur = torch.cuda.current_stream()
-            for ev in self.events[b]:
-                cur.wait_event(ev)
-        self.handles.append(dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=getattr(self.comm, "group", None),
-                                            async_op=True))
+        grp = getattr(self.comm, "group", None)
+        if self.issue_stream is None:                      # CPU tensors (gloo tests)
+            self.handles.append(dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=grp, async_op=True))
+        else:
+            s = self.issue_stream
+            if self.events[b]:
+                for ev in self.events[b]:
+                    s.wait_event(ev)
+            else:                                          # never marked ready: ordered after the current stream
+                s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):                     # the process group's stream orders itself after `s` only
+                self.handles.append(dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=grp, async_op=True))
         self.issued[b] = True
 
     def finish(self):
         """Start whatever was never marked ready (ordered after the current stream), then wait for everything."""
         if self.comm.world_size == 1:
             return
-        if self.deferred is not None:
-            self._issue(self.deferred)
-            self.deferred = None
         for b in range(len(self.buckets)):
             if not self.issued[b]:
                 self._issue(b)
         for h in self.handles:
             h.wait()                      # stream-ordered: the current stream waits, the host does not
+        if self.issue_stream is not None and self.handles:
+            torch.cuda.current_stream().wait_stream(self.issue_stream)      # rejoin (CUDA-graph capture needs every fork joined)
         self.handles = []
