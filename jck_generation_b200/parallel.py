@@ -271,8 +271,10 @@ class GradBuckets:
     weight gradient, 100 us in front of Adam; issued from the home stream it made the sweep itself wait for the lagging
     weight-gradient stream.)  Issue order = completion order in host program order, identical on every rank."""
 
-    def __init__(self, flat, comm, min_elems=1 << 19):
+    def __init__(self, flat, comm, min_elems=1 << 19, merge_tail=None):
         self.flat, self.comm = flat, comm
+        if merge_tail is None:
+            merge_tail = os.environ.get("JCK_MERGE_TAIL", "1") != "0"
         self.buckets = []                # [lo, hi, {param ids}]
         lo, ids = 0, set()
         for idx in flat.layout:
@@ -284,6 +286,13 @@ class GradBuckets:
                 lo, ids = end, set()
         if ids:
             self.buckets.append([lo, flat.numel, ids])
+        # The last buckets complete when the sweep is over: nothing is left to hide them behind, they run back to back in
+        # front of Adam and each pays the collective's latency (8-GPU timeline, profiles/r02_scale_timeline.md: the
+        # generator's conv2.w and conv1.w buckets 82 + 51 us).  One collective for the tail instead of two.
+        if merge_tail and len(self.buckets) >= 3:
+            lo2, _, ids2 = self.buckets[-2]
+            _, hi3, ids3 = self.buckets[-1]
+            self.buckets[-2:] = [[lo2, hi3, ids2 | ids3]]
         self.bucket_of = {pid: b for b, (_, _, ids) in enumerate(self.buckets) for pid in ids}
         self.issue_stream = torch.cuda.Stream(device=flat.grad.device) if (flat.grad.is_cuda and comm.world_size > 1) else None
         self.begin()
