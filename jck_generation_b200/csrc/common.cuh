@@ -73,6 +73,15 @@ __device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
 
 bool pdl_enabled();   // JCK_PDL=0 in the environment turns the attribute off (A/B timing)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: the "already configured" memo of a
+// launcher is kept per device (one process per GPU is the rule here, but the C ABI does not forbid a caller with several).
+struct DeviceOnce {
+    bool flags[64] = {};
+    int dev() const { int d = 0; return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : -1; }
+    bool done() const { const int d = dev(); return d >= 0 && flags[d]; }
+    void mark() { const int d = dev(); if (d >= 0) flags[d] = true; }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};

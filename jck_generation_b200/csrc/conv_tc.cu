@@ -684,12 +684,12 @@ template <int BN_, int STAGES, int MODE, int EPIM>
 int launch_pair_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
                     int m_tiles, int n_tiles, const BnBwdEpi& bb, cudaStream_t st) {
     using L = PairSmem<BN_, STAGES>;
-    static bool configured = false;
+    static DeviceOnce configured;
     auto kern = conv_tc_pair_kernel<BN_, STAGES, MODE, EPIM>;
-    if (!configured) {
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_pair smem attr: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.mark();
     }
     const int total_pairs = ((m_tiles + 1) / 2) * n_tiles * (MODE == kUpM ? 4 : 1);
     const int max_clusters = BN_ == 256 ? kNumSMs / 2 : kNumSMs;            // BN = 256 fills TMEM: one CTA per SM; else two
@@ -718,18 +718,19 @@ template <int BN_, int STAGES, int MODE, int EPI, int CTAS_PER_SM, int EPIM>
 int launch_persist_cfg(const CUtensorMap& mA, const CUtensorMap& mB, void* out, float* stats, const ConvTcParams& p,
                        int m_tiles, int n_tiles, const BnBwdEpi& bb, cudaStream_t st) {
     using L = PersistSmem<BN_, STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, STAGES, MODE, EPI, EPIM>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_persist smem attr: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.mark();
     }
     const int total = m_tiles * n_tiles * (MODE == kUpM ? 4 : 1);
     const int cap = kNumSMs * CTAS_PER_SM;
     const int grid = total < cap ? total : cap;
-    launch_pdl(conv_tc_persist_kernel<BN_, STAGES, MODE, EPI, EPIM>, dim3(grid), dim3(64 + 32 * EPI), L::kTotal, st, 
-        mA, mB, (__nv_bfloat16*)out, stats, p, n_tiles, total, bb);
+    cudaError_t e = launch_pdl(conv_tc_persist_kernel<BN_, STAGES, MODE, EPI, EPIM>, dim3(grid), dim3(64 + 32 * EPI), L::kTotal, st,
+                               mA, mB, (__nv_bfloat16*)out, stats, p, n_tiles, total, bb);
+    if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_tc_persist launch: %s", cudaGetErrorString(e));
     return JCK_OK;
 }
 
@@ -1081,12 +1082,12 @@ int conv_up_win(const void* in, const void* w, void* out, float* stats, int B, i
     int rc;
     if ((rc = map_small(&mA, in, Ca, Ws, Hs, B, kWinBW, kWinBH, 1))) return rc;
     if ((rc = map_matrix(&mB, w, 4 * 64, 4 * Ca, 32))) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(conv_up_win_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_up_win_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWinSmem);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_up_win smem attr: %s", cudaGetErrorString(e));
-        configured = true;
+        configured.mark();
     }
     ConvWinParams p{B, Hs, Ws, Ca, Ws / kWinTW, (Ws / kWinTW) * (Hs / kWinTH), ipg};
     const int total_pairs = B * p.tiles_img / 2;
@@ -1376,19 +1377,19 @@ int wgrad_tc(const void* small, const void* large, float* part, const WgradPlan&
     WgradTcParams p{B, Hs, Ws, Ca, Cb, pl.g.bw, pl.g.bh, pl.g.nb, Ws / pl.g.bw, Hs / pl.g.bh,
                     pl.total_steps, pl.steps_per_split, Cb / pl.bnw};
     dim3 grid(pl.splits, (Ca / 128) * (Cb / pl.bnw), 16 / pl.G);
-    static bool cfg64 = false, cfg128 = false;
+    static DeviceOnce cfg64, cfg128;
     if (pl.bnw == 64) {
-        if (!cfg64) {
+        if (!cfg64.done()) {
             cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
             if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
-            cfg64 = true;
+            cfg64.mark();
         }
         launch_pdl(wgrad_tc_kernel<64>, dim3(grid), dim3(kConvThreads), kWgradSmem, st, mS, mL, mP, p);
     } else {
-        if (!cfg128) {
+        if (!cfg128.done()) {
             cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmem);
             if (e != cudaSuccess) return set_error(JCK_E_CUDA, "wgrad_tc smem attr: %s", cudaGetErrorString(e));
-            cfg128 = true;
+            cfg128.mark();
         }
         launch_pdl(wgrad_tc_kernel<128>, dim3(grid), dim3(kConvThreads), kWgradSmem, st, mS, mL, mP, p);
     }
@@ -2138,12 +2139,12 @@ GemmPlan gemm_plan(int M, int N, int K) {
 
 template <int A_MN, int B_MN>
 int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, void* C, const GemmParams& p, dim3 grid, cudaStream_t st) {
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;
+    if (!cfg.done()) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              gemm_smem(kGemmMaxStages));
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "gemm_tc smem attr: %s", cudaGetErrorString(e));
-        cfg = true;
+        cfg.mark();
     }
     launch_pdl(gemm_tc_kernel<A_MN, B_MN>, dim3(grid), dim3(kConvThreads), gemm_smem(p.stages), st, mA, mB, C, p);
     JCK_LAUNCH_CHECK("gemm_tc");
@@ -2281,11 +2282,11 @@ extern "C" int jck_edge_down_img(const void* img_p4, const void* w_down_e, void*
     int rc;
     if ((rc = map_matrix(&mB, w_down_e, Ca, 64, 64))) return rc;
     if ((rc = map_rows64(&mOut, out_small, (long long)B * Hs * Ws, kTileM))) return rc;
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;
+    if (!cfg.done()) {
         cudaError_t e = cudaFuncSetAttribute(edge_down_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_down_img smem attr: %s", cudaGetErrorString(e));
-        cfg = true;
+        cfg.mark();
     }
     const int total = B * p.tiles_y;
     const int grid = total < 3 * kNumSMs ? total : 3 * kNumSMs;
@@ -2329,11 +2330,11 @@ extern "C" int jck_edge_wgrad_img(const void* small, const void* img_p4, float* 
     p.raw_stride = (p.raw_bytes + 127) & ~127;
     const int smem = (2 * kEdgeWDStages + 1) * kWgradKPix * 128 + kEdgeWDStages * p.raw_stride + 256 + 1024;
     JCK_REQUIRE(smem <= 100 * 1024, "edge_wgrad_img: raw ring too large (%d bytes)", smem);
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;
+    if (!cfg.done()) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_edge_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_wgrad_img smem attr: %s", cudaGetErrorString(e));
-        cfg = true;
+        cfg.mark();
     }
     launch_pdl(wgrad_edge_direct_kernel, dim3(pl.splits), dim3(kConvThreads), smem, st, mS, (const __nv_bfloat16*)img_p4, (float*)workspace, p);
     JCK_LAUNCH_CHECK("edge_wgrad_img");
@@ -2395,11 +2396,11 @@ extern "C" int jck_edge_up_scatter(const void* in_small, const void* w_down_e, v
     if ((rc = map_gemm_operand(&mB, w_down_e, 1, 64, 64, 64))) return rc;
     const int tiles_img = (2 * Hs + 6) / 6;                // tile t completes output rows 6t-1 .. 6t+4
     const int total = B * tiles_img;
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;
+    if (!cfg.done()) {
         cudaError_t e = cudaFuncSetAttribute(edge_up_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEUSmem);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "edge_up_scatter smem attr: %s", cudaGetErrorString(e));
-        cfg = true;
+        cfg.mark();
     }
     const int grid = total < 2 * kNumSMs ? total : 2 * kNumSMs;
     launch_pdl(edge_up_scatter_kernel, dim3(grid), dim3(192), kEUSmem, as_stream(stream), mA, mB, (__nv_bfloat16*)img_p4, B, Hs,

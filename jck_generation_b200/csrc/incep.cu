@@ -756,12 +756,12 @@ extern "C" int jck_conv_gemm(const void* act, long long lda, const void* w, cons
     if ((rc = encode_bf16_2d(&mB, w, (unsigned long long)ntaps * p.Cp, (unsigned long long)N, (unsigned long long)ntaps * p.Cp * 2,
                              (unsigned)p.kw, (unsigned)p.BN, sw64)))
         return rc;
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;
+    if (!cfg.done()) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return set_error(JCK_E_CUDA, "conv_gemm smem attr: %s", cudaGetErrorString(e));
-        cfg = true;
+        cfg.mark();
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     // window kernel: multi-tap layers whose filter bank is resident (measured: the two 32-channel 3 x 3 stem layers 531 -> 480 and

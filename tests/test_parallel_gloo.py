@@ -142,3 +142,25 @@ def test_rank_rows_of_a_global_batch():
         assert torch.equal(torch.cat([parts[r][b][1] for r in range(4)]), full[b][1])
     plain = list(SyntheticLoader(16, 1, pin=False, rank=1, world=2))
     assert plain[0][0].shape[0] == 8 and plain[0][1].shape[0] == 8
+
+
+def test_gradient_buckets_of_the_dcgan_networks():
+    """parallel.GradBuckets on the real parameter lists: reverse parameter order, >= 2 MB per bucket, and the buckets that
+    complete with the last gradients merged into one collective (profiles/r02_scale_timeline.md).  D: [conv5.w .. conv4.w]
+    (hidden behind the sweep) + [norm3 .. conv1.w]; G: [conv5.w .. conv3.w] + [norm2, conv2.w, norm1, conv1.w]."""
+    from jck_generation_b200 import parallel
+    from oracle import models
+    g, d = models.build("DCGAN", seed=1)
+    for net, first, tail in ((d, {"conv5.weight", "norm4.weight", "norm4.bias", "conv4.weight"}, "conv1.weight"),
+                             (g, {"conv5.weight", "norm4.weight", "norm4.bias", "conv4.weight", "norm3.weight", "norm3.bias",
+                                  "conv3.weight"}, "conv1.weight")):
+        flat = parallel.FlatParams(net)
+        names = {id(p): n for n, p in net.named_parameters()}
+        merged = parallel.GradBuckets(flat, parallel.LocalComm(), merge_tail=True)
+        plain = parallel.GradBuckets(flat, parallel.LocalComm(), merge_tail=False)
+        assert len(plain.buckets) == 3 and len(merged.buckets) == 2
+        assert {names[i] for i in merged.buckets[0][2]} == first
+        assert "conv2.weight" in {names[i] for i in merged.buckets[1][2]} and tail in {names[i] for i in merged.buckets[1][2]}
+        # contiguous cover of the flat buffer, every parameter in exactly one bucket
+        assert merged.buckets[0][0] == 0 and merged.buckets[0][1] == merged.buckets[1][0] and merged.buckets[1][1] == flat.numel
+        assert sorted(i for b in merged.buckets for i in b[2]) == sorted(names)
